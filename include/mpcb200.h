@@ -1,0 +1,137 @@
+/* libmpcb200 -- B200 (sm_100a) native S-T MPC hot path, C ABI.
+ *
+ * Drop-in boundary for the one native component of jlubars/RL-MPC-LaneMerging
+ * (the CPython extension `st_cy`, reference st_cy.pyx:315 `solve_s_t_path_fast`, called from
+ * st.py:740-746) widened batch-first to the functions around it on the hot path
+ * (SURVEY.md §8a/§8b).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - every `d_*` pointer is a DEVICE pointer on the handle's device, every `h_*` pointer a HOST
+ *    pointer (pinned memory gives asynchronous copies);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - all entry points return 0 on success or a negative MPC_E_* code; mpc_last_error() returns
+ *    a thread-local message for the last failure;
+ *  - an infeasible plan is NOT an error (reference st.py:762-767): it is reported as
+ *    reached_t < num_t-1, idx = -1 and s_seq = 0.0 for the unreached layers;
+ *  - traffic state layout (structure of arrays, fp64 like the reference's HighwayState,
+ *    prediction.py:9-20):  ego[B][4] = (x, y, speed, acceleration); cars_x/v/a[B][nmax] sorted
+ *    front->back (descending x), entries >= n_cars[b] ignored; n_cars[B] int32.
+ *  - a handle is bound to one device and is not thread-safe; use one handle per stream.
+ */
+#ifndef MPCB200_H
+#define MPCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_ABI_VERSION 1
+
+enum {
+    MPC_OK = 0,
+    MPC_E_INVALID = -1,      /* bad argument */
+    MPC_E_CUDA = -2,         /* CUDA runtime failure (message has the cudaError string) */
+    MPC_E_CAPACITY = -3,     /* batch / nmax / grid larger than the handle was created for */
+    MPC_E_NODEVICE = -4      /* no usable CUDA device: the library has NO CPU fallback */
+};
+
+/* arithmetic of the DP solve */
+enum {
+    MPC_MODE_FAST = 0,   /* integer-cell kinematics, fp32 labels (north_star tolerance 1e-4 rel)  */
+    MPC_MODE_EXACT = 1   /* fp64, reference operation order: index-identical to st_cy            */
+};
+
+/* Snapshot of the reference's global `Settings` scalars the path reads (config.py:30-37,94-110,
+ * 143,146-153).  Taken at mpc_create / mpc_set_params; later Settings mutation needs a refresh. */
+typedef struct mpc_params {
+    double s_disc, t_disc, future_s, future_t;             /* S/T_DISCRETIZATION, FUTURE_S/T        */
+    double start_uncertainty, uncertainty_per_second;
+    double d_weight, v_weight, a_weight, j_weight;
+    double desired_speed, max_speed;
+    double a_min, a_max, j_min, j_max;                     /* MAX_NEGATIVE/POSITIVE_ACCELERATION, MINIMUM_NEGATIVE/MAXIMUM_POSITIVE_JERK */
+    double min_allowed_distance, crash_min_s, car_length;
+    double max_predicted_decel;                            /* MAX_PREDICTED_DECELERATION            */
+    double tick_length, sensor_radius;
+    double combination_min_distance;
+} mpc_params;
+
+typedef struct mpc_handle mpc_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int         mpc_abi_version(void);
+const char *mpc_last_error(void);
+void        mpc_default_params(mpc_params *p);           /* configs/st_*.json values               */
+int         mpc_device_count(void);                      /* 0 when there is no GPU                 */
+/* Scratch (layer descriptors, back-pointers, work counters) is sized here; nothing is allocated
+ * on the hot path.  nmax <= 32. */
+int mpc_create(const mpc_params *p, int device, int max_batch, int nmax, mpc_handle **out);
+int mpc_set_params(mpc_handle *h, const mpc_params *p);
+int mpc_destroy(mpc_handle *h);
+/* num_t is fixed by the params; num_s depends on start_s through numpy.arange's length rule
+ * (st.py:31), so only its maximum is a handle constant. */
+int mpc_grid_dims(const mpc_handle *h, int *num_t, int *num_s_max);
+/* counters of the last call on this handle: [0] kernels launched, [1] problems that overflowed
+ * the fast kernel's shared-memory window / bucket capacity and were re-solved by the exact kernel */
+int mpc_last_counters(const mpc_handle *h, int64_t *out2);
+
+/* ---- K1: traffic prediction + S-T rasterisation (st.find_s_t_obstacles_from_state, st.py:25-70,
+ *      with prediction.py:22-105 and control.py:373-389) ------------------------------------- */
+/* Dense grids, the layout st_cy consumes: d_obstacles u8[B][num_t][num_s_max],
+ * d_distances f64 (dist_f32=0) or f32 (dist_f32=1) [B][num_t][num_s_max]; cells >= num_s[b] are
+ * written as obstacle=1 / distance=0.  d_start_s f64[B], d_delta_s f64[B] (= s_values[1]-s_values[0]),
+ * d_num_s i32[B] may each be NULL. */
+int mpc_build_grid(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
+                   const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars,
+                   uint8_t *d_obstacles, void *d_distances, int dist_f32,
+                   double *d_start_s, double *d_delta_s, int32_t *d_num_s, void *stream);
+
+/* ---- K2: the drop-in for st_cy.solve_s_t_path_fast (st_cy.pyx:315-399) on caller-supplied dense
+ *      grids.  s_values are implied by (start_s, delta_s, num_s) exactly as numpy.arange fills
+ *      them.  Outputs: d_idx i32[B][num_t], d_s_seq f64[B][num_t], d_cost f64[B] (sum of edge
+ *      costs along the returned path), d_reached_t i32[B]; any output may be NULL. ------------- */
+int mpc_solve_dense(mpc_handle *h, int B, int num_t, int num_s_stride, const uint8_t *d_obstacles,
+                    const void *d_distances, int dist_f32, const double *d_start_s,
+                    const double *d_delta_s, const int32_t *d_num_s, const double *d_v0,
+                    const double *d_a0, int mode, int32_t *d_idx, double *d_s_seq, double *d_cost,
+                    int32_t *d_reached_t, void *stream);
+
+/* ---- K3: fused gap-evaluation = st.get_appropriate_base_st_path_and_obstacles (st.py:726-754)
+ *      + st.test_guaranteed_crash_from_state (st.py:790-802) without materialising the grid.
+ *      Extra outputs: d_crash u8[B] (guaranteed-crash verdict), d_min_dist f64[B] (smallest
+ *      distance-field value along the path, +inf when the plan is incomplete),
+ *      d_start_s f64[B].  Any output may be NULL. ---------------------------------------------- */
+int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
+             const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars, int mode,
+             int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
+             uint8_t *d_crash, double *d_min_dist, double *d_start_s, void *stream);
+
+/* Same call with HOST buffers: copies the state in, plans, copies the results out and
+ * synchronises the stream (the end-to-end path a CPU caller such as the reference's
+ * control.run_episode loop uses). */
+int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const double *h_cars_x,
+                  const double *h_cars_v, const double *h_cars_a, const int32_t *h_n_cars, int mode,
+                  int32_t *h_idx, double *h_s_seq, double *h_cost, int32_t *h_reached_t,
+                  uint8_t *h_crash, double *h_min_dist, double *h_start_s, void *stream);
+
+/* ---- K4: rollout tick pieces ------------------------------------------------------------------
+ * HighwayState.predict_step_with_ego (prediction.py:46-105), batched, in place allowed
+ * (out pointers may alias in pointers).  d_selected_speed f64[B]; d_crashed u8[B]. */
+int mpc_predict_step_with_ego(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
+                              const double *d_cars_v, const double *d_cars_a,
+                              const int32_t *d_n_cars, const double *d_selected_speed, double dt,
+                              double min_crash_distance, double *d_ego_out, double *d_cars_x_out,
+                              double *d_cars_v_out, double *d_cars_a_out, uint8_t *d_crashed,
+                              void *stream);
+/* dqn.get_state_vector_from_base_state (dqn.py:389-446) -> f32 [B][out_stride] (first 20 columns
+ * written); control.get_ego_speed_from_jerk (control.py:160-171) -> f64[B]. */
+int mpc_state_vector(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
+                     const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars,
+                     float *d_out, int out_stride, void *stream);
+int mpc_speed_from_jerk(mpc_handle *h, int B, const double *d_ego, const double *d_jerk,
+                        double *d_speed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB200_H */

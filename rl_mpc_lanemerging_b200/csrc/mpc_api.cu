@@ -1,0 +1,375 @@
+// C-ABI entry points of libmpcb200 (see include/mpcb200.h).  Host-side only: parameter derivation,
+// scratch ownership, launch configuration.  There is deliberately no CPU fallback: without a CUDA
+// device every compute entry point fails with MPC_E_NODEVICE.
+#include "mpc_common.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+// ---- launchers implemented in the kernel translation units ----------------------------------------
+cudaError_t launch_solve_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
+cudaError_t launch_solve_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
+                               int dist_f32, int stride, cudaStream_t st);
+cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
+                                  const int32_t *n, LayerDesc *desc, double *s0, double *ds, int32_t *ns, cudaStream_t st);
+cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const LayerDesc *desc, const double *s0, const double *ds,
+                             const int32_t *ns, uint8_t *obstacles, void *distances, int dist_f32, cudaStream_t st);
+cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
+                                const double *ca, const int32_t *n, const double *sel, double dt, double mcd, double *ego_out,
+                                double *ox, double *ov, double *oa, uint8_t *crashed, cudaStream_t st);
+cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
+                                const double *ca, const int32_t *n, float *out, int stride, cudaStream_t st);
+cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st);
+int solve_occupancy(int mode, int desc, int threads, size_t smem);
+
+// ---- errors ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+int mpc_set_error(int code, const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
+int mpc_set_cuda_error(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return MPC_E_CUDA;
+}
+extern "C" const char *mpc_last_error(void) { return g_err; }
+extern "C" int mpc_abi_version(void) { return MPC_ABI_VERSION; }
+extern "C" int mpc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+extern "C" void mpc_default_params(mpc_params *p) {
+    p->s_disc = 0.05; p->t_disc = 0.30; p->future_s = 150.0; p->future_t = 5.0;
+    p->start_uncertainty = 0.0; p->uncertainty_per_second = 0.0;
+    p->d_weight = 10.0; p->v_weight = 0.5; p->a_weight = 10.0; p->j_weight = 10.0;
+    p->desired_speed = 30.0; p->max_speed = 30.0;
+    p->a_min = -6.0; p->a_max = 4.5; p->j_min = -5.0; p->j_max = 5.0;
+    p->min_allowed_distance = 5.0; p->crash_min_s = 20.0; p->car_length = 5.0;
+    p->max_predicted_decel = -4.0; p->tick_length = 0.2; p->sensor_radius = 125.0;
+    p->combination_min_distance = 5.1;
+}
+
+// ---- handle ------------------------------------------------------------------------------------------
+struct mpc_handle {
+    DevParams P;
+    int device, max_batch, nmax;
+    int sm_count; size_t smem_optin;
+    // launch configuration
+    int W;                       // label-array length (cells)
+    size_t smem;                 // dynamic shared memory of the DP kernels (0 -> exact kernel uses global scratch)
+    int threads, grid_fast, grid_exact, grid_max;
+    // scratch
+    LayerDesc *desc; double *s0, *ds; int32_t *num_s;
+    uint16_t *bp; int *counters; int32_t *fallback_list;
+    unsigned long long *glab; unsigned *ghist;
+    // staging for the host-buffer entry point
+    double *st_ego, *st_cx, *st_cv, *st_ca; int32_t *st_n;
+    int32_t *st_idx; double *st_seq, *st_cost, *st_mind, *st_s0; int32_t *st_reached; uint8_t *st_crash;
+    int64_t kernels_launched;
+};
+
+static int host_arange_len(double start, double stop, double step) {
+    double c = ceil((stop - start) / step);
+    return c < 0 ? 0 : (int)c;
+}
+static bool near_int(double x, double eps) { return fabs(x - nearbyint(x)) < eps; }
+
+static int derive_params(const mpc_params *p, DevParams *D) {
+    memset(D, 0, sizeof(*D));
+    D->p = *p;
+    if (!(p->s_disc > 0) || !(p->t_disc > 0) || !(p->future_s > 0) || !(p->future_t >= 0))
+        return mpc_set_error(MPC_E_INVALID, "discretisation / horizon must be positive");
+    D->num_t = host_arange_len(0.0, p->future_t + p->t_disc, p->t_disc);
+    if (D->num_t < 3 || D->num_t > MPC_MAX_T) return mpc_set_error(MPC_E_INVALID, "num_t must be in [3,128]");
+    D->num_s_max = host_arange_len(0.0, p->future_s + p->s_disc, p->s_disc) + 1;
+    if (D->num_s_max > 65000) return mpc_set_error(MPC_E_INVALID, "num_s too large for 16-bit back-pointers");
+    D->discrete_length = (int)(p->car_length / p->s_disc);
+    D->dt2 = pow(p->t_disc, 2.0);
+    D->dt3 = pow(p->t_disc, 3.0);
+    D->obs_min_s = p->crash_min_s - p->min_allowed_distance;
+    D->crash_thresh = p->combination_min_distance - p->car_length;
+    // jerk / acceleration / speed limits in cells per step^n
+    double ds = p->s_disc, dt = p->t_disc;
+    double jlo = p->j_min * dt * dt * dt / ds, jhi = p->j_max * dt * dt * dt / ds;
+    double alo = p->a_min * dt * dt / ds, ahi = p->a_max * dt * dt / ds;
+    double vmax = p->max_speed * dt / ds;
+    D->lmax = (int)floor(jhi - jlo) + 3;
+    const double eps = 1e-6;
+    D->jlo_c = (int)ceil(jlo); D->jhi_c = (int)floor(jhi);
+    D->alo_c = (int)ceil(alo); D->ahi_c = (int)floor(ahi);
+    D->vmax_is_int = near_int(vmax, 1e-9) ? 1 : 0;
+    D->vmax_c = D->vmax_is_int ? (int)nearbyint(vmax) : (int)floor(vmax);
+    D->jhi_r = jhi; D->ahi_r = ahi; D->vmax_r = vmax;
+    bool ok = !near_int(jlo, eps) && !near_int(jhi, eps) && !near_int(alo, eps) && !near_int(ahi, eps);
+    if (!D->vmax_is_int) ok = ok && !near_int(vmax, eps) && !near_int(vmax - jhi, eps) && !near_int(vmax - ahi, eps);
+    ok = ok && D->vmax_c <= 250 && D->alo_c >= -120 && D->ahi_c <= 120 && D->lmax <= 64 && alo < 0 && ahi > 0;
+    D->fast_ok = ok ? 1 : 0;
+    D->cv = (float)(p->v_weight * (ds / dt) * (ds / dt));
+    D->ca = (float)(p->a_weight * (ds / (dt * dt)) * (ds / (dt * dt)));
+    D->cj = (float)(p->j_weight * (ds / (dt * dt * dt)) * (ds / (dt * dt * dt)));
+    D->vdes_c = (float)(p->desired_speed * dt / ds);
+    D->dw = (float)p->d_weight;
+    return MPC_OK;
+}
+
+static void free_scratch(mpc_handle *h) {
+    void *ptrs[] = {h->desc, h->s0, h->ds, h->num_s, h->bp, h->counters, h->fallback_list, h->glab, h->ghist, h->st_ego,
+                    h->st_cx, h->st_cv, h->st_ca, h->st_n, h->st_idx, h->st_seq, h->st_cost, h->st_mind, h->st_s0,
+                    h->st_reached, h->st_crash};
+    for (void *p : ptrs) if (p) cudaFree(p);
+}
+
+static int configure(mpc_handle *h) {
+    const DevParams &P = h->P;
+    h->W = (P.num_s_max + 7) & ~7;
+    size_t need = (size_t)h->W * 24;
+    size_t static_smem = 4096;                       // BlockShared + LayerDesc + path buffer (upper bound)
+    const char *env_threads = getenv("MPC_THREADS");
+    if (need + static_smem <= h->smem_optin) {
+        h->smem = need;
+        int bps = (int)((h->smem_optin + 1024) / (need + static_smem + 1024));
+        if (bps < 1) bps = 1;
+        h->threads = bps >= 3 ? 256 : 512;
+        if (env_threads) { int t = atoi(env_threads); if (t >= 64 && t <= 512 && t % 32 == 0) h->threads = t; }
+        int occ_fast = solve_occupancy(MPC_MODE_FAST, 1, h->threads, h->smem);
+        int occ_exact = solve_occupancy(MPC_MODE_EXACT, 1, h->threads, h->smem);
+        if (occ_fast < 1) occ_fast = 1;
+        if (occ_exact < 1) occ_exact = 1;
+        h->grid_fast = h->sm_count * occ_fast;
+        h->grid_exact = h->sm_count * occ_exact;
+    } else {                                         // e.g. H = 100: labels live in per-block global scratch
+        h->smem = 0;
+        h->threads = 512;
+        h->grid_fast = 0;
+        h->grid_exact = h->sm_count * 2;
+    }
+    h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
+    return MPC_OK;
+}
+
+static int alloc_scratch(mpc_handle *h) {
+    const DevParams &P = h->P;
+    size_t B = (size_t)h->max_batch, T = (size_t)P.num_t, N = (size_t)h->nmax;
+    MPC_CUDA_OK(cudaMalloc(&h->desc, B * T * sizeof(LayerDesc)));
+    MPC_CUDA_OK(cudaMalloc(&h->s0, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->ds, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->num_s, B * 4));
+    MPC_CUDA_OK(cudaMalloc(&h->bp, (size_t)h->grid_max * T * h->W * sizeof(uint16_t)));
+    MPC_CUDA_OK(cudaMalloc(&h->counters, 16 * sizeof(int)));
+    MPC_CUDA_OK(cudaMalloc(&h->fallback_list, B * 4));
+    if (h->smem == 0) {
+        MPC_CUDA_OK(cudaMalloc(&h->glab, (size_t)h->grid_exact * 2 * h->W * 8));
+        MPC_CUDA_OK(cudaMalloc(&h->ghist, (size_t)h->grid_exact * 2 * h->W * 4));
+    }
+    MPC_CUDA_OK(cudaMalloc(&h->st_ego, B * 4 * 8));
+    MPC_CUDA_OK(cudaMalloc(&h->st_cx, B * N * 8)); MPC_CUDA_OK(cudaMalloc(&h->st_cv, B * N * 8)); MPC_CUDA_OK(cudaMalloc(&h->st_ca, B * N * 8));
+    MPC_CUDA_OK(cudaMalloc(&h->st_n, B * 4));
+    MPC_CUDA_OK(cudaMalloc(&h->st_idx, B * T * 4)); MPC_CUDA_OK(cudaMalloc(&h->st_seq, B * T * 8));
+    MPC_CUDA_OK(cudaMalloc(&h->st_cost, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->st_mind, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->st_s0, B * 8));
+    MPC_CUDA_OK(cudaMalloc(&h->st_reached, B * 4)); MPC_CUDA_OK(cudaMalloc(&h->st_crash, B));
+    return MPC_OK;
+}
+
+extern "C" int mpc_create(const mpc_params *p, int device, int max_batch, int nmax, mpc_handle **out) {
+    if (!p || !out || max_batch <= 0) return mpc_set_error(MPC_E_INVALID, "mpc_create: bad argument");
+    if (nmax <= 0 || nmax > MPC_NMAX) return mpc_set_error(MPC_E_CAPACITY, "mpc_create: nmax must be in [1,32]");
+    int ndev = mpc_device_count();
+    if (ndev <= 0) return mpc_set_error(MPC_E_NODEVICE, "no CUDA device: libmpcb200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return mpc_set_error(MPC_E_INVALID, "mpc_create: bad device index");
+    MPC_CUDA_OK(cudaSetDevice(device));
+    mpc_handle *h = (mpc_handle *)calloc(1, sizeof(mpc_handle));
+    int rc = derive_params(p, &h->P);
+    if (rc) { free(h); return rc; }
+    h->device = device; h->max_batch = max_batch; h->nmax = nmax;
+    cudaDeviceProp prop;
+    MPC_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    configure(h);
+    rc = alloc_scratch(h);
+    if (rc) { free_scratch(h); free(h); return rc; }
+    *out = h;
+    return MPC_OK;
+}
+
+extern "C" int mpc_set_params(mpc_handle *h, const mpc_params *p) {
+    if (!h || !p) return mpc_set_error(MPC_E_INVALID, "mpc_set_params: bad argument");
+    DevParams D;
+    int rc = derive_params(p, &D);
+    if (rc) return rc;
+    if (D.num_t != h->P.num_t || D.num_s_max != h->P.num_s_max)
+        return mpc_set_error(MPC_E_CAPACITY, "mpc_set_params: grid dimensions changed; create a new handle");
+    h->P = D;
+    return MPC_OK;
+}
+
+extern "C" int mpc_destroy(mpc_handle *h) {
+    if (!h) return MPC_OK;
+    cudaSetDevice(h->device);
+    free_scratch(h);
+    free(h);
+    return MPC_OK;
+}
+
+extern "C" int mpc_grid_dims(const mpc_handle *h, int *num_t, int *num_s_max) {
+    if (!h) return mpc_set_error(MPC_E_INVALID, "null handle");
+    if (num_t) *num_t = h->P.num_t;
+    if (num_s_max) *num_s_max = h->P.num_s_max;
+    return MPC_OK;
+}
+
+extern "C" int mpc_last_counters(const mpc_handle *h, int64_t *out2) {
+    if (!h || !out2) return mpc_set_error(MPC_E_INVALID, "null argument");
+    int c[16];
+    MPC_CUDA_OK(cudaSetDevice(h->device));
+    MPC_CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out2[0] = h->kernels_launched;
+    out2[1] = c[2];
+    return MPC_OK;
+}
+
+static int check_batch(mpc_handle *h, int B) {
+    if (!h) return mpc_set_error(MPC_E_INVALID, "null handle");
+    if (B < 0) return mpc_set_error(MPC_E_INVALID, "negative batch");
+    if (B > h->max_batch) return mpc_set_error(MPC_E_CAPACITY, "batch larger than the handle's max_batch");
+    MPC_CUDA_OK(cudaSetDevice(h->device));
+    return MPC_OK;
+}
+
+// ---- K1 ----------------------------------------------------------------------------------------------
+extern "C" int mpc_build_grid(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                              const double *d_cars_a, const int32_t *d_n_cars, uint8_t *d_obstacles, void *d_distances,
+                              int dist_f32, double *d_start_s, double *d_delta_s, int32_t *d_num_s, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars || !d_obstacles || !d_distances) return mpc_set_error(MPC_E_INVALID, "mpc_build_grid: null pointer");
+    (void)d_cars_a;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, h->s0, h->ds, h->num_s, st));
+    MPC_CUDA_OK(launch_rasterise(h->P, B, h->P.num_s_max, h->desc, h->s0, h->ds, h->num_s, d_obstacles, d_distances, dist_f32, st));
+    if (d_start_s) MPC_CUDA_OK(cudaMemcpyAsync(d_start_s, h->s0, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_delta_s) MPC_CUDA_OK(cudaMemcpyAsync(d_delta_s, h->ds, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_num_s) MPC_CUDA_OK(cudaMemcpyAsync(d_num_s, h->num_s, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    h->kernels_launched = 2;
+    return MPC_OK;
+}
+
+// ---- K2 / K3 -----------------------------------------------------------------------------------------
+static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, const uint8_t *ob, const void *dist, int dist_f32,
+                     int stride, cudaStream_t st) {
+    if (mode != MPC_MODE_FAST && mode != MPC_MODE_EXACT) return mpc_set_error(MPC_E_INVALID, "unknown mode");
+    if (mode == MPC_MODE_FAST && (!h->P.fast_ok || h->grid_fast == 0)) mode = MPC_MODE_EXACT;   // still on the GPU
+    MPC_CUDA_OK(cudaMemsetAsync(h->counters, 0, 16 * sizeof(int), st));
+    io.bp = h->bp; io.bp_stride = h->W;
+    io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
+    io.subset = nullptr; io.B_dev = nullptr;
+    SolveLaunch L;
+    L.mode = mode; L.B = B; L.threads = h->threads; L.smem = h->smem; L.W = h->W;
+    L.glab = h->smem ? nullptr : h->glab; L.ghist = h->smem ? nullptr : h->ghist;
+    L.grid = mode == MPC_MODE_FAST ? h->grid_fast : h->grid_exact;
+    if (L.grid > B) L.grid = B;
+    io.work_counter = h->counters + 0;
+    cudaError_t e = dense ? launch_solve_dense(h->P, L, io, ob, dist, dist_f32, stride, st) : launch_solve_desc(h->P, L, io, h->desc, st);
+    if (e != cudaSuccess) return mpc_set_cuda_error(e, "solve launch");
+    h->kernels_launched++;
+    if (mode == MPC_MODE_FAST) {          // re-solve (on the device) whatever the fast kernel handed back
+        SolveLaunch L2 = L;
+        L2.mode = MPC_MODE_EXACT;
+        L2.grid = h->grid_exact < 16 ? h->grid_exact : 16;
+        if (L2.grid > B) L2.grid = B;
+        io.work_counter = h->counters + 1;
+        io.subset = h->fallback_list; io.B_dev = h->counters + 2;
+        e = dense ? launch_solve_dense(h->P, L2, io, ob, dist, dist_f32, stride, st) : launch_solve_desc(h->P, L2, io, h->desc, st);
+        if (e != cudaSuccess) return mpc_set_cuda_error(e, "fallback solve launch");
+        h->kernels_launched++;
+    }
+    return MPC_OK;
+}
+
+extern "C" int mpc_solve_dense(mpc_handle *h, int B, int num_t, int num_s_stride, const uint8_t *d_obstacles, const void *d_distances,
+                               int dist_f32, const double *d_start_s, const double *d_delta_s, const int32_t *d_num_s,
+                               const double *d_v0, const double *d_a0, int mode, int32_t *d_idx, double *d_s_seq, double *d_cost,
+                               int32_t *d_reached_t, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (num_t != h->P.num_t) return mpc_set_error(MPC_E_INVALID, "mpc_solve_dense: num_t does not match the handle's horizon");
+    if (num_s_stride > h->W) return mpc_set_error(MPC_E_CAPACITY, "mpc_solve_dense: row stride larger than the handle's num_s_max");
+    if (!d_obstacles || !d_distances || !d_start_s || !d_delta_s || !d_num_s || !d_v0 || !d_a0) return mpc_set_error(MPC_E_INVALID, "mpc_solve_dense: null pointer");
+    SolveIO io; memset(&io, 0, sizeof(io));
+    io.s0 = d_start_s; io.ds = d_delta_s; io.num_s = d_num_s; io.v0 = d_v0; io.a0 = d_a0;
+    io.idx = d_idx; io.s_seq = d_s_seq; io.cost = d_cost; io.reached = d_reached_t;
+    h->kernels_launched = 0;
+    return run_solve(h, B, mode, true, io, d_obstacles, d_distances, dist_f32, num_s_stride, (cudaStream_t)stream);
+}
+
+extern "C" int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v, const double *d_cars_a,
+                        const int32_t *d_n_cars, int mode, int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
+                        uint8_t *d_crash, double *d_min_dist, double *d_start_s, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars) return mpc_set_error(MPC_E_INVALID, "mpc_plan: null pointer");
+    (void)d_cars_a;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, d_start_s ? d_start_s : h->s0, h->ds, h->num_s, st));
+    h->kernels_launched = 1;
+    SolveIO io; memset(&io, 0, sizeof(io));
+    io.ego = d_ego;
+    io.idx = d_idx; io.s_seq = d_s_seq; io.cost = d_cost; io.reached = d_reached_t; io.crash = d_crash; io.min_dist = d_min_dist;
+    return run_solve(h, B, mode, false, io, nullptr, nullptr, 0, 0, st);
+}
+
+extern "C" int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const double *h_cars_x, const double *h_cars_v, const double *h_cars_a,
+                             const int32_t *h_n_cars, int mode, int32_t *h_idx, double *h_s_seq, double *h_cost, int32_t *h_reached_t,
+                             uint8_t *h_crash, double *h_min_dist, double *h_start_s, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!h_ego || !h_cars_x || !h_cars_v || !h_n_cars) return mpc_set_error(MPC_E_INVALID, "mpc_plan_host: null pointer");
+    (void)h_cars_a;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t N = (size_t)h->nmax, T = (size_t)h->P.num_t, b = (size_t)B;
+    MPC_CUDA_OK(cudaMemcpyAsync(h->st_ego, h_ego, b * 32, cudaMemcpyHostToDevice, st));
+    MPC_CUDA_OK(cudaMemcpyAsync(h->st_cx, h_cars_x, b * N * 8, cudaMemcpyHostToDevice, st));
+    MPC_CUDA_OK(cudaMemcpyAsync(h->st_cv, h_cars_v, b * N * 8, cudaMemcpyHostToDevice, st));
+    MPC_CUDA_OK(cudaMemcpyAsync(h->st_n, h_n_cars, b * 4, cudaMemcpyHostToDevice, st));
+    rc = mpc_plan(h, B, h->st_ego, h->st_cx, h->st_cv, nullptr, h->st_n, mode, h_idx ? h->st_idx : nullptr, h_s_seq ? h->st_seq : nullptr,
+                  h_cost ? h->st_cost : nullptr, h_reached_t ? h->st_reached : nullptr, h_crash ? h->st_crash : nullptr,
+                  h_min_dist ? h->st_mind : nullptr, h_start_s ? h->st_s0 : nullptr, stream);
+    if (rc) return rc;
+    if (h_idx) MPC_CUDA_OK(cudaMemcpyAsync(h_idx, h->st_idx, b * T * 4, cudaMemcpyDeviceToHost, st));
+    if (h_s_seq) MPC_CUDA_OK(cudaMemcpyAsync(h_s_seq, h->st_seq, b * T * 8, cudaMemcpyDeviceToHost, st));
+    if (h_cost) MPC_CUDA_OK(cudaMemcpyAsync(h_cost, h->st_cost, b * 8, cudaMemcpyDeviceToHost, st));
+    if (h_reached_t) MPC_CUDA_OK(cudaMemcpyAsync(h_reached_t, h->st_reached, b * 4, cudaMemcpyDeviceToHost, st));
+    if (h_crash) MPC_CUDA_OK(cudaMemcpyAsync(h_crash, h->st_crash, b, cudaMemcpyDeviceToHost, st));
+    if (h_min_dist) MPC_CUDA_OK(cudaMemcpyAsync(h_min_dist, h->st_mind, b * 8, cudaMemcpyDeviceToHost, st));
+    if (h_start_s) MPC_CUDA_OK(cudaMemcpyAsync(h_start_s, h->st_s0, b * 8, cudaMemcpyDeviceToHost, st));
+    MPC_CUDA_OK(cudaStreamSynchronize(st));
+    return MPC_OK;
+}
+
+// ---- K4 ----------------------------------------------------------------------------------------------
+extern "C" int mpc_predict_step_with_ego(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                                         const double *d_cars_a, const int32_t *d_n_cars, const double *d_selected_speed, double dt,
+                                         double min_crash_distance, double *d_ego_out, double *d_cars_x_out, double *d_cars_v_out,
+                                         double *d_cars_a_out, uint8_t *d_crashed, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars || !d_selected_speed || !d_ego_out || !d_cars_x_out || !d_cars_v_out)
+        return mpc_set_error(MPC_E_INVALID, "mpc_predict_step_with_ego: null pointer");
+    MPC_CUDA_OK(launch_predict_step(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, d_selected_speed, dt,
+                                    min_crash_distance, d_ego_out, d_cars_x_out, d_cars_v_out, d_cars_a_out, d_crashed, (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}
+
+extern "C" int mpc_state_vector(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                                const double *d_cars_a, const int32_t *d_n_cars, float *d_out, int out_stride, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_cars_a || !d_n_cars || !d_out || out_stride < 20) return mpc_set_error(MPC_E_INVALID, "mpc_state_vector: bad argument");
+    MPC_CUDA_OK(launch_state_vector(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, d_out, out_stride, (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}
+
+extern "C" int mpc_speed_from_jerk(mpc_handle *h, int B, const double *d_ego, const double *d_jerk, double *d_speed, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_jerk || !d_speed) return mpc_set_error(MPC_E_INVALID, "mpc_speed_from_jerk: null pointer");
+    MPC_CUDA_OK(launch_speed_from_jerk(h->P, B, d_ego, d_jerk, d_speed, (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}

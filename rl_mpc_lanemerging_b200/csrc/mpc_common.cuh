@@ -1,0 +1,128 @@
+// Shared device-side definitions for libmpcb200 (sm_100a).
+// All fp64 arithmetic that must be bit-identical to the reference is written with explicit
+// round-to-nearest intrinsics (__dadd_rn/__dmul_rn/__ddiv_rn) so that nvcc never contracts a
+// multiply-add into an FMA; the library is also compiled with -fmad=false and uses fmaf()
+// explicitly where a fused fp32 multiply-add is wanted.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mpcb200.h"
+
+#define MPC_NMAX 32            // cars per problem handled by one warp (lane == car)
+#define MPC_MAX_T 128          // time layers supported (H <= 127)
+
+// Device copy of the parameters plus everything the host derives once per mpc_set_params.
+struct DevParams {
+    mpc_params p;
+    int num_t;                 // len(arange(0, FUTURE_T + dt, dt))            (st.py:32)
+    int num_s_max;             // upper bound of len(arange(s0, s0+FUTURE_S+ds, ds)) over s0
+    int discrete_length;       // int(CAR_LENGTH / delta_s)                     (st.py:37)
+    int lmax;                  // max successor-window length in cells (+1 safety)
+    double dt2, dt3;           // pow(dt,2), pow(dt,3) as libm computes them     (st_cy.pyx:48-49)
+    double obs_min_s;          // CRASH_MIN_S - MIN_ALLOWED_DISTANCE            (st.py:46)
+    double crash_thresh;       // COMBINATION_MIN_DISTANCE - CAR_LENGTH         (st.py:800)
+    // ---- fast mode (integer-cell kinematics); valid only when fast_ok != 0 --------------------
+    int fast_ok;
+    int jlo_c, jhi_c;          // jerk window in cells/step^3:   a' in [a+jlo_c, a+jhi_c]
+    int alo_c, ahi_c;          // accel bounds in cells/step^2
+    int vmax_c;                // floor(max_speed*dt/ds)
+    int vmax_is_int;           // max_speed*dt/ds sits on an integer -> per-cell fp64 check needed
+    double jhi_r, ahi_r, vmax_r; // real-valued (cells) jerk/accel/speed upper bounds for the non-integer clamp test
+    float cv, ca, cj;          // v_w*(ds/dt)^2, a_w*(ds/dt^2)^2, j_w*(ds/dt^3)^2
+    float vdes_c;              // desired speed in cells/step
+    float dw;                  // d_weight
+};
+
+// ---- geometry: control.py:366-380 ---------------------------------------------------------------
+__device__ __forceinline__ double dist2d(double x0, double y0, double x1, double y1) {
+    double dx = __dsub_rn(x0, x1), dy = __dsub_rn(y0, y1);
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+__device__ __forceinline__ double get_ego_s(double x, double y) {
+    if (x < -50.9) return -dist2d(x, y, -50.9, 1.72);
+    else if (x < 1.5) return dist2d(x, y, -50.9, 1.72);
+    else return __dadd_rn(__dsub_rn(x, 1.5), 52.5);
+}
+
+// numpy.arange(start, start + future_s + ds, ds): length and fill rule (st.py:31)
+__device__ __forceinline__ int arange_len(double start, double stop, double step) {
+    double c = ceil(__ddiv_rn(__dsub_rn(stop, start), step));
+    return c < 0.0 ? 0 : (int)c;
+}
+struct SGrid {
+    double s0, ds;     // s_values[0], s_values[1]-s_values[0]
+    int num_s;
+    __device__ __forceinline__ double sval(int k) const { return __dadd_rn(s0, __dmul_rn((double)k, ds)); }
+};
+__device__ __forceinline__ SGrid make_sgrid(const DevParams &P, double ex, double ey) {
+    SGrid g;
+    g.s0 = get_ego_s(ex, ey);
+    g.num_s = arange_len(g.s0, __dadd_rn(__dadd_rn(g.s0, P.p.future_s), P.p.s_disc), P.p.s_disc);
+    g.ds = __dsub_rn(__dadd_rn(g.s0, P.p.s_disc), g.s0);
+    return g;
+}
+
+// st_cy.pyx:34-38
+__device__ __forceinline__ double distance_penalty_f64(double d, double min_allowed) {
+    if (d < min_allowed) return __ddiv_rn(1000000.0, d > 1.0 ? d : 1.0);
+    return __ddiv_rn(1.0, d);
+}
+
+// One layer of the compact obstacle description produced by the traffic predictor (K1a) and
+// consumed by the rasteriser (K1b) and the fused planner (K3).  For every car that passes the
+// reference's range filters (st.py:46-49): the two edges the distance field is measured to
+// (st.py:52-53) and the obstacle band [imin, imax) in cells (st.py:60-65).
+struct LayerDesc {
+    int n_act;
+    int pad[3];
+    double ef[MPC_NMAX];
+    double eb[MPC_NMAX];
+    int2 band[MPC_NMAX];
+};
+
+// distance-field value and obstacle flag of cell k in a layer (st.py:52-65), exact fp64
+__device__ __forceinline__ double cell_distance(const LayerDesc &L, double s, int k, bool &obstacle) {
+    double d = 1E10;
+    bool ob = false;
+    for (int c = 0; c < L.n_act; c++) {
+        double df = fabs(__dsub_rn(s, L.ef[c])), db = fabs(__dsub_rn(s, L.eb[c]));
+        d = df < d ? df : d;
+        d = db < d ? db : d;
+        int2 b = L.band[c];
+        ob = ob || (k >= b.x && k < b.y);
+    }
+    obstacle = ob;
+    return ob ? 0.0 : d;
+}
+
+// ---- solver I/O shared by the kernel file and the API file ---------------------------------------
+struct SolveIO {
+    // per-problem inputs
+    const double *s0, *ds;       // s_values[0], s_values[1]-s_values[0]
+    const int32_t *num_s;
+    const double *v0, *a0;       // ego speed / acceleration;  v0 == NULL -> read ego[4b+2], ego[4b+3]
+    const double *ego;
+    // outputs (any may be NULL)
+    int32_t *idx; double *s_seq; double *cost; int32_t *reached; uint8_t *crash; double *min_dist;
+    // scratch
+    uint16_t *bp;                // [gridDim.x][num_t][bp_stride]
+    int bp_stride;
+    int *work_counter;
+    const int32_t *subset;       // optional list of problem ids (fallback re-solve); NULL = 0..B-1
+    const int *B_dev;            // optional: number of problems read on the device (overrides B)
+    int32_t *fallback_list; int *fallback_count;   // fast kernel: problems that need the exact kernel
+};
+
+struct SolveLaunch {
+    int mode;               // MPC_MODE_*
+    int B;
+    int grid, threads;
+    size_t smem;
+    int W;
+    unsigned long long *glab; unsigned *ghist;    // exact kernel global label scratch (or NULL)
+};
+
+
+#define MPC_CUDA_OK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return mpc_set_cuda_error(e__, #call); } while (0)
+int mpc_set_cuda_error(cudaError_t e, const char *what);
+int mpc_set_error(int code, const char *msg);

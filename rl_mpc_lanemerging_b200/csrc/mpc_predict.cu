@@ -1,0 +1,271 @@
+// K1a traffic predictor -> per-layer obstacle descriptors, K1b dense S-T rasteriser,
+// K4 rollout-tick pieces (predict_step_with_ego, observation vector, jerk->speed).
+//
+// One warp per problem, lane == car (front -> back).  The reference updates the cars strictly
+// sequentially because a follower reads its leader's *already updated* position and speed
+// (prediction.py:93-94).  That chain is a fixed point new_i = F(old_i, new_{i-1}); we iterate all
+// lanes in parallel (Jacobi) until nothing changes, which yields exactly the sequential result
+// (after m sweeps the first m cars are final) in 1-3 sweeps for ordinary traffic.
+#include "mpc_common.cuh"
+
+#define FULL 0xffffffffu
+
+struct EgoState { double x, y, v, a; };
+
+// prediction.py:46-105 for one warp.  (x,v) are this lane's car (lane < n valid).
+// Returns crashed; writes the predicted ego and this lane's new car state.
+__device__ __forceinline__ bool warp_predict_with_ego(const DevParams &P, int lane, int n, const EgoState &ego,
+                                                      double x, double v, double sel, double dt,
+                                                      double min_crash_distance, EgoState &ego_out,
+                                                      double &nx, double &nv, double &na) {
+    double px, py;
+    if (ego.x < 1.5) {                                              // 48-56
+        double dx = __dsub_rn(1.5, ego.x), dy = __dsub_rn(-1.5, ego.y);
+        double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        dx = __ddiv_rn(dx, nrm); dy = __ddiv_rn(dy, nrm);
+        double step = __dmul_rn(sel, dt);
+        dx = __dmul_rn(dx, step); dy = __dmul_rn(dy, step);
+        px = __dadd_rn(ego.x, dx); py = __dadd_rn(ego.y, dy);
+        if (py < -1.6) py = -1.6;
+    } else {                                                        // 57-59
+        py = ego.y; px = __dadd_rn(ego.x, __dmul_rn(sel, dt));
+    }
+    ego_out.a = __ddiv_rn(__dsub_rn(sel, ego.v), dt);               // 61
+    ego_out.x = px; ego_out.y = py; ego_out.v = sel;
+    double pes = get_ego_s(px, py);
+    bool can_crash = pes > 11.0, merged = pes > 8.0;                // 64, 66
+    bool valid = lane < n;
+    unsigned behind = __ballot_sync(FULL, valid && x < px);         // 78: first car behind the predicted ego
+    int enc = behind ? __ffs(behind) - 1 : -1;
+    bool ego_leads = merged && lane == enc;
+
+    nv = v; na = 0.0; nx = __dadd_rn(x, __dmul_rn(v, dt));         // free-flow guess
+    for (int it = 0; it <= n; it++) {
+        double lx = __shfl_up_sync(FULL, nx, 1), lv = __shfl_up_sync(FULL, nv, 1);
+        if (lane == 0) { lx = __longlong_as_double(0x7ff0000000000000LL); lv = 0.0; }   // 72-73
+        if (ego_leads) { lx = px; lv = sel; }                       // 80-82
+        double speed_diff = __dsub_rn(lv, v), x_diff = __dsub_rn(lx, x), a2, v2;
+        if (speed_diff < 0.0 && x_diff < 30.0) {                    // 85-87
+            a2 = (P.p.max_predicted_decel > speed_diff) ? P.p.max_predicted_decel : speed_diff;
+            v2 = __dadd_rn(v, __dmul_rn(a2, dt));
+        } else { a2 = 0.0; v2 = v; }                                // 88-90
+        double x2 = __dadd_rn(x, __dmul_rn(v2, dt));                // 91
+        bool changed = valid && (x2 != nx || v2 != nv || a2 != na);
+        nx = x2; nv = v2; na = a2;
+        if (!__any_sync(FULL, changed)) break;
+    }
+    double cdd = min_crash_distance > P.p.car_length ? min_crash_distance : P.p.car_length;   // 100
+    bool hit = valid && can_crash && fabs(__dsub_rn(nx, px)) < cdd;                           // 101-103
+    return __any_sync(FULL, hit);
+}
+
+// prediction.py:22-44: choose the pseudo-ego, then step.
+__device__ __forceinline__ void warp_predict_without_ego(const DevParams &P, int lane, int n, EgoState &ego,
+                                                         double &x, double &v, double dt) {
+    double ego_s = get_ego_s(ego.x, ego.y);
+    EgoState e = ego;
+    double sel;
+    double x0 = __shfl_sync(FULL, x, 0);
+    if (ego_s < 8.0 || n == 0) { sel = 0.0; }                       // 26-27
+    else if (x0 < ego.x) { e.x = -20.0; e.y = -10.0; e.v = 0.0; e.a = 0.0; sel = 0.0; }   // 28-31
+    else {                                                          // 33-44
+        unsigned behind = __ballot_sync(FULL, lane < n && x < ego.x);
+        int first = behind ? __ffs(behind) - 1 : n;                 // first >= 1 here
+        double lx = __shfl_sync(FULL, x, first - 1), lv = __shfl_sync(FULL, v, first - 1);
+        sel = lv;
+        if (behind) { e.x = __dsub_rn(__dsub_rn(lx, P.p.car_length), 5.0); e.v = lv; e.a = 0.0; }
+    }
+    EgoState out; double nx, nv, na;
+    warp_predict_with_ego(P, lane, n, e, x, v, sel, dt, 5.0, out, nx, nv, na);
+    ego = out; x = nx; v = nv;
+}
+
+// ---- K1a -----------------------------------------------------------------------------------------
+// desc[B][num_t]; hdr_s0/ds/num_s per problem.
+__global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B, const double *__restrict__ ego,
+                                                            const double *__restrict__ cars_x,
+                                                            const double *__restrict__ cars_v,
+                                                            const int32_t *__restrict__ n_cars, int nmax,
+                                                            LayerDesc *__restrict__ desc, double *__restrict__ o_s0,
+                                                            double *__restrict__ o_ds, int32_t *__restrict__ o_num_s) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    int b = warp;
+    int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
+    EgoState e = {ego[4 * b], ego[4 * b + 1], ego[4 * b + 2], ego[4 * b + 3]};
+    double x = lane < n ? cars_x[(size_t)b * nmax + lane] : 0.0;
+    double v = lane < n ? cars_v[(size_t)b * nmax + lane] : 0.0;
+    SGrid g = make_sgrid(P, e.x, e.y);
+    if (lane == 0) { if (o_s0) o_s0[b] = g.s0; if (o_ds) o_ds[b] = g.ds; if (o_num_s) o_num_s[b] = g.num_s; }
+    double s_last = g.sval(g.num_s - 1);
+    double far_lim = __dadd_rn(s_last, P.p.car_length);
+    for (int t = 0; t < P.num_t; t++) {
+        if (t) warp_predict_without_ego(P, lane, n, e, x, v, P.p.t_disc);         // st.py:42-43
+        double tt = __dmul_rn((double)t, P.p.t_disc);
+        double unc = __dadd_rn(P.p.start_uncertainty, __dmul_rn(P.p.uncertainty_per_second, tt));   // 40
+        int du = (int)__ddiv_rn(unc, P.p.s_disc);                                  // 41
+        double obs_s = __dadd_rn(x, 51.0);                                          // control.py:388-389
+        bool valid = lane < n;
+        unsigned stop = __ballot_sync(FULL, valid && obs_s < P.obs_min_s);          // 46-47: break
+        int first_stop = stop ? __ffs(stop) - 1 : 32;
+        bool act = valid && lane < first_stop && !(obs_s > far_lim);                // 48-49: continue
+        unsigned am = __ballot_sync(FULL, act);
+        LayerDesc *L = desc + (size_t)b * P.num_t + t;
+        if (lane == 0) L->n_act = __popc(am);
+        if (act) {
+            int slot = __popc(am & ((1u << lane) - 1));
+            L->ef[slot] = __dsub_rn(__dsub_rn(obs_s, P.p.car_length), unc);        // 52
+            L->eb[slot] = __dadd_rn(__dadd_rn(obs_s, P.p.car_length), unc);        // 53
+            int si = (int)__ddiv_rn(__dsub_rn(obs_s, g.s0), P.p.s_disc);           // 60
+            int imin = si - P.discrete_length - du; imin = imin < 0 ? 0 : imin;    // 61
+            int imax = si + P.discrete_length + du; imax = imax > g.num_s ? g.num_s : imax;   // 62
+            if (!(imin < g.num_s && imax > 0)) { imin = 0; imax = 0; }              // 63
+            L->band[slot] = make_int2(imin, imax);
+        }
+    }
+}
+
+// ---- K1b: dense grids in the layout st_cy consumes ---------------------------------------------
+template <typename DT>
+__global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int stride_s, const LayerDesc *__restrict__ desc,
+                                                        const double *__restrict__ s0v, const double *__restrict__ dsv,
+                                                        const int32_t *__restrict__ nsv, uint8_t *__restrict__ obstacles,
+                                                        DT *__restrict__ distances) {
+    __shared__ LayerDesc L;
+    int bt = blockIdx.x;                       // one block per (problem, layer)
+    int b = bt / P.num_t;
+    const int *src = reinterpret_cast<const int *>(desc + bt);
+    int *dst = reinterpret_cast<int *>(&L);
+    for (int i = threadIdx.x; i < (int)(sizeof(LayerDesc) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    SGrid g; g.s0 = s0v[b]; g.ds = dsv[b]; g.num_s = nsv[b];
+    size_t row = (size_t)bt * stride_s;
+    for (int k = threadIdx.x; k < stride_s; k += blockDim.x) {
+        bool ob = true; double d = 0.0;
+        if (k < g.num_s) d = cell_distance(L, g.sval(k), k, ob);
+        obstacles[row + k] = ob ? 1 : 0;
+        distances[row + k] = (DT)d;
+    }
+}
+
+// ---- K4 -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) predict_step_with_ego_kernel(DevParams P, int B, int nmax, const double *ego,
+                                                                   const double *cars_x, const double *cars_v,
+                                                                   const double *cars_a, const int32_t *n_cars,
+                                                                   const double *sel_speed, double dt, double mcd,
+                                                                   double *ego_out, double *ox, double *ov, double *oa,
+                                                                   uint8_t *crashed) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    int b = warp;
+    int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
+    EgoState e = {ego[4 * b], ego[4 * b + 1], ego[4 * b + 2], ego[4 * b + 3]}, eo;
+    double x = lane < n ? cars_x[(size_t)b * nmax + lane] : 0.0;
+    double v = lane < n ? cars_v[(size_t)b * nmax + lane] : 0.0;
+    double nx, nv, na;
+    bool cr = warp_predict_with_ego(P, lane, n, e, x, v, sel_speed[b], dt, mcd, eo, nx, nv, na);
+    if (lane == 0) {
+        ego_out[4 * b] = eo.x; ego_out[4 * b + 1] = eo.y; ego_out[4 * b + 2] = eo.v; ego_out[4 * b + 3] = eo.a;
+        if (crashed) crashed[b] = cr ? 1 : 0;
+    }
+    if (lane < nmax) {
+        size_t o = (size_t)b * nmax + lane;
+        bool ok = lane < n;
+        ox[o] = ok ? nx : (cars_x == ox ? cars_x[o] : 0.0);
+        ov[o] = ok ? nv : (cars_v == ov ? cars_v[o] : 0.0);
+        if (oa) oa[o] = ok ? na : ((cars_a && cars_a == oa) ? cars_a[o] : 0.0);
+    }
+}
+
+// dqn.py:389-446 with CARS_AHEAD = CARS_BEHIND = 2, acceleration + speed difference, normalised.
+__global__ void __launch_bounds__(128) state_vector_kernel(DevParams P, int B, int nmax, const double *ego,
+                                                          const double *cars_x, const double *cars_v,
+                                                          const double *cars_a, const int32_t *n_cars, float *out,
+                                                          int out_stride) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    int b = warp;
+    int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
+    double ex = ego[4 * b], ey = ego[4 * b + 1], ev = ego[4 * b + 2], ea = ego[4 * b + 3];
+    bool valid = lane < n;
+    size_t o = (size_t)b * nmax + lane;
+    double x = valid ? cars_x[o] : 0.0, v = valid ? cars_v[o] : 0.0, a = valid ? cars_a[o] : 0.0;
+    unsigned front = __ballot_sync(FULL, valid && x > ex);          // 411-414
+    unsigned back = __ballot_sync(FULL, valid && !(x > ex));
+    // front list is reversed (nearest first): the highest set lane is slot 0, next highest slot 1
+    int slot = -1;
+    if (valid && x > ex) { int above = __popc(front >> lane) - 1; if (above < 2) slot = above; }
+    if (valid && !(x > ex)) { int below = __popc(back & ((1u << lane) - 1)); if (below < 2) slot = 2 + below; }
+    float *row = out + (size_t)b * out_stride;
+    if (slot >= 0) {
+        row[4 * slot + 0] = (float)__ddiv_rn(a, 9.0);
+        row[4 * slot + 1] = (float)__ddiv_rn(__dsub_rn(v, ev), P.p.max_speed);
+        row[4 * slot + 2] = (float)__ddiv_rn(__dsub_rn(x, ex), P.p.sensor_radius);
+        row[4 * slot + 3] = 1.0f;
+    }
+    int nf = __popc(front), nb = __popc(back);
+    if (lane < 4) {                       // zero the absent slots
+        int s = lane; bool present = s < 2 ? (s < nf) : (s - 2 < nb);
+        if (!present) { row[4 * s] = 0.f; row[4 * s + 1] = 0.f; row[4 * s + 2] = 0.f; row[4 * s + 3] = 0.f; }
+    }
+    if (lane == 0) {
+        row[16] = (float)__ddiv_rn(ev, P.p.max_speed); row[17] = (float)__ddiv_rn(ea, 9.0);
+        row[18] = (float)__ddiv_rn(ex, 300.0); row[19] = (float)__ddiv_rn(ey, 100.0);
+    }
+}
+
+// control.py:160-171
+__global__ void speed_from_jerk_kernel(DevParams P, int B, const double *ego, const double *jerk, double *speed) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double v = ego[4 * b + 2], a = ego[4 * b + 3];
+    double na = __dadd_rn(a, __dmul_rn(jerk[b], P.p.tick_length));
+    if (na > P.p.a_max) na = P.p.a_max;
+    if (na < P.p.a_min) na = P.p.a_min;
+    double nv = __dadd_rn(v, __dmul_rn(na, P.p.tick_length));
+    if (nv > P.p.max_speed) nv = P.p.max_speed;
+    if (nv < 0.0) nv = 0.0;
+    speed[b] = nv;
+}
+
+// ---- host launchers (called from mpc_api.cu) -----------------------------------------------------
+cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
+                                  const double *cv, const int32_t *n, LayerDesc *desc, double *s0, double *ds,
+                                  int32_t *ns, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    int wpb = 4;
+    predict_layers_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, ego, cx, cv, n, nmax, desc, s0, ds, ns);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const LayerDesc *desc, const double *s0,
+                             const double *ds, const int32_t *ns, uint8_t *obstacles, void *distances, int dist_f32,
+                             cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    if (dist_f32) rasterise_kernel<float><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances);
+    else rasterise_kernel<double><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
+                                const double *ca, const int32_t *n, const double *sel, double dt, double mcd,
+                                double *ego_out, double *ox, double *ov, double *oa, uint8_t *crashed, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    int wpb = 4;
+    predict_step_with_ego_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, sel, dt, mcd, ego_out, ox, ov, oa, crashed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
+                                const double *ca, const int32_t *n, float *out, int stride, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    int wpb = 4;
+    state_vector_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, out, stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    speed_from_jerk_kernel<<<(B + 127) / 128, 128, 0, st>>>(P, B, ego, jerk, speed);
+    return cudaGetLastError();
+}

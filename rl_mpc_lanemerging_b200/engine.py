@@ -1,0 +1,219 @@
+"""Batched planner engine: the Python face of libmpcb200 (one engine per GPU / stream).
+
+PyTorch is used for device memory and streams only; every computation on the hot path is a
+hand-written CUDA kernel reached through the C ABI (include/mpcb200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MODE_EXACT, MODE_FAST, MpcParams
+
+
+def params_from_settings(S) -> MpcParams:
+    """Snapshot of the reference-style global Settings (reference config.py:30-37,94-110,143,153)."""
+    p = MpcParams()
+    p.s_disc, p.t_disc = float(S.S_DISCRETIZATION), float(S.T_DISCRETIZATION)
+    p.future_s, p.future_t = float(S.FUTURE_S), float(S.FUTURE_T)
+    p.start_uncertainty, p.uncertainty_per_second = float(S.START_UNCERTAINTY), float(S.UNCERTAINTY_PER_SECOND)
+    p.d_weight, p.v_weight, p.a_weight, p.j_weight = (float(S.D_WEIGHT), float(S.V_WEIGHT), float(S.A_WEIGHT),
+                                                      float(S.J_WEIGHT))
+    p.desired_speed, p.max_speed = float(S.DESIRED_SPEED), float(S.MAX_SPEED)
+    p.a_min, p.a_max = float(S.MAX_NEGATIVE_ACCELERATION), float(S.MAX_POSITIVE_ACCELERATION)
+    p.j_min, p.j_max = float(S.MINIMUM_NEGATIVE_JERK), float(S.MAXIMUM_POSITIVE_JERK)
+    p.min_allowed_distance, p.crash_min_s = float(S.MIN_ALLOWED_DISTANCE), float(S.CRASH_MIN_S)
+    p.car_length = float(S.CAR_LENGTH)
+    p.max_predicted_decel = float(S.MAX_PREDICTED_DECELERATION)
+    p.tick_length, p.sensor_radius = float(S.TICK_LENGTH), float(S.SENSOR_RADIUS)
+    p.combination_min_distance = float(S.COMBINATION_MIN_DISTANCE)
+    return p
+
+
+def params_key(p: MpcParams):
+    return tuple(getattr(p, n) for n in _lib.PARAM_FIELDS)
+
+
+def _mode(mode) -> int:
+    if mode in (MODE_FAST, "fast"):
+        return MODE_FAST
+    if mode in (MODE_EXACT, "exact"):
+        return MODE_EXACT
+    raise ValueError(f"unknown mode {mode!r}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class MpcEngine:
+    """Owns one mpc_handle.  All tensor arguments live on `device`; states are fp64:
+    ego [B,4] = (x, y, speed, acceleration); cars_x/v/a [B,nmax]; n_cars [B] int32."""
+
+    def __init__(self, params: Optional[MpcParams] = None, device: int | str | torch.device = 0,
+                 max_batch: int = 4096, nmax: int = 32):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available() or self.lib.mpc_device_count() <= 0:
+            raise _lib.MpcError(_lib.E_NODEVICE, "no CUDA device: the MPC hot path has no CPU fallback")
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.device = dev
+        self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.params = params if params is not None else _lib.default_params()
+        self.max_batch, self.nmax = int(max_batch), int(nmax)
+        torch.cuda.init()
+        with torch.cuda.device(self.dev_index):
+            torch.zeros(1, device=dev)            # make sure the primary context exists before the library uses it
+            h = C.c_void_p()
+            _lib.check(self.lib.mpc_create(C.byref(self.params), self.dev_index, self.max_batch, self.nmax, C.byref(h)))
+        self.h = h
+        nt, ns = C.c_int(), C.c_int()
+        _lib.check(self.lib.mpc_grid_dims(self.h, C.byref(nt), C.byref(ns)))
+        self.num_t, self.num_s_max = nt.value, ns.value
+        self._pinned = {}
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.mpc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_state(self, ego, cars_x, cars_v, cars_a, n_cars):
+        B = ego.shape[0]
+        assert ego.dtype == torch.float64 and ego.shape == (B, 4) and ego.is_contiguous() and ego.is_cuda
+        for c in (cars_x, cars_v) + ((cars_a,) if cars_a is not None else ()):
+            assert c.dtype == torch.float64 and c.shape == (B, self.nmax) and c.is_contiguous() and c.is_cuda
+        assert n_cars.dtype == torch.int32 and n_cars.shape == (B,) and n_cars.is_contiguous() and n_cars.is_cuda
+        return B
+
+    def counters(self):
+        out = (C.c_int64 * 2)()
+        _lib.check(self.lib.mpc_last_counters(self.h, out))
+        return {"kernels_launched": int(out[0]), "fallback_problems": int(out[1])}
+
+    # ------------------------------------------------------------------------------------------
+    def plan(self, ego, cars_x, cars_v, cars_a, n_cars, mode="fast", out: Optional[dict] = None):
+        """Fused gap-evaluation (K3).  Returns dict(idx i32[B,T], s_seq f64[B,T], cost f64[B], reached_t i32[B],
+        crash u8[B], min_dist f64[B], start_s f64[B]) of device tensors (re-used when `out` is passed)."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        T = self.num_t
+        if out is None:
+            o = dict(device=self.device)
+            out = dict(idx=torch.empty((B, T), dtype=torch.int32, **o), s_seq=torch.empty((B, T), dtype=torch.float64, **o),
+                       cost=torch.empty(B, dtype=torch.float64, **o), reached_t=torch.empty(B, dtype=torch.int32, **o),
+                       crash=torch.empty(B, dtype=torch.uint8, **o), min_dist=torch.empty(B, dtype=torch.float64, **o),
+                       start_s=torch.empty(B, dtype=torch.float64, **o))
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_plan(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                         _mode(mode), _ptr(out["idx"]), _ptr(out["s_seq"]), _ptr(out["cost"]),
+                                         _ptr(out["reached_t"]), _ptr(out["crash"]), _ptr(out["min_dist"]),
+                                         _ptr(out["start_s"]), self._stream()))
+        return out
+
+    def _pin(self, name, shape, dtype):
+        t = self._pinned.get(name)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[name] = t
+        return t
+
+    def plan_host(self, ego, cars_x, cars_v, cars_a, n_cars, mode="fast"):
+        """Same through HOST buffers (numpy in, numpy out): the end-to-end call a CPU rollout loop makes.
+        Inputs are staged through pinned memory; results come back in (re-used) pinned arrays."""
+        B, T = int(ego.shape[0]), self.num_t
+        f64, i32 = torch.float64, torch.int32
+        pe = self._pin("ego", (B, 4), f64); pe.numpy()[...] = ego
+        px = self._pin("cx", (B, self.nmax), f64); px.numpy()[...] = cars_x
+        pv = self._pin("cv", (B, self.nmax), f64); pv.numpy()[...] = cars_v
+        pn = self._pin("n", (B,), i32); pn.numpy()[...] = n_cars
+        o = dict(idx=self._pin("idx", (B, T), i32), s_seq=self._pin("seq", (B, T), f64), cost=self._pin("cost", (B,), f64),
+                 reached_t=self._pin("reached", (B,), i32), crash=self._pin("crash", (B,), torch.uint8),
+                 min_dist=self._pin("mind", (B,), f64), start_s=self._pin("s0", (B,), f64))
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_plan_host(self.h, B, _ptr(pe), _ptr(px), _ptr(pv), None, _ptr(pn), _mode(mode),
+                                              _ptr(o["idx"]), _ptr(o["s_seq"]), _ptr(o["cost"]), _ptr(o["reached_t"]),
+                                              _ptr(o["crash"]), _ptr(o["min_dist"]), _ptr(o["start_s"]), self._stream()))
+        return {k: v.numpy() for k, v in o.items()}
+
+    # ------------------------------------------------------------------------------------------
+    def build_grid(self, ego, cars_x, cars_v, cars_a, n_cars, dist_dtype=torch.float64):
+        """K1: dense S-T grids in the layout the reference's solver consumes.
+        Returns obstacles u8[B,T,S], distances [B,T,S], start_s[B], delta_s[B], num_s[B] (S = num_s_max)."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        T, S = self.num_t, self.num_s_max
+        o = dict(device=self.device)
+        obstacles = torch.empty((B, T, S), dtype=torch.uint8, **o)
+        distances = torch.empty((B, T, S), dtype=dist_dtype, **o)
+        s0 = torch.empty(B, dtype=torch.float64, **o)
+        ds = torch.empty(B, dtype=torch.float64, **o)
+        ns = torch.empty(B, dtype=torch.int32, **o)
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_build_grid(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                               _ptr(obstacles), _ptr(distances), int(dist_dtype == torch.float32),
+                                               _ptr(s0), _ptr(ds), _ptr(ns), self._stream()))
+        return dict(obstacles=obstacles, distances=distances, start_s=s0, delta_s=ds, num_s=ns)
+
+    def solve_dense(self, obstacles, distances, start_s, delta_s, num_s, v0, a0, mode="exact"):
+        """K2: the drop-in for st_cy.solve_s_t_path_fast on caller-supplied grids [B,T,S]."""
+        B, T, S = obstacles.shape
+        assert obstacles.dtype == torch.uint8 and obstacles.is_contiguous() and distances.is_contiguous()
+        assert distances.shape == obstacles.shape and distances.dtype in (torch.float64, torch.float32)
+        o = dict(device=self.device)
+        out = dict(idx=torch.empty((B, T), dtype=torch.int32, **o), s_seq=torch.empty((B, T), dtype=torch.float64, **o),
+                   cost=torch.empty(B, dtype=torch.float64, **o), reached_t=torch.empty(B, dtype=torch.int32, **o))
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_solve_dense(self.h, B, T, S, _ptr(obstacles), _ptr(distances),
+                                                int(distances.dtype == torch.float32), _ptr(start_s), _ptr(delta_s),
+                                                _ptr(num_s), _ptr(v0), _ptr(a0), _mode(mode), _ptr(out["idx"]),
+                                                _ptr(out["s_seq"]), _ptr(out["cost"]), _ptr(out["reached_t"]), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def predict_step_with_ego(self, ego, cars_x, cars_v, cars_a, n_cars, selected_speed, dt, min_crash_distance=5.0,
+                              inplace=False):
+        """K4: HighwayState.predict_step_with_ego for the whole batch."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        if inplace:
+            eo, xo, vo, ao = ego, cars_x, cars_v, cars_a
+        else:
+            eo, xo, vo, ao = torch.empty_like(ego), torch.empty_like(cars_x), torch.empty_like(cars_v), torch.empty_like(cars_x)
+        crashed = torch.empty(B, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_predict_step_with_ego(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a),
+                                                          _ptr(n_cars), _ptr(selected_speed), float(dt), float(min_crash_distance),
+                                                          _ptr(eo), _ptr(xo), _ptr(vo), _ptr(ao), _ptr(crashed), self._stream()))
+        return eo, xo, vo, ao, crashed
+
+    def state_vector(self, ego, cars_x, cars_v, cars_a, n_cars, out=None):
+        """dqn.get_state_vector_from_base_state -> f32 [B, >=20] (column 20, if present, is left for the time feature)."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        if out is None:
+            out = torch.zeros((B, 21), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_state_vector(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                                 _ptr(out), out.shape[1], self._stream()))
+        return out
+
+    def speed_from_jerk(self, ego, jerk):
+        B = ego.shape[0]
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_speed_from_jerk(self.h, B, _ptr(ego), _ptr(jerk), _ptr(out), self._stream()))
+        return out
+
+
+def states_to_device(S: dict, device) -> dict:
+    """numpy state dict (synthetic.make_states) -> dict of device tensors."""
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in S.items()}
