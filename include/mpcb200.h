@@ -75,6 +75,13 @@ int mpc_grid_dims(const mpc_handle *h, int *num_t, int *num_s_max);
  * the fast kernel's shared-memory window / bucket capacity and were re-solved by the exact kernel */
 int mpc_last_counters(const mpc_handle *h, int64_t *out2);
 
+/* Optional per-kernel device timing (used by bench.py for the roofline of the dominant kernel):
+ * after mpc_set_timing(h,1), mpc_last_kernel_ms returns {traffic-predictor ms, DP-kernel ms,
+ * fallback-DP ms} of the last mpc_plan / mpc_solve_dense call, measured with CUDA events on the
+ * stream the kernels were launched on. */
+int mpc_set_timing(mpc_handle *h, int enable);
+int mpc_last_kernel_ms(mpc_handle *h, float *out3);
+
 /* ---- K1: traffic prediction + S-T rasterisation (st.find_s_t_obstacles_from_state, st.py:25-70,
  *      with prediction.py:22-105 and control.py:373-389) ------------------------------------- */
 /* Dense grids, the layout st_cy consumes: d_obstacles u8[B][num_t][num_s_max],

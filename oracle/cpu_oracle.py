@@ -153,6 +153,20 @@ def solve(p, obstacles, distances, s_values, delta_t, v0, a0, layered=False):
     return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value, stats=stats)
 
 
+def solve_fast_model(p, obstacles, distances, s_values, delta_t, v0, a0, f32_labels=False):
+    """CPU model of the CUDA fast kernel (integer kinematics, fp32 labels); NOT the reference."""
+    nt, ns = obstacles.shape
+    idx = np.zeros(nt, np.int32)
+    seq = np.zeros(nt, np.float64)
+    cost = C.c_double()
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.uint8)
+    distances = np.ascontiguousarray(distances, dtype=np.float64)
+    s_values = np.ascontiguousarray(s_values, dtype=np.float64)
+    r = lib().orc_solve_fast_model(C.byref(p), nt, ns, obstacles.ctypes.data_as(C.c_void_p), _dp(distances), _dp(s_values),
+                                   C.c_double(delta_t), C.c_double(v0), C.c_double(a0), C.c_int(int(f32_labels)), _ip(idx), _dp(seq), C.byref(cost))
+    return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value)
+
+
 def path_cost(p, idx, s_values, distances, delta_t, v0, a0):
     idx = np.ascontiguousarray(idx, np.int32)
     distances = np.ascontiguousarray(distances, np.float64)

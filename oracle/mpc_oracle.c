@@ -371,6 +371,126 @@ int orc_solve_layered(const orc_params *p, int num_t, int num_s, const uint8_t *
     return r;
 }
 
+
+/* ---- CPU model of the CUDA fast kernel's arithmetic (integer-cell kinematics, fp32 labels, penalty
+ * added after the min).  NOT part of the reference: it exists so that the fast mode's tolerance claim
+ * can be checked on CPU over many states, and to debug the kernel.  Mirrors fast_pull_kernel in
+ * rl_mpc_lanemerging_b200/csrc/mpc_solve.cu (same window rules, same operation order in fp32). */
+#include <float.h>
+int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+                         const double *distances, const double *s_values, double delta_t,
+                         double v0, double a0, int f32_labels, int *idx_out, double *s_seq_out, double *cost_out) {
+#define RND(x) (f32_labels ? (double)(float)(x) : (double)(x))
+    double dsn = p->s_disc, dt = p->t_disc;
+    double jlo = p->j_min * dt * dt * dt / dsn, jhi = p->j_max * dt * dt * dt / dsn;
+    double alo_r = p->a_min * dt * dt / dsn, ahi_r = p->a_max * dt * dt / dsn, vmax_r = p->max_speed * dt / dsn;
+    int jlo_c = (int)ceil(jlo), jhi_c = (int)floor(jhi), alo_c = (int)ceil(alo_r), ahi_c = (int)floor(ahi_r);
+    int vmax_is_int = fabs(vmax_r - nearbyint(vmax_r)) < 1e-9;
+    int vmax_c = vmax_is_int ? (int)nearbyint(vmax_r) : (int)floor(vmax_r);
+    float cv = (float)(p->v_weight * (dsn / dt) * (dsn / dt));
+    float ca = (float)(p->a_weight * (dsn / (dt * dt)) * (dsn / (dt * dt)));
+    float cj = (float)(p->j_weight * (dsn / (dt * dt * dt)) * (dsn / (dt * dt * dt)));
+    float vdes = (float)(p->desired_speed * dt / dsn), dw = (float)p->d_weight;
+    double delta_s = s_values[1] - s_values[0], start_s = s_values[0];
+    int *previous = (int *)calloc((size_t)num_t * num_s, sizeof(int));
+    double *lab[2]; int *vv[2], *aa[2]; uint8_t *has[2];
+    for (int b = 0; b < 2; b++) { lab[b] = (double *)malloc(8 * num_s); vv[b] = (int *)malloc(4 * num_s); aa[b] = (int *)malloc(4 * num_s); has[b] = (uint8_t *)calloc(num_s, 1); }
+    int *pred = (int *)malloc(4 * num_s);
+    double est_prev = start_s - v0 * delta_t, est_second = est_prev - delta_t * (v0 - a0 * delta_t);
+    int best_t = 0, best_k = 0; double best_lab = 0;
+    /* layer 0 -> 1 (exact fp64, full cost) */
+    int imin, imax;
+    next_index_range(p, start_s, delta_s, start_s, est_prev, est_second, delta_t, &imin, &imax);
+    int lo = num_s, hi = -1;
+    for (int k = imin; k < imax && k < num_s; k++) {
+        if (obstacles[(size_t)num_s + k]) continue;
+        lab[1][k] = RND(cost_with_jerk(p, s_values[k], start_s, est_prev, est_second, delta_t, distances[(size_t)num_s + k]));
+        has[1][k] = 1; previous[(size_t)num_s + k] = 0; if (k < lo) lo = k; if (k > hi) hi = k;
+    }
+    int t = 1;
+    if (hi >= 0) {
+        /* layer 1 -> 2: exact windows and fp64 kinematic cost, fp32 accumulate, penalty later */
+        double *cand = (double *)malloc(8 * num_s); uint8_t *hc = (uint8_t *)calloc(num_s, 1);
+        int nlo = num_s, nhi = -1;
+        for (int k1 = lo; k1 <= hi; k1++) if (has[1][k1]) {
+            double s = s_values[k1];
+            next_index_range(p, start_s, delta_s, s, start_s, est_prev, delta_t, &imin, &imax);
+            for (int kk = imin; kk < imax && kk < num_s; kk++) {
+                double sn = s_values[kk];
+                double v = (sn - s) / delta_t, a = (sn - 2 * s + start_s) / pow(delta_t, 2.0), j = (sn - 3 * s + 3 * start_s - est_prev) / pow(delta_t, 3.0);
+                double kin = p->v_weight * ((v - p->desired_speed) * (v - p->desired_speed)) + p->a_weight * (a * a) + p->j_weight * (j * j);
+                double tot = RND(lab[1][k1] + (f32_labels ? (double)(float)kin : kin));
+                if (!hc[kk] || tot < cand[kk]) { cand[kk] = tot; pred[kk] = k1; hc[kk] = 1; }
+                if (kk < nlo) nlo = kk; if (kk > nhi) nhi = kk;
+            }
+        }
+        /* best of layer 1 in case layer 2 is empty */
+        best_t = 1; best_k = -1;
+        for (int k = lo; k <= hi; k++) if (has[1][k] && (best_k < 0 || lab[1][k] < best_lab)) { best_k = k; best_lab = lab[1][k]; }
+        int cur = 0;   /* buffers: layer t nodes live in [cur] after finalisation; layer 1 is in [1] */
+        int plo = lo, phi = hi;   /* span of previous layer */
+        int dlo = nlo, dhi = nhi;
+        int prevbuf = 1;
+        for (t = 2; t < num_t && dhi >= 0; t++) {
+            /* finalise layer t from cand/pred */
+            int any = 0; cur = prevbuf ^ 1;
+            for (int k = dlo; k <= dhi; k++) has[cur][k] = 0;
+            int wlo_min = num_s, whi_max = -1;
+            /* per-node windows stored temporarily */
+            int *wl = (int *)malloc(4 * (dhi - dlo + 1)), *wn = (int *)malloc(4 * (dhi - dlo + 1));
+            for (int k = dlo; k <= dhi; k++) {
+                wn[k - dlo] = 0;
+                if (!hc[k]) continue;
+                size_t id = (size_t)t * num_s + k;
+                if (obstacles[id]) continue;
+                double d = distances[id];
+                float df = (float)d;
+                double pen = f32_labels ? (double)((d < p->min_allowed_distance) ? 1000000.0f / fmaxf(df, 1.0f) : 1.0f / df)
+                                        : ((d < p->min_allowed_distance) ? 1000000.0 / (d > 1.0 ? d : 1.0) : (double)(1.0f / df));
+                lab[cur][k] = RND((double)dw * pen + cand[k]);
+                int pr = pred[k], v = k - pr, vp = (t == 2) ? pr : vv[prevbuf][pr], a = v - vp;
+                vv[cur][k] = v; aa[cur][k] = a; has[cur][k] = 1; previous[id] = pr; any = 1;
+                int al = a + jlo_c > alo_c ? a + jlo_c : alo_c, ah = a + jhi_c < ahi_c ? a + jhi_c : ahi_c;
+                int vlo = v + al, vhi = v + ah;
+                double s = s_values[k];
+                if (vlo <= 0) { double me = (s - start_s) / delta_s; int mi = (int)me; if (mi < me) mi++; vlo = mi - k; }
+                int clamp = vmax_is_int ? (vhi >= vmax_c) : ((double)v + fmin((double)a + jhi, ahi_r) > vmax_r);
+                if (clamp) vhi = vmax_is_int ? (int)((s + p->max_speed * dt - start_s) / delta_s) - k : vmax_c;
+                int wlo = k + vlo, whi = k + vhi; if (whi > num_s - 1) whi = num_s - 1;
+                int n = whi - wlo + 1; if (n < 0) n = 0;
+                wl[k - dlo] = wlo; wn[k - dlo] = n;
+                if (n > 0) { if (wlo < wlo_min) wlo_min = wlo; if (whi > whi_max) whi_max = whi; }
+            }
+            if (!any) { free(wl); free(wn); break; }
+            best_t = t; best_k = -1;
+            for (int k = dlo; k <= dhi; k++) if (has[cur][k] && (best_k < 0 || lab[cur][k] < best_lab)) { best_k = k; best_lab = lab[cur][k]; }
+            if (t == num_t - 1 || whi_max < 0) { free(wl); free(wn); break; }
+            /* candidates of layer t+1 */
+            for (int k = wlo_min; k <= whi_max; k++) hc[k] = 0;
+            for (int k = dlo; k <= dhi; k++) {
+                if (!has[cur][k]) continue;
+                for (int i = 0; i < wn[k - dlo]; i++) {
+                    int kk = wl[k - dlo] + i;
+                    int vn = kk - k, an = vn - vv[cur][k], jn = an - aa[cur][k];
+                    float fv = (float)vn - vdes, fa = (float)an, fj = (float)jn;
+                    double tot = RND(lab[cur][k] + (double)fmaf(cv * fv, fv, fmaf(ca * fa, fa, cj * fj * fj)));
+                    if (!hc[kk] || tot < cand[kk]) { cand[kk] = tot; pred[kk] = k; hc[kk] = 1; }
+                }
+            }
+            free(wl); free(wn);
+            plo = dlo; phi = dhi; dlo = wlo_min; dhi = whi_max; prevbuf = cur;
+        }
+        (void)plo; (void)phi;
+        free(cand); free(hc);
+    } else { best_t = 0; best_k = 0; best_lab = 0; }
+#undef RND
+    if (cost_out) *cost_out = (double)best_lab;
+    int r = backtrack(num_t, num_s, previous, s_values, best_t, best_k, idx_out, s_seq_out);
+    for (int b = 0; b < 2; b++) { free(lab[b]); free(vv[b]); free(aa[b]); free(has[b]); }
+    free(previous); free(pred);
+    return r;
+}
+
 /* ---- cost of a given index path (the solver's own history convention) ----------------------- */
 double orc_path_cost(const orc_params *p, int n, const int *idx, const double *s_values,
                      const double *distances, int num_s, double delta_t, double v0, double a0) {

@@ -42,6 +42,8 @@ SYMBOLS = {
     "mpc_destroy": (_i, [_vp]),
     "mpc_grid_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "mpc_last_counters": (_i, [_vp, C.POINTER(C.c_int64)]),
+    "mpc_set_timing": (_i, [_vp, _i]),
+    "mpc_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "mpc_build_grid": (_i, [_vp, _i] + [_vp] * 5 + [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mpc_solve_dense": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mpc_plan": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),

@@ -1,0 +1,72 @@
+"""`Settings`: the global, mutable, class-attribute registry the reference reads everywhere
+(reference config.py:7-170), restricted to what the MPC hot path and its callers consume.
+
+`Settings.load_from_file(path)` accepts the reference's configs/*.json unchanged: every key becomes
+a class attribute (unknown keys are kept, dict values get int keys like the reference's loader,
+config.py:161-170).  The CUDA library snapshots the scalars at engine creation; after mutating
+Settings call `st.refresh_engine()` (or just let the shims notice the changed snapshot key).
+"""
+from __future__ import annotations
+
+import json
+
+_HOT_PATH_DEFAULTS = {
+    # task / bookkeeping
+    "TASK": "ST", "NUM_EPISODES": 2000, "LOG_DIR": "last_run", "MODEL_NAME": "", "SEED": "Random",
+    # simulation limits
+    "TICK_LENGTH": 0.2, "MAX_POSITIVE_ACCELERATION": 4.5, "MAX_NEGATIVE_ACCELERATION": -6.0,
+    "MINIMUM_NEGATIVE_JERK": -5.0, "MAXIMUM_POSITIVE_JERK": 5.0, "MAX_SPEED": 30, "CAR_LENGTH": 5.0,
+    "MERGE_POINT_X": -50, "MAX_EPISODE_LENGTH": 100,
+    # synthetic traffic (reference spawner parameters)
+    "BASE_TRAFFIC_INTERVAL": 1.2, "OTHER_CAR_SPEED": 7.0, "VARY_TRAFFIC_START_TIMES": True,
+    "START_SPEED": 15, "RANDOMIZE_START_SPEED": True, "START_SPEED_VARIANCE": 5, "MIN_START_SPEED": 5, "MAX_START_SPEED": 25,
+    # sensing / observation vector
+    "SENSOR_RADIUS": 125, "CARS_AHEAD": 2, "CARS_BEHIND": 2, "USE_ACCELERATION_OF_OTHER_CARS": True,
+    "USE_SPEED_DIFFERENCE": True, "NORMALIZE_VECTOR_INPUT": True,
+    # reward (every published config: "Slotted Jerk")
+    "REWARD_FUNCTION": "Slotted Jerk", "CRASH_REWARD": -10, "SUCCESS_REWARD": 10, "TIME_REWARD": -0.1, "ALT_J_WEIGHT": 0.05,
+    "INVALID_ACTION_PENALTY": 0.0,
+    # S-T planner
+    "DESIRED_SPEED": 30.0, "USE_CYTHON": True, "USE_FAST_ST_SOLVER": True, "S_DISCRETIZATION": 0.05, "T_DISCRETIZATION": 0.30,
+    "FUTURE_S": 150.0, "FUTURE_T": 5.0, "START_UNCERTAINTY": 0.0, "UNCERTAINTY_PER_SECOND": 0.0,
+    "V_WEIGHT": 0.5, "A_WEIGHT": 10.0, "J_WEIGHT": 10.0, "D_WEIGHT": 10.0, "MIN_ALLOWED_DISTANCE": 5, "CRASH_MIN_S": 12,
+    # predictor
+    "MAX_PREDICTED_DECELERATION": -4,
+    # RL + MPC combination
+    "ROLLOUT_LENGTH": 5, "ST_TEST_ROLLOUTS": 5, "LIMIT_DQN_SPEED": False, "TEST_ST_STRICTLY_BETTER": True,
+    "TEST_ROLLOUT_STATE": True, "CHECK_ROLLOUT_CRASH": True, "COMBINATION_MIN_DISTANCE": 5.1, "STOP_X": 65,
+    "REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED": False, "LEARNING_RATE": 2e-4,
+    # this implementation only
+    "ST_MODE": "exact",       # arithmetic of the single-state drop-in calls: "exact" (fp64, st_cy-identical) or "fast"
+    "CUDA_DEVICE": 0,
+}
+
+
+class _SettingsMeta(type):
+    def __repr__(cls):
+        return f"Settings({cls.export_settings()})"
+
+
+class Settings(metaclass=_SettingsMeta):
+    @classmethod
+    def export_settings(cls):
+        return {k: v for k, v in vars(cls).items() if k.isupper()}
+
+    @classmethod
+    def load_from_file(cls, filename):
+        with open(filename, "rb") as f:
+            contents = json.load(f)
+        for key, value in contents.items():
+            if isinstance(value, dict):
+                value = {int(k): v for k, v in value.items()}
+            setattr(cls, key, value)
+
+    @classmethod
+    def reset(cls):
+        for key in [k for k in vars(cls) if k.isupper()]:
+            delattr(cls, key)
+        for key, value in _HOT_PATH_DEFAULTS.items():
+            setattr(cls, key, value)
+
+
+Settings.reset()

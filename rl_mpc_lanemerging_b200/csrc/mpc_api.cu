@@ -8,9 +8,14 @@
 #include <string.h>
 
 // ---- launchers implemented in the kernel translation units ----------------------------------------
-cudaError_t launch_solve_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
-cudaError_t launch_solve_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
+cudaError_t launch_exact_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
+cudaError_t launch_exact_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
                                int dist_f32, int stride, cudaStream_t st);
+cudaError_t launch_fast_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
+cudaError_t launch_fast_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
+                              int dist_f32, int stride, cudaStream_t st);
+int exact_occupancy(int threads, size_t smem);
+int fast_occupancy(int threads, size_t smem, int wrap);
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
                                   const int32_t *n, LayerDesc *desc, double *s0, double *ds, int32_t *ns, cudaStream_t st);
 cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const LayerDesc *desc, const double *s0, const double *ds,
@@ -21,7 +26,6 @@ cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const doubl
 cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
                                 const double *ca, const int32_t *n, float *out, int stride, cudaStream_t st);
 cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st);
-int solve_occupancy(int mode, int desc, int threads, size_t smem);
 
 // ---- errors ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -51,9 +55,11 @@ struct mpc_handle {
     int device, max_batch, nmax;
     int sm_count; size_t smem_optin;
     // launch configuration
-    int W;                       // label-array length (cells)
-    size_t smem;                 // dynamic shared memory of the DP kernels (0 -> exact kernel uses global scratch)
-    int threads, grid_fast, grid_exact, grid_max;
+    int W;                       // full-row label-array length (cells), also the back-pointer row stride
+    size_t smem;                 // dynamic shared memory of the exact kernel (0 -> it uses global label scratch)
+    int threads, grid_exact;
+    int Wc, wrap_fast, threads_fast, grid_fast; size_t smem_fast;   // fast kernel: ring capacity / launch shape
+    int grid_max;
     // scratch
     LayerDesc *desc; double *s0, *ds; int32_t *num_s;
     uint16_t *bp; int *counters; int32_t *fallback_list;
@@ -62,6 +68,8 @@ struct mpc_handle {
     double *st_ego, *st_cx, *st_cv, *st_ca; int32_t *st_n;
     int32_t *st_idx; double *st_seq, *st_cost, *st_mind, *st_s0; int32_t *st_reached; uint8_t *st_crash;
     int64_t kernels_launched;
+    // optional per-kernel timing (bench.py roofline): events around [predict | DP | fallback DP]
+    int timing; cudaEvent_t ev[4]; int ev_valid;
 };
 
 static int host_arange_len(double start, double stop, double step) {
@@ -89,7 +97,7 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     double jlo = p->j_min * dt * dt * dt / ds, jhi = p->j_max * dt * dt * dt / ds;
     double alo = p->a_min * dt * dt / ds, ahi = p->a_max * dt * dt / ds;
     double vmax = p->max_speed * dt / ds;
-    D->lmax = (int)floor(jhi - jlo) + 3;
+    D->lmax_exact = (int)floor(jhi - jlo) + 2;
     const double eps = 1e-6;
     D->jlo_c = (int)ceil(jlo); D->jhi_c = (int)floor(jhi);
     D->alo_c = (int)ceil(alo); D->ahi_c = (int)floor(ahi);
@@ -98,7 +106,8 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     D->jhi_r = jhi; D->ahi_r = ahi; D->vmax_r = vmax;
     bool ok = !near_int(jlo, eps) && !near_int(jhi, eps) && !near_int(alo, eps) && !near_int(ahi, eps);
     if (!D->vmax_is_int) ok = ok && !near_int(vmax, eps) && !near_int(vmax - jhi, eps) && !near_int(vmax - ahi, eps);
-    ok = ok && D->vmax_c <= 250 && D->alo_c >= -120 && D->ahi_c <= 120 && D->lmax <= 64 && alo < 0 && ahi > 0;
+    D->lmax = D->jhi_c - D->jlo_c + 1;              // longest on-grid successor window
+    ok = ok && D->vmax_c <= 250 && D->alo_c >= -16 && D->ahi_c <= 15 && D->lmax >= 1 && D->lmax <= 7 && alo < 0 && ahi > 0;
     D->fast_ok = ok ? 1 : 0;
     D->cv = (float)(p->v_weight * (ds / dt) * (ds / dt));
     D->ca = (float)(p->a_weight * (ds / (dt * dt)) * (ds / (dt * dt)));
@@ -115,30 +124,39 @@ static void free_scratch(mpc_handle *h) {
     for (void *p : ptrs) if (p) cudaFree(p);
 }
 
+static int env_int(const char *name, int lo, int hi, int dflt) {
+    const char *v = getenv(name);
+    if (!v) return dflt;
+    int x = atoi(v);
+    return (x >= lo && x <= hi && x % 32 == 0) ? x : dflt;
+}
+
 static int configure(mpc_handle *h) {
     const DevParams &P = h->P;
     h->W = (P.num_s_max + 7) & ~7;
+    const size_t static_smem = 6144;                 // static shared of the kernels (upper bound) + 1 KB/block reserve
+    // ---- exact kernel: 24 B per cell, full row ----
     size_t need = (size_t)h->W * 24;
-    size_t static_smem = 4096;                       // BlockShared + LayerDesc + path buffer (upper bound)
-    const char *env_threads = getenv("MPC_THREADS");
     if (need + static_smem <= h->smem_optin) {
         h->smem = need;
-        int bps = (int)((h->smem_optin + 1024) / (need + static_smem + 1024));
-        if (bps < 1) bps = 1;
-        h->threads = bps >= 3 ? 256 : 512;
-        if (env_threads) { int t = atoi(env_threads); if (t >= 64 && t <= 512 && t % 32 == 0) h->threads = t; }
-        int occ_fast = solve_occupancy(MPC_MODE_FAST, 1, h->threads, h->smem);
-        int occ_exact = solve_occupancy(MPC_MODE_EXACT, 1, h->threads, h->smem);
-        if (occ_fast < 1) occ_fast = 1;
-        if (occ_exact < 1) occ_exact = 1;
-        h->grid_fast = h->sm_count * occ_fast;
-        h->grid_exact = h->sm_count * occ_exact;
+        int bps = (int)(h->smem_optin / (need + static_smem));
+        h->threads = env_int("MPC_EXACT_THREADS", 64, 512, bps >= 3 ? 256 : 512);
+        int occ = exact_occupancy(h->threads, h->smem);
+        h->grid_exact = h->sm_count * (occ < 1 ? 1 : occ);
     } else {                                         // e.g. H = 100: labels live in per-block global scratch
         h->smem = 0;
         h->threads = 512;
-        h->grid_fast = 0;
         h->grid_exact = h->sm_count * 2;
     }
+    // ---- fast kernel: 28 B per cell (fp64 label + u16 meta, double buffered; two multimaps), ring window ----
+    size_t cap = (h->smem_optin - static_smem) / 28;
+    h->wrap_fast = (size_t)h->W > cap;
+    h->Wc = h->wrap_fast ? (int)(cap & ~(size_t)7) : h->W;
+    h->smem_fast = (size_t)h->Wc * 28;
+    int bps = (int)(h->smem_optin / (h->smem_fast + static_smem));
+    h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 2 ? 512 : 1024);
+    int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
+    h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     return MPC_OK;
 }
@@ -200,6 +218,7 @@ extern "C" int mpc_set_params(mpc_handle *h, const mpc_params *p) {
 extern "C" int mpc_destroy(mpc_handle *h) {
     if (!h) return MPC_OK;
     cudaSetDevice(h->device);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     free_scratch(h);
     free(h);
     return MPC_OK;
@@ -219,6 +238,28 @@ extern "C" int mpc_last_counters(const mpc_handle *h, int64_t *out2) {
     MPC_CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
     out2[0] = h->kernels_launched;
     out2[1] = c[2];
+    return MPC_OK;
+}
+
+extern "C" int mpc_set_timing(mpc_handle *h, int enable) {
+    if (!h) return mpc_set_error(MPC_E_INVALID, "null handle");
+    MPC_CUDA_OK(cudaSetDevice(h->device));
+    if (enable && !h->ev[0]) for (int i = 0; i < 4; i++) MPC_CUDA_OK(cudaEventCreate(&h->ev[i]));
+    h->timing = enable ? 1 : 0; h->ev_valid = 0;
+    return MPC_OK;
+}
+
+// out3 = {traffic-predictor ms, DP kernel ms, fallback DP kernel ms} of the last mpc_plan / mpc_solve_dense call
+// (waits for that call to finish).  Needs mpc_set_timing(h, 1) before the call.
+extern "C" int mpc_last_kernel_ms(mpc_handle *h, float *out3) {
+    if (!h || !out3) return mpc_set_error(MPC_E_INVALID, "null argument");
+    if (!h->timing || !h->ev_valid) return mpc_set_error(MPC_E_INVALID, "timing not enabled or no timed call yet");
+    MPC_CUDA_OK(cudaSetDevice(h->device));
+    MPC_CUDA_OK(cudaEventSynchronize(h->ev[3]));
+    out3[0] = 0.f;
+    if (h->ev_valid == 1) MPC_CUDA_OK(cudaEventElapsedTime(&out3[0], h->ev[0], h->ev[1]));
+    MPC_CUDA_OK(cudaEventElapsedTime(&out3[1], h->ev[1], h->ev[2]));
+    MPC_CUDA_OK(cudaEventElapsedTime(&out3[2], h->ev[2], h->ev[3]));
     return MPC_OK;
 }
 
@@ -257,26 +298,37 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
     io.bp = h->bp; io.bp_stride = h->W;
     io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
     io.subset = nullptr; io.B_dev = nullptr;
-    SolveLaunch L;
-    L.mode = mode; L.B = B; L.threads = h->threads; L.smem = h->smem; L.W = h->W;
-    L.glab = h->smem ? nullptr : h->glab; L.ghist = h->smem ? nullptr : h->ghist;
-    L.grid = mode == MPC_MODE_FAST ? h->grid_fast : h->grid_exact;
-    if (L.grid > B) L.grid = B;
-    io.work_counter = h->counters + 0;
-    cudaError_t e = dense ? launch_solve_dense(h->P, L, io, ob, dist, dist_f32, stride, st) : launch_solve_desc(h->P, L, io, h->desc, st);
-    if (e != cudaSuccess) return mpc_set_cuda_error(e, "solve launch");
-    h->kernels_launched++;
-    if (mode == MPC_MODE_FAST) {          // re-solve (on the device) whatever the fast kernel handed back
-        SolveLaunch L2 = L;
-        L2.mode = MPC_MODE_EXACT;
-        L2.grid = h->grid_exact < 16 ? h->grid_exact : 16;
-        if (L2.grid > B) L2.grid = B;
+    SolveLaunch X;                                   // exact-kernel launch shape
+    X.B = B; X.threads = h->threads; X.smem = h->smem; X.W = h->W; X.wrap = 0;
+    X.glab = h->smem ? nullptr : h->glab; X.ghist = h->smem ? nullptr : h->ghist;
+    X.grid = h->grid_exact < B ? h->grid_exact : B;
+    cudaError_t e;
+    if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[1], st));
+    if (mode == MPC_MODE_EXACT) {
+        io.work_counter = h->counters + 0;
+        e = dense ? launch_exact_dense(h->P, X, io, ob, dist, dist_f32, stride, st) : launch_exact_desc(h->P, X, io, h->desc, st);
+        if (e != cudaSuccess) return mpc_set_cuda_error(e, "exact solve launch");
+        h->kernels_launched++;
+        if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
+    } else {
+        SolveLaunch F;
+        F.B = B; F.threads = h->threads_fast; F.smem = h->smem_fast; F.W = h->Wc; F.wrap = h->wrap_fast;
+        F.glab = nullptr; F.ghist = nullptr;
+        F.grid = h->grid_fast < B ? h->grid_fast : B;
+        io.work_counter = h->counters + 0;
+        e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
+        if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch");
+        h->kernels_launched++;
+        if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
+        // re-solve (on the device) whatever the fast kernel handed back: the batch size is read on the device
+        X.grid = X.grid < 16 ? X.grid : 16;
         io.work_counter = h->counters + 1;
         io.subset = h->fallback_list; io.B_dev = h->counters + 2;
-        e = dense ? launch_solve_dense(h->P, L2, io, ob, dist, dist_f32, stride, st) : launch_solve_desc(h->P, L2, io, h->desc, st);
+        e = dense ? launch_exact_dense(h->P, X, io, ob, dist, dist_f32, stride, st) : launch_exact_desc(h->P, X, io, h->desc, st);
         if (e != cudaSuccess) return mpc_set_cuda_error(e, "fallback solve launch");
         h->kernels_launched++;
     }
+    if (h->timing) { MPC_CUDA_OK(cudaEventRecord(h->ev[3], st)); h->ev_valid = dense ? 2 : 1; }
     return MPC_OK;
 }
 
@@ -304,6 +356,8 @@ extern "C" int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double 
     if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars) return mpc_set_error(MPC_E_INVALID, "mpc_plan: null pointer");
     (void)d_cars_a;
     cudaStream_t st = (cudaStream_t)stream;
+    h->ev_valid = 0;
+    if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[0], st));
     MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, d_start_s ? d_start_s : h->s0, h->ds, h->num_s, st));
     h->kernels_launched = 1;
     SolveIO io; memset(&io, 0, sizeof(io));

@@ -17,7 +17,8 @@ struct DevParams {
     int num_t;                 // len(arange(0, FUTURE_T + dt, dt))            (st.py:32)
     int num_s_max;             // upper bound of len(arange(s0, s0+FUTURE_S+ds, ds)) over s0
     int discrete_length;       // int(CAR_LENGTH / delta_s)                     (st.py:37)
-    int lmax;                  // max successor-window length in cells (+1 safety)
+    int lmax;                  // max successor-window length in cells, on-grid layers (fast kernel)
+    int lmax_exact;            // same for the off-grid first layers (+1 safety)
     double dt2, dt3;           // pow(dt,2), pow(dt,3) as libm computes them     (st_cy.pyx:48-49)
     double obs_min_s;          // CRASH_MIN_S - MIN_ALLOWED_DISTANCE            (st.py:46)
     double crash_thresh;       // COMBINATION_MIN_DISTANCE - CAR_LENGTH         (st.py:800)
@@ -72,13 +73,48 @@ __device__ __forceinline__ double distance_penalty_f64(double d, double min_allo
 // consumed by the rasteriser (K1b) and the fused planner (K3).  For every car that passes the
 // reference's range filters (st.py:46-49): the two edges the distance field is measured to
 // (st.py:52-53) and the obstacle band [imin, imax) in cells (st.py:60-65).
+#define MPC_BUCKET_SHIFT 6       // lookup buckets of 64 cells (3.2 m at the published discretisation)
+#define MPC_MAX_BUCKETS 288      // supports num_s <= 18432 (H = 100 needs 18001)
 struct LayerDesc {
-    int n_act;
-    int pad[3];
+    int n_act;                   // cars in reference order (exact kernel, rasteriser)
+    int n_edge;                  // sorted distance-field edges (= 2 * n_act)
+    int n_band;                  // obstacle bands merged into disjoint intervals
+    int pad;
     double ef[MPC_NMAX];
     double eb[MPC_NMAX];
     int2 band[MPC_NMAX];
+    // ---- search structure for the fast kernel (same information, sorted) ----
+    double edge[2 * MPC_NMAX];               // ascending
+    int2 mband[MPC_NMAX];                    // disjoint [x, y), ascending
+    unsigned char bucket_edge[MPC_MAX_BUCKETS];   // #edges  <  s_values[64*j]
+    unsigned char bucket_band[MPC_MAX_BUCKETS];   // #merged bands with y <= 64*j
 };
+
+// the part of a LayerDesc the fast kernel stages in shared memory
+struct LayerSearch {
+    int n_edge, n_band, pad0, pad1;
+    double edge[2 * MPC_NMAX];
+    int2 mband[MPC_NMAX];
+    unsigned char bucket_edge[MPC_MAX_BUCKETS];
+    unsigned char bucket_band[MPC_MAX_BUCKETS];
+};
+
+// distance-field value / obstacle flag through the sorted structure: bit-identical to cell_distance()
+// (the nearest edge on either side decides the min; |s-e| is monotone in e on each side).
+template <class LS>
+__device__ __forceinline__ double cell_distance_sorted(const LS &L, double s, int k, bool &obstacle) {
+    int j = k >> MPC_BUCKET_SHIFT;
+    int e = L.bucket_edge[j], M = L.n_edge;
+    while (e < M && L.edge[e] < s) e++;
+    double d = 1E10;
+    if (e > 0) { double x = __dsub_rn(s, L.edge[e - 1]); d = x < d ? x : d; }
+    if (e < M) { double x = fabs(__dsub_rn(s, L.edge[e])); d = x < d ? x : d; }
+    int i = L.bucket_band[j], m = L.n_band;
+    while (i < m && L.mband[i].y <= k) i++;
+    bool ob = i < m && L.mband[i].x <= k;
+    obstacle = ob;
+    return ob ? 0.0 : d;
+}
 
 // distance-field value and obstacle flag of cell k in a layer (st.py:52-65), exact fp64
 __device__ __forceinline__ double cell_distance(const LayerDesc &L, double s, int k, bool &obstacle) {
@@ -114,14 +150,13 @@ struct SolveIO {
 };
 
 struct SolveLaunch {
-    int mode;               // MPC_MODE_*
     int B;
     int grid, threads;
     size_t smem;
-    int W;
+    int W;                  // label-array length in cells (exact: full row; fast: ring capacity)
+    int wrap;               // fast kernel: ring shorter than the row
     unsigned long long *glab; unsigned *ghist;    // exact kernel global label scratch (or NULL)
 };
-
 
 #define MPC_CUDA_OK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return mpc_set_cuda_error(e__, #call); } while (0)
 int mpc_set_cuda_error(cudaError_t e, const char *what);

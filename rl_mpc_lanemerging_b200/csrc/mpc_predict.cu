@@ -7,6 +7,7 @@
 // lanes in parallel (Jacobi) until nothing changes, which yields exactly the sequential result
 // (after m sweeps the first m cars are final) in 1-3 sweeps for ordinary traffic.
 #include "mpc_common.cuh"
+#include <limits.h>
 
 #define FULL 0xffffffffu
 
@@ -88,7 +89,9 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
                                                             const int32_t *__restrict__ n_cars, int nmax,
                                                             LayerDesc *__restrict__ desc, double *__restrict__ o_s0,
                                                             double *__restrict__ o_ds, int32_t *__restrict__ o_num_s) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    __shared__ double s_edge[4][2 * MPC_NMAX];
+    __shared__ int2 s_band[4][MPC_NMAX];
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (warp >= B) return;
     int b = warp;
     int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
@@ -111,17 +114,68 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
         bool act = valid && lane < first_stop && !(obs_s > far_lim);                // 48-49: continue
         unsigned am = __ballot_sync(FULL, act);
         LayerDesc *L = desc + (size_t)b * P.num_t + t;
-        if (lane == 0) L->n_act = __popc(am);
+        int n_act = __popc(am);
+        double ef = 0.0, eb = 0.0; int imin = 0, imax = 0;
         if (act) {
             int slot = __popc(am & ((1u << lane) - 1));
-            L->ef[slot] = __dsub_rn(__dsub_rn(obs_s, P.p.car_length), unc);        // 52
-            L->eb[slot] = __dadd_rn(__dadd_rn(obs_s, P.p.car_length), unc);        // 53
-            int si = (int)__ddiv_rn(__dsub_rn(obs_s, g.s0), P.p.s_disc);           // 60
-            int imin = si - P.discrete_length - du; imin = imin < 0 ? 0 : imin;    // 61
-            int imax = si + P.discrete_length + du; imax = imax > g.num_s ? g.num_s : imax;   // 62
-            if (!(imin < g.num_s && imax > 0)) { imin = 0; imax = 0; }              // 63
-            L->band[slot] = make_int2(imin, imax);
+            ef = __dsub_rn(__dsub_rn(obs_s, P.p.car_length), unc);                  // 52
+            eb = __dadd_rn(__dadd_rn(obs_s, P.p.car_length), unc);                  // 53
+            int si = (int)__ddiv_rn(__dsub_rn(obs_s, g.s0), P.p.s_disc);            // 60
+            imin = si - P.discrete_length - du; imin = imin < 0 ? 0 : imin;         // 61
+            imax = si + P.discrete_length + du; imax = imax > g.num_s ? g.num_s : imax;   // 62
+            if (!(imin < g.num_s && imax > 0)) { imin = 0; imax = 0; }               // 63
+            L->ef[slot] = ef; L->eb[slot] = eb; L->band[slot] = make_int2(imin, imax);
         }
+        // ---- the same information sorted, for the fast kernel's O(1) lookups ----
+        // rank of each edge among all 2*n_act edges (ties by edge id) and of each band by start cell
+        int r_f = 0, r_b = 0, r_band = 0;
+        bool hasband = act && imin < imax;
+        unsigned bm = __ballot_sync(FULL, hasband);
+        for (int j = 0; j < 32; j++) {
+            if (!((am >> j) & 1u)) continue;                                        // warp-uniform
+            double fj = __shfl_sync(FULL, ef, j), bj = __shfl_sync(FULL, eb, j);
+            int ij = __shfl_sync(FULL, imin, j);
+            r_f += (fj < ef || (fj == ef && 2 * j < 2 * lane)) + (bj < ef || (bj == ef && 2 * j + 1 < 2 * lane));
+            r_b += (fj < eb || (fj == eb && 2 * j < 2 * lane + 1)) + (bj < eb || (bj == eb && 2 * j + 1 < 2 * lane + 1));
+            if ((bm >> j) & 1u) r_band += (ij < imin || (ij == imin && j < lane));
+        }
+        double *se = s_edge[wib]; int2 *sb = s_band[wib];
+        if (act) { se[r_f] = ef; se[r_b] = eb; }
+        if (hasband) sb[r_band] = make_int2(imin, imax);
+        __syncwarp();
+        int n_edge = 2 * n_act, nb = __popc(bm);
+        // merge overlapping / touching bands (sorted by start): lane r holds sorted band r
+        int2 mine = lane < nb ? sb[lane] : make_int2(INT_MAX, INT_MIN);
+        int pm = lane < nb ? mine.y : INT_MIN;                                      // inclusive prefix max of band ends
+        for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(FULL, pm, o); if (lane >= o) pm = max(pm, x); }
+        int pm_excl = __shfl_up_sync(FULL, pm, 1);
+        bool start = lane < nb && (lane == 0 || mine.x > pm_excl);
+        unsigned sm = __ballot_sync(FULL, start);
+        int gid = __popc(sm & ((2u << lane) - 1)) - 1;                              // group of this band
+        unsigned below = sm & ((2u << lane) - 1);
+        int first = below ? 31 - __clz(below) : 0;                                  // lane that opened my group
+        int gstart = __shfl_sync(FULL, mine.x, first);
+        bool last = lane < nb && (lane == nb - 1 || ((sm >> (lane + 1)) & 1u));
+        __syncwarp();                                                               // every lane has read sb[lane]
+        if (last) sb[gid] = make_int2(gstart, pm);                                  // sb now holds the merged bands
+        int n_band = __popc(sm);
+        __syncwarp();
+        for (int i = lane; i < n_edge; i += 32) L->edge[i] = se[i];
+        if (lane < n_band) L->mband[lane] = sb[lane];
+        if (lane == 0) { L->n_act = n_act; L->n_edge = n_edge; L->n_band = n_band; L->pad = 0; }
+        __syncwarp();
+        // bucket tables: bucket j starts at cell 64*j
+        int nbuck = (g.num_s + (1 << MPC_BUCKET_SHIFT) - 1) >> MPC_BUCKET_SHIFT;
+        for (int j = lane; j < nbuck; j += 32) {
+            double sj = g.sval(j << MPC_BUCKET_SHIFT);
+            int lo_ = 0, hi_ = n_edge;                                              // first index with edge >= sj
+            while (lo_ < hi_) { int mid = (lo_ + hi_) >> 1; if (se[mid] < sj) lo_ = mid + 1; else hi_ = mid; }
+            L->bucket_edge[j] = (unsigned char)lo_;
+            int cnt = 0, cell = j << MPC_BUCKET_SHIFT;
+            for (int q = 0; q < n_band; q++) cnt += (sb[q].y <= cell);
+            L->bucket_band[j] = (unsigned char)cnt;
+        }
+        __syncwarp();
     }
 }
 

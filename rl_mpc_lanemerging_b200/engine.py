@@ -103,6 +103,15 @@ class MpcEngine:
         _lib.check(self.lib.mpc_last_counters(self.h, out))
         return {"kernels_launched": int(out[0]), "fallback_problems": int(out[1])}
 
+    def set_timing(self, enable=True):
+        _lib.check(self.lib.mpc_set_timing(self.h, int(enable)))
+
+    def last_kernel_ms(self):
+        """(predictor, DP kernel, fallback DP) device milliseconds of the last plan()/solve_dense() call."""
+        out = (C.c_float * 3)()
+        _lib.check(self.lib.mpc_last_kernel_ms(self.h, out))
+        return float(out[0]), float(out[1]), float(out[2])
+
     # ------------------------------------------------------------------------------------------
     def plan(self, ego, cars_x, cars_v, cars_a, n_cars, mode="fast", out: Optional[dict] = None):
         """Fused gap-evaluation (K3).  Returns dict(idx i32[B,T], s_seq f64[B,T], cost f64[B], reached_t i32[B],

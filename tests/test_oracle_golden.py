@@ -1,0 +1,94 @@
+"""-m "not gpu": the CPU oracle against the committed golden vectors (generated from the unmodified
+reference by tests/golden/make_golden.py) and against the anchors recorded in SURVEY.md §8(c)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# (state, start_s, index sequence, DP cost) recorded from the reference's st_cy
+ANCHORS = [
+    (((-200.0, 21.7), 15.0, 0.0, [], [], []), -150.43274377608088,
+     [0, 91, 184, 279, 376, 475, 576, 679, 784, 891, 1000, 1111, 1224, 1339, 1456, 1575, 1696, 1819], 1550.107167368958),
+    (((-100.0, 8.3), 12.0, 0.5, [-20, -45, -70], [11, 11, 11], [0, 0, 0]), -49.538938220353494,
+     [0, 74, 150, 228, 308, 390, 474, 560, 648, 738, 830, 924, 1020, 1118, 1218, 1320, 1424, 1530], 2196.073112911568),
+    (((10.0, -1.6), 11.0, 0.0, [30, -8, -30], [11, 11, 11], [0, 0, 0]), 61.0,
+     [0, 67, 135, 204, 274, 346, 420, 496, 574, 653, 733, 814, 896, 979, 1063, 1148, 1234, 1321], 2689.9431438858037),
+]
+
+
+@pytest.mark.parametrize("layered", [False, True])
+@pytest.mark.parametrize("anchor", range(3))
+def test_survey_anchors(oracle, anchor, layered):
+    (pos, v, a, xs, vs, acs), s0, idx, cost = ANCHORS[anchor]
+    p = oracle.default_params()
+    r = oracle.plan(p, oracle.make_state(pos, v, a, xs, vs, acs), layered=layered)
+    assert r["start_s"] == s0
+    assert r["idx"].tolist() == idx
+    assert abs(r["cost"] - cost) <= 1e-9 * cost
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLD, name)))
+
+
+@pytest.mark.parametrize("name,H", [("plan_h17.npz", 17), ("plan_h50.npz", 50)])
+def test_plan_matches_reference(oracle, name, H):
+    G = _load(name)
+    p = oracle.horizon_params(H)
+    B = G["ego"].shape[0]
+    stride = int(G["sample_stride"])
+    for layered in (False, True):
+        r = helpers.oracle_plan_batch(oracle, p, G, H + 1, layered=layered)
+        assert np.array_equal(r["s_seq"], G["s_seq"])                      # bit-identical positions, incl. zero tails
+        assert np.array_equal(r["crash"], G["crash"])
+        # the golden cost is summed with the Python twin st.cost (st.py:140-144) whose penalty folds D_WEIGHT in a
+        # different order than st_cy (st.py:127-131 vs st_cy.pyx:34-38,50): equal to rounding only
+        assert np.all(helpers.rel(r["cost"], G["cost"])[G["cost"] > 0] < 1e-12)
+    for b in range(B):
+        st = helpers.oracle_state(oracle, G, b)
+        ob, di, sv = oracle.build_grid(p, st)
+        assert sv[0] == G["start_s"][b] and sv.size == G["num_s"][b] and sv[1] - sv[0] == G["delta_s"][b]
+        assert np.array_equal(ob.sum(1), G["obs_count"][b])
+        assert np.array_equal(di[:, ::stride][:, :49], G["dist_samples"][b])
+        if b < G["masks"].shape[0]:
+            assert np.array_equal(np.packbits(ob.astype(bool), axis=1), G["masks"][b])
+
+
+def test_dijkstra_equals_layered_dp(oracle):
+    """The equivalence the CUDA kernels rely on: same path, same cost, every state."""
+    from rl_mpc_lanemerging_b200 import synthetic
+    p = oracle.default_params()
+    for traffic, kind in (("moderate", "mixed"), ("default", "onramp"), ("fast", "mixed")):
+        S = synthetic.make_states(48, traffic, seed=21, kind=kind)
+        a = helpers.oracle_plan_batch(oracle, p, S, 18, layered=False)
+        b = helpers.oracle_plan_batch(oracle, p, S, 18, layered=True)
+        assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["cost"], b["cost"])
+        assert np.array_equal(a["reached_t"], b["reached_t"])
+
+
+def test_rollout_pieces_match_reference(oracle):
+    G = _load("rollout.npz")
+    p = oracle.default_params()
+    B = G["ego"].shape[0]
+    for b in range(B):
+        st = helpers.oracle_state(oracle, G, b)
+        n = st.n
+        nxt, crashed = oracle.predict_step_with_ego(p, st, G["sel"][b], 0.2, 5.1)
+        # the reference normalises the ramp direction with numpy.linalg.norm (BLAS dot): allow 1 ulp on the ego position
+        assert np.allclose([nxt.ego_x, nxt.ego_y], G["with_ego"][b, :2], rtol=4e-16, atol=0)
+        assert nxt.ego_v == G["with_ego"][b, 2] and nxt.ego_a == G["with_ego"][b, 3]
+        assert np.array_equal(nxt.x[:n], G["with_x"][b, :n]) and np.array_equal(nxt.v[:n], G["with_v"][b, :n])
+        assert np.array_equal(nxt.a[:n], G["with_a"][b, :n])
+        assert crashed == bool(G["with_crash"][b])
+        cur = st
+        for _ in range(17):
+            cur, _c = oracle.predict_step_without_ego(p, cur, 0.3)
+        assert np.allclose([cur.ego_x, cur.ego_y], G["chain_ego"][b, :2], rtol=1e-14, atol=0)
+        assert np.array_equal(cur.x[:n], G["chain_x"][b, :n]) and np.array_equal(cur.v[:n], G["chain_v"][b, :n])
+        assert np.array_equal(oracle.state_vector(p, st), G["state_vec"][b])
+        assert oracle.speed_from_jerk(p, st.ego_v, st.ego_a, G["jerk"][b]) == G["speed"][b]
+        assert oracle.path_mean_abs_jerk(G["jerk_paths"][b], st.ego_v, st.ego_a, 0.2) == G["mean_abs_jerk"][b]
