@@ -82,6 +82,11 @@ int mpc_last_counters(const mpc_handle *h, int64_t *out2);
 int mpc_set_timing(mpc_handle *h, int enable);
 int mpc_last_kernel_ms(mpc_handle *h, float *out3);
 
+/* Self-test: rebuilds the layer descriptors for the given states and counts the cells whose sorted O(1)
+ * obstacle/distance lookup (fast kernel) differs from the reference-order evaluation (must be 0). */
+int mpc_selftest_search(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                        const int32_t *d_n_cars, int64_t *mismatching_cells, void *stream);
+
 /* ---- K1: traffic prediction + S-T rasterisation (st.find_s_t_obstacles_from_state, st.py:25-70,
  *      with prediction.py:22-105 and control.py:373-389) ------------------------------------- */
 /* Dense grids, the layout st_cy consumes: d_obstacles u8[B][num_t][num_s_max],

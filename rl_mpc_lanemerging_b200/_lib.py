@@ -44,6 +44,7 @@ SYMBOLS = {
     "mpc_last_counters": (_i, [_vp, C.POINTER(C.c_int64)]),
     "mpc_set_timing": (_i, [_vp, _i]),
     "mpc_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
+    "mpc_selftest_search": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp]),
     "mpc_build_grid": (_i, [_vp, _i] + [_vp] * 5 + [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mpc_solve_dense": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mpc_plan": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),

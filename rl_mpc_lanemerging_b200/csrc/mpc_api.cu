@@ -14,6 +14,8 @@ cudaError_t launch_exact_dense(const DevParams &P, const SolveLaunch &L, const S
 cudaError_t launch_fast_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
 cudaError_t launch_fast_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
                               int dist_f32, int stride, cudaStream_t st);
+cudaError_t launch_check_sorted(const DevParams &P, int B, const LayerDesc *desc, const double *s0, const double *ds,
+                                const int32_t *ns, unsigned long long *mismatches, cudaStream_t st);
 int exact_occupancy(int threads, size_t smem);
 int fast_occupancy(int threads, size_t smem, int wrap);
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
@@ -148,11 +150,11 @@ static int configure(mpc_handle *h) {
         h->threads = 512;
         h->grid_exact = h->sm_count * 2;
     }
-    // ---- fast kernel: 28 B per cell (fp64 label + u16 meta, double buffered; two multimaps), ring window ----
-    size_t cap = (h->smem_optin - static_smem) / 28;
+    // ---- fast kernel: 32 B per cell (fp64 label + u16 meta, double buffered; three multimaps), ring window ----
+    size_t cap = (h->smem_optin - static_smem) / 32;
     h->wrap_fast = (size_t)h->W > cap;
     h->Wc = h->wrap_fast ? (int)(cap & ~(size_t)7) : h->W;
-    h->smem_fast = (size_t)h->Wc * 28;
+    h->smem_fast = (size_t)h->Wc * 32;
     int bps = (int)(h->smem_optin / (h->smem_fast + static_smem));
     h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 2 ? 512 : 1024);
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
@@ -285,6 +287,25 @@ extern "C" int mpc_build_grid(mpc_handle *h, int B, const double *d_ego, const d
     if (d_start_s) MPC_CUDA_OK(cudaMemcpyAsync(d_start_s, h->s0, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
     if (d_delta_s) MPC_CUDA_OK(cudaMemcpyAsync(d_delta_s, h->ds, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
     if (d_num_s) MPC_CUDA_OK(cudaMemcpyAsync(d_num_s, h->num_s, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    h->kernels_launched = 2;
+    return MPC_OK;
+}
+
+// Self-test of the per-layer search structure the fast kernel uses: rebuilds the layer descriptors for the given
+// states and compares, for every cell of every layer, the sorted O(1) lookup with the reference-order evaluation.
+extern "C" int mpc_selftest_search(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                                   const int32_t *d_n_cars, int64_t *mismatching_cells, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars || !mismatching_cells) return mpc_set_error(MPC_E_INVALID, "mpc_selftest_search: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *cnt = reinterpret_cast<unsigned long long *>(h->counters + 8);
+    MPC_CUDA_OK(cudaMemsetAsync(cnt, 0, 8, st));
+    MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, h->s0, h->ds, h->num_s, st));
+    MPC_CUDA_OK(launch_check_sorted(h->P, B, h->desc, h->s0, h->ds, h->num_s, cnt, st));
+    unsigned long long v = 0;
+    MPC_CUDA_OK(cudaMemcpyAsync(&v, cnt, 8, cudaMemcpyDeviceToHost, st));
+    MPC_CUDA_OK(cudaStreamSynchronize(st));
+    *mismatching_cells = (int64_t)v;
     h->kernels_launched = 2;
     return MPC_OK;
 }

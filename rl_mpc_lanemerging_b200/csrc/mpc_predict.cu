@@ -202,6 +202,30 @@ __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int 
     }
 }
 
+// ---- self-test: the sorted search structure must reproduce the reference-order evaluation bit for bit ----
+__global__ void __launch_bounds__(256) check_sorted_kernel(DevParams P, int B, const LayerDesc *__restrict__ desc,
+                                                           const double *__restrict__ s0v, const double *__restrict__ dsv,
+                                                           const int32_t *__restrict__ nsv, unsigned long long *mismatches) {
+    int bt = blockIdx.x, b = bt / P.num_t;
+    const LayerDesc &L = desc[bt];
+    SGrid g; g.s0 = s0v[b]; g.ds = dsv[b]; g.num_s = nsv[b];
+    unsigned long long bad = 0;
+    for (int k = threadIdx.x; k < g.num_s; k += blockDim.x) {
+        bool o1, o2;
+        double s = g.sval(k);
+        double d1 = cell_distance(L, s, k, o1), d2 = cell_distance_sorted(L, s, k, o2);
+        if (o1 != o2 || d1 != d2) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_check_sorted(const DevParams &P, int B, const LayerDesc *desc, const double *s0, const double *ds,
+                                const int32_t *ns, unsigned long long *mismatches, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    check_sorted_kernel<<<B * P.num_t, 256, 0, st>>>(P, B, desc, s0, ds, ns, mismatches);
+    return cudaGetLastError();
+}
+
 // ---- K4 -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) predict_step_with_ego_kernel(DevParams P, int B, int nmax, const double *ego,
                                                                    const double *cars_x, const double *cars_v,

@@ -6,7 +6,7 @@
 #define FULL 0xffffffffu
 #define INF_BITS 0x7ff0000000000000ULL
 #define EMPTY64 0xffffffffffffffffULL
-#define OVF_CAP 256
+#define OVF_CAP 128
 
 // ------------------------------------------------------------------------------------------------
 // cell providers
@@ -79,15 +79,15 @@ __device__ __forceinline__ int warp_max_i(int v) { for (int o = 16; o; o >>= 1) 
 
 struct BlockShared {
     int b;                  // current problem
-    int nlo[2], nhi[2];     // next-layer span (double buffered by layer parity)
-    int any[2];
+    int nlo[3], nhi[3];     // next-layer span (buffered by layer index mod 2 or 3)
+    int any[3];
     unsigned long long best_bits;
     int best_k;
     unsigned long long mind_bits;
     int crash;
-    int ovf_cnt[2];
+    int ovf_cnt[3];
     int need_fallback;
-    unsigned ovf[OVF_CAP];
+    unsigned ovf[3 * OVF_CAP];
 };
 
 // Write outputs for a finished DP: back-track from (bt, bk), then the crash test of st.py:790-802.

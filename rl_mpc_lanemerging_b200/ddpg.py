@@ -1,0 +1,104 @@
+"""DDPG actor for action proposal (reference ddpg.py:24-93).  The reference wraps the third-party
+`autonomous-learning-library` preset; its deployed computation is a 21->400->300->1 MLP followed by
+tanh * 5 on the 20-dim observation plus a time feature.  That forward stays in PyTorch (north_star), on
+device tensors produced by the K4 observation kernel -- no host round trip.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import dqn, st
+from .config import Settings
+from .prediction import BatchedState, HighwayState
+
+TIME_FEATURE_SCALE = 0.001          # autonomous-learning-library 0.5.3 TimeFeature default (unpinned)
+
+
+class PolicyNet(nn.Module):
+    """Same layout / state_dict keys as the reference checkpoints (`model.{0,2,4}.{weight,bias}`)."""
+
+    def __init__(self, obs_dim=21, tanh_scale=5.0, tanh_mean=0.0):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(obs_dim, 400), nn.ReLU(), nn.Linear(400, 300), nn.ReLU(), nn.Linear(300, 1))
+        self.tanh_scale, self.tanh_mean = tanh_scale, tanh_mean
+
+    def forward(self, obs):
+        return torch.tanh(self.model(obs)).squeeze(-1) * self.tanh_scale + self.tanh_mean
+
+
+def _load_legacy_state_dict(path):
+    """The published checkpoints are whole-module pickles of `all` classes; unpickle them against stand-ins."""
+    names = {"all": {}, "all.policies": {}, "all.policies.deterministic": {"DeterministicPolicyNetwork": nn.Module},
+             "all.approximation": {}, "all.approximation.q_continuous": {"QContinuousModule": nn.Module},
+             "all.nn": {"Linear0": nn.Linear, "RLNetwork": nn.Module}}
+    added = []
+    for mod, attrs in names.items():
+        if mod not in sys.modules:
+            m = types.ModuleType(mod)
+            for k, base in attrs.items():
+                setattr(m, k, type(k, (base,), {}))
+            sys.modules[mod] = m
+            added.append(mod)
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+        return obj.state_dict() if hasattr(obj, "state_dict") else obj
+    finally:
+        for mod in added:
+            sys.modules.pop(mod, None)
+
+
+class DDPGAgent(dqn.RLAgent):
+    def __init__(self, device=None, seed: int = 0):
+        super().__init__()
+        self.device = torch.device(device if device is not None else f"cuda:{int(getattr(Settings, 'CUDA_DEVICE', 0))}")
+        g = torch.Generator().manual_seed(seed)
+        self.policy = PolicyNet()
+        for p in self.policy.parameters():                     # deterministic random init (no checkpoint in the container)
+            with torch.no_grad():
+                p.copy_(torch.empty_like(p).uniform_(-0.05, 0.05, generator=g))
+        self.policy.to(self.device).eval()
+        self.timestep: Optional[torch.Tensor] = None
+        self._obs: Optional[torch.Tensor] = None
+
+    @classmethod
+    def load(cls, path, device=None) -> "DDPGAgent":
+        """`path` is a run directory holding policy.pt (reference ddpg.py:37-44)."""
+        agent = cls(device)
+        f = os.path.join(path, "policy.pt")
+        sd = _load_legacy_state_dict(f)
+        agent.policy.load_state_dict({k: v for k, v in sd.items() if k.startswith("model.")})
+        agent.policy.to(agent.device).eval()
+        return agent
+
+    def reset_time(self, mask: Optional[torch.Tensor] = None):
+        if self.timestep is not None:
+            if mask is None:
+                self.timestep.zero_()
+            else:
+                self.timestep[mask] = 0
+
+    @torch.no_grad()
+    def get_control(self, state):
+        """Jerk proposed by the actor (reference ddpg.py:83-87).  The time feature advances on every call,
+        like the reference's TimeFeature wrapper."""
+        single = isinstance(state, HighwayState)
+        eng = st.get_engine(1 if single else state.batch)
+        bs = BatchedState.from_states([state], eng.device, eng.nmax) if single else state
+        B = bs.batch
+        if self._obs is None or self._obs.shape[0] != B:
+            self._obs = torch.zeros((B, 21), dtype=torch.float32, device=self.device)
+            self.timestep = torch.zeros(B, dtype=torch.float32, device=self.device)
+        eng.state_vector(*bs.args(), out=self._obs)
+        self._obs[:, 20] = self.timestep * TIME_FEATURE_SCALE
+        self.timestep += 1
+        jerk = self.policy(self._obs)
+        return float(jerk.item()) if single else jerk
+
+    def end_episode_callback(self, last_state=None):
+        self.reset_time()

@@ -1,0 +1,123 @@
+"""Agent-side pieces of the hot path with the reference's names (reference dqn.py:70-200, 389-446, 557-563):
+observation vector, reward, and the RL-proposes / MPC-vetoes decision loop -- all batched.
+
+The reference evaluates one episode at a time with Python branches; here the same decision chain runs
+for B episodes with masks, the predictor / observation / clamp steps in K4 kernels and the veto in the
+fused K3 planner.  The policy forward is plain PyTorch on device tensors (north_star: "PyTorch only for
+the existing Q-network forward").
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import control, st
+from .config import Settings
+from .prediction import BatchedState, HighwayState
+
+
+def get_state_vector_from_base_state(state, out: Optional[torch.Tensor] = None):
+    """20-dim observation (reference dqn.py:389-446 with CARS_AHEAD = CARS_BEHIND = 2, accelerations, speed
+    differences, normalisation -- the only variant the published configs use).
+    HighwayState -> float32 numpy[20];  BatchedState -> float32 tensor [B,21] whose last column is left for the
+    time feature the DDPG policy appends."""
+    if isinstance(state, BatchedState):
+        return st.get_engine(state.batch).state_vector(*state.args(), out=out)
+    eng = st.get_engine()
+    bs = BatchedState.from_states([state], eng.device, eng.nmax)
+    return eng.state_vector(*bs.args())[0, :20].cpu().numpy()
+
+
+def slotted_reward_with_jerk(state, jerk, crashed, arrived):
+    """Reference dqn.py:557-563.  Scalars or tensors."""
+    step = Settings.TIME_REWARD * Settings.TICK_LENGTH - Settings.ALT_J_WEIGHT * jerk ** 2 * Settings.TICK_LENGTH
+    if torch.is_tensor(jerk):
+        r = torch.where(arrived, torch.full_like(step, float(Settings.SUCCESS_REWARD)), step)
+        return torch.where(crashed, torch.full_like(step, float(Settings.CRASH_REWARD)), r)
+    if crashed:
+        return Settings.CRASH_REWARD
+    if arrived:
+        return Settings.SUCCESS_REWARD
+    return step
+
+
+def get_reward_function():
+    if Settings.REWARD_FUNCTION != "Slotted Jerk":
+        raise NotImplementedError("only the 'Slotted Jerk' reward of the published configs is provided")
+    return slotted_reward_with_jerk
+
+
+class RLAgent:
+    """Base class: subclasses provide get_control(state) -> jerk (reference dqn.py:70-77)."""
+
+    def __init__(self):
+        self.takeover_history: List = []
+
+    def get_control(self, state):
+        raise NotImplementedError
+
+    def select_action(self, state):                 # north_star alias
+        return self.get_control(state)
+
+    def _setup(self):
+        self.takeover_history = []
+
+    # ---- reference dqn.py:117-200 ----------------------------------------------------------------
+    def do_combined_control(self, state):
+        """RL proposes a jerk, a short policy rollout and the MPC planner decide whether the planner takes over.
+        HighwayState -> commanded speed (float); BatchedState -> (speed tensor [B], takeover mask [B])."""
+        single = isinstance(state, HighwayState)
+        eng = st.get_engine(1 if single else state.batch)
+        start = BatchedState.from_states([state], eng.device, eng.nmax) if single else state
+        speed, takeover = self._combined_batched(start, eng)
+        self.takeover_history.append(bool(takeover.item()) if single else takeover)
+        return float(speed.item()) if single else (speed, takeover)
+
+    def _combined_batched(self, start: BatchedState, eng):
+        if Settings.TEST_ST_STRICTLY_BETTER:
+            raise NotImplementedError("the 'b' configs compare against the QP-smoothed plan (finer_fit), which is the next "
+                                      "row of the scope table (SURVEY.md §8 f-1)")
+        B, dev = start.batch, eng.device
+        first_action = self.get_control(start)
+        cur = start.clone()
+        alive = torch.ones(B, dtype=torch.bool, device=dev)
+        crash_predicted = torch.zeros(B, dtype=torch.bool, device=dev)
+        selected_speed = torch.zeros(B, dtype=torch.float64, device=dev)
+        snap, has_snap = None, torch.zeros(B, dtype=torch.bool, device=dev)
+        steps = max(int(Settings.ROLLOUT_LENGTH), 1)
+        for i in range(1, steps + 1):                                               # dqn.py:129-141
+            action = first_action if i == 1 else self.get_control(cur)
+            sel = control.get_ego_speed_from_jerk(cur.ego[:, 2].contiguous(), cur.ego[:, 3].contiguous(), action.double())
+            eo, xo, vo, ao, crashed = eng.predict_step_with_ego(*cur.args(), sel, Settings.TICK_LENGTH, Settings.COMBINATION_MIN_DISTANCE)
+            m = alive.unsqueeze(1)
+            cur = BatchedState(torch.where(m, eo, cur.ego), torch.where(m, xo, cur.cars_x), torch.where(m, vo, cur.cars_v),
+                               torch.where(m, ao, cur.cars_a), cur.n_cars)
+            selected_speed = torch.where(alive, sel, selected_speed)
+            crash_predicted |= alive & crashed.bool()
+            if i == int(Settings.ST_TEST_ROLLOUTS):
+                snap, has_snap = cur.clone(), alive.clone()
+            alive = alive & ~crashed.bool() & ~(cur.ego[:, 0] > Settings.STOP_X)
+        if snap is not None:                                                        # dqn.py:142-143
+            m = has_snap.unsqueeze(1)
+            test = BatchedState(torch.where(m, snap.ego, cur.ego), torch.where(m, snap.cars_x, cur.cars_x),
+                                torch.where(m, snap.cars_v, cur.cars_v), torch.where(m, snap.cars_a, cur.cars_a), cur.n_cars)
+        else:
+            test = cur
+        takeover = torch.zeros(B, dtype=torch.bool, device=dev)
+        if Settings.CHECK_ROLLOUT_CRASH:                                            # 144-147
+            takeover |= crash_predicted
+        if Settings.LIMIT_DQN_SPEED:                                                # 148-151
+            takeover |= selected_speed > Settings.DESIRED_SPEED
+        if Settings.TEST_ROLLOUT_STATE:                                             # 152-155: full gap-evaluation from the rollout state
+            takeover |= st.test_guaranteed_crash_from_state(test)
+        rl_speed = control.get_ego_speed_from_jerk(start.ego[:, 2].contiguous(), start.ego[:, 3].contiguous(), first_action.double())
+        speed = rl_speed
+        n_take = int(takeover.sum().item())
+        if n_take:                                                                  # planner takes over: st.do_st_control(start_state)
+            idx = takeover.nonzero().squeeze(1)
+            sub = BatchedState(*(t[idx].contiguous() for t in start.args()))
+            speed = rl_speed.clone()
+            speed[idx] = st.do_st_control(sub)
+        return speed, takeover

@@ -103,6 +103,14 @@ class MpcEngine:
         _lib.check(self.lib.mpc_last_counters(self.h, out))
         return {"kernels_launched": int(out[0]), "fallback_problems": int(out[1])}
 
+    def selftest_search(self, ego, cars_x, cars_v, cars_a, n_cars) -> int:
+        """Cells whose sorted-structure lookup differs from the reference-order evaluation (must be 0)."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        out = C.c_int64(-1)
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_selftest_search(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(n_cars), C.byref(out), self._stream()))
+        return int(out.value)
+
     def set_timing(self, enable=True):
         _lib.check(self.lib.mpc_set_timing(self.h, int(enable)))
 

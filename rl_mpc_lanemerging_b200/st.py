@@ -1,0 +1,140 @@
+"""Spatio-temporal planner front end with the reference's function names (reference st.py:726-802).
+
+Every function accepts either one `HighwayState` (drop-in: numpy results shaped like the reference's)
+or a `BatchedState` (device tensors in, device tensors out).  All computation happens in libmpcb200
+(K1 grid build, K2 dense solve, K3 fused plan); there is no CPU implementation here.
+
+Arithmetic: single-state calls default to Settings.ST_MODE ("exact": fp64, index-identical to the
+reference's st_cy); batched calls default to "fast" (integer kinematics, fp64 labels; sequences match
+the reference on >99% of states, cost within 1e-6 rel -- DESIGN.md §Parity).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .config import Settings
+from .engine import MpcEngine, params_from_settings, params_key
+from .prediction import BatchedState, HighwayState
+
+_engine: Optional[MpcEngine] = None
+_engine_key = None
+
+
+def get_engine(min_batch: int = 1) -> MpcEngine:
+    """The process-wide engine for the current Settings snapshot (rebuilt when Settings or capacity change)."""
+    global _engine, _engine_key
+    p = params_from_settings(Settings)
+    dev = int(getattr(Settings, "CUDA_DEVICE", 0))
+    key = (params_key(p), dev)
+    if _engine is None or key != _engine_key or _engine.max_batch < min_batch:
+        if _engine is not None:
+            _engine.close()
+        cap = max(min_batch, 64)
+        _engine = MpcEngine(p, device=dev, max_batch=cap)
+        _engine_key = key
+    return _engine
+
+
+def refresh_engine():
+    """Drop the cached engine (call after mutating Settings in place with unusual values)."""
+    global _engine, _engine_key
+    if _engine is not None:
+        _engine.close()
+    _engine, _engine_key = None, None
+
+
+def _t_values(eng: MpcEngine):
+    return np.arange(eng.num_t) * float(Settings.T_DISCRETIZATION)
+
+
+def _s_values(start_s: float, delta_s: float, num_s: int):
+    s = start_s + np.arange(num_s) * delta_s
+    if num_s > 1:
+        s[1] = start_s + float(Settings.S_DISCRETIZATION)
+    return s
+
+
+def find_s_t_obstacles_from_state(current_state: HighwayState, *_ignored, **_kw):
+    """(obstacles bool[num_t,num_s], s_values, t_values, ego_speed, distances f64[num_t,num_s]) -- reference st.py:25-70.
+    Discretisation / horizon come from Settings (the reference passes the same Settings values positionally)."""
+    eng = get_engine()
+    bs = BatchedState.from_states([current_state], eng.device, eng.nmax)
+    g = eng.build_grid(*bs.args())
+    ns = int(g["num_s"].item())
+    obstacles = g["obstacles"][0, :, :ns].cpu().numpy().astype(bool)
+    distances = g["distances"][0, :, :ns].cpu().numpy()
+    s_values = _s_values(g["start_s"].item(), g["delta_s"].item(), ns)
+    return obstacles, s_values, _t_values(eng), current_state.ego_speed, distances
+
+
+def plan_batch(batch: BatchedState, mode: Optional[str] = None, out: Optional[dict] = None) -> dict:
+    """Fused gap-evaluation for a batch: dict(idx, s_seq, cost, reached_t, crash, min_dist, start_s) of device tensors."""
+    eng = get_engine(batch.batch)
+    return eng.plan(*batch.args(), mode=mode or "fast", out=out)
+
+
+def get_appropriate_base_st_path_and_obstacles(state):
+    """Reference st.py:726-754.  HighwayState -> (s_sequence, obstacles, s_values, t_values, distances) as numpy
+    (unreached layers are 0.0 like the reference).  BatchedState -> plan_batch(state)."""
+    if isinstance(state, BatchedState):
+        return plan_batch(state)
+    obstacles, s_values, t_values, _v, distances = find_s_t_obstacles_from_state(state)
+    eng = get_engine()
+    bs = BatchedState.from_states([state], eng.device, eng.nmax)
+    r = eng.plan(*bs.args(), mode=getattr(Settings, "ST_MODE", "exact"))
+    return r["s_seq"][0].cpu().numpy(), obstacles, s_values, t_values, distances
+
+
+solve = get_appropriate_base_st_path_and_obstacles          # the name BASELINE.json's north_star uses
+
+
+def test_guaranteed_crash_from_state(state):
+    """Reference st.py:790-802: True when the plan is incomplete or touches a cell closer than
+    COMBINATION_MIN_DISTANCE - CAR_LENGTH to traffic.  BatchedState -> bool tensor [B]."""
+    if isinstance(state, BatchedState):
+        return plan_batch(state)["crash"].bool()
+    eng = get_engine()
+    bs = BatchedState.from_states([state], eng.device, eng.nmax)
+    return bool(eng.plan(*bs.args(), mode=getattr(Settings, "ST_MODE", "exact"))["crash"].item())
+
+
+test_guaranteed_crash_from_state.__test__ = False            # not a pytest test
+
+
+def first_step_speed(plan: dict) -> torch.Tensor:
+    """Speed command from a plan (reference st.py:774-783) for the whole batch.
+
+    The reference smooths the 0.3 s plan onto the 0.2 s tick with a QP (finer_fit, st.py:584-723) before taking
+    (s[1]-s[0])/TICK; that QP is the next row of the scope table and is not ported yet, so the
+    plan's own first-step mean speed (s[1]-s[0])/T_DISCRETIZATION is used.  Where the plan has a single point
+    (crash inevitable) the caller keeps its current speed (st.py:775-777): those entries are NaN here."""
+    s = plan["s_seq"]
+    v = (s[:, 1] - s[:, 0]) / float(Settings.T_DISCRETIZATION)
+    return torch.where(plan["reached_t"] >= 1, v, torch.full_like(v, float("nan")))
+
+
+def do_st_control(state):
+    """Reference st.py:757-783.  Returns the commanded ego speed (float, or tensor [B] for a BatchedState)."""
+    if isinstance(state, BatchedState):
+        v = first_step_speed(plan_batch(state))
+        return torch.where(torch.isnan(v), state.ego[:, 2], v)
+    eng = get_engine()
+    bs = BatchedState.from_states([state], eng.device, eng.nmax)
+    v = first_step_speed(eng.plan(*bs.args(), mode=getattr(Settings, "ST_MODE", "exact")))
+    v = float(v.item())
+    return state.ego_speed if v != v else v
+
+
+def get_path_mean_abs_jerk(s_sequence, ego_start_speed, ego_start_acceleration, delta_t):
+    """Reference st.py:274-288 (host bookkeeping on a short path)."""
+    s = np.asarray(s_sequence, dtype=np.float64)
+    v = np.diff(s) / delta_t
+    a = np.diff(np.concatenate([[ego_start_speed], v])) / delta_t
+    j = np.diff(np.concatenate([[ego_start_acceleration], a])) / delta_t
+    total = 0.0
+    for x in j:                       # sequential accumulation like the reference's loop
+        total += abs(float(x))
+    return total / (len(s) - 1)

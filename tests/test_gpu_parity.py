@@ -82,7 +82,13 @@ def test_plan_fast_within_tolerance(oracle, engines, torch_mod, H, B, traffic, k
         assert abs(ours - ref["cost"][b]) <= 1e-4 * ref["cost"][b], (b, ours, ref["cost"][b])
         # and the path must be feasible on the oracle's grid
         assert not obst[np.arange(1, n), idx[b, 1:n]].any()
-    assert n_diff <= max(2, B // 8), f"{n_diff} of {B} sequences differ from the oracle"
+    assert n_diff <= max(1, B // 16), f"{n_diff} of {B} sequences differ from the oracle"
+    # the kernel's arithmetic is modelled on the CPU (oracle/mpc_oracle.c: orc_solve_fast_model): bit-identical
+    for b in range(0, B, 7):
+        st = helpers.oracle_state(oracle, S, b)
+        obst, dist, sv = oracle.build_grid(op, st)
+        m = oracle.solve_fast_model(op, obst, dist, sv, op.t_disc, st.ego_v, st.ego_a)
+        assert np.array_equal(m["idx"], idx[b]) and m["cost"] == cost[b], (b, m["cost"], cost[b])
     # first-step acceleration (what the controller acts on)
     a_ref = ((ref["s_seq"][:, 1] - ref["s_seq"][:, 0]) / op.t_disc - S["ego"][:, 2]) / op.t_disc
     s = out["s_seq"].cpu().numpy()
@@ -106,6 +112,15 @@ def test_build_grid_matches_oracle(oracle, engines, torch_mod, traffic, kind):
         assert g["start_s"][b].item() == sv[0] and g["delta_s"][b].item() == sv[1] - sv[0]
         assert np.array_equal(ob[b, :, :ns[b]], o2)
         assert np.array_equal(di[b, :, :ns[b]], d2)              # bit-identical fp64 distance field
+
+
+@pytest.mark.parametrize("H", [17, 50])
+@pytest.mark.parametrize("traffic,kind", CASES)
+def test_sorted_search_structure_is_exact(engines, torch_mod, H, traffic, kind):
+    """The fast kernel's O(1) obstacle/distance lookup equals the reference-order evaluation on every cell."""
+    _, eng = engines[H]
+    D = _dev(_states(traffic, kind, 64, seed=16), torch_mod)
+    assert eng.selftest_search(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"]) == 0
 
 
 @pytest.mark.parametrize("mode", ["exact", "fast"])
