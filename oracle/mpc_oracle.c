@@ -372,46 +372,58 @@ int orc_solve_layered(const orc_params *p, int num_t, int num_s, const uint8_t *
 }
 
 
-/* ---- CPU model of the CUDA fast kernel's arithmetic (integer-cell kinematics, fp32 labels, penalty
- * added after the min).  NOT part of the reference: it exists so that the fast mode's tolerance claim
- * can be checked on CPU over many states, and to debug the kernel.  Mirrors fast_pull_kernel in
- * rl_mpc_lanemerging_b200/csrc/mpc_solve.cu (same window rules, same operation order in fp32). */
+/* ---- CPU model of the CUDA fast kernel's arithmetic.  NOT part of the reference: it exists so that the
+ * fast mode's tolerance claim can be checked on CPU over many states, and so that the GPU kernel can be
+ * tested bit for bit.  Mirrors fast_pull_kernel (rl_mpc_lanemerging_b200/csrc/mpc_fast.cu): layers 0/1 in
+ * exact fp64 then quantised to 2^-18 fixed point, integer-cell kinematics with tabulated edge costs from
+ * layer 2 on, 48-bit integer labels, ties to the larger v' (= smaller predecessor index).
+ * label_bits: 0 = the kernel's arithmetic; 32 = (rejected design) fp32 labels, kept to document why. */
 #include <float.h>
+#define FXONE 262144.0
+static uint64_t fx(double x) { return (uint64_t)llrint(x * FXONE); }
+
 int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
                          const double *distances, const double *s_values, double delta_t,
                          double v0, double a0, int f32_labels, int *idx_out, double *s_seq_out, double *cost_out) {
-#define RND(x) (f32_labels ? (double)(float)(x) : (double)(x))
     double dsn = p->s_disc, dt = p->t_disc;
     double jlo = p->j_min * dt * dt * dt / dsn, jhi = p->j_max * dt * dt * dt / dsn;
     double alo_r = p->a_min * dt * dt / dsn, ahi_r = p->a_max * dt * dt / dsn, vmax_r = p->max_speed * dt / dsn;
     int jlo_c = (int)ceil(jlo), jhi_c = (int)floor(jhi), alo_c = (int)ceil(alo_r), ahi_c = (int)floor(ahi_r);
     int vmax_is_int = fabs(vmax_r - nearbyint(vmax_r)) < 1e-9;
     int vmax_c = vmax_is_int ? (int)nearbyint(vmax_r) : (int)floor(vmax_r);
-    float cv = (float)(p->v_weight * (dsn / dt) * (dsn / dt));
-    float ca = (float)(p->a_weight * (dsn / (dt * dt)) * (dsn / (dt * dt)));
-    float cj = (float)(p->j_weight * (dsn / (dt * dt * dt)) * (dsn / (dt * dt * dt)));
-    float vdes = (float)(p->desired_speed * dt / dsn), dw = (float)p->d_weight;
+    uint32_t vtab[256], atab[32], jtab[16];
+    for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * dsn / dt - p->desired_speed) * (v * dsn / dt - p->desired_speed); vtab[v] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
+    for (int i = 0; i < 32; i++) { double acc = (i - 16) * dsn / (dt * dt), x = p->a_weight * acc * acc; atab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
+    for (int i = 0; i < 16; i++) { double jk = (i - 8) * dsn / (dt * dt * dt), x = p->j_weight * jk * jk; jtab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
+    float cvf = (float)(p->v_weight * (dsn / dt) * (dsn / dt)), caf = (float)(p->a_weight * (dsn / (dt * dt)) * (dsn / (dt * dt)));
+    float cjf = (float)(p->j_weight * (dsn / (dt * dt * dt)) * (dsn / (dt * dt * dt))), vdes = (float)(p->desired_speed * dt / dsn);
     double delta_s = s_values[1] - s_values[0], start_s = s_values[0];
     int *previous = (int *)calloc((size_t)num_t * num_s, sizeof(int));
-    double *lab[2]; int *vv[2], *aa[2]; uint8_t *has[2];
-    for (int b = 0; b < 2; b++) { lab[b] = (double *)malloc(8 * num_s); vv[b] = (int *)malloc(4 * num_s); aa[b] = (int *)malloc(4 * num_s); has[b] = (uint8_t *)calloc(num_s, 1); }
-    int *pred = (int *)malloc(4 * num_s);
+    /* per cell: label (integer fixed point, or float bits when f32_labels), v, a */
+    uint64_t *lab[2]; float *labf[2]; int *vv[2], *aa[2]; uint8_t *has[2];
+    for (int b = 0; b < 2; b++) { lab[b] = (uint64_t *)malloc(8 * num_s); labf[b] = (float *)malloc(4 * num_s); vv[b] = (int *)malloc(4 * num_s);
+                                  aa[b] = (int *)malloc(4 * num_s); has[b] = (uint8_t *)calloc(num_s, 1); }
     double est_prev = start_s - v0 * delta_t, est_second = est_prev - delta_t * (v0 - a0 * delta_t);
-    int best_t = 0, best_k = 0; double best_lab = 0;
-    /* layer 0 -> 1 (exact fp64, full cost) */
+    int best_t = 0, best_k = 0; uint64_t best_lab = 0; float best_labf = 0;
     int imin, imax;
     next_index_range(p, start_s, delta_s, start_s, est_prev, est_second, delta_t, &imin, &imax);
     int lo = num_s, hi = -1;
+    /* layer 1: complete label */
     for (int k = imin; k < imax && k < num_s; k++) {
         if (obstacles[(size_t)num_s + k]) continue;
-        lab[1][k] = RND(cost_with_jerk(p, s_values[k], start_s, est_prev, est_second, delta_t, distances[(size_t)num_s + k]));
-        has[1][k] = 1; previous[(size_t)num_s + k] = 0; if (k < lo) lo = k; if (k > hi) hi = k;
+        double c = cost_with_jerk(p, s_values[k], start_s, est_prev, est_second, delta_t, distances[(size_t)num_s + k]);
+        lab[1][k] = fx(c); labf[1][k] = (float)c; vv[1][k] = k; aa[1][k] = 0; has[1][k] = 1; previous[(size_t)num_s + k] = 0;
+        if (k < lo) lo = k; if (k > hi) hi = k;
     }
-    int t = 1;
+#define BETTER(nl, nlf, nv, kk, buf) (!has[buf][kk] || (f32_labels ? ((nlf) < labf[buf][kk]) : ((nl) < lab[buf][kk] || ((nl) == lab[buf][kk] && (nv) > vv[buf][kk]))))
     if (hi >= 0) {
-        /* layer 1 -> 2: exact windows and fp64 kinematic cost, fp32 accumulate, penalty later */
-        double *cand = (double *)malloc(8 * num_s); uint8_t *hc = (uint8_t *)calloc(num_s, 1);
-        int nlo = num_s, nhi = -1;
+        best_t = 1; best_k = -1;
+        for (int k = lo; k <= hi; k++) if (has[1][k]) {
+            int better = best_k < 0 || (f32_labels ? labf[1][k] < best_labf : lab[1][k] < best_lab);
+            if (better) { best_k = k; best_lab = lab[1][k]; best_labf = labf[1][k]; }
+        }
+        /* layer 1 -> 2: exact windows, exact kinematic cost quantised; penalty of layer 2 added when layer 2 is finalised */
+        int dlo = num_s, dhi = -1;
         for (int k1 = lo; k1 <= hi; k1++) if (has[1][k1]) {
             double s = s_values[k1];
             next_index_range(p, start_s, delta_s, s, start_s, est_prev, delta_t, &imin, &imax);
@@ -419,37 +431,32 @@ int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_
                 double sn = s_values[kk];
                 double v = (sn - s) / delta_t, a = (sn - 2 * s + start_s) / pow(delta_t, 2.0), j = (sn - 3 * s + 3 * start_s - est_prev) / pow(delta_t, 3.0);
                 double kin = p->v_weight * ((v - p->desired_speed) * (v - p->desired_speed)) + p->a_weight * (a * a) + p->j_weight * (j * j);
-                double tot = RND(lab[1][k1] + (f32_labels ? (double)(float)kin : kin));
-                if (!hc[kk] || tot < cand[kk]) { cand[kk] = tot; pred[kk] = k1; hc[kk] = 1; }
-                if (kk < nlo) nlo = kk; if (kk > nhi) nhi = kk;
+                uint64_t tot = lab[1][k1] + fx(kin); float totf = labf[1][k1] + (float)kin;
+                int vn = kk - k1;
+                if (BETTER(tot, totf, vn, kk, 0)) { lab[0][kk] = tot; labf[0][kk] = totf; vv[0][kk] = vn; aa[0][kk] = vn - k1; has[0][kk] = 1; }
+                if (kk < dlo) dlo = kk; if (kk > dhi) dhi = kk;
             }
         }
-        /* best of layer 1 in case layer 2 is empty */
-        best_t = 1; best_k = -1;
-        for (int k = lo; k <= hi; k++) if (has[1][k] && (best_k < 0 || lab[1][k] < best_lab)) { best_k = k; best_lab = lab[1][k]; }
-        int cur = 0;   /* buffers: layer t nodes live in [cur] after finalisation; layer 1 is in [1] */
-        int plo = lo, phi = hi;   /* span of previous layer */
-        int dlo = nlo, dhi = nhi;
-        int prevbuf = 1;
-        for (t = 2; t < num_t && dhi >= 0; t++) {
-            /* finalise layer t from cand/pred */
-            int any = 0; cur = prevbuf ^ 1;
-            for (int k = dlo; k <= dhi; k++) has[cur][k] = 0;
-            int wlo_min = num_s, whi_max = -1;
-            /* per-node windows stored temporarily */
-            int *wl = (int *)malloc(4 * (dhi - dlo + 1)), *wn = (int *)malloc(4 * (dhi - dlo + 1));
+        for (int k = lo; k <= hi; k++) has[1][k] = 0;
+        /* pass t: finalise layer t (buffer t&1), push into layer t+1 */
+        for (int t = 2; t < num_t && dhi >= 0; t++) {
+            int cur = t & 1, nxt = cur ^ 1, any = 0, nlo = num_s, nhi = -1, bk = -1; uint64_t bl = 0; float blf = 0;
             for (int k = dlo; k <= dhi; k++) {
-                wn[k - dlo] = 0;
-                if (!hc[k]) continue;
+                if (!has[cur][k]) continue;
+                has[cur][k] = 0;
                 size_t id = (size_t)t * num_s + k;
                 if (obstacles[id]) continue;
                 double d = distances[id];
                 float df = (float)d;
-                double pen = f32_labels ? (double)((d < p->min_allowed_distance) ? 1000000.0f / fmaxf(df, 1.0f) : 1.0f / df)
-                                        : ((d < p->min_allowed_distance) ? 1000000.0 / (d > 1.0 ? d : 1.0) : (double)(1.0f / df));
-                lab[cur][k] = RND((double)dw * pen + cand[k]);
-                int pr = pred[k], v = k - pr, vp = (t == 2) ? pr : vv[prevbuf][pr], a = v - vp;
-                vv[cur][k] = v; aa[cur][k] = a; has[cur][k] = 1; previous[id] = pr; any = 1;
+                double pen = (d < p->min_allowed_distance) ? 1000000.0 / (d > 1.0 ? d : 1.0) : (double)(1.0f / df);
+                uint64_t label = lab[cur][k] + fx(p->d_weight * pen);
+                float penf = (d < p->min_allowed_distance) ? 1000000.0f / fmaxf(df, 1.0f) : 1.0f / df;
+                float labelf = fmaf((float)p->d_weight, penf, labf[cur][k]);
+                int v = vv[cur][k], a = aa[cur][k];
+                previous[id] = k - v; any = 1;
+                int better = bk < 0 || (f32_labels ? labelf < blf : label < bl);
+                if (better) { bk = k; bl = label; blf = labelf; }
+                if (t == num_t - 1) continue;
                 int al = a + jlo_c > alo_c ? a + jlo_c : alo_c, ah = a + jhi_c < ahi_c ? a + jhi_c : ahi_c;
                 int vlo = v + al, vhi = v + ah;
                 double s = s_values[k];
@@ -457,37 +464,25 @@ int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_
                 int clamp = vmax_is_int ? (vhi >= vmax_c) : ((double)v + fmin((double)a + jhi, ahi_r) > vmax_r);
                 if (clamp) vhi = vmax_is_int ? (int)((s + p->max_speed * dt - start_s) / delta_s) - k : vmax_c;
                 int wlo = k + vlo, whi = k + vhi; if (whi > num_s - 1) whi = num_s - 1;
-                int n = whi - wlo + 1; if (n < 0) n = 0;
-                wl[k - dlo] = wlo; wn[k - dlo] = n;
-                if (n > 0) { if (wlo < wlo_min) wlo_min = wlo; if (whi > whi_max) whi_max = whi; }
-            }
-            if (!any) { free(wl); free(wn); break; }
-            best_t = t; best_k = -1;
-            for (int k = dlo; k <= dhi; k++) if (has[cur][k] && (best_k < 0 || lab[cur][k] < best_lab)) { best_k = k; best_lab = lab[cur][k]; }
-            if (t == num_t - 1 || whi_max < 0) { free(wl); free(wn); break; }
-            /* candidates of layer t+1 */
-            for (int k = wlo_min; k <= whi_max; k++) hc[k] = 0;
-            for (int k = dlo; k <= dhi; k++) {
-                if (!has[cur][k]) continue;
-                for (int i = 0; i < wn[k - dlo]; i++) {
-                    int kk = wl[k - dlo] + i;
-                    int vn = kk - k, an = vn - vv[cur][k], jn = an - aa[cur][k];
+                for (int kk = wlo; kk <= whi; kk++) {
+                    int vn = kk - k, an = vn - v, jn = an - a;
+                    uint64_t tot = label + vtab[vn] + atab[an + 16] + jtab[jn + 8];
                     float fv = (float)vn - vdes, fa = (float)an, fj = (float)jn;
-                    double tot = RND(lab[cur][k] + (double)fmaf(cv * fv, fv, fmaf(ca * fa, fa, cj * fj * fj)));
-                    if (!hc[kk] || tot < cand[kk]) { cand[kk] = tot; pred[kk] = k; hc[kk] = 1; }
+                    float totf = labelf + fmaf(cvf * fv, fv, fmaf(caf * fa, fa, cjf * fj * fj));
+                    if (BETTER(tot, totf, vn, kk, nxt)) { lab[nxt][kk] = tot; labf[nxt][kk] = totf; vv[nxt][kk] = vn; aa[nxt][kk] = an; has[nxt][kk] = 1; }
+                    if (kk < nlo) nlo = kk; if (kk > nhi) nhi = kk;
                 }
             }
-            free(wl); free(wn);
-            plo = dlo; phi = dhi; dlo = wlo_min; dhi = whi_max; prevbuf = cur;
+            if (!any) break;
+            best_t = t; best_k = bk; best_lab = bl; best_labf = blf;
+            dlo = nlo; dhi = nhi;
         }
-        (void)plo; (void)phi;
-        free(cand); free(hc);
-    } else { best_t = 0; best_k = 0; best_lab = 0; }
-#undef RND
-    if (cost_out) *cost_out = (double)best_lab;
+    }
+#undef BETTER
+    if (cost_out) *cost_out = f32_labels ? (double)best_labf : (double)best_lab * (1.0 / FXONE);
     int r = backtrack(num_t, num_s, previous, s_values, best_t, best_k, idx_out, s_seq_out);
-    for (int b = 0; b < 2; b++) { free(lab[b]); free(vv[b]); free(aa[b]); free(has[b]); }
-    free(previous); free(pred);
+    for (int b = 0; b < 2; b++) { free(lab[b]); free(labf[b]); free(vv[b]); free(aa[b]); free(has[b]); }
+    free(previous);
     return r;
 }
 

@@ -116,6 +116,12 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     D->cj = (float)(p->j_weight * (ds / (dt * dt * dt)) * (ds / (dt * dt * dt)));
     D->vdes_c = (float)(p->desired_speed * dt / ds);
     D->dw = (float)p->d_weight;
+    // fixed-point cost tables (fast kernel): every entry must fit 32 bits
+    double mx = 0.0;
+    for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * ds / dt - p->desired_speed) * (v * ds / dt - p->desired_speed); mx = fmax(mx, x); D->vtab[v] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
+    for (int i = 0; i < 32; i++) { double acc = (i - 16) * ds / (dt * dt), x = p->a_weight * acc * acc; mx = fmax(mx, x); D->atab[i] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
+    for (int i = 0; i < 16; i++) { double jk = (i - 8) * ds / (dt * dt * dt), x = p->j_weight * jk * jk; mx = fmax(mx, x); D->jtab[i] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
+    if (mx >= 16000.0 || D->jlo_c < -8 || D->jhi_c > 7 || !(p->d_weight >= 0) || p->d_weight > 1e4) D->fast_ok = 0;
     return MPC_OK;
 }
 
@@ -150,13 +156,13 @@ static int configure(mpc_handle *h) {
         h->threads = 512;
         h->grid_exact = h->sm_count * 2;
     }
-    // ---- fast kernel: 32 B per cell (fp64 label + u16 meta, double buffered; three multimaps), ring window ----
-    size_t cap = (h->smem_optin - static_smem) / 32;
+    // ---- fast kernel: 16 B per cell (one packed 64-bit word, double buffered), ring window, two blocks per SM ----
+    size_t cap = ((h->smem_optin + 1024) / 2 - 1024 - static_smem) / 16;
     h->wrap_fast = (size_t)h->W > cap;
     h->Wc = h->wrap_fast ? (int)(cap & ~(size_t)7) : h->W;
-    h->smem_fast = (size_t)h->Wc * 32;
+    h->smem_fast = (size_t)h->Wc * 16;
     int bps = (int)(h->smem_optin / (h->smem_fast + static_smem));
-    h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 2 ? 512 : 1024);
+    h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 4 ? 256 : 512);
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;

@@ -32,7 +32,12 @@ struct DevParams {
     float cv, ca, cj;          // v_w*(ds/dt)^2, a_w*(ds/dt^2)^2, j_w*(ds/dt^3)^2
     float vdes_c;              // desired speed in cells/step
     float dw;                  // d_weight
+    // fixed-point (2^-MPC_FX_FRAC) kinematic edge-cost tables of the fast kernel, indexed by the integer
+    // speed v' in [0,255], acceleration a'+16 in [0,31], jerk j'+8 in [0,15] (cells per step^n)
+    unsigned vtab[256], atab[32], jtab[16];
 };
+#define MPC_FX_FRAC 18
+#define MPC_FX_ONE 262144.0
 
 // ---- geometry: control.py:366-380 ---------------------------------------------------------------
 __device__ __forceinline__ double dist2d(double x0, double y0, double x1, double y1) {
