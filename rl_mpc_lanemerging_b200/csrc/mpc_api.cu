@@ -61,6 +61,7 @@ struct mpc_handle {
     size_t smem;                 // dynamic shared memory of the exact kernel (0 -> it uses global label scratch)
     int threads, grid_exact;
     int Wc, wrap_fast, threads_fast, grid_fast; size_t smem_fast;   // fast kernel: ring capacity / launch shape
+    size_t smem_fast_big;        // full-row variant used to re-solve ring overflows (0 = does not fit)
     int grid_max;
     // scratch
     LayerDesc *desc; double *s0, *ds; int32_t *num_s;
@@ -165,6 +166,7 @@ static int configure(mpc_handle *h) {
     h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 4 ? 256 : 512);
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
+    h->smem_fast_big = ((size_t)h->W * 16 + static_smem <= h->smem_optin) ? (size_t)h->W * 16 : 0;
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     return MPC_OK;
 }
@@ -176,7 +178,7 @@ static int alloc_scratch(mpc_handle *h) {
     MPC_CUDA_OK(cudaMalloc(&h->s0, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->ds, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->num_s, B * 4));
     MPC_CUDA_OK(cudaMalloc(&h->bp, (size_t)h->grid_max * T * h->W * sizeof(uint16_t)));
     MPC_CUDA_OK(cudaMalloc(&h->counters, 16 * sizeof(int)));
-    MPC_CUDA_OK(cudaMalloc(&h->fallback_list, B * 4));
+    MPC_CUDA_OK(cudaMalloc(&h->fallback_list, 2 * B * 4));
     if (h->smem == 0) {
         MPC_CUDA_OK(cudaMalloc(&h->glab, (size_t)h->grid_exact * 2 * h->W * 8));
         MPC_CUDA_OK(cudaMalloc(&h->ghist, (size_t)h->grid_exact * 2 * h->W * 4));
@@ -245,7 +247,7 @@ extern "C" int mpc_last_counters(const mpc_handle *h, int64_t *out2) {
     MPC_CUDA_OK(cudaSetDevice(h->device));
     MPC_CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
     out2[0] = h->kernels_launched;
-    out2[1] = c[2];
+    out2[1] = c[2];          // problems the first fast launch handed back (c[4]: of those, the ones that needed the exact kernel)
     return MPC_OK;
 }
 
@@ -347,10 +349,25 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
         if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch");
         h->kernels_launched++;
         if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
-        // re-solve (on the device) whatever the fast kernel handed back: the batch size is read on the device
+        // Problems the fast kernel handed back are re-solved on the device (their count is read on the device):
+        // first by the fast kernel with a full-row window (ring overflow), then by the exact kernel (label saturation).
+        const int32_t *pending = h->fallback_list; const int *pending_n = h->counters + 2;
+        if (h->wrap_fast && h->smem_fast_big) {
+            SolveLaunch G = F;
+            G.threads = 512; G.smem = h->smem_fast_big; G.W = h->W; G.wrap = 0;
+            G.grid = h->sm_count < B ? h->sm_count : B; if (G.grid > 32) G.grid = 32;
+            io.work_counter = h->counters + 3;
+            io.subset = pending; io.B_dev = pending_n;
+            io.fallback_list = h->fallback_list + h->max_batch; io.fallback_count = h->counters + 4;
+            e = dense ? launch_fast_dense(h->P, G, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, G, io, h->desc, st);
+            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast full-row re-solve launch");
+            h->kernels_launched++;
+            pending = h->fallback_list + h->max_batch; pending_n = h->counters + 4;
+        }
         X.grid = X.grid < 16 ? X.grid : 16;
         io.work_counter = h->counters + 1;
-        io.subset = h->fallback_list; io.B_dev = h->counters + 2;
+        io.subset = pending; io.B_dev = pending_n;
+        io.fallback_list = nullptr; io.fallback_count = nullptr;
         e = dense ? launch_exact_dense(h->P, X, io, ob, dist, dist_f32, stride, st) : launch_exact_desc(h->P, X, io, h->desc, st);
         if (e != cudaSuccess) return mpc_set_cuda_error(e, "fallback solve launch");
         h->kernels_launched++;

@@ -25,7 +25,7 @@
 #define EMPTY_LAB 0x7ff0000000000000ULL      // +inf
 
 struct __align__(16) FastShared {
-    LayerSearch layer[2];        // first: staged with 16-byte vector stores
+    LayerSearch layer[3];        // first: staged with 16-byte vector stores; layer t lives in slot t % 3
     BlockShared S;
 };
 static_assert(sizeof(LayerSearch) % 16 == 0, "LayerSearch buffers must stay 16-byte aligned");
@@ -42,14 +42,33 @@ struct FastDescProv {
         if (threadIdx.x < kTail) pre = reinterpret_cast<const int4 *>(reinterpret_cast<const char *>(src) + offsetof(LayerDesc, edge))[threadIdx.x];
         else if (threadIdx.x == kTail) pre = make_int4(src->n_edge, src->n_band, 0, 0);
     }
-    __device__ __forceinline__ void store(int t) {         // park them in buffer t&1
-        LayerSearch *dst = sm + (t & 1);
+    __device__ __forceinline__ void store(int t) {         // park them in slot t % 3
+        LayerSearch *dst = sm + (t % 3);
         if (threadIdx.x < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(dst) + 16)[threadIdx.x] = pre;
         else if (threadIdx.x == kTail) *reinterpret_cast<int4 *>(dst) = pre;
     }
-    __device__ __forceinline__ double eval_staged(int t, int k, double s, bool &ob) const { return cell_distance_sorted(sm[t & 1], s, k, ob); }
+    static constexpr bool kClipAtPush = true;               // successors are tested against the next layer's bands before the push
+    __device__ __forceinline__ double eval_staged(int t, int k, double s, bool &ob) const { return cell_distance_sorted(sm[t % 3], s, k, ob); }
+    // distance only (the caller knows the cell is not in a band)
+    __device__ __forceinline__ double distance_staged(int t, int k, double s) const {
+        const LayerSearch &L = sm[t % 3];
+        int e = L.bucket_edge[k >> MPC_BUCKET_SHIFT], M = L.n_edge;
+        while (e < M && L.edge[e] < s) e++;
+        double d = 1E10;
+        if (e > 0) { double x = __dsub_rn(s, L.edge[e - 1]); d = x < d ? x : d; }
+        if (e < M) { double x = fabs(__dsub_rn(s, L.edge[e])); d = x < d ? x : d; }
+        return d;
+    }
+    // the (at most two) merged bands of layer t that can intersect the short cell window starting at k
+    __device__ __forceinline__ void bands_near(int t, int k, int2 &b0, int2 &b1) const {
+        const LayerSearch &L = sm[t % 3];
+        int i = L.bucket_band[k >> MPC_BUCKET_SHIFT], m = L.n_band;
+        while (i < m && L.mband[i].y <= k) i++;
+        b0 = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX);
+        b1 = i + 1 < m ? L.mband[i + 1] : make_int2(INT_MAX, INT_MAX);
+    }
     __device__ __forceinline__ bool is_obstacle(int t, int k, int j) const {
-        const LayerSearch &L = sm[t & 1];
+        const LayerSearch &L = sm[t % 3];
         int i = L.bucket_band[j], m = L.n_band;
         while (i < m && L.mband[i].y <= k) i++;
         return i < m && L.mband[i].x <= k;
@@ -74,11 +93,14 @@ struct FastDenseProv {
         ob = ob_base[o] != 0;
         return (double)d_base[o];
     }
+    static constexpr bool kClipAtPush = false;              // dense grids: the obstacle test stays at the destination
+    __device__ __forceinline__ double distance_staged(int t, int k, double s) const { bool ob; return eval_staged(t, k, s, ob); }
+    __device__ __forceinline__ void bands_near(int, int, int2 &b0, int2 &b1) const { b0 = make_int2(INT_MAX, INT_MAX); b1 = b0; }
     __device__ __forceinline__ bool is_obstacle(int t, int k, int) const { return ob_base[(size_t)t * stride + k] != 0; }
 };
 
 #define FX_EMPTY 0xffffffffffffffffULL
-#define FX_LABEL_LIMIT (1ULL << 46)      // labels above this hand the problem to the exact kernel
+#define FX_LABEL_LIMIT ((1ULL << 48) - (1ULL << 36))   // labels above this (1.07e9) hand the problem to the exact kernel
 
 // integer successor window of a node (k, v, a): cells [wlo, wlo+n).  Mirrors st_cy.pyx:65-93 for on-grid history.
 __device__ __forceinline__ void int_window(const DevParams &P, const SGrid &g, int k, int v, int a, int &wlo, int &n) {
@@ -129,6 +151,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
     __shared__ FastShared FS;
     __shared__ FxTables TB;
     __shared__ unsigned long long s_layer_best[2];
+    __shared__ int s_chunk[3];
     BlockShared &S = FS.S;
     unsigned long long *buf[2];
     buf[0] = reinterpret_cast<unsigned long long *>(smem_raw); buf[1] = buf[0] + Wc;
@@ -158,7 +181,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         prov.load(1);
         double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
         double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
-        if (tid == 0) { S.need_fallback = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; }
+        if (tid == 0) { S.need_fallback = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
         // ---- prologue: layers 0 -> 1 -> 2 have off-grid history (st_cy.pyx:329-330): exact fp64, then quantised ----
         int imin0, imax0;
         exact_window(P, g.s0, g.ds, g.s0, est_prev, est_second, imin0, imax0);
@@ -181,7 +204,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             }
         }
         prov.store(2);
+        if (T > 3) prov.load(3);
         __syncthreads();
+        if (T > 3) prov.store(3);
         int bt = 0; unsigned long long best_word = 0ULL;      // deepest non-empty layer and its (label << 16 | k)
         int dlo = 0, dhi = -1;
         bool done = false;
@@ -201,6 +226,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 exact_window(P, g.s0, g.ds, s, g.s0, est_prev, imin, imax);
                 int kk = imin + j;
                 if (kk >= imax || kk >= g.num_s) continue;
+                if (prov.is_obstacle(2, kk, kk >> MPC_BUCKET_SHIFT)) continue;          // st_cy.pyx:383-384
                 int vn = kk - k1, an = vn - k1;
                 if (vn > 255 || an < -16 || an > 15) { S.need_fallback = 1; continue; }
                 unsigned long long tot = (w1 >> 16) + fx_from_double(exact_kin(P, g.sval(kk), s, g.s0, est_prev));
@@ -215,26 +241,35 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             if (dhi < 0) done = true;                         // layer-1 nodes have no successors
         }
         // ---- main loop: pass t finalises the cells of layer t (buffer t&1) and pushes their successors ----
+        const int lane = tid & 31;
         for (int t = 2; !done && t < T; t++) {
             const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
             unsigned long long *cur = buf[par], *nxt = buf[par ^ 1];
             if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
-            if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; }
-            (void)s3;
-            __syncthreads();                                  // pushes into layer t complete; staging of layer t visible
-            if (t + 1 < T) prov.load(t + 1);                  // prefetch the next layer's search structure
+            if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; s_chunk[n3] = 0; }
+            __syncthreads();                                  // pushes into layer t complete; staging of layers t, t+1 visible
+            if (t + 2 < T) prov.load(t + 2);                  // prefetch the search structure of layer t+2
             uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
             unsigned long long mybest = FX_EMPTY;
             int mylo = INT_MAX, myhi = -1;
             const bool last = (t == T - 1);
-            for (int k = dlo + tid; k <= dhi; k += nth) {
+            // warps take 32-cell chunks from a shared counter: obstacle bands leave long empty runs, static striding would idle
+            for (;;) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_chunk[s3], 1);
+                c = __shfl_sync(FULL, c, 0);
+                const int base = dlo + (c << 5);
+                if (base > dhi) break;
+                const int k = base + lane;
+                if (k > dhi) continue;
                 const int rk = ring(k);
                 unsigned long long w = cur[rk];
                 if (w == FX_EMPTY) continue;
                 cur[rk] = FX_EMPTY;                           // this buffer receives layer t+2
                 double s = g.sval(k);
-                bool ob; double d = prov.eval_staged(t, k, s, ob);
-                if (ob) continue;                             // st_cy.pyx:383-384
+                double d;
+                if (Prov::kClipAtPush) d = prov.distance_staged(t, k, s);      // pushes never land in a band
+                else { bool ob; d = prov.eval_staged(t, k, s, ob); if (ob) continue; }   // st_cy.pyx:383-384
                 unsigned long long label = (w >> 16) + fx_penalty(P, d);
                 if (label >= FX_LABEL_LIMIT) { S.need_fallback = 1; continue; }
                 const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
@@ -244,25 +279,34 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 if (last) continue;
                 int wlo, n;
                 int_window(P, g, k, v, a, wlo, n);
-                if (n > 0) {
-                    int vn = wlo - k, an = vn - v, jn = an - a;
-                    if (vn + n - 1 > 255 || an < -16 || an + n - 1 > 15 || jn < -8 || jn + n - 1 > 7) { S.need_fallback = 1; continue; }
-                    for (int i = 0; i < n; i++) {
-                        unsigned long long tot = label + TB.v[vn + i] + TB.a[an + i + 16] + TB.j[jn + i + 8];
-                        smem_min64(&nxt[ring(wlo + i)], (tot << 16) | ((unsigned long long)(255 - vn - i) << 8) | (unsigned long long)(an + i + 128));
+                if (n <= 0) continue;
+                const int vn = wlo - k, an = vn - v, jn = an - a;
+                if (vn + n - 1 > 255 || an < -16 || an + n - 1 > 15 || jn < -8 || jn + n - 1 > 7) { S.need_fallback = 1; continue; }
+                int2 b0, b1;
+                prov.bands_near(t + 1, wlo, b0, b1);
+                int r = ring(wlo);
+                unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
+                for (int i = 0; i < n; i++) {
+                    const int kk = wlo + i;
+                    const bool blocked = (kk >= b0.x && kk < b0.y) || (kk >= b1.x && kk < b1.y);
+                    if (!blocked) {
+                        const unsigned long long kin = (unsigned long long)TB.v[vn + i] + TB.a[an + i + 16] + TB.j[jn + i + 8];
+                        smem_min64(&nxt[r], word + (kin << 16));
+                        mylo = min(mylo, kk); myhi = max(myhi, kk);
                     }
-                    mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
+                    word = word - 255ULL;                      // v' + 1 (bits 8..15 hold 255 - v'), a' + 1 (bits 0..7)
+                    r = (WRAP && r + 1 == Wc) ? 0 : r + 1;
                 }
             }
             for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, mybest, o); mybest = x < mybest ? x : mybest; }
             mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
-            if ((tid & 31) == 0) {
+            if (lane == 0) {
                 if (mybest != FX_EMPTY) atomicMin(&s_layer_best[par], mybest);
                 if (myhi >= 0) { atomicMin(&S.nlo[n3], mylo); atomicMax(&S.nhi[n3], myhi); }
             }
-            if (t + 1 < T) prov.store(t + 1);
+            if (t + 2 < T) prov.store(t + 2);
             __syncthreads();
-            if (s_layer_best[par] == FX_EMPTY) break;         // every reachable cell of layer t is an obstacle: layer t-1 is deepest
+            if (s_layer_best[par] == FX_EMPTY) break;         // no cell of layer t survived: layer t-1 is deepest
             bt = t; best_word = s_layer_best[par];
             dlo = S.nlo[n3]; dhi = S.nhi[n3];
             if (dhi < 0) break;                               // no successors (or last layer)
