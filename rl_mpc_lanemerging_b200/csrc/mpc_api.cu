@@ -143,7 +143,7 @@ static int env_int(const char *name, int lo, int hi, int dflt) {
 static int configure(mpc_handle *h) {
     const DevParams &P = h->P;
     h->W = (P.num_s_max + 7) & ~7;
-    const size_t static_smem = 6144;                 // static shared of the kernels (upper bound) + 1 KB/block reserve
+    const size_t static_smem = 8192;                 // static shared of the kernels (upper bound) + 1 KB/block reserve
     // ---- exact kernel: 24 B per cell, full row ----
     size_t need = (size_t)h->W * 24;
     if (need + static_smem <= h->smem_optin) {
@@ -157,16 +157,18 @@ static int configure(mpc_handle *h) {
         h->threads = 512;
         h->grid_exact = h->sm_count * 2;
     }
-    // ---- fast kernel: 16 B per cell (one packed 64-bit word, double buffered), ring window, two blocks per SM ----
-    size_t cap = ((h->smem_optin + 1024) / 2 - 1024 - static_smem) / 16;
+    // ---- fast kernel: 16 B per cell (one packed 64-bit word, double buffered) behind a ring window ----
+    int fast_blocks = env_int("MPC_FAST_BLOCKS", 32, 64, 64) / 32;     // 64 -> size the ring for 2 blocks/SM (default), 32 -> 1 block/SM
+    const size_t clamp_bytes = 2 * (((size_t)P.num_s_max + 31) / 32) * 4 + 16;   // two bit arrays behind the word buffers
+    size_t cap = ((h->smem_optin + 1024) / fast_blocks - 1024 - static_smem - clamp_bytes) / 16;
     h->wrap_fast = (size_t)h->W > cap;
     h->Wc = h->wrap_fast ? (int)(cap & ~(size_t)7) : h->W;
-    h->smem_fast = (size_t)h->Wc * 16;
+    h->smem_fast = (size_t)h->Wc * 16 + clamp_bytes;
     int bps = (int)(h->smem_optin / (h->smem_fast + static_smem));
-    h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 4 ? 256 : 512);
+    h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 3 ? 256 : (bps >= 2 ? 512 : 1024));
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
-    h->smem_fast_big = ((size_t)h->W * 16 + static_smem <= h->smem_optin) ? (size_t)h->W * 16 : 0;
+    h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     return MPC_OK;
 }

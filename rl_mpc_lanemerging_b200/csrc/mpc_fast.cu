@@ -102,34 +102,50 @@ struct FastDenseProv {
 #define FX_EMPTY 0xffffffffffffffffULL
 #define FX_LABEL_LIMIT ((1ULL << 48) - (1ULL << 36))   // labels above this (1.07e9) hand the problem to the exact kernel
 
+// The two places where the reference's successor window depends on fp64 rounding (SURVEY.md §7 "hard part 1"):
+//   lower clamp at speed 0:   first index = ceil((s_k - s0)/ds)            in {k, k+1}
+//   upper clamp at MAX_SPEED: last index  = int((s_k + v_max*dt - s0)/ds)  in {k+vmax_c-1, k+vmax_c}   (when v_max*dt/ds is an integer)
+// Both are functions of the cell index only, so they are evaluated once per problem for every cell (exact fp64, the
+// reference's expression) and kept as two bit arrays; the per-node window is then pure integer arithmetic.
+struct ClampBits { unsigned *lo, *hi; };      // (num_s_max + 31) / 32 words each, in dynamic shared memory
+
+__device__ __forceinline__ void build_clamp_bits(const DevParams &P, const SGrid &g, const ClampBits &C) {
+    const int words = (g.num_s + 31) >> 5, lane = threadIdx.x & 31;
+    for (int wd = threadIdx.x >> 5; wd < words; wd += blockDim.x >> 5) {           // one warp per 32 cells, one cell per lane
+        const int k = (wd << 5) + lane;
+        const double s = g.sval(k);
+        const double me = __ddiv_rn(__dsub_rn(s, g.s0), g.ds);
+        int mi = (int)me; if ((double)mi < me) mi += 1;
+        bool hi_short = false;
+        if (P.vmax_is_int) hi_short = ((int)__ddiv_rn(__dsub_rn(__dadd_rn(s, __dmul_rn(P.p.max_speed, P.p.t_disc)), g.s0), g.ds) - k) != P.vmax_c;
+        const unsigned lo = __ballot_sync(0xffffffffu, mi != k);                    // own cell excluded: window starts at k+1
+        const unsigned hi = __ballot_sync(0xffffffffu, hi_short);                   // last index one short of k + vmax_c
+        if (lane == 0) { C.lo[wd] = lo; C.hi[wd] = hi; }
+    }
+}
+
 // integer successor window of a node (k, v, a): cells [wlo, wlo+n).  Mirrors st_cy.pyx:65-93 for on-grid history.
-__device__ __forceinline__ void int_window(const DevParams &P, const SGrid &g, int k, int v, int a, int &wlo, int &n) {
+__device__ __forceinline__ void int_window(const DevParams &P, const SGrid &g, const ClampBits &C, int k, int v, int a, int &wlo, int &n) {
     int alo = max(a + P.jlo_c, P.alo_c), ahi = min(a + P.jhi_c, P.ahi_c);
     int vlo = v + alo, vhi = v + ahi;
-    if (vlo <= 0) {                        // clamp at speed 0: the reference's index sits on an integer -> exact check
-        double s = g.sval(k);
-        double me = __ddiv_rn(__dsub_rn(s, g.s0), g.ds);
-        int mi = (int)me; if ((double)mi < me) mi += 1;
-        vlo = mi - k;
-    }
+    if (vlo <= 0) vlo = (C.lo[k >> 5] >> (k & 31)) & 1;
     bool clamp_hi = P.vmax_is_int ? (vhi >= P.vmax_c) : ((double)v + fmin((double)a + P.jhi_r, P.ahi_r) > P.vmax_r);
-    if (clamp_hi) {
-        if (P.vmax_is_int) { double s = g.sval(k); vhi = (int)__ddiv_rn(__dsub_rn(__dadd_rn(s, __dmul_rn(P.p.max_speed, P.p.t_disc)), g.s0), g.ds) - k; }
-        else vhi = P.vmax_c;
-    }
+    if (clamp_hi) vhi = P.vmax_c - (P.vmax_is_int ? (int)((C.hi[k >> 5] >> (k & 31)) & 1) : 0);
     wlo = k + vlo;
     int whi = min(k + vhi, g.num_s - 1);
     n = whi - wlo + 1; n = n < 0 ? 0 : n;
 }
 
-// min-combine into shared memory; the CAS is only issued when the candidate beats the stored word
-__device__ __forceinline__ void smem_min64(unsigned long long *addr, unsigned long long val) {
+// min-combine into shared memory; the CAS is only issued when the candidate beats the stored word.
+// Returns true when this call turned an EMPTY cell into a node (exactly one caller per cell sees that).
+__device__ __forceinline__ bool smem_min64(unsigned long long *addr, unsigned long long val) {
     unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(addr);
     while (val < old) {
         unsigned long long assumed = old;
         old = atomicCAS(addr, assumed, val);
-        if (old == assumed) break;
+        if (old == assumed) return assumed == 0xffffffffffffffffULL;
     }
+    return false;
 }
 
 __device__ __forceinline__ unsigned long long fx_from_double(double x) { return (unsigned long long)__double2ll_rn(__dmul_rn(x, MPC_FX_ONE)); }
@@ -151,10 +167,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
     __shared__ FastShared FS;
     __shared__ FxTables TB;
     __shared__ unsigned long long s_layer_best[2];
-    __shared__ int s_chunk[3];
+    __shared__ int s_count[2];          // non-zero when buf[i] received at least one node
+    __shared__ int s_chunk[3];          // dense traversal: next 32-cell chunk of a pass
     BlockShared &S = FS.S;
     unsigned long long *buf[2];
     buf[0] = reinterpret_cast<unsigned long long *>(smem_raw); buf[1] = buf[0] + Wc;
+    ClampBits CB;
+    CB.lo = reinterpret_cast<unsigned *>(buf[1] + Wc); CB.hi = CB.lo + ((P.num_s_max + 31) >> 5);
     uint16_t *bp = io.bp + (size_t)blockIdx.x * P.num_t * io.bp_stride;
     const int T = P.num_t, tid = threadIdx.x, nth = blockDim.x;
     auto ring = [Wc](int k) -> int { return WRAP ? (k >= Wc ? k - Wc : k) : k; };
@@ -179,9 +198,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                prov.d_base = reinterpret_cast<decltype(prov.d_base)>(dense_d) + (size_t)b * T * dense_stride;
                prov.stride = dense_stride; }
         prov.load(1);
+        build_clamp_bits(P, g, CB);
         double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
         double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
-        if (tid == 0) { S.need_fallback = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
+        if (tid == 0) { S.need_fallback = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_count[0] = 0; s_count[1] = 0; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
         // ---- prologue: layers 0 -> 1 -> 2 have off-grid history (st_cy.pyx:329-330): exact fp64, then quantised ----
         int imin0, imax0;
         exact_window(P, g.s0, g.ds, g.s0, est_prev, est_second, imin0, imax0);
@@ -230,7 +250,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 int vn = kk - k1, an = vn - k1;
                 if (vn > 255 || an < -16 || an > 15) { S.need_fallback = 1; continue; }
                 unsigned long long tot = (w1 >> 16) + fx_from_double(exact_kin(P, g.sval(kk), s, g.s0, est_prev));
-                smem_min64(&buf[0][ring(kk)], (tot << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128));
+                if (smem_min64(&buf[0][ring(kk)], (tot << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128)))
+                    s_count[0] = 1;
                 mylo = min(mylo, kk); myhi = max(myhi, kk);
             }
             mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
@@ -238,22 +259,58 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             __syncthreads();
             for (int k1 = lo1 + tid; k1 <= hi1; k1 += nth) buf[1][ring(k1)] = FX_EMPTY;     // layer 1 is consumed
             dlo = S.nlo[2]; dhi = S.nhi[2];
-            if (dhi < 0) done = true;                         // layer-1 nodes have no successors
+            if (s_count[0] == 0) done = true;                 // layer-1 nodes have no successors
         }
-        // ---- main loop: pass t finalises the cells of layer t (buffer t&1) and pushes their successors ----
+        // ---- main loop: pass t finalises the nodes of layer t (buffer t&1) and pushes their successors ----
         const int lane = tid & 31;
         for (int t = 2; !done && t < T; t++) {
             const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
             unsigned long long *cur = buf[par], *nxt = buf[par ^ 1];
             if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
-            if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; s_chunk[n3] = 0; }
+            if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; s_count[par ^ 1] = 0; s_chunk[n3] = 0; }
             __syncthreads();                                  // pushes into layer t complete; staging of layers t, t+1 visible
             if (t + 2 < T) prov.load(t + 2);                  // prefetch the search structure of layer t+2
             uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
             unsigned long long mybest = FX_EMPTY;
             int mylo = INT_MAX, myhi = -1;
             const bool last = (t == T - 1);
-            // warps take 32-cell chunks from a shared counter: obstacle bands leave long empty runs, static striding would idle
+            auto process = [&](const int k, const int rk, const unsigned long long w) {
+                cur[rk] = FX_EMPTY;                           // this buffer receives layer t+2
+                double s = g.sval(k);
+                double d;
+                if (Prov::kClipAtPush) d = prov.distance_staged(t, k, s);      // pushes never land in a band
+                else { bool ob; d = prov.eval_staged(t, k, s, ob); if (ob) return; }   // st_cy.pyx:383-384
+                unsigned long long label = (w >> 16) + fx_penalty(P, d);
+                if (label >= FX_LABEL_LIMIT) { S.need_fallback = 1; return; }
+                const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
+                bp_row[k] = (uint16_t)(k - v);
+                unsigned long long key = (label << 16) | (unsigned long long)k;
+                mybest = key < mybest ? key : mybest;
+                if (last) return;
+                int wlo, n;
+                int_window(P, g, CB, k, v, a, wlo, n);
+                if (n <= 0) return;
+                const int vn = wlo - k, an = vn - v, jn = an - a;
+                if (vn + n - 1 > 255 || an < -16 || an + n - 1 > 15 || jn < -8 || jn + n - 1 > 7) { S.need_fallback = 1; return; }
+                int2 b0, b1;
+                prov.bands_near(t + 1, wlo, b0, b1);
+                int r = ring(wlo);
+                unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
+                mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
+                for (int e = 0; e < n; e++) {
+                    const int kk = wlo + e;
+                    const bool blocked = (kk >= b0.x && kk < b0.y) || (kk >= b1.x && kk < b1.y);
+                    if (!blocked) {
+                        const unsigned long long kin = (unsigned long long)TB.v[vn + e] + TB.a[an + e + 16] + TB.j[jn + e + 8];
+                        if (smem_min64(&nxt[r], word + (kin << 16))) s_count[par ^ 1] = 1;     // "layer t+1 is not empty"
+                    }
+                    word = word - 255ULL;                      // v' + 1 (bits 8..15 hold 255 - v'), a' + 1 (bits 0..7)
+                    r = (WRAP && r + 1 == Wc) ? 0 : r + 1;
+                }
+            };
+            // dense traversal of the layer's cell span: warps take 32-cell chunks from a shared counter (obstacle bands leave
+            // long empty runs, static striding would idle whole warps).  A node-list traversal was measured 1.6-1.9x slower:
+            // arrival order scatters neighbouring cells over warps (bank conflicts, uncoalesced back-pointer stores).
             for (;;) {
                 int c = 0;
                 if (lane == 0) c = atomicAdd(&s_chunk[s3], 1);
@@ -261,42 +318,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 const int base = dlo + (c << 5);
                 if (base > dhi) break;
                 const int k = base + lane;
-                if (k > dhi) continue;
-                const int rk = ring(k);
-                unsigned long long w = cur[rk];
-                if (w == FX_EMPTY) continue;
-                cur[rk] = FX_EMPTY;                           // this buffer receives layer t+2
-                double s = g.sval(k);
-                double d;
-                if (Prov::kClipAtPush) d = prov.distance_staged(t, k, s);      // pushes never land in a band
-                else { bool ob; d = prov.eval_staged(t, k, s, ob); if (ob) continue; }   // st_cy.pyx:383-384
-                unsigned long long label = (w >> 16) + fx_penalty(P, d);
-                if (label >= FX_LABEL_LIMIT) { S.need_fallback = 1; continue; }
-                const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
-                bp_row[k] = (uint16_t)(k - v);
-                unsigned long long key = (label << 16) | (unsigned long long)k;
-                mybest = key < mybest ? key : mybest;
-                if (last) continue;
-                int wlo, n;
-                int_window(P, g, k, v, a, wlo, n);
-                if (n <= 0) continue;
-                const int vn = wlo - k, an = vn - v, jn = an - a;
-                if (vn + n - 1 > 255 || an < -16 || an + n - 1 > 15 || jn < -8 || jn + n - 1 > 7) { S.need_fallback = 1; continue; }
-                int2 b0, b1;
-                prov.bands_near(t + 1, wlo, b0, b1);
-                int r = ring(wlo);
-                unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
-                for (int i = 0; i < n; i++) {
-                    const int kk = wlo + i;
-                    const bool blocked = (kk >= b0.x && kk < b0.y) || (kk >= b1.x && kk < b1.y);
-                    if (!blocked) {
-                        const unsigned long long kin = (unsigned long long)TB.v[vn + i] + TB.a[an + i + 16] + TB.j[jn + i + 8];
-                        smem_min64(&nxt[r], word + (kin << 16));
-                        mylo = min(mylo, kk); myhi = max(myhi, kk);
-                    }
-                    word = word - 255ULL;                      // v' + 1 (bits 8..15 hold 255 - v'), a' + 1 (bits 0..7)
-                    r = (WRAP && r + 1 == Wc) ? 0 : r + 1;
-                }
+                if (k <= dhi) { const int rk = ring(k); const unsigned long long w = cur[rk]; if (w != FX_EMPTY) process(k, rk, w); }
             }
             for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, mybest, o); mybest = x < mybest ? x : mybest; }
             mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
@@ -306,10 +328,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             }
             if (t + 2 < T) prov.store(t + 2);
             __syncthreads();
-            if (s_layer_best[par] == FX_EMPTY) break;         // no cell of layer t survived: layer t-1 is deepest
+            if (s_layer_best[par] == FX_EMPTY) break;         // no node of layer t survived: layer t-1 is deepest
             bt = t; best_word = s_layer_best[par];
             dlo = S.nlo[n3]; dhi = S.nhi[n3];
-            if (dhi < 0) break;                               // no successors (or last layer)
+            if (s_count[par ^ 1] == 0) break;                 // no successors (or last layer)
         }
         __syncthreads();
         if (S.need_fallback) {        // saturated label / out-of-range code / ring too small: hand the problem to the exact kernel
@@ -319,7 +341,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             continue;
         }
         // an early exit leaves pushed-but-unprocessed words of layer bt+1 behind: clear them
-        if (dhi >= 0 && bt < T - 1) { unsigned long long *nb = buf[(bt + 1) & 1]; for (int k = dlo + tid; k <= dhi; k += nth) nb[ring(k)] = FX_EMPTY; }
+        if (bt < T - 1 && bt >= 1) {
+            const int q = (bt + 1) & 1; unsigned long long *nb = buf[q];
+            if (dhi >= 0) { for (int k = dlo + tid; k <= dhi; k += nth) nb[ring(k)] = FX_EMPTY; }
+        }
         int fbk = (int)(best_word & 0xffff);
         double best_cost = (double)(best_word >> 16) * (1.0 / MPC_FX_ONE);
         finish_problem(P, io, prov, &S, b, g, bt, fbk, best_cost, bp, DESC || io.crash != nullptr);

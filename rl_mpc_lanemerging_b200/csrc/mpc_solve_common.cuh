@@ -85,9 +85,7 @@ struct BlockShared {
     int best_k;
     unsigned long long mind_bits;
     int crash;
-    int ovf_cnt[3];
     int need_fallback;
-    unsigned ovf[3 * OVF_CAP];
 };
 
 // Write outputs for a finished DP: back-track from (bt, bk), then the crash test of st.py:790-802.

@@ -5,8 +5,10 @@ import numpy as np, torch
 from rl_mpc_lanemerging_b200 import synthetic, _lib
 from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
 
-def run(H, B, mode, reps=3, threads=None):
+def run(H, B, mode, reps=3, threads=None, blocks=None, lst=0):
+    os.environ["MPC_FAST_LIST"] = str(lst)
     if threads: os.environ["MPC_FAST_THREADS"] = str(threads)
+    os.environ["MPC_FAST_BLOCKS"] = str(blocks or 32)
     p = _lib.default_params()
     p.future_t, p.future_s = synthetic.horizon_settings(H)
     eng = MpcEngine(p, 0, max_batch=B)
@@ -23,11 +25,11 @@ def run(H, B, mode, reps=3, threads=None):
         t = ev[0].elapsed_time(ev[1])
         if t < best: best, km = t, eng.last_kernel_ms()
     c = eng.counters()
-    print(f"H={H} B={B} mode={mode} threads={threads or 'default'}: {best:.3f} ms -> {B/best*1e3:.0f} gap-evals/s  kernels(pred,dp,fb)={tuple(round(x,3) for x in km)} fallback={c['fallback_problems']}", flush=True)
+    print(f"H={H} B={B} mode={mode} threads={threads or 'default'} blocks/SM={(blocks or 32)//32} list={lst}: {best:.3f} ms -> {B/best*1e3:.0f} gap-evals/s  kernels(pred,dp,fb)={tuple(round(x,3) for x in km)} fallback={c['fallback_problems']}", flush=True)
     eng.close()
 
 if __name__ == "__main__":
     cfgs = sys.argv[1:] or ["17:4096:fast:0", "17:4096:fast:256", "17:4096:fast:512", "17:4096:fast:1024", "50:4096:fast:512", "50:4096:fast:1024", "50:4096:fast:768", "17:4096:exact:0", "50:2048:exact:0"]
     for c in cfgs:
-        H, B, mode, th = c.split(":")
-        run(int(H), int(B), mode, threads=int(th) or None)
+        f = c.split(":")
+        run(int(f[0]), int(f[1]), f[2], threads=int(f[3]) or None, blocks=int(f[4]) if len(f) > 4 else None, lst=int(f[5]) if len(f) > 5 else 0)
