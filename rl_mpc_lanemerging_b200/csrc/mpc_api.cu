@@ -356,7 +356,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
         const int32_t *pending = h->fallback_list; const int *pending_n = h->counters + 2;
         if (h->wrap_fast && h->smem_fast_big) {
             SolveLaunch G = F;
-            G.threads = 512; G.smem = h->smem_fast_big; G.W = h->W; G.wrap = 0;
+            G.threads = 1024; G.smem = h->smem_fast_big; G.W = h->W; G.wrap = 0;      // one wide block per hard problem
             G.grid = h->sm_count < B ? h->sm_count : B; if (G.grid > 32) G.grid = 32;
             io.work_counter = h->counters + 3;
             io.subset = pending; io.B_dev = pending_n;

@@ -158,7 +158,7 @@ __device__ __forceinline__ unsigned long long fx_penalty(const DevParams &P, dou
     return fx_from_double(__dmul_rn(P.p.d_weight, pen));
 }
 
-struct FxTables { unsigned v[256], a[32], j[16]; };
+struct FxTables { unsigned v[256], aj[32 * 16]; };     // aj[(a'+16)*16 + (j'+8)] = A[a'] + J[j']: one lookup, stride 17 along a window
 
 template <class Prov, bool DESC, bool WRAP, int MAXT>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
@@ -167,7 +167,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
     __shared__ FastShared FS;
     __shared__ FxTables TB;
     __shared__ unsigned long long s_layer_best[2];
-    __shared__ int s_count[2];          // non-zero when buf[i] received at least one node
     __shared__ int s_chunk[3];          // dense traversal: next 32-cell chunk of a pass
     BlockShared &S = FS.S;
     unsigned long long *buf[2];
@@ -178,8 +177,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
     const int T = P.num_t, tid = threadIdx.x, nth = blockDim.x;
     auto ring = [Wc](int k) -> int { return WRAP ? (k >= Wc ? k - Wc : k) : k; };
     for (int i = tid; i < 256; i += nth) TB.v[i] = P.vtab[i];
-    if (tid < 32) TB.a[tid] = P.atab[tid];
-    if (tid < 16) TB.j[tid] = P.jtab[tid];
+    for (int i = tid; i < 512; i += nth) TB.aj[i] = P.atab[i >> 4] + P.jtab[i & 15];
     for (int k = tid; k < 2 * Wc; k += nth) buf[0][k] = FX_EMPTY;       // both buffers; every pass leaves them empty again
     if (io.B_dev) B = *io.B_dev;
     for (;;) {
@@ -201,7 +199,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         build_clamp_bits(P, g, CB);
         double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
         double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
-        if (tid == 0) { S.need_fallback = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_count[0] = 0; s_count[1] = 0; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
+        if (tid == 0) { S.need_fallback = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
         // ---- prologue: layers 0 -> 1 -> 2 have off-grid history (st_cy.pyx:329-330): exact fp64, then quantised ----
         int imin0, imax0;
         exact_window(P, g.s0, g.ds, g.s0, est_prev, est_second, imin0, imax0);
@@ -250,8 +248,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 int vn = kk - k1, an = vn - k1;
                 if (vn > 255 || an < -16 || an > 15) { S.need_fallback = 1; continue; }
                 unsigned long long tot = (w1 >> 16) + fx_from_double(exact_kin(P, g.sval(kk), s, g.s0, est_prev));
-                if (smem_min64(&buf[0][ring(kk)], (tot << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128)))
-                    s_count[0] = 1;
+                smem_min64(&buf[0][ring(kk)], (tot << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128));
                 mylo = min(mylo, kk); myhi = max(myhi, kk);
             }
             mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
@@ -259,7 +256,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             __syncthreads();
             for (int k1 = lo1 + tid; k1 <= hi1; k1 += nth) buf[1][ring(k1)] = FX_EMPTY;     // layer 1 is consumed
             dlo = S.nlo[2]; dhi = S.nhi[2];
-            if (s_count[0] == 0) done = true;                 // layer-1 nodes have no successors
+            if (dhi < 0) done = true;                         // layer-1 nodes have no successors
         }
         // ---- main loop: pass t finalises the nodes of layer t (buffer t&1) and pushes their successors ----
         const int lane = tid & 31;
@@ -267,7 +264,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
             unsigned long long *cur = buf[par], *nxt = buf[par ^ 1];
             if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
-            if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; s_count[par ^ 1] = 0; s_chunk[n3] = 0; }
+            if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; s_chunk[n3] = 0; }
             __syncthreads();                                  // pushes into layer t complete; staging of layers t, t+1 visible
             if (t + 2 < T) prov.load(t + 2);                  // prefetch the search structure of layer t+2
             uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
@@ -290,21 +287,29 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 int wlo, n;
                 int_window(P, g, CB, k, v, a, wlo, n);
                 if (n <= 0) return;
-                const int vn = wlo - k, an = vn - v, jn = an - a;
-                if (vn + n - 1 > 255 || an < -16 || an + n - 1 > 15 || jn < -8 || jn + n - 1 > 7) { S.need_fallback = 1; return; }
+                const int vn = wlo - k, an = vn - v, jn = an - a;      // table indices stay in range: derive_params() validated the limits
                 int2 b0, b1;
                 prov.bands_near(t + 1, wlo, b0, b1);
+                // bit e of `open` = successor e is not inside an obstacle band of layer t+1 (st_cy.pyx:383-384)
+                unsigned open = (1u << n) - 1;
+                {
+                    const int l0 = max(b0.x - wlo, 0), h0 = min(b0.y - wlo, n), l1 = max(b1.x - wlo, 0), h1 = min(b1.y - wlo, n);
+                    if (h0 > l0) open &= ~(((1u << h0) - 1) & ~((1u << l0) - 1));
+                    if (h1 > l1) open &= ~(((1u << h1) - 1) & ~((1u << l1) - 1));
+                }
+                mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
                 int r = ring(wlo);
                 unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
-                mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
-                for (int e = 0; e < n; e++) {
-                    const int kk = wlo + e;
-                    const bool blocked = (kk >= b0.x && kk < b0.y) || (kk >= b1.x && kk < b1.y);
-                    if (!blocked) {
-                        const unsigned long long kin = (unsigned long long)TB.v[vn + e] + TB.a[an + e + 16] + TB.j[jn + e + 8];
-                        if (smem_min64(&nxt[r], word + (kin << 16))) s_count[par ^ 1] = 1;     // "layer t+1 is not empty"
-                    }
-                    word = word - 255ULL;                      // v' + 1 (bits 8..15 hold 255 - v'), a' + 1 (bits 0..7)
+                const unsigned *tv = TB.v + vn, *taj = TB.aj + (an + 16) * 16 + (jn + 8);
+#pragma unroll
+                for (int e = 0; e < 5; e++) {                               // the common window has 5 cells: unrolled, predicated
+                    if ((open >> e) & 1u) smem_min64(&nxt[r], word + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                    word = word - 255ULL;                                   // v' + 1 (bits 8..15 hold 255 - v'), a' + 1 (bits 0..7)
+                    r = (WRAP && r + 1 == Wc) ? 0 : r + 1;
+                }
+                for (int e = 5; e < n; e++) {                               // longer windows (other Settings)
+                    if ((open >> e) & 1u) smem_min64(&nxt[r], word + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                    word = word - 255ULL;
                     r = (WRAP && r + 1 == Wc) ? 0 : r + 1;
                 }
             };
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             if (s_layer_best[par] == FX_EMPTY) break;         // no node of layer t survived: layer t-1 is deepest
             bt = t; best_word = s_layer_best[par];
             dlo = S.nlo[n3]; dhi = S.nhi[n3];
-            if (s_count[par ^ 1] == 0) break;                 // no successors (or last layer)
+            if (dhi < 0) break;                               // no successors (or last layer)
         }
         __syncthreads();
         if (S.need_fallback) {        // saturated label / out-of-range code / ring too small: hand the problem to the exact kernel
