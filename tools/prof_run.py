@@ -10,7 +10,7 @@ mode = sys.argv[3] if len(sys.argv) > 3 else "fast"
 p = _lib.default_params(); p.future_t, p.future_s = synthetic.horizon_settings(H)
 eng = MpcEngine(p, 0, max_batch=B)
 D = states_to_device(synthetic.make_states(B, "moderate", seed=0), "cuda:0")
-for _ in range(2):
+for _ in range(3):
     out = eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=mode)
 torch.cuda.synchronize()
 print("done", eng.counters())
