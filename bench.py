@@ -203,7 +203,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from rl_mpc_lanemerging_b200 import synthetic
+    from rl_mpc_lanemerging_b200 import sharding, synthetic
     from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,7 +216,8 @@ def run_ours(args):
     H, B, K, W = args.horizon, args.batch, args.steps, max(args.warmup, 3)
     eng = MpcEngine(make_params(H), device=local, max_batch=B)
     # episodes are sharded by global id: rank r owns episodes [r*B, (r+1)*B) (replicas, no exchange on the path)
-    S = synthetic.make_states(B, args.traffic, seed=args.seed, first_episode=rank * B)
+    first, _last = sharding.shard_range(world * B, rank, world)
+    S = synthetic.make_states(B, args.traffic, seed=args.seed, first_episode=first)
     D = states_to_device(S, dev)
     out = eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=args.mode)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)           # > 126 MB L2
@@ -272,18 +273,13 @@ def run_ours(args):
     d2h = B * (T * 4 + T * 8 + 8 + 4 + 1 + 8 + 8)
     full = float((r["reached_t"] == T - 1).mean())
 
-    t = torch.tensor([step_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, e2e_ms = float(t[0]), float(t[1])
+    step_ms, e2e_ms = sharding.reduce_max([step_ms, e2e_ms], dev)        # the slowest rank defines the step
     env_res = None
     if args.env_ticks > 0:              # every rank runs its own environments; the job rate is the sum over ranks
         try:
             eng.close()
             rate, take = env_steps_per_sec(local, world, args.env_envs, args.env_ticks, args.seed + rank)
-            r = torch.tensor([rate, take], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(r, op=dist.ReduceOp.SUM)
+            r = sharding.reduce_sum([rate, take], dev)
             env_res = {"value": float(r[0]), "unit": "env-steps/s", "envs_per_gpu": args.env_envs, "ticks": args.env_ticks,
                        "controller": "RL proposes + MPC vetoes (combined_moderate_1 semantics), H=17 grid, fast mode",
                        "planner_takeover_fraction": float(r[1]) / world,

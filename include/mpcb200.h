@@ -126,6 +126,16 @@ int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const double *h_car
                   int32_t *h_idx, double *h_s_seq, double *h_cost, int32_t *h_reached_t,
                   uint8_t *h_crash, double *h_min_dist, double *h_start_s, void *stream);
 
+/* ---- finer_fit (st.py:584-723): re-sample each plan from T_DISCRETIZATION to TICK_LENGTH by linear interpolation and
+ * project it onto the speed / acceleration / jerk limits (the QP the reference gives to cvxopt; solved here by a
+ * primal-dual interior-point method, one thread per episode).  d_s_seq f64[B][num_t] and d_reached_t i32[B] are mpc_plan's
+ * outputs; d_fine f64[B][fine_stride] receives the smoothed positions, d_n_fine i32[B] their count (1 = the plan had a
+ * single point, st.py:587-588), d_speed f64[B] (optional) the speed command (fine[1]-fine[0])/TICK_LENGTH of
+ * st.py:780-781 (the current ego speed when the plan has a single point, st.py:775-777), d_iterations i32[B] (optional). */
+int mpc_finer_fit(mpc_handle *h, int B, const double *d_s_seq, const int32_t *d_reached_t, const double *d_ego,
+                  double *d_fine, int fine_stride, int32_t *d_n_fine, double *d_speed, int32_t *d_iterations, void *stream);
+int mpc_finer_fit_max_points(void);
+
 /* ---- K4: rollout tick pieces ------------------------------------------------------------------
  * HighwayState.predict_step_with_ego (prediction.py:46-105), batched, in place allowed
  * (out pointers may alias in pointers).  d_selected_speed f64[B]; d_crashed u8[B]. */

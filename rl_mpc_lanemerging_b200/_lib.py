@@ -49,6 +49,8 @@ SYMBOLS = {
     "mpc_solve_dense": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mpc_plan": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),
     "mpc_plan_host": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),
+    "mpc_finer_fit": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "mpc_finer_fit_max_points": (_i, []),
     "mpc_predict_step_with_ego": (_i, [_vp, _i] + [_vp] * 6 + [_d, _d] + [_vp] * 5 + [_vp]),
     "mpc_state_vector": (_i, [_vp, _i] + [_vp] * 5 + [_vp, _i, _vp]),
     "mpc_speed_from_jerk": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),

@@ -16,6 +16,10 @@ cudaError_t launch_fast_dense(const DevParams &P, const SolveLaunch &L, const So
                               int dist_f32, int stride, cudaStream_t st);
 cudaError_t launch_check_sorted(const DevParams &P, int B, const LayerDesc *desc, const double *s0, const double *ds,
                                 const int32_t *ns, unsigned long long *mismatches, cudaStream_t st);
+cudaError_t launch_finer_fit(const DevParams &P, int B, int T, const double *s_seq, const int32_t *reached, const double *ego,
+                             int max_iter, double tol, double *fine, int fine_stride, int32_t *n_fine, double *speed,
+                             int32_t *iters, cudaStream_t st);
+int qp_max_fine();
 int exact_occupancy(int threads, size_t smem);
 int fast_occupancy(int threads, size_t smem, int wrap);
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
@@ -439,6 +443,21 @@ extern "C" int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const do
     MPC_CUDA_OK(cudaStreamSynchronize(st));
     return MPC_OK;
 }
+
+// ---- finer_fit (st.py:584-723): tick-rate re-sampling + speed/accel/jerk projection of the plans ------------------------
+extern "C" int mpc_finer_fit(mpc_handle *h, int B, const double *d_s_seq, const int32_t *d_reached_t, const double *d_ego,
+                             double *d_fine, int fine_stride, int32_t *d_n_fine, double *d_speed, int32_t *d_iterations, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_s_seq || !d_reached_t || !d_ego || !d_fine || !d_n_fine || fine_stride < 2) return mpc_set_error(MPC_E_INVALID, "mpc_finer_fit: bad argument");
+    if (!(h->P.p.tick_length > 0)) return mpc_set_error(MPC_E_INVALID, "mpc_finer_fit: tick_length must be positive");
+    MPC_CUDA_OK(launch_finer_fit(h->P, B, h->P.num_t, d_s_seq, d_reached_t, d_ego, 40, 1e-9, d_fine, fine_stride, d_n_fine, d_speed,
+                                 d_iterations, (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}
+
+extern "C" int mpc_finer_fit_max_points(void) { return qp_max_fine(); }
 
 // ---- K4 ----------------------------------------------------------------------------------------------
 extern "C" int mpc_predict_step_with_ego(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,

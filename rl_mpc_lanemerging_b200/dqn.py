@@ -76,9 +76,6 @@ class RLAgent:
         return float(speed.item()) if single else (speed, takeover)
 
     def _combined_batched(self, start: BatchedState, eng):
-        if Settings.TEST_ST_STRICTLY_BETTER:
-            raise NotImplementedError("the 'b' configs compare against the QP-smoothed plan (finer_fit), which is the next "
-                                      "row of the scope table (SURVEY.md §8 f-1)")
         B, dev = start.batch, eng.device
         first_action = self.get_control(start)
         cur = start.clone()
@@ -87,6 +84,10 @@ class RLAgent:
         selected_speed = torch.zeros(B, dtype=torch.float64, device=dev)
         snap, has_snap = None, torch.zeros(B, dtype=torch.bool, device=dev)
         steps = max(int(Settings.ROLLOUT_LENGTH), 1)
+        # rollout_s_history (dqn.py:121,139): ego arclength after every rollout step the episode actually took
+        roll_s = torch.zeros((B, steps + 1), dtype=torch.float64, device=dev)
+        roll_s[:, 0] = _ego_s(start.ego)
+        roll_len = torch.ones(B, dtype=torch.int64, device=dev)
         for i in range(1, steps + 1):                                               # dqn.py:129-141
             action = first_action if i == 1 else self.get_control(cur)
             sel = control.get_ego_speed_from_jerk(cur.ego[:, 2].contiguous(), cur.ego[:, 3].contiguous(), action.double())
@@ -95,6 +96,8 @@ class RLAgent:
             cur = BatchedState(torch.where(m, eo, cur.ego), torch.where(m, xo, cur.cars_x), torch.where(m, vo, cur.cars_v),
                                torch.where(m, ao, cur.cars_a), cur.n_cars)
             selected_speed = torch.where(alive, sel, selected_speed)
+            roll_s[:, i] = torch.where(alive, _ego_s(cur.ego), roll_s[:, i - 1])
+            roll_len = roll_len + alive.long()
             crash_predicted |= alive & crashed.bool()
             if i == int(Settings.ST_TEST_ROLLOUTS):
                 snap, has_snap = cur.clone(), alive.clone()
@@ -114,10 +117,47 @@ class RLAgent:
             takeover |= st.test_guaranteed_crash_from_state(test)
         rl_speed = control.get_ego_speed_from_jerk(start.ego[:, 2].contiguous(), start.ego[:, 3].contiguous(), first_action.double())
         speed = rl_speed
+        if Settings.TEST_ST_STRICTLY_BETTER:                                        # 156-197 ("b" configs)
+            if Settings.REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED:
+                raise NotImplementedError("REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED is False in every published config")
+            plan = st.plan_batch(start)
+            st_speed, fine, n_fine = st.smoothed_speed(start, plan)
+            tick = float(Settings.TICK_LENGTH)
+            mlen = torch.minimum(n_fine.long(), roll_len)                           # min_planning_length (171)
+            st_jerk = _mean_abs_jerk(fine, mlen, start.ego[:, 2], start.ego[:, 3], tick)
+            rl_jerk = _mean_abs_jerk(roll_s, mlen, start.ego[:, 2], start.ego[:, 3], tick)
+            last = (mlen - 1).clamp(min=0).unsqueeze(1)
+            st_dist = fine.gather(1, last).squeeze(1) - fine[:, 0]
+            rl_dist = roll_s.gather(1, last).squeeze(1) - roll_s[:, 0]
+            better = ((st_jerk < rl_jerk) & (st_dist > rl_dist)) | (rl_dist == 0)   # 177
+            better &= (n_fine > 1) & ~takeover                                       # 166-169: single-point plan -> keep the RL action
+            speed = torch.where(better, st_speed, rl_speed)
+            takeover_b = better
+        else:
+            takeover_b = None
         n_take = int(takeover.sum().item())
         if n_take:                                                                  # planner takes over: st.do_st_control(start_state)
             idx = takeover.nonzero().squeeze(1)
             sub = BatchedState(*(t[idx].contiguous() for t in start.args()))
-            speed = rl_speed.clone()
+            speed = speed.clone()
             speed[idx] = st.do_st_control(sub)
+        if takeover_b is not None:
+            takeover = takeover | takeover_b
         return speed, takeover
+
+
+def _ego_s(ego: torch.Tensor) -> torch.Tensor:
+    """control.get_ego_s (control.py:373-380) for a batch (device tensor ops on 3 columns; rollout bookkeeping only)."""
+    x, y = ego[:, 0], ego[:, 1]
+    d = torch.sqrt((x - control.merge_point[0]) ** 2 + (y - control.merge_point[1]) ** 2)
+    return torch.where(x < control.merge_point[0], -d, torch.where(x < control.merge_point2[0], d, x - control.merge_point2[0] + control.common_s))
+
+
+def _mean_abs_jerk(seq: torch.Tensor, length: torch.Tensor, v0: torch.Tensor, a0: torch.Tensor, dt: float) -> torch.Tensor:
+    """st.get_path_mean_abs_jerk (st.py:274-288) over the first `length[b]` points of every row."""
+    B, N = seq.shape
+    v = (seq[:, 1:] - seq[:, :-1]) / dt
+    a = (v - torch.cat([v0.unsqueeze(1), v[:, :-1]], 1)) / dt
+    j = (a - torch.cat([a0.unsqueeze(1), a[:, :-1]], 1)) / dt
+    mask = torch.arange(N - 1, device=seq.device).unsqueeze(0) < (length - 1).unsqueeze(1)
+    return (j.abs() * mask).sum(1) / (length - 1).clamp(min=1)

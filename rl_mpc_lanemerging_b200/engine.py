@@ -197,6 +197,20 @@ class MpcEngine:
                                                 _ptr(out["s_seq"]), _ptr(out["cost"]), _ptr(out["reached_t"]), self._stream()))
         return out
 
+    def finer_fit(self, s_seq, reached_t, ego):
+        """st.finer_fit for a batch of plans: returns (fine [B,Nf] f64, n_fine [B] i32, speed [B] f64, iterations [B] i32)."""
+        B = s_seq.shape[0]
+        nf = int(self.lib.mpc_finer_fit_max_points())
+        o = dict(device=self.device)
+        fine = torch.zeros((B, nf), dtype=torch.float64, **o)
+        n_fine = torch.empty(B, dtype=torch.int32, **o)
+        speed = torch.empty(B, dtype=torch.float64, **o)
+        iters = torch.empty(B, dtype=torch.int32, **o)
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_finer_fit(self.h, B, _ptr(s_seq), _ptr(reached_t), _ptr(ego), _ptr(fine), nf, _ptr(n_fine),
+                                              _ptr(speed), _ptr(iters), self._stream()))
+        return fine, n_fine, speed, iters
+
     # ------------------------------------------------------------------------------------------
     def predict_step_with_ego(self, ego, cars_x, cars_v, cars_a, n_cars, selected_speed, dt, min_crash_distance=5.0,
                               inplace=False):

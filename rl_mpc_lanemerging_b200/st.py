@@ -104,28 +104,49 @@ def test_guaranteed_crash_from_state(state):
 test_guaranteed_crash_from_state.__test__ = False            # not a pytest test
 
 
-def first_step_speed(plan: dict) -> torch.Tensor:
-    """Speed command from a plan (reference st.py:774-783) for the whole batch.
+def finer_fit(s_sequence, delta_t=None, coarse_delta_t=None, start_speed=0.0, start_acceleration=0.0, before_after_cars=None):
+    """Reference st.py:584-723: re-sample a coarse plan to the control tick and project it onto the speed / acceleration /
+    jerk limits.  Same QP as the reference's (cvxopt) one, solved on the GPU by an interior-point kernel (mpc_finer_fit).
+    numpy in -> numpy out (one plan).  `before_after_cars` (unused by every caller in the reference) is not supported."""
+    if before_after_cars is not None:
+        raise NotImplementedError("before_after_cars is never passed by the reference's callers")
+    s = np.asarray(s_sequence, dtype=np.float64)
+    if len(s) == 1:
+        return s
+    if delta_t is not None and abs(delta_t - float(Settings.TICK_LENGTH)) > 1e-12 or \
+            coarse_delta_t is not None and abs(coarse_delta_t - float(Settings.T_DISCRETIZATION)) > 1e-12:
+        raise ValueError("finer_fit runs with Settings.TICK_LENGTH / Settings.T_DISCRETIZATION")
+    eng = get_engine()
+    if len(s) > eng.num_t:
+        raise ValueError("plan longer than the planning horizon")
+    seq = torch.zeros((1, eng.num_t), dtype=torch.float64, device=eng.device)
+    seq[0, :len(s)] = torch.from_numpy(s).to(eng.device)
+    reached = torch.tensor([len(s) - 1], dtype=torch.int32, device=eng.device)
+    ego = torch.tensor([[0.0, 0.0, float(start_speed), float(start_acceleration)]], dtype=torch.float64, device=eng.device)
+    fine, n_fine, _speed, _it = eng.finer_fit(seq, reached, ego)
+    return fine[0, :int(n_fine.item())].cpu().numpy()
 
-    The reference smooths the 0.3 s plan onto the 0.2 s tick with a QP (finer_fit, st.py:584-723) before taking
-    (s[1]-s[0])/TICK; that QP is the next row of the scope table and is not ported yet, so the
-    plan's own first-step mean speed (s[1]-s[0])/T_DISCRETIZATION is used.  Where the plan has a single point
-    (crash inevitable) the caller keeps its current speed (st.py:775-777): those entries are NaN here."""
+
+def smoothed_speed(batch: BatchedState, plan: dict):
+    """Speed command of reference st.py:757-783 for a batch: trim the 0.0 tail, finer_fit (TICK_LENGTH < T_DISCRETIZATION in
+    every published config), then (x[1]-x[0])/TICK_LENGTH; plans with a single point keep the current speed."""
+    eng = get_engine(batch.batch)
+    if float(Settings.TICK_LENGTH) < float(Settings.T_DISCRETIZATION):
+        fine, n_fine, speed, _it = eng.finer_fit(plan["s_seq"], plan["reached_t"], batch.ego)
+        return speed, fine, n_fine
     s = plan["s_seq"]
-    v = (s[:, 1] - s[:, 0]) / float(Settings.T_DISCRETIZATION)
-    return torch.where(plan["reached_t"] >= 1, v, torch.full_like(v, float("nan")))
+    v = (s[:, 1] - s[:, 0]) / float(Settings.TICK_LENGTH)
+    return torch.where(plan["reached_t"] >= 1, v, batch.ego[:, 2]), s, plan["reached_t"] + 1
 
 
 def do_st_control(state):
     """Reference st.py:757-783.  Returns the commanded ego speed (float, or tensor [B] for a BatchedState)."""
     if isinstance(state, BatchedState):
-        v = first_step_speed(plan_batch(state))
-        return torch.where(torch.isnan(v), state.ego[:, 2], v)
+        return smoothed_speed(state, plan_batch(state))[0]
     eng = get_engine()
     bs = BatchedState.from_states([state], eng.device, eng.nmax)
-    v = first_step_speed(eng.plan(*bs.args(), mode=getattr(Settings, "ST_MODE", "exact")))
-    v = float(v.item())
-    return state.ego_speed if v != v else v
+    plan = eng.plan(*bs.args(), mode=getattr(Settings, "ST_MODE", "exact"))
+    return float(smoothed_speed(bs, plan)[0].item())
 
 
 def get_path_mean_abs_jerk(s_sequence, ego_start_speed, ego_start_acceleration, delta_t):
