@@ -71,14 +71,17 @@ int mpc_destroy(mpc_handle *h);
 /* num_t is fixed by the params; num_s depends on start_s through numpy.arange's length rule
  * (st.py:31), so only its maximum is a handle constant. */
 int mpc_grid_dims(const mpc_handle *h, int *num_t, int *num_s_max);
+/* Row stride (cells) of the dense grids mpc_build_grid writes: num_s_max rounded up to a multiple of 8 so that rows can be
+ * written with vector stores. */
+int mpc_grid_stride(const mpc_handle *h);
 /* counters of the last call on this handle: [0] kernels launched, [1] problems that overflowed
  * the fast kernel's shared-memory window / bucket capacity and were re-solved by the exact kernel */
 int mpc_last_counters(const mpc_handle *h, int64_t *out2);
 
 /* Optional per-kernel device timing (used by bench.py for the roofline of the dominant kernel):
  * after mpc_set_timing(h,1), mpc_last_kernel_ms returns {traffic-predictor ms, DP-kernel ms,
- * fallback-DP ms} of the last mpc_plan / mpc_solve_dense call, measured with CUDA events on the
- * stream the kernels were launched on. */
+ * fallback-DP ms} of the last mpc_plan / mpc_solve_dense call ({traffic-predictor ms, rasteriser ms, 0} after
+ * mpc_build_grid), measured with CUDA events on the stream the kernels were launched on. */
 int mpc_set_timing(mpc_handle *h, int enable);
 int mpc_last_kernel_ms(mpc_handle *h, float *out3);
 
@@ -89,8 +92,8 @@ int mpc_selftest_search(mpc_handle *h, int B, const double *d_ego, const double 
 
 /* ---- K1: traffic prediction + S-T rasterisation (st.find_s_t_obstacles_from_state, st.py:25-70,
  *      with prediction.py:22-105 and control.py:373-389) ------------------------------------- */
-/* Dense grids, the layout st_cy consumes: d_obstacles u8[B][num_t][num_s_max],
- * d_distances f64 (dist_f32=0) or f32 (dist_f32=1) [B][num_t][num_s_max]; cells >= num_s[b] are
+/* Dense grids, the layout st_cy consumes: d_obstacles u8[B][num_t][stride], d_distances f64 (dist_f32=0) or f32
+ * (dist_f32=1) [B][num_t][stride] with stride = mpc_grid_stride(h); cells >= num_s[b] are
  * written as obstacle=1 / distance=0.  d_start_s f64[B], d_delta_s f64[B] (= s_values[1]-s_values[0]),
  * d_num_s i32[B] may each be NULL. */
 int mpc_build_grid(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,

@@ -247,6 +247,8 @@ extern "C" int mpc_grid_dims(const mpc_handle *h, int *num_t, int *num_s_max) {
     return MPC_OK;
 }
 
+extern "C" int mpc_grid_stride(const mpc_handle *h) { return h ? h->W : 0; }
+
 extern "C" int mpc_last_counters(const mpc_handle *h, int64_t *out2) {
     if (!h || !out2) return mpc_set_error(MPC_E_INVALID, "null argument");
     int c[16];
@@ -296,8 +298,12 @@ extern "C" int mpc_build_grid(mpc_handle *h, int B, const double *d_ego, const d
     if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars || !d_obstacles || !d_distances) return mpc_set_error(MPC_E_INVALID, "mpc_build_grid: null pointer");
     (void)d_cars_a;
     cudaStream_t st = (cudaStream_t)stream;
+    h->ev_valid = 0;
+    if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[0], st));
     MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, h->s0, h->ds, h->num_s, st));
-    MPC_CUDA_OK(launch_rasterise(h->P, B, h->P.num_s_max, h->desc, h->s0, h->ds, h->num_s, d_obstacles, d_distances, dist_f32, st));
+    if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[1], st));
+    MPC_CUDA_OK(launch_rasterise(h->P, B, h->W, h->desc, h->s0, h->ds, h->num_s, d_obstacles, d_distances, dist_f32, st));
+    if (h->timing) { MPC_CUDA_OK(cudaEventRecord(h->ev[2], st)); MPC_CUDA_OK(cudaEventRecord(h->ev[3], st)); h->ev_valid = 1; }
     if (d_start_s) MPC_CUDA_OK(cudaMemcpyAsync(d_start_s, h->s0, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
     if (d_delta_s) MPC_CUDA_OK(cudaMemcpyAsync(d_delta_s, h->ds, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
     if (d_num_s) MPC_CUDA_OK(cudaMemcpyAsync(d_num_s, h->num_s, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));

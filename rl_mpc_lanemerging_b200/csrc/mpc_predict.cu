@@ -180,25 +180,42 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
 }
 
 // ---- K1b: dense grids in the layout st_cy consumes ---------------------------------------------
+// One block per (episode, layer); the layer's sorted search structure is staged in shared memory, every thread
+// evaluates 4 consecutive cells (O(1) lookups) and writes them with one 32-bit mask store and one/two 128-bit distance
+// stores.  This is the one kernel of the path that is bound by HBM writes (1 + 8 or 1 + 4 bytes per cell).
 template <typename DT>
 __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int stride_s, const LayerDesc *__restrict__ desc,
                                                         const double *__restrict__ s0v, const double *__restrict__ dsv,
                                                         const int32_t *__restrict__ nsv, uint8_t *__restrict__ obstacles,
-                                                        DT *__restrict__ distances) {
-    __shared__ LayerDesc L;
-    int bt = blockIdx.x;                       // one block per (problem, layer)
-    int b = bt / P.num_t;
-    const int *src = reinterpret_cast<const int *>(desc + bt);
-    int *dst = reinterpret_cast<int *>(&L);
-    for (int i = threadIdx.x; i < (int)(sizeof(LayerDesc) / 4); i += blockDim.x) dst[i] = src[i];
+                                                        DT *__restrict__ distances, int vec_ok) {
+    __shared__ __align__(16) LayerSearch L;
+    const int bt = blockIdx.x, b = bt / P.num_t;
+    {
+        const char *src = reinterpret_cast<const char *>(desc + bt);
+        constexpr int kTail = (int)(sizeof(LayerSearch) - 16) / 16;
+        if (threadIdx.x < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(&L) + 16)[threadIdx.x] =
+            reinterpret_cast<const int4 *>(src + offsetof(LayerDesc, edge))[threadIdx.x];
+        else if (threadIdx.x == kTail) *reinterpret_cast<int4 *>(&L) = make_int4(desc[bt].n_edge, desc[bt].n_band, 0, 0);
+    }
     __syncthreads();
     SGrid g; g.s0 = s0v[b]; g.ds = dsv[b]; g.num_s = nsv[b];
-    size_t row = (size_t)bt * stride_s;
-    for (int k = threadIdx.x; k < stride_s; k += blockDim.x) {
-        bool ob = true; double d = 0.0;
-        if (k < g.num_s) d = cell_distance(L, g.sval(k), k, ob);
-        obstacles[row + k] = ob ? 1 : 0;
-        distances[row + k] = (DT)d;
+    const size_t row = (size_t)bt * stride_s;
+    for (int k4 = threadIdx.x * 4; k4 < stride_s; k4 += blockDim.x * 4) {
+        unsigned char ob4[4]; DT d4[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int k = k4 + c;
+            bool ob = true; double d = 0.0;
+            if (k < g.num_s) d = cell_distance_sorted(L, g.sval(k), k, ob);
+            ob4[c] = ob ? 1 : 0; d4[c] = (DT)d;
+        }
+        if (vec_ok && k4 + 3 < stride_s) {
+            *reinterpret_cast<uchar4 *>(obstacles + row + k4) = make_uchar4(ob4[0], ob4[1], ob4[2], ob4[3]);
+            if (sizeof(DT) == 4) *reinterpret_cast<float4 *>(distances + row + k4) = make_float4((float)d4[0], (float)d4[1], (float)d4[2], (float)d4[3]);
+            else { double2 *q = reinterpret_cast<double2 *>(distances + row + k4); q[0] = make_double2((double)d4[0], (double)d4[1]); q[1] = make_double2((double)d4[2], (double)d4[3]); }
+        } else {
+            for (int c = 0; c < 4 && k4 + c < stride_s; c++) { obstacles[row + k4 + c] = ob4[c]; distances[row + k4 + c] = d4[c]; }
+        }
     }
 }
 
@@ -320,8 +337,9 @@ cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const Laye
                              const double *ds, const int32_t *ns, uint8_t *obstacles, void *distances, int dist_f32,
                              cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    if (dist_f32) rasterise_kernel<float><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances);
-    else rasterise_kernel<double><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances);
+    const int vec_ok = (stride_s % 4 == 0) && ((uintptr_t)obstacles % 4 == 0) && ((uintptr_t)distances % 16 == 0);
+    if (dist_f32) rasterise_kernel<float><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances, vec_ok);
+    else rasterise_kernel<double><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances, vec_ok);
     return cudaGetLastError();
 }
 

@@ -73,6 +73,7 @@ class MpcEngine:
         nt, ns = C.c_int(), C.c_int()
         _lib.check(self.lib.mpc_grid_dims(self.h, C.byref(nt), C.byref(ns)))
         self.num_t, self.num_s_max = nt.value, ns.value
+        self.num_s_stride = int(self.lib.mpc_grid_stride(self.h))     # row stride of dense grids (multiple of 8)
         self._pinned = {}
 
     # ------------------------------------------------------------------------------------------
@@ -167,9 +168,9 @@ class MpcEngine:
     # ------------------------------------------------------------------------------------------
     def build_grid(self, ego, cars_x, cars_v, cars_a, n_cars, dist_dtype=torch.float64):
         """K1: dense S-T grids in the layout the reference's solver consumes.
-        Returns obstacles u8[B,T,S], distances [B,T,S], start_s[B], delta_s[B], num_s[B] (S = num_s_max)."""
+        Returns obstacles u8[B,T,S], distances [B,T,S], start_s[B], delta_s[B], num_s[B] (S = num_s_stride >= num_s_max)."""
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
-        T, S = self.num_t, self.num_s_max
+        T, S = self.num_t, self.num_s_stride
         o = dict(device=self.device)
         obstacles = torch.empty((B, T, S), dtype=torch.uint8, **o)
         distances = torch.empty((B, T, S), dtype=dist_dtype, **o)
