@@ -372,7 +372,7 @@ def env_steps_per_sec(local, world, n_envs, ticks, seed):
     env = merge_gym.MergeEnv(n_envs, seed=seed)
     agent = ddpg.DDPGAgent(device=f"cuda:{local}", seed=seed)
     env.reset()
-    take = 0.0
+    take = torch.zeros((), dtype=torch.float32, device=f"cuda:{local}")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for phase, n in (("warm", 3), ("timed", ticks)):
         if phase == "timed":
@@ -383,12 +383,12 @@ def env_steps_per_sec(local, world, n_envs, ticks, seed):
             _obs, _r, done, _info = env.step(jerk)
             agent.reset_time(done)
             if phase == "timed":
-                take += float(takeover.float().mean())
+                take += takeover.float().mean()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     st.refresh_engine()
     Settings.reset()
-    return n_envs * ticks / (ms * 1e-3), take / ticks
+    return n_envs * ticks / (ms * 1e-3), float(take) / ticks
 
 
 def main():

@@ -155,6 +155,16 @@ int mpc_state_vector(mpc_handle *h, int B, const double *d_ego, const double *d_
                      float *d_out, int out_stride, void *stream);
 int mpc_speed_from_jerk(mpc_handle *h, int B, const double *d_ego, const double *d_jerk,
                         double *d_speed, void *stream);
+/* One step of RLAgent.do_combined_control's policy rollout (dqn.py:129-141), masked and IN PLACE: for every episode
+ * with d_alive[b] != 0 the proposed jerk becomes a speed (control.py:160-171), the state advances with
+ * predict_step_with_ego, d_selected_speed[b] is that speed, d_roll_s[b][step] the new ego arclength
+ * (rollout_s_history), d_roll_len[b] += 1, d_crash_predicted[b] |= crashed, and d_alive[b] is cleared when the step
+ * crashed or passed stop_x (Settings.STOP_X).  Finished episodes keep their state; d_roll_s[b][step] repeats
+ * d_roll_s[b][step-1].  1 <= step < roll_stride. */
+int mpc_rollout_step(mpc_handle *h, int B, double *d_ego, double *d_cars_x, double *d_cars_v, double *d_cars_a,
+                     const int32_t *d_n_cars, const double *d_jerk, double dt, double min_crash_distance,
+                     double stop_x, int step, uint8_t *d_alive, double *d_selected_speed, double *d_roll_s,
+                     int roll_stride, int32_t *d_roll_len, uint8_t *d_crash_predicted, void *stream);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,11 @@ int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_
                          const double *distances, const double *s_values, double delta_t,
                          double v0, double a0, int f32_labels, int *idx_out, double *s_seq_out, double *cost_out);
 
+int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+                            const double *distances, const double *s_values, double delta_t,
+                            double v0, double a0, int f32_labels, uint64_t prune_fx, int stride,
+                            int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts);
+
 /* Sum of st.cost (st.py:140-144) along an index path with the solver's history convention. */
 double orc_path_cost(const orc_params *p, int n, const int *idx, const double *s_values,
                      const double *distances, int num_s, double delta_t, double v0, double a0);

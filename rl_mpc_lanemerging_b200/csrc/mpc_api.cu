@@ -32,6 +32,10 @@ cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const doubl
 cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
                                 const double *ca, const int32_t *n, float *out, int stride, cudaStream_t st);
 cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st);
+cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
+                                const int32_t *n, const double *jerk, double dt, double mcd, double stop_x, int step,
+                                uint8_t *alive, double *sel_speed, double *roll_s, int roll_stride, int32_t *roll_len,
+                                uint8_t *crash_pred, cudaStream_t st);
 
 // ---- errors ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -66,6 +70,7 @@ struct mpc_handle {
     int threads, grid_exact;
     int Wc, wrap_fast, threads_fast, grid_fast; size_t smem_fast;   // fast kernel: ring capacity / launch shape
     size_t smem_fast_big;        // full-row variant used to re-solve ring overflows (0 = does not fit)
+    int use_bound;               // first fast pass runs under DevParams::bound_fx (MPC_FAST_BOUND=0|1 overrides)
     int grid_max;
     // scratch
     LayerDesc *desc; double *s0, *ds; int32_t *num_s;
@@ -127,6 +132,12 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     for (int i = 0; i < 32; i++) { double acc = (i - 16) * ds / (dt * dt), x = p->a_weight * acc * acc; mx = fmax(mx, x); D->atab[i] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
     for (int i = 0; i < 16; i++) { double jk = (i - 8) * ds / (dt * dt * dt), x = p->j_weight * jk * jk; mx = fmax(mx, x); D->jtab[i] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
     if (mx >= 16000.0 || D->jlo_c < -8 || D->jhi_c > 7 || !(p->d_weight >= 0) || p->d_weight > 1e4) D->fast_ok = 0;
+    // cheapest label of a path with one step inside a penalty zone: d_w * 1e6 / max(d,1) with d < min_allowed (st_cy.pyx:34-38)
+    D->bound_fx = 0;
+    if (p->d_weight > 0 && p->min_allowed_distance > 0) {
+        double zone = p->d_weight * 1000000.0 / fmax(p->min_allowed_distance, 1.0);
+        if (zone > 64.0) D->bound_fx = (unsigned long long)llrint(zone * MPC_FX_ONE) - 2;
+    }
     return MPC_OK;
 }
 
@@ -162,8 +173,11 @@ static int configure(mpc_handle *h) {
         h->grid_exact = h->sm_count * 2;
     }
     // ---- fast kernel: 16 B per cell (one packed 64-bit word, double buffered) behind a ring window ----
-    int fast_blocks = env_int("MPC_FAST_BLOCKS", 32, 64, 64) / 32;     // 64 -> size the ring for 2 blocks/SM (default), 32 -> 1 block/SM
     const size_t clamp_bytes = 2 * (((size_t)P.num_s_max + 31) / 32) * 4 + 16;   // two bit arrays behind the word buffers
+    // Ring sized for two blocks per SM when that still covers 2/3 of the row (frontier spans measured: <= 0.6 of the row on
+    // ordinary traffic; H=50: ring = 0.73 row, 7.7+0.5 ms vs 9.7 ms with one block per SM), else for one block per SM (long horizons).  MPC_FAST_BLOCKS=32|64 overrides (1 | 2 blocks/SM).
+    const size_t cap2 = ((h->smem_optin + 1024) / 2 - 1024 - static_smem - clamp_bytes) / 16;
+    int fast_blocks = env_int("MPC_FAST_BLOCKS", 32, 64, (cap2 * 3 >= (size_t)h->W * 2) ? 64 : 32) / 32;
     size_t cap = ((h->smem_optin + 1024) / fast_blocks - 1024 - static_smem - clamp_bytes) / 16;
     h->wrap_fast = (size_t)h->W > cap;
     h->Wc = h->wrap_fast ? (int)(cap & ~(size_t)7) : h->W;
@@ -173,6 +187,7 @@ static int configure(mpc_handle *h) {
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
+    h->use_bound = env_int("MPC_FAST_BOUND", 0, 1, 1) && P.bound_fx != 0;
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     return MPC_OK;
 }
@@ -340,7 +355,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
     io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
     io.subset = nullptr; io.B_dev = nullptr;
     SolveLaunch X;                                   // exact-kernel launch shape
-    X.B = B; X.threads = h->threads; X.smem = h->smem; X.W = h->W; X.wrap = 0;
+    X.B = B; X.threads = h->threads; X.smem = h->smem; X.W = h->W; X.wrap = 0; X.bound = ~0ULL;
     X.glab = h->smem ? nullptr : h->glab; X.ghist = h->smem ? nullptr : h->ghist;
     X.grid = h->grid_exact < B ? h->grid_exact : B;
     cudaError_t e;
@@ -355,6 +370,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
         SolveLaunch F;
         F.B = B; F.threads = h->threads_fast; F.smem = h->smem_fast; F.W = h->Wc; F.wrap = h->wrap_fast;
         F.glab = nullptr; F.ghist = nullptr;
+        F.bound = h->use_bound ? h->P.bound_fx : ~0ULL;
         F.grid = h->grid_fast < B ? h->grid_fast : B;
         io.work_counter = h->counters + 0;
         e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
@@ -362,17 +378,21 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
         h->kernels_launched++;
         if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
         // Problems the fast kernel handed back are re-solved on the device (their count is read on the device):
-        // first by the fast kernel with a full-row window (ring overflow), then by the exact kernel (label saturation).
+        // first by the fast kernel without the cost bound and with a full-row window (bound too low, ring overflow),
+        // then by the exact kernel (label saturation).
         const int32_t *pending = h->fallback_list; const int *pending_n = h->counters + 2;
-        if (h->wrap_fast && h->smem_fast_big) {
+        if ((h->wrap_fast && h->smem_fast_big) || h->use_bound) {
             SolveLaunch G = F;
-            G.threads = 1024; G.smem = h->smem_fast_big; G.W = h->W; G.wrap = 0;      // one wide block per hard problem
-            G.grid = h->sm_count < B ? h->sm_count : B; if (G.grid > 32) G.grid = 32;
+            G.bound = ~0ULL;                                                              // unbounded
+            if (h->wrap_fast && h->smem_fast_big) {
+                G.threads = 1024; G.smem = h->smem_fast_big; G.W = h->W; G.wrap = 0;      // one wide block per hard problem
+                G.grid = h->sm_count < B ? h->sm_count : B; if (G.grid > 32 && !h->use_bound) G.grid = 32;
+            }
             io.work_counter = h->counters + 3;
             io.subset = pending; io.B_dev = pending_n;
             io.fallback_list = h->fallback_list + h->max_batch; io.fallback_count = h->counters + 4;
             e = dense ? launch_fast_dense(h->P, G, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, G, io, h->desc, st);
-            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast full-row re-solve launch");
+            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast unbounded / full-row re-solve launch");
             h->kernels_launched++;
             pending = h->fallback_list + h->max_batch; pending_n = h->counters + 4;
         }
@@ -495,6 +515,23 @@ extern "C" int mpc_speed_from_jerk(mpc_handle *h, int B, const double *d_ego, co
     if (B == 0) return MPC_OK;
     if (!d_ego || !d_jerk || !d_speed) return mpc_set_error(MPC_E_INVALID, "mpc_speed_from_jerk: null pointer");
     MPC_CUDA_OK(launch_speed_from_jerk(h->P, B, d_ego, d_jerk, d_speed, (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}
+
+extern "C" int mpc_rollout_step(mpc_handle *h, int B, double *d_ego, double *d_cars_x, double *d_cars_v, double *d_cars_a,
+                                const int32_t *d_n_cars, const double *d_jerk, double dt, double min_crash_distance, double stop_x,
+                                int step, uint8_t *d_alive, double *d_selected_speed, double *d_roll_s, int roll_stride,
+                                int32_t *d_roll_len, uint8_t *d_crash_predicted, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_cars_a || !d_n_cars || !d_jerk || !d_alive || !d_selected_speed || !d_roll_s ||
+        !d_roll_len || !d_crash_predicted)
+        return mpc_set_error(MPC_E_INVALID, "mpc_rollout_step: null pointer");
+    if (step < 1 || step >= roll_stride) return mpc_set_error(MPC_E_INVALID, "mpc_rollout_step: step must be in [1, roll_stride)");
+    MPC_CUDA_OK(launch_rollout_step(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, d_jerk, dt, min_crash_distance,
+                                    stop_x, step, d_alive, d_selected_speed, d_roll_s, roll_stride, d_roll_len, d_crash_predicted,
+                                    (cudaStream_t)stream));
     h->kernels_launched = 1;
     return MPC_OK;
 }

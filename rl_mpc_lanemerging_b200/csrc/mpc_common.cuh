@@ -35,6 +35,7 @@ struct DevParams {
     // fixed-point (2^-MPC_FX_FRAC) kinematic edge-cost tables of the fast kernel, indexed by the integer
     // speed v' in [0,255], acceleration a'+16 in [0,31], jerk j'+8 in [0,15] (cells per step^n)
     unsigned vtab[256], atab[32], jtab[16];
+    unsigned long long bound_fx;   // first-pass cost bound of the fast kernel in label units (0 = none), see mpc_fast.cu
 };
 #define MPC_FX_FRAC 18
 #define MPC_FX_ONE 262144.0
@@ -160,6 +161,7 @@ struct SolveLaunch {
     size_t smem;
     int W;                  // label-array length in cells (exact: full row; fast: ring capacity)
     int wrap;               // fast kernel: ring shorter than the row
+    unsigned long long bound;   // fast kernel: cost bound in label units (~0ULL = none)
     unsigned long long *glab; unsigned *ghist;    // exact kernel global label scratch (or NULL)
 };
 

@@ -158,11 +158,20 @@ __device__ __forceinline__ unsigned long long fx_penalty(const DevParams &P, dou
     return fx_from_double(__dmul_rn(P.p.d_weight, pen));
 }
 
+// Cost bound.  Labels only grow along a path (every term of st_cy.pyx:46-50 is >= 0) and a cell keeps the arrival with
+// the smallest label, so dropping every node whose label exceeds a bound U leaves all nodes with label <= U -- label,
+// speed/acceleration code and back-pointer -- exactly as the unbounded pass computes them (induction over the layers:
+// the winner of such a node has a smaller label and survives too).  If the bounded pass reaches the horizon its answer
+// IS the unbounded answer; if it does not, the problem is solved again without the bound.  The first pass uses
+// U = d_weight * 1e6 / min_allowed_distance (DevParams::bound_fx): the cheapest possible label of a path that spends one
+// step inside a penalty zone (st_cy.pyx:34-38).  Ordinary plans never do, and the sub-trees behind those zones are
+// ~30 % of all nodes at H=50 (oracle model counts).
 struct FxTables { unsigned v[256], aj[32 * 16]; };     // aj[(a'+16)*16 + (j'+8)] = A[a'] + J[j']: one lookup, stride 17 along a window
 
 template <class Prov, bool DESC, bool WRAP, int MAXT>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
-                                                                              const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc) {
+                                                                              const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc,
+                                                                              unsigned long long bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ FastShared FS;
     __shared__ FxTables TB;
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         build_clamp_bits(P, g, CB);
         double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
         double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
-        if (tid == 0) { S.need_fallback = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
+        if (tid == 0) { S.need_fallback = 0; S.bound_hit = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
         // ---- prologue: layers 0 -> 1 -> 2 have off-grid history (st_cy.pyx:329-330): exact fp64, then quantised ----
         int imin0, imax0;
         exact_window(P, g.s0, g.ds, g.s0, est_prev, est_second, imin0, imax0);
@@ -278,6 +287,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 if (Prov::kClipAtPush) d = prov.distance_staged(t, k, s);      // pushes never land in a band
                 else { bool ob; d = prov.eval_staged(t, k, s, ob); if (ob) return; }   // st_cy.pyx:383-384
                 unsigned long long label = (w >> 16) + fx_penalty(P, d);
+                if (label > bound) { S.bound_hit = 1; return; }               // cost bound: see the note above the kernel
                 if (label >= FX_LABEL_LIMIT) { S.need_fallback = 1; return; }
                 const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
                 bp_row[k] = (uint16_t)(k - v);
@@ -339,7 +349,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             if (dhi < 0) break;                               // no successors (or last layer)
         }
         __syncthreads();
-        if (S.need_fallback) {        // saturated label / out-of-range code / ring too small: hand the problem to the exact kernel
+        // nodes were dropped by the cost bound and the horizon was not reached: the bound was too low for this problem
+        // (its best path crosses a penalty zone, or it has no full-horizon path at all) -> unbounded re-solve
+        if (S.bound_hit && bt < T - 1) S.need_fallback = 1;
+        if (S.need_fallback) {        // saturated label / out-of-range code / ring too small / bound too low: hand the problem on
             for (int k = tid; k < 2 * Wc; k += nth) buf[0][k] = FX_EMPTY;
             if (tid == 0) { int p = atomicAdd(io.fallback_count, 1); io.fallback_list[p] = b; }
             __syncthreads();
@@ -371,7 +384,7 @@ static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const
     do {                                                                                                   \
         auto k = fast_pull_kernel<Prov, DESC, WRAPV, MAXTV>;                                               \
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;                                            \
-        k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, desc, ob, dist, stride, L.W);                     \
+        k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, desc, ob, dist, stride, L.W, L.bound);                     \
     } while (0)
     if (L.threads <= 512) { if (L.wrap) MPC_LAUNCH_FAST(true, 512); else MPC_LAUNCH_FAST(false, 512); }
     else { if (L.wrap) MPC_LAUNCH_FAST(true, 1024); else MPC_LAUNCH_FAST(false, 1024); }

@@ -202,11 +202,24 @@ __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int 
     const size_t row = (size_t)bt * stride_s;
     for (int k4 = threadIdx.x * 4; k4 < stride_s; k4 += blockDim.x * 4) {
         unsigned char ob4[4]; DT d4[4];
+        // the four cells are consecutive: look the bucket up once, then only advance the edge / band cursors
+        const int jb = min(k4, g.num_s - 1) >> MPC_BUCKET_SHIFT;
+        int e = L.bucket_edge[jb], i = L.bucket_band[jb];
+        const int M = L.n_edge, m = L.n_band;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int k = k4 + c;
             bool ob = true; double d = 0.0;
-            if (k < g.num_s) d = cell_distance_sorted(L, g.sval(k), k, ob);
+            if (k < g.num_s) {
+                const double sv = g.sval(k);
+                while (e < M && L.edge[e] < sv) e++;
+                d = 1E10;
+                if (e > 0) { double x = __dsub_rn(sv, L.edge[e - 1]); d = x < d ? x : d; }
+                if (e < M) { double x = fabs(__dsub_rn(sv, L.edge[e])); d = x < d ? x : d; }
+                while (i < m && L.mband[i].y <= k) i++;
+                ob = i < m && L.mband[i].x <= k;
+                if (ob) d = 0.0;
+            }
             ob4[c] = ob ? 1 : 0; d4[c] = (DT)d;
         }
         if (vec_ok && k4 + 3 < stride_s) {
@@ -323,6 +336,41 @@ __global__ void speed_from_jerk_kernel(DevParams P, int B, const double *ego, co
     speed[b] = nv;
 }
 
+// One step of the combined controller's policy rollout (dqn.py:129-141), masked and in place: jerk -> speed
+// (control.py:160-171), predict_step_with_ego, and the per-episode bookkeeping the loop carries.
+__global__ void __launch_bounds__(128) rollout_step_kernel(DevParams P, int B, int nmax, double *ego, double *cars_x,
+                                                          double *cars_v, double *cars_a, const int32_t *n_cars,
+                                                          const double *jerk, double dt, double mcd, double stop_x,
+                                                          int step, uint8_t *alive, double *sel_speed, double *roll_s,
+                                                          int roll_stride, int32_t *roll_len, uint8_t *crash_pred) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    int b = warp;
+    double *rs = roll_s + (size_t)b * roll_stride;
+    if (!alive[b]) {                                                 // the episode's rollout ended earlier (dqn.py:140-141)
+        if (lane == 0) rs[step] = rs[step - 1];
+        return;
+    }
+    int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
+    EgoState e = {ego[4 * b], ego[4 * b + 1], ego[4 * b + 2], ego[4 * b + 3]}, eo;
+    double na = __dadd_rn(e.a, __dmul_rn(jerk[b], P.p.tick_length));    // control.py:160-171
+    na = na > P.p.a_max ? P.p.a_max : na; na = na < P.p.a_min ? P.p.a_min : na;
+    double sel = __dadd_rn(e.v, __dmul_rn(na, P.p.tick_length));
+    sel = sel > P.p.max_speed ? P.p.max_speed : sel; sel = sel < 0.0 ? 0.0 : sel;
+    size_t o = (size_t)b * nmax + lane;
+    double x = lane < n ? cars_x[o] : 0.0, v = lane < n ? cars_v[o] : 0.0, nx, nv, nacc;
+    bool cr = warp_predict_with_ego(P, lane, n, e, x, v, sel, dt, mcd, eo, nx, nv, nacc);
+    if (lane < n) { cars_x[o] = nx; cars_v[o] = nv; cars_a[o] = nacc; }
+    if (lane == 0) {
+        ego[4 * b] = eo.x; ego[4 * b + 1] = eo.y; ego[4 * b + 2] = eo.v; ego[4 * b + 3] = eo.a;
+        sel_speed[b] = sel;
+        rs[step] = get_ego_s(eo.x, eo.y);                            // rollout_s_history (dqn.py:139)
+        roll_len[b] += 1;
+        if (cr) crash_pred[b] = 1;
+        if (cr || eo.x > stop_x) alive[b] = 0;
+    }
+}
+
 // ---- host launchers (called from mpc_api.cu) -----------------------------------------------------
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
                                   const double *cv, const int32_t *n, LayerDesc *desc, double *s0, double *ds,
@@ -363,5 +411,15 @@ cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const doubl
 cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     speed_from_jerk_kernel<<<(B + 127) / 128, 128, 0, st>>>(P, B, ego, jerk, speed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
+                                const int32_t *n, const double *jerk, double dt, double mcd, double stop_x, int step,
+                                uint8_t *alive, double *sel_speed, double *roll_s, int roll_stride, int32_t *roll_len,
+                                uint8_t *crash_pred, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    rollout_step_kernel<<<(B + 3) / 4, 128, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, jerk, dt, mcd, stop_x, step, alive,
+                                                     sel_speed, roll_s, roll_stride, roll_len, crash_pred);
     return cudaGetLastError();
 }

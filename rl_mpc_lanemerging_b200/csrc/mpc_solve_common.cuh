@@ -86,6 +86,7 @@ struct BlockShared {
     unsigned long long mind_bits;
     int crash;
     int need_fallback;
+    int bound_hit;          // fast kernel: the cost bound dropped at least one node of this problem
 };
 
 // Write outputs for a finished DP: back-track from (bt, bk), then the crash test of st.py:790-802.

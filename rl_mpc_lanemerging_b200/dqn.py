@@ -79,35 +79,24 @@ class RLAgent:
         B, dev = start.batch, eng.device
         first_action = self.get_control(start)
         cur = start.clone()
-        alive = torch.ones(B, dtype=torch.bool, device=dev)
-        crash_predicted = torch.zeros(B, dtype=torch.bool, device=dev)
-        selected_speed = torch.zeros(B, dtype=torch.float64, device=dev)
-        snap, has_snap = None, torch.zeros(B, dtype=torch.bool, device=dev)
         steps = max(int(Settings.ROLLOUT_LENGTH), 1)
+        alive = torch.ones(B, dtype=torch.uint8, device=dev)
+        crash_u8 = torch.zeros(B, dtype=torch.uint8, device=dev)
+        selected_speed = torch.zeros(B, dtype=torch.float64, device=dev)
         # rollout_s_history (dqn.py:121,139): ego arclength after every rollout step the episode actually took
         roll_s = torch.zeros((B, steps + 1), dtype=torch.float64, device=dev)
         roll_s[:, 0] = _ego_s(start.ego)
-        roll_len = torch.ones(B, dtype=torch.int64, device=dev)
-        for i in range(1, steps + 1):                                               # dqn.py:129-141
+        roll_len32 = torch.ones(B, dtype=torch.int32, device=dev)
+        test = cur
+        for i in range(1, steps + 1):                                               # dqn.py:129-141, one fused kernel per step
             action = first_action if i == 1 else self.get_control(cur)
-            sel = control.get_ego_speed_from_jerk(cur.ego[:, 2].contiguous(), cur.ego[:, 3].contiguous(), action.double())
-            eo, xo, vo, ao, crashed = eng.predict_step_with_ego(*cur.args(), sel, Settings.TICK_LENGTH, Settings.COMBINATION_MIN_DISTANCE)
-            m = alive.unsqueeze(1)
-            cur = BatchedState(torch.where(m, eo, cur.ego), torch.where(m, xo, cur.cars_x), torch.where(m, vo, cur.cars_v),
-                               torch.where(m, ao, cur.cars_a), cur.n_cars)
-            selected_speed = torch.where(alive, sel, selected_speed)
-            roll_s[:, i] = torch.where(alive, _ego_s(cur.ego), roll_s[:, i - 1])
-            roll_len = roll_len + alive.long()
-            crash_predicted |= alive & crashed.bool()
-            if i == int(Settings.ST_TEST_ROLLOUTS):
-                snap, has_snap = cur.clone(), alive.clone()
-            alive = alive & ~crashed.bool() & ~(cur.ego[:, 0] > Settings.STOP_X)
-        if snap is not None:                                                        # dqn.py:142-143
-            m = has_snap.unsqueeze(1)
-            test = BatchedState(torch.where(m, snap.ego, cur.ego), torch.where(m, snap.cars_x, cur.cars_x),
-                                torch.where(m, snap.cars_v, cur.cars_v), torch.where(m, snap.cars_a, cur.cars_a), cur.n_cars)
-        else:
-            test = cur
+            eng.rollout_step(cur.args(), action.double().reshape(B).contiguous(), Settings.TICK_LENGTH,
+                             Settings.COMBINATION_MIN_DISTANCE, Settings.STOP_X, i, alive, selected_speed, roll_s, roll_len32, crash_u8)
+            if i == 1:
+                rl_speed = selected_speed.clone()                                    # every episode takes step 1: the RL command
+            if i == int(Settings.ST_TEST_ROLLOUTS) and i < steps:                   # dqn.py:142-143 (finished episodes are frozen in
+                test = cur.clone()                                                   # place, so the snapshot is the test state for all)
+        crash_predicted, roll_len = crash_u8.bool(), roll_len32.long()
         takeover = torch.zeros(B, dtype=torch.bool, device=dev)
         if Settings.CHECK_ROLLOUT_CRASH:                                            # 144-147
             takeover |= crash_predicted
@@ -115,7 +104,6 @@ class RLAgent:
             takeover |= selected_speed > Settings.DESIRED_SPEED
         if Settings.TEST_ROLLOUT_STATE:                                             # 152-155: full gap-evaluation from the rollout state
             takeover |= st.test_guaranteed_crash_from_state(test)
-        rl_speed = control.get_ego_speed_from_jerk(start.ego[:, 2].contiguous(), start.ego[:, 3].contiguous(), first_action.double())
         speed = rl_speed
         if Settings.TEST_ST_STRICTLY_BETTER:                                        # 156-197 ("b" configs)
             if Settings.REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED:

@@ -238,6 +238,20 @@ class MpcEngine:
                                                  _ptr(out), out.shape[1], self._stream()))
         return out
 
+    def rollout_step(self, state_args, jerk, dt, min_crash_distance, stop_x, step, alive, selected_speed, roll_s, roll_len,
+                     crash_predicted):
+        """K4: one masked, in-place step of the combined controller's policy rollout (dqn.py:129-141)."""
+        ego, cars_x, cars_v, cars_a, n_cars = state_args
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        assert jerk.dtype == torch.float64 and jerk.is_contiguous() and jerk.numel() == B
+        assert alive.dtype == torch.uint8 and crash_predicted.dtype == torch.uint8 and roll_len.dtype == torch.int32
+        assert roll_s.dtype == torch.float64 and roll_s.is_contiguous() and roll_s.shape[0] == B
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_rollout_step(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                                 _ptr(jerk), float(dt), float(min_crash_distance), float(stop_x), int(step),
+                                                 _ptr(alive), _ptr(selected_speed), _ptr(roll_s), roll_s.shape[1], _ptr(roll_len),
+                                                 _ptr(crash_predicted), self._stream()))
+
     def speed_from_jerk(self, ego, jerk):
         B = ego.shape[0]
         out = torch.empty(B, dtype=torch.float64, device=self.device)

@@ -10,9 +10,6 @@ geometry of control.py:366-380.  Parity of this world against SUMO's Krauss mode
 """
 from __future__ import annotations
 
-from typing import Optional
-
-import numpy as np
 import torch
 
 from . import dqn, st, synthetic
@@ -27,8 +24,9 @@ EGO_START_X = -215.0     # rampRoute departPos 40 (control.py:41-44)
 class MergeEnv:
     """Vectorised environment.  reset() -> obs [B,20] f32;  step(jerk [B]) -> (obs, reward, done, info).
 
-    The world keeps, per episode, the nmax (32) cars nearest to the action: cars that fall more than
-    SENSOR_RADIUS behind the ego or run far ahead are recycled, new ones enter at the highway start."""
+    The world keeps, per episode, the nmax (32) cars nearest to the action: a car that runs more than SENSOR_RADIUS
+    ahead of the ego is recycled, new ones enter at the highway start.  Everything stays on the device and is
+    branch-free (masks instead of host-side `if any()`), so a tick never synchronises with the host."""
 
     def __init__(self, num_envs: int, seed: int = 0, auto_reset: bool = True):
         self.B = int(num_envs)
@@ -36,51 +34,56 @@ class MergeEnv:
         self.device = self.eng.device
         self.N = self.eng.nmax
         self.seed, self.auto_reset = seed, auto_reset
-        self.episode_id = np.arange(self.B, dtype=np.int64)
-        self.next_episode = self.B
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed))
         f64 = dict(dtype=torch.float64, device=self.device)
         self.state = BatchedState(torch.zeros((self.B, 4), **f64), torch.zeros((self.B, self.N), **f64),
                                   torch.zeros((self.B, self.N), **f64), torch.zeros((self.B, self.N), **f64),
                                   torch.zeros(self.B, dtype=torch.int32, device=self.device))
         self.delay = torch.zeros(self.B, **f64)
         self.ticks = torch.zeros(self.B, dtype=torch.int32, device=self.device)
-        self.spawn_draws = np.zeros(self.B, dtype=np.int64)
+        self.episodes_started = 0
         self.max_ticks = int(Settings.MAX_EPISODE_LENGTH / Settings.TICK_LENGTH)
         self.prev_acc = torch.zeros(self.B, **f64)
-
-    # ---- initial conditions: spawner-spaced traffic on the whole road, ego at the ramp start ------------
-    def _reset_rows(self, rows: np.ndarray):
-        ids = self.episode_id[rows]
-        n = len(ids)
-        interval, speed = float(Settings.BASE_TRAFFIC_INTERVAL), float(Settings.OTHER_CAR_SPEED)
-        u = lambda d: synthetic.uniform(self.seed, ids, d)   # noqa: E731
-        d = np.arange(self.N)[None, :]
-        gaps = speed * (interval + synthetic.uniform(self.seed, ids[:, None], 16 + d))
-        gaps[:, 0] = u(16) * speed * (interval + 0.5)
-        # nearest nmax cars around the ramp end: start the platoon a little ahead of the merge area
-        xs = (EGO_START_X + float(Settings.SENSOR_RADIUS)) - np.cumsum(gaps, axis=1)
-        keep = xs >= SPAWN_X
-        cnt = keep.sum(1).astype(np.int32)
-        xs = np.where(keep, xs, 0.0)
-        z = np.sqrt(-2.0 * np.log(1.0 - u(1))) * np.cos(2.0 * np.pi * u(2))
-        if Settings.RANDOMIZE_START_SPEED:
-            v0 = np.clip(Settings.START_SPEED + Settings.START_SPEED_VARIANCE * z, Settings.MIN_START_SPEED, Settings.MAX_START_SPEED)
-        else:
-            v0 = np.full(n, float(Settings.START_SPEED))
+        self._col = torch.arange(self.N, device=self.device).unsqueeze(0)
         frac = (EGO_START_X - synthetic.RAMP_A[0]) / (synthetic.RAMP_B[0] - synthetic.RAMP_A[0])
-        ey = synthetic.RAMP_A[1] + frac * (synthetic.RAMP_B[1] - synthetic.RAMP_A[1])
-        ego = np.stack([np.full(n, EGO_START_X), np.full(n, ey), v0, np.zeros(n)], 1)
-        r = torch.from_numpy(rows).to(self.device)
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)   # noqa: E731
-        S = self.state
-        S.ego[r] = t(ego); S.cars_x[r] = t(xs); S.cars_v[r] = t(np.where(keep, speed, 0.0)); S.cars_a[r] = 0.0
-        S.n_cars[r] = t(cnt)
-        self.delay[r] = t(interval + u(3))
-        self.ticks[r] = 0; self.prev_acc[r] = 0.0
-        self.spawn_draws[rows] = 0
+        self._ego_y0 = synthetic.RAMP_A[1] + frac * (synthetic.RAMP_B[1] - synthetic.RAMP_A[1])
+
+    def _rand(self, *shape):
+        return torch.rand(shape, generator=self.gen, dtype=torch.float64, device=self.device)
+
+    # ---- initial conditions: spawner-spaced traffic (control.py:215-226), ego at the ramp start (control.py:41-44, 198-204) ----
+    def _fresh(self):
+        """A complete set of initial conditions for all B slots (cheap; rows are selected with a mask afterwards)."""
+        S = Settings
+        interval, speed = float(S.BASE_TRAFFIC_INTERVAL), float(S.OTHER_CAR_SPEED)
+        gaps = speed * (interval + self._rand(self.B, self.N))
+        gaps[:, 0] = self._rand(self.B) * speed * (interval + 0.5)
+        xs = (EGO_START_X + float(S.SENSOR_RADIUS)) - torch.cumsum(gaps, 1)
+        keep = xs >= SPAWN_X
+        n = keep.sum(1).to(torch.int32)
+        xs = torch.where(keep, xs, torch.zeros_like(xs))
+        vs = torch.where(keep, torch.full_like(xs, speed), torch.zeros_like(xs))
+        if S.RANDOMIZE_START_SPEED:
+            v0 = (S.START_SPEED + S.START_SPEED_VARIANCE * torch.randn(self.B, generator=self.gen, dtype=torch.float64, device=self.device)) \
+                .clamp(S.MIN_START_SPEED, S.MAX_START_SPEED)
+        else:
+            v0 = torch.full((self.B,), float(S.START_SPEED), dtype=torch.float64, device=self.device)
+        ego = torch.stack([torch.full_like(v0, EGO_START_X), torch.full_like(v0, self._ego_y0), v0, torch.zeros_like(v0)], 1)
+        return ego, xs, vs, n, interval + self._rand(self.B)
+
+    def _reset_where(self, mask: torch.Tensor):
+        ego, xs, vs, n, delay = self._fresh()
+        m1, S = mask.unsqueeze(1), self.state
+        S.ego = torch.where(m1, ego, S.ego); S.cars_x = torch.where(m1, xs, S.cars_x); S.cars_v = torch.where(m1, vs, S.cars_v)
+        S.cars_a = torch.where(m1, torch.zeros_like(S.cars_a), S.cars_a); S.n_cars = torch.where(mask, n, S.n_cars)
+        self.delay = torch.where(mask, delay, self.delay)
+        self.ticks = torch.where(mask, torch.zeros_like(self.ticks), self.ticks)
+        self.prev_acc = torch.where(mask, torch.zeros_like(self.prev_acc), self.prev_acc)
 
     def reset(self):
-        self._reset_rows(np.arange(self.B))
+        self._reset_where(torch.ones(self.B, dtype=torch.bool, device=self.device))
+        self.episodes_started = self.B
         return self._obs()
 
     def _obs(self):
@@ -99,41 +102,35 @@ class MergeEnv:
         acc = torch.where(clipped, (spd - st8.ego[:, 2]) / tick, acc)
         projected_jerk = (acc - self.prev_acc) / tick
         # world step: the reference predictor as dynamics (K4 kernel, in place)
+        for t in st8.args():
+            assert t.is_contiguous()
         _, _, _, _, crashed = self.eng.predict_step_with_ego(*st8.args(), spd.contiguous(), tick, S.CAR_LENGTH, inplace=True)
         crashed = crashed.bool()
         self.prev_acc = st8.ego[:, 3].clone()
         # recycle the front car once it is out of sensor range ahead; enter a new car at the back (control.py:215-226)
-        n = st8.n_cars.long()
+        n = st8.n_cars
         gone = (n > 0) & (st8.cars_x[:, 0] - st8.ego[:, 0] > float(S.SENSOR_RADIUS))
-        if bool(gone.any()):
-            r = gone.nonzero().squeeze(1)
-            for arr in (st8.cars_x, st8.cars_v, st8.cars_a):
-                arr[r] = torch.roll(arr[r], -1, dims=1)
-                arr[r, -1] = 0.0
-            st8.n_cars[r] -= 1
-        self.delay -= tick
-        spawn = (self.delay <= 0) & (st8.n_cars < self.N)
-        if bool(spawn.any()):
-            r = spawn.nonzero().squeeze(1)
-            slot = st8.n_cars[r].long()
-            st8.cars_x[r, slot] = SPAWN_X; st8.cars_v[r, slot] = float(S.OTHER_CAR_SPEED); st8.cars_a[r, slot] = 0.0
-            st8.n_cars[r] += 1
-            rows = r.cpu().numpy()
-            u = synthetic.uniform(self.seed + 7919, self.episode_id[rows], self.spawn_draws[rows]) if S.VARY_TRAFFIC_START_TIMES \
-                else np.zeros(len(rows))
-            self.delay[r] = torch.from_numpy(u + float(S.BASE_TRAFFIC_INTERVAL)).to(self.device)
-            self.spawn_draws[rows] += 1
-        self.ticks += 1
+        g1 = gone.unsqueeze(1)
+        shift = lambda a: torch.where(g1, torch.cat([a[:, 1:], torch.zeros_like(a[:, :1])], 1), a)   # noqa: E731
+        st8.cars_x, st8.cars_v, st8.cars_a = shift(st8.cars_x), shift(st8.cars_v), shift(st8.cars_a)
+        n = n - gone.to(torch.int32)
+        self.delay = self.delay - tick
+        spawn = (self.delay <= 0) & (n < self.N)
+        slot = spawn.unsqueeze(1) & (self._col == n.unsqueeze(1))
+        st8.cars_x = torch.where(slot, torch.full_like(st8.cars_x, SPAWN_X), st8.cars_x)
+        st8.cars_v = torch.where(slot, torch.full_like(st8.cars_v, float(S.OTHER_CAR_SPEED)), st8.cars_v)
+        st8.cars_a = torch.where(slot, torch.zeros_like(st8.cars_a), st8.cars_a)
+        st8.n_cars = n + spawn.to(torch.int32)
+        u = self._rand(self.B) if S.VARY_TRAFFIC_START_TIMES else torch.zeros(self.B, dtype=torch.float64, device=self.device)
+        self.delay = torch.where(spawn, u + float(S.BASE_TRAFFIC_INTERVAL), self.delay)
+        self.ticks = self.ticks + 1
         arrived = (st8.ego[:, 0] > ARRIVAL_X) & ~crashed
         timeout = (self.ticks >= self.max_ticks) & ~crashed & ~arrived
         done = crashed | arrived | timeout
         reward = dqn.slotted_reward_with_jerk(None, projected_jerk, crashed, arrived)
         info = {"crashed": crashed, "merged": arrived, "timeout": timeout, "projected_jerk": projected_jerk}
-        if self.auto_reset and bool(done.any()):
-            rows = done.nonzero().squeeze(1).cpu().numpy()
-            self.episode_id[rows] = np.arange(self.next_episode, self.next_episode + len(rows))
-            self.next_episode += len(rows)
-            self._reset_rows(rows)
+        if self.auto_reset:
+            self._reset_where(done)
         obs = self._obs()
         if not self.auto_reset:
             obs = torch.where(done.unsqueeze(1), torch.zeros_like(obs), obs)

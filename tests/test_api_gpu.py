@@ -150,3 +150,44 @@ def test_merge_env_steps(api):
             assert bool((x[b, 1:k] < x[b, :k - 1]).all())          # cars stay ordered front -> back
         done_total += int(done.sum())
     assert api["merge_gym"].JerkEnv is not None
+
+
+def test_fused_rollout_step_equals_its_pieces(api):
+    """mpc_rollout_step (one launch per rollout step) == jerk->speed + predict_step_with_ego + the masked bookkeeping of
+    dqn.py:129-141 composed from the individually parity-tested K4 entry points, bit for bit, over 5 steps."""
+    torch, st, dqn = api["torch"], api["st"], api["dqn"]
+    from rl_mpc_lanemerging_b200 import synthetic
+    from rl_mpc_lanemerging_b200.prediction import BatchedState
+    S = synthetic.make_states(96, "default", seed=11, kind="mixed")
+    eng = st.get_engine(96)
+    dev = eng.device
+    t = lambda a, dt: torch.as_tensor(a, dtype=dt, device=dev).contiguous()   # noqa: E731
+    start = BatchedState(t(S["ego"], torch.float64), t(S["cars_x"], torch.float64), t(S["cars_v"], torch.float64),
+                         torch.zeros((96, eng.nmax), dtype=torch.float64, device=dev), t(S["n_cars"], torch.int32))
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    B, steps, Se = 96, 5, api["Settings"]
+    fused, ref = start.clone(), start.clone()
+    alive = torch.ones(B, dtype=torch.uint8, device=dev); crash = torch.zeros(B, dtype=torch.uint8, device=dev)
+    sel = torch.zeros(B, dtype=torch.float64, device=dev); rlen = torch.ones(B, dtype=torch.int32, device=dev)
+    rs = torch.zeros((B, steps + 1), dtype=torch.float64, device=dev); rs[:, 0] = dqn._ego_s(start.ego)
+    r_alive = torch.ones(B, dtype=torch.bool, device=dev); r_crash = torch.zeros(B, dtype=torch.bool, device=dev)
+    r_sel, r_len, r_rs = sel.clone(), rlen.clone(), rs.clone()
+    for i in range(1, steps + 1):
+        jerk = (torch.rand(B, generator=g, dtype=torch.float64, device=dev) - 0.5) * 12.0
+        eng.rollout_step(fused.args(), jerk, Se.TICK_LENGTH, Se.COMBINATION_MIN_DISTANCE, Se.STOP_X, i, alive, sel, rs, rlen, crash)
+        s1 = eng.speed_from_jerk(ref.ego, jerk)
+        eo, xo, vo, ao, cr = eng.predict_step_with_ego(*ref.args(), s1, Se.TICK_LENGTH, Se.COMBINATION_MIN_DISTANCE)
+        m = r_alive.unsqueeze(1)
+        ref = BatchedState(torch.where(m, eo, ref.ego), torch.where(m, xo, ref.cars_x), torch.where(m, vo, ref.cars_v),
+                           torch.where(m, ao, ref.cars_a), ref.n_cars)
+        r_sel = torch.where(r_alive, s1, r_sel)
+        r_rs[:, i] = torch.where(r_alive, dqn._ego_s(ref.ego), r_rs[:, i - 1])
+        r_len = r_len + r_alive.int()
+        r_crash |= r_alive & cr.bool()
+        r_alive = r_alive & ~cr.bool() & ~(ref.ego[:, 0] > Se.STOP_X)
+        for a, b in zip(fused.args(), ref.args()):
+            assert torch.equal(a, b)
+        assert torch.equal(alive.bool(), r_alive) and torch.equal(crash.bool(), r_crash)
+        assert torch.equal(sel, r_sel) and torch.equal(rlen, r_len)
+        assert torch.allclose(rs, r_rs, rtol=0, atol=1e-12)         # arclength: kernel fp64 get_ego_s vs the torch expression
+    assert 0 < int(r_alive.sum()) and int(r_crash.sum()) > 0        # both branches exercised

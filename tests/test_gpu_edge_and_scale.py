@@ -131,3 +131,28 @@ def test_full_size_properties_h50(oracle):
         n = int(ref["reached_t"][i]) + 1
         assert not ob[i, np.arange(1, n), fi[i, 1:n]].any()
     eng.close()
+
+
+@pytest.mark.parametrize("H,traffic,B", [(25, "low", 16), (25, "fast", 16), (100, "default", 6), (100, "moderate", 6)])
+def test_horizon_and_density_sweep(oracle, H, traffic, B):
+    """BASELINE.json configs[4]: traffic-density sweep x horizon in {25, 100} (50 and 17 are covered elsewhere).  Exact mode is
+    index-identical to the oracle, fast mode within tolerance (H=100 runs the fast kernel behind a ring window)."""
+    import torch
+    from rl_mpc_lanemerging_b200 import synthetic
+    from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
+    op = oracle.horizon_params(H)
+    eng = MpcEngine(helpers.mpc_params_from_oracle(op), device=0, max_batch=B)
+    assert eng.num_t == H + 1
+    S = synthetic.make_states(B, traffic, seed=37, kind="mixed")
+    ref = helpers.oracle_plan_batch(oracle, op, S, H + 1)
+    D = states_to_device(S, "cuda:0")
+    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
+    ex = eng.plan(*a, mode="exact")
+    assert np.array_equal(ex["idx"].cpu().numpy(), ref["idx"]) and np.array_equal(ex["cost"].cpu().numpy(), ref["cost"])
+    fa = eng.plan(*a, mode="fast")
+    torch.cuda.synchronize()
+    assert np.array_equal(fa["reached_t"].cpu().numpy(), ref["reached_t"])
+    ok = ref["cost"] > 0
+    assert np.all(helpers.rel(fa["cost"].cpu().numpy()[ok], ref["cost"][ok]) < 1e-6)
+    assert (fa["idx"].cpu().numpy() == ref["idx"]).all(1).sum() >= B - 1
+    eng.close()
