@@ -167,8 +167,8 @@ def solve_fast_model(p, obstacles, distances, s_values, delta_t, v0, a0, f32_lab
     return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value)
 
 
-def solve_fast_model_ex(p, obstacles, distances, s_values, delta_t, v0, a0, prune_cost=0.0, stride=1):
-    """Fast-kernel model with the cost bound (labels above prune_cost dropped; 0 = none) and the scout stride.
+def solve_fast_model_ex(p, obstacles, distances, s_values, delta_t, v0, a0, prune_cost=0.0):
+    """Fast-kernel model with the cost bound (nodes with a label above prune_cost are dropped; 0 = none).
     Also returns the node / push counts."""
     nt, ns = obstacles.shape
     idx = np.zeros(nt, np.int32); seq = np.zeros(nt, np.float64); cost = C.c_double(); counts = (C.c_int64 * 2)()
@@ -178,7 +178,7 @@ def solve_fast_model_ex(p, obstacles, distances, s_values, delta_t, v0, a0, prun
     fxb = int(round(prune_cost * 262144.0)) if prune_cost else 0
     r = lib().orc_solve_fast_model_ex(C.byref(p), nt, ns, obstacles.ctypes.data_as(C.c_void_p), _dp(distances), _dp(s_values),
                                       C.c_double(delta_t), C.c_double(v0), C.c_double(a0), C.c_int(0), C.c_uint64(fxb),
-                                      C.c_int(stride), _ip(idx), _dp(seq), C.byref(cost), counts)
+                                      _ip(idx), _dp(seq), C.byref(cost), counts)
     return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value, nodes=int(counts[0]), pushes=int(counts[1]))
 
 

@@ -384,10 +384,10 @@ static uint64_t fx(double x) { return (uint64_t)llrint(x * FXONE); }
 
 int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
                             const double *distances, const double *s_values, double delta_t,
-                            double v0, double a0, int f32_labels, uint64_t prune_fx, int stride,
+                            double v0, double a0, int f32_labels, uint64_t prune_fx,
                             int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
-    /* prune_fx != 0: labels above it are dropped (push-time test, see the kernel's cost bound); stride > 1: the scout
-     * pass, which only enters cells whose index is a multiple of `stride` from layer 2 on; counts[0..1] = nodes, pushes */
+    /* prune_fx != 0: nodes whose label exceeds it are dropped (the fast kernel's cost bound, mpc_fast.cu);
+     * counts[0..1] = nodes expanded, pushes */
     int64_t n_nodes = 0, n_push = 0;
     double dsn = p->s_disc, dt = p->t_disc;
     double jlo = p->j_min * dt * dt * dt / dsn, jhi = p->j_max * dt * dt * dt / dsn;
@@ -437,7 +437,7 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                 double kin = p->v_weight * ((v - p->desired_speed) * (v - p->desired_speed)) + p->a_weight * (a * a) + p->j_weight * (j * j);
                 uint64_t tot = lab[1][k1] + fx(kin); float totf = labf[1][k1] + (float)kin;
                 int vn = kk - k1;
-                if ((stride > 1 && kk % stride) || (prune_fx && tot > prune_fx)) continue;
+                if (prune_fx && tot > prune_fx) continue;
                 n_push++;
                 if (BETTER(tot, totf, vn, kk, 0)) { lab[0][kk] = tot; labf[0][kk] = totf; vv[0][kk] = vn; aa[0][kk] = vn - k1; has[0][kk] = 1; }
                 if (kk < dlo) dlo = kk; if (kk > dhi) dhi = kk;
@@ -447,34 +447,6 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
         /* pass t: finalise layer t (buffer t&1), push into layer t+1 */
         for (int t = 2; t < num_t && dhi >= 0; t++) {
             int cur = t & 1, nxt = cur ^ 1, any = 0, nlo = num_s, nhi = -1, bk = -1; uint64_t bl = 0; float blf = 0;
-            uint64_t beam_cut = 0;
-            uint8_t *keep = NULL;
-            if (stride <= -1000) {                  /* experiment: spatial beam, one survivor (min final label) per bucket of G cells */
-                int G = -stride - 1000; keep = (uint8_t *)calloc(num_s, 1);
-                for (int b0 = (dlo / G) * G; b0 <= dhi; b0 += G) {
-                    int bestk = -1; uint64_t bestl = 0;
-                    for (int k = b0 > dlo ? b0 : dlo; k < b0 + G && k <= dhi; k++) if (has[cur][k] && !obstacles[(size_t)t * num_s + k]) {
-                        double d = distances[(size_t)t * num_s + k];
-                        double pen = (d < p->min_allowed_distance) ? 1000000.0 / (d > 1.0 ? d : 1.0) : (double)(1.0f / (float)d);
-                        uint64_t l = lab[cur][k] + fx(p->d_weight * pen);
-                        if (bestk < 0 || l < bestl) { bestk = k; bestl = l; }
-                    }
-                    if (bestk >= 0) keep[bestk] = 1;
-                }
-            } else
-            if (stride < 0) {                       /* experiment: top-W beam, W = -stride (final labels) */
-                int W = -stride, cnt = 0; uint64_t *tmp = (uint64_t *)malloc(8 * (size_t)(dhi - dlo + 1));
-                for (int k = dlo; k <= dhi; k++) if (has[cur][k] && !obstacles[(size_t)t * num_s + k]) {
-                    double d = distances[(size_t)t * num_s + k];
-                    double pen = (d < p->min_allowed_distance) ? 1000000.0 / (d > 1.0 ? d : 1.0) : (double)(1.0f / (float)d);
-                    tmp[cnt++] = lab[cur][k] + fx(p->d_weight * pen);
-                }
-                if (cnt > W) { /* W-th smallest */
-                    for (int i = 0; i < W; i++) { int m = i; for (int j = i + 1; j < cnt; j++) if (tmp[j] < tmp[m]) m = j; uint64_t x = tmp[i]; tmp[i] = tmp[m]; tmp[m] = x; }
-                    beam_cut = tmp[W - 1];
-                }
-                free(tmp);
-            }
             for (int k = dlo; k <= dhi; k++) {
                 if (!has[cur][k]) continue;
                 has[cur][k] = 0;
@@ -488,8 +460,6 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                 float labelf = fmaf((float)p->d_weight, penf, labf[cur][k]);
                 int v = vv[cur][k], a = aa[cur][k];
                 if (prune_fx && label > prune_fx) continue;
-                if (beam_cut && label > beam_cut) continue;
-                if (keep && !keep[k]) continue;
                 previous[id] = k - v; any = 1; n_nodes++;
                 int better = bk < 0 || (f32_labels ? labelf < blf : label < bl);
                 if (better) { bk = k; bl = label; blf = labelf; }
@@ -504,7 +474,7 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                 for (int kk = wlo; kk <= whi; kk++) {
                     int vn = kk - k, an = vn - v, jn = an - a;
                     uint64_t tot = label + vtab[vn] + atab[an + 16] + jtab[jn + 8];
-                    if ((stride > 1 && kk % stride) || (prune_fx && tot > prune_fx)) continue;
+                    if (prune_fx && tot > prune_fx) continue;
                     n_push++;
                     float fv = (float)vn - vdes, fa = (float)an, fj = (float)jn;
                     float totf = labelf + fmaf(cvf * fv, fv, fmaf(caf * fa, fa, cjf * fj * fj));
@@ -512,7 +482,6 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                     if (kk < nlo) nlo = kk; if (kk > nhi) nhi = kk;
                 }
             }
-            free(keep);
             if (!any) break;
             best_t = t; best_k = bk; best_lab = bl; best_labf = blf;
             dlo = nlo; dhi = nhi;
@@ -530,7 +499,7 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
 int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
                          const double *distances, const double *s_values, double delta_t,
                          double v0, double a0, int f32_labels, int *idx_out, double *s_seq_out, double *cost_out) {
-    return orc_solve_fast_model_ex(p, num_t, num_s, obstacles, distances, s_values, delta_t, v0, a0, f32_labels, 0, 1,
+    return orc_solve_fast_model_ex(p, num_t, num_s, obstacles, distances, s_values, delta_t, v0, a0, f32_labels, 0,
                                    idx_out, s_seq_out, cost_out, NULL);
 }
 

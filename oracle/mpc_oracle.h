@@ -87,7 +87,7 @@ int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_
 
 int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
                             const double *distances, const double *s_values, double delta_t,
-                            double v0, double a0, int f32_labels, uint64_t prune_fx, int stride,
+                            double v0, double a0, int f32_labels, uint64_t prune_fx,
                             int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts);
 
 /* Sum of st.cost (st.py:140-144) along an index path with the solver's history convention. */

@@ -137,6 +137,10 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     if (p->d_weight > 0 && p->min_allowed_distance > 0) {
         double zone = p->d_weight * 1000000.0 / fmax(p->min_allowed_distance, 1.0);
         if (zone > 64.0) D->bound_fx = (unsigned long long)llrint(zone * MPC_FX_ONE) - 2;
+        // band cell range vs metric band edge differ by < 3 cells (int() of the car position, of CAR_LENGTH/ds and of the
+        // uncertainty, st.py:52-66): cells within floor(min_allowed/ds) - 4 of a band are strictly inside the zone
+        int zc = (int)floor(p->min_allowed_distance / ds) - 4;
+        D->zone_cells = (D->bound_fx && zc > 0) ? zc : 0;
     }
     return MPC_OK;
 }
@@ -378,21 +382,18 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
         h->kernels_launched++;
         if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
         // Problems the fast kernel handed back are re-solved on the device (their count is read on the device):
-        // first by the fast kernel without the cost bound and with a full-row window (bound too low, ring overflow),
-        // then by the exact kernel (label saturation).
+        // first by the fast kernel with a full-row window (ring overflow), then by the exact kernel (label saturation).
+        // (A cost bound that proved too low is handled inside the kernel: the same block repeats the problem without it.)
         const int32_t *pending = h->fallback_list; const int *pending_n = h->counters + 2;
-        if ((h->wrap_fast && h->smem_fast_big) || h->use_bound) {
+        if (h->wrap_fast && h->smem_fast_big) {
             SolveLaunch G = F;
-            G.bound = ~0ULL;                                                              // unbounded
-            if (h->wrap_fast && h->smem_fast_big) {
-                G.threads = 1024; G.smem = h->smem_fast_big; G.W = h->W; G.wrap = 0;      // one wide block per hard problem
-                G.grid = h->sm_count < B ? h->sm_count : B; if (G.grid > 32 && !h->use_bound) G.grid = 32;
-            }
+            G.threads = 1024; G.smem = h->smem_fast_big; G.W = h->W; G.wrap = 0;      // one wide block per hard problem
+            G.grid = h->sm_count < B ? h->sm_count : B; if (G.grid > 32) G.grid = 32;
             io.work_counter = h->counters + 3;
             io.subset = pending; io.B_dev = pending_n;
             io.fallback_list = h->fallback_list + h->max_batch; io.fallback_count = h->counters + 4;
             e = dense ? launch_fast_dense(h->P, G, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, G, io, h->desc, st);
-            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast unbounded / full-row re-solve launch");
+            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast full-row re-solve launch");
             h->kernels_launched++;
             pending = h->fallback_list + h->max_batch; pending_n = h->counters + 4;
         }

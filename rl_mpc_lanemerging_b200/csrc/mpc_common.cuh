@@ -36,6 +36,7 @@ struct DevParams {
     // speed v' in [0,255], acceleration a'+16 in [0,31], jerk j'+8 in [0,15] (cells per step^n)
     unsigned vtab[256], atab[32], jtab[16];
     unsigned long long bound_fx;   // first-pass cost bound of the fast kernel in label units (0 = none), see mpc_fast.cu
+    int zone_cells;                // cells next to a band that are certainly inside its penalty zone (>= 0)
 };
 #define MPC_FX_FRAC 18
 #define MPC_FX_ONE 262144.0

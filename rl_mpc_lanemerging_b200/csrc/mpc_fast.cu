@@ -162,7 +162,7 @@ __device__ __forceinline__ unsigned long long fx_penalty(const DevParams &P, dou
 // the smallest label, so dropping every node whose label exceeds a bound U leaves all nodes with label <= U -- label,
 // speed/acceleration code and back-pointer -- exactly as the unbounded pass computes them (induction over the layers:
 // the winner of such a node has a smaller label and survives too).  If the bounded pass reaches the horizon its answer
-// IS the unbounded answer; if it does not, the problem is solved again without the bound.  The first pass uses
+// IS the unbounded answer; if it does not, the same block solves the problem again without the bound.  The first pass uses
 // U = d_weight * 1e6 / min_allowed_distance (DevParams::bound_fx): the cheapest possible label of a path that spends one
 // step inside a penalty zone (st_cy.pyx:34-38).  Ordinary plans never do, and the sub-trees behind those zones are
 // ~30 % of all nodes at H=50 (oracle model counts).
@@ -204,10 +204,17 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         else { prov.ob_base = dense_ob + (size_t)b * T * dense_stride;
                prov.d_base = reinterpret_cast<decltype(prov.d_base)>(dense_d) + (size_t)b * T * dense_stride;
                prov.stride = dense_stride; }
-        prov.load(1);
         build_clamp_bits(P, g, CB);
-        double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
-        double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
+        const double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
+        const double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
+        int bt = 0; unsigned long long best_word = 0ULL;      // deepest non-empty layer and its (label << 16 | k)
+        int dlo = 0, dhi = -1;
+        // first attempt under the cost bound (and with its penalty zones closed), second attempt without -- see the note above
+        unsigned long long bnd = bound;
+        int zone = (Prov::kClipAtPush && bound != FX_EMPTY) ? P.zone_cells : 0;
+      for (;;) {
+        prov.load(1);
+        bt = 0; best_word = 0ULL; dlo = 0; dhi = -1;
         if (tid == 0) { S.need_fallback = 0; S.bound_hit = 0; for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; } s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0; }
         // ---- prologue: layers 0 -> 1 -> 2 have off-grid history (st_cy.pyx:329-330): exact fp64, then quantised ----
         int imin0, imax0;
@@ -234,8 +241,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         if (T > 3) prov.load(3);
         __syncthreads();
         if (T > 3) prov.store(3);
-        int bt = 0; unsigned long long best_word = 0ULL;      // deepest non-empty layer and its (label << 16 | k)
-        int dlo = 0, dhi = -1;
         bool done = false;
         if (S.nhi[1] < 0) done = true;                        // nothing reachable at layer 1: best node is (0,0)
         else {
@@ -279,6 +284,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
             unsigned long long mybest = FX_EMPTY;
             int mylo = INT_MAX, myhi = -1;
+            bool hit = false;                                 // this thread dropped a node / closed a zone cell under the bound
             const bool last = (t == T - 1);
             auto process = [&](const int k, const int rk, const unsigned long long w) {
                 cur[rk] = FX_EMPTY;                           // this buffer receives layer t+2
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 if (Prov::kClipAtPush) d = prov.distance_staged(t, k, s);      // pushes never land in a band
                 else { bool ob; d = prov.eval_staged(t, k, s, ob); if (ob) return; }   // st_cy.pyx:383-384
                 unsigned long long label = (w >> 16) + fx_penalty(P, d);
-                if (label > bound) { S.bound_hit = 1; return; }               // cost bound: see the note above the kernel
+                if (label > bnd) { hit = true; return; }                      // cost bound: see the note above the kernel
                 if (label >= FX_LABEL_LIMIT) { S.need_fallback = 1; return; }
                 const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
                 bp_row[k] = (uint16_t)(k - v);
@@ -299,13 +305,17 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 if (n <= 0) return;
                 const int vn = wlo - k, an = vn - v, jn = an - a;      // table indices stay in range: derive_params() validated the limits
                 int2 b0, b1;
-                prov.bands_near(t + 1, wlo, b0, b1);
-                // bit e of `open` = successor e is not inside an obstacle band of layer t+1 (st_cy.pyx:383-384)
+                prov.bands_near(t + 1, max(wlo - zone, 0), b0, b1);
+                // bit e of `open` = successor e is not inside an obstacle band of layer t+1 (st_cy.pyx:383-384) -- nor, under
+                // the cost bound, within `zone` cells of one: every such cell is closer than MIN_ALLOWED_DISTANCE to the band's
+                // metric edge, its penalty alone exceeds the bound, the node would be dropped when it is finalised
                 unsigned open = (1u << n) - 1;
                 {
-                    const int l0 = max(b0.x - wlo, 0), h0 = min(b0.y - wlo, n), l1 = max(b1.x - wlo, 0), h1 = min(b1.y - wlo, n);
+                    const int l0 = max(b0.x - zone - wlo, 0), h0 = b0.x == INT_MAX ? 0 : min(b0.y + zone - wlo, n);
+                    const int l1 = max(b1.x - zone - wlo, 0), h1 = b1.x == INT_MAX ? 0 : min(b1.y + zone - wlo, n);
                     if (h0 > l0) open &= ~(((1u << h0) - 1) & ~((1u << l0) - 1));
                     if (h1 > l1) open &= ~(((1u << h1) - 1) & ~((1u << l1) - 1));
+                    if (zone && open != (1u << n) - 1) hit = true;          // (counts real band cells too: only costs a spare retry)
                 }
                 mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
                 int r = ring(wlo);
@@ -337,7 +347,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             }
             for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, mybest, o); mybest = x < mybest ? x : mybest; }
             mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
+            hit = __any_sync(FULL, hit);
             if (lane == 0) {
+                if (hit) S.bound_hit = 1;
                 if (mybest != FX_EMPTY) atomicMin(&s_layer_best[par], mybest);
                 if (myhi >= 0) { atomicMin(&S.nlo[n3], mylo); atomicMax(&S.nhi[n3], myhi); }
             }
@@ -350,8 +362,15 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         }
         __syncthreads();
         // nodes were dropped by the cost bound and the horizon was not reached: the bound was too low for this problem
-        // (its best path crosses a penalty zone, or it has no full-horizon path at all) -> unbounded re-solve
-        if (S.bound_hit && bt < T - 1) S.need_fallback = 1;
+        // (its best path crosses a penalty zone, or it has no full-horizon path at all) -> solve it again without
+        if (bnd != FX_EMPTY && S.bound_hit && bt < T - 1 && !S.need_fallback) {
+            for (int k = tid; k < 2 * Wc; k += nth) buf[0][k] = FX_EMPTY;
+            bnd = FX_EMPTY; zone = 0;
+            __syncthreads();
+            continue;
+        }
+        break;
+      }
         if (S.need_fallback) {        // saturated label / out-of-range code / ring too small / bound too low: hand the problem on
             for (int k = tid; k < 2 * Wc; k += nth) buf[0][k] = FX_EMPTY;
             if (tid == 0) { int p = atomicAdd(io.fallback_count, 1); io.fallback_list[p] = b; }

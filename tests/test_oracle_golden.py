@@ -92,3 +92,29 @@ def test_rollout_pieces_match_reference(oracle):
         assert np.array_equal(oracle.state_vector(p, st), G["state_vec"][b])
         assert oracle.speed_from_jerk(p, st.ego_v, st.ego_a, G["jerk"][b]) == G["speed"][b]
         assert oracle.path_mean_abs_jerk(G["jerk_paths"][b], st.ego_v, st.ego_a, 0.2) == G["mean_abs_jerk"][b]
+
+
+def test_cost_bound_is_exact_when_the_horizon_is_reached(oracle):
+    """The fast kernel's first attempt drops every node whose label exceeds a bound (mpc_fast.cu).  In the CPU model of
+    that kernel: whenever the bounded pass reaches the horizon its path and cost ARE the unbounded ones -- for the
+    kernel's own bound (one step inside a penalty zone), for a bound just above the optimum, and it never reaches the
+    horizon with a bound below the optimum."""
+    G = dict(np.load(os.path.join(GOLD, "plan_h17.npz")))
+    p = oracle.default_params()
+    zone = p.d_weight * 1e6 / max(p.min_allowed_distance, 1.0)
+    reached_bounded = pruned = 0
+    for b in range(0, G["ego"].shape[0], 3):
+        stt = helpers.oracle_state(oracle, G, b)
+        ob, di, sv = oracle.build_grid(p, stt)
+        full = oracle.solve_fast_model_ex(p, ob, di, sv, p.t_disc, stt.ego_v, stt.ego_a)
+        feasible = full["reached_t"] == ob.shape[0] - 1
+        for bound in (zone, full["cost"] + 1e-3, full["cost"] * 0.99):
+            r = oracle.solve_fast_model_ex(p, ob, di, sv, p.t_disc, stt.ego_v, stt.ego_a, prune_cost=bound)
+            if r["reached_t"] == ob.shape[0] - 1:
+                assert feasible and bound >= full["cost"]
+                assert np.array_equal(r["idx"], full["idx"]) and r["cost"] == full["cost"]
+                reached_bounded += 1
+                pruned += r["nodes"] < full["nodes"]
+            else:
+                assert (not feasible) or bound < full["cost"]
+    assert reached_bounded > 40 and pruned > 20
