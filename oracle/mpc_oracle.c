@@ -399,6 +399,7 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
     for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * dsn / dt - p->desired_speed) * (v * dsn / dt - p->desired_speed); vtab[v] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
     for (int i = 0; i < 32; i++) { double acc = (i - 16) * dsn / (dt * dt), x = p->a_weight * acc * acc; atab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
     for (int i = 0; i < 16; i++) { double jk = (i - 8) * dsn / (dt * dt * dt), x = p->j_weight * jk * jk; jtab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
+    const float kwf = (float)(p->d_weight * FXONE);
     float cvf = (float)(p->v_weight * (dsn / dt) * (dsn / dt)), caf = (float)(p->a_weight * (dsn / (dt * dt)) * (dsn / (dt * dt)));
     float cjf = (float)(p->j_weight * (dsn / (dt * dt * dt)) * (dsn / (dt * dt * dt))), vdes = (float)(p->desired_speed * dt / dsn);
     double delta_s = s_values[1] - s_values[0], start_s = s_values[0];
@@ -454,8 +455,10 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                 if (obstacles[id]) continue;
                 double d = distances[id];
                 float df = (float)d;
-                double pen = (d < p->min_allowed_distance) ? 1000000.0 / (d > 1.0 ? d : 1.0) : (double)(1.0f / df);
-                uint64_t label = lab[cur][k] + fx(p->d_weight * pen);
+                /* zone: fp64 as the reference; elsewhere d_w/d in fp32: rint(kw * (1.0f / (float)d)), the kernel's fx_inv_penalty */
+                uint64_t penfx = (d < p->min_allowed_distance) ? fx(p->d_weight * (1000000.0 / (d > 1.0 ? d : 1.0)))
+                                                               : (uint64_t)lrintf(kwf * (1.0f / df));
+                uint64_t label = lab[cur][k] + penfx;
                 float penf = (d < p->min_allowed_distance) ? 1000000.0f / fmaxf(df, 1.0f) : 1.0f / df;
                 float labelf = fmaf((float)p->d_weight, penf, labf[cur][k]);
                 int v = vv[cur][k], a = aa[cur][k];

@@ -141,7 +141,11 @@ static int derive_params(const mpc_params *p, DevParams *D) {
         // uncertainty, st.py:52-66): cells within floor(min_allowed/ds) - 4 of a band are strictly inside the zone
         int zc = (int)floor(p->min_allowed_distance / ds) - 4;
         D->zone_cells = (D->bound_fx && zc > 0) ? zc : 0;
+        // LayerDesc::blk joins a car's band with the two penalty zones next to it into ONE interval; that is the exact set of
+        // blocked cells as long as the zones (m wide) cover the few cells by which int() rounding lets the band miss its edges
+        D->zone_ok = (D->bound_fx && p->min_allowed_distance >= 4.0 * ds && p->min_allowed_distance >= 1.0) ? 1 : 0;
     }
+    D->kw = (float)(p->d_weight * MPC_FX_ONE);
     return MPC_OK;
 }
 
@@ -162,7 +166,7 @@ static int env_int(const char *name, int lo, int hi, int dflt) {
 static int configure(mpc_handle *h) {
     const DevParams &P = h->P;
     h->W = (P.num_s_max + 7) & ~7;
-    const size_t static_smem = 8192;                 // static shared of the kernels (upper bound) + 1 KB/block reserve
+    const size_t static_smem = 11264;                // static shared of the kernels (upper bound: 10.2 KB in the fast kernel) + 1 KB/block reserve
     // ---- exact kernel: 24 B per cell, full row ----
     size_t need = (size_t)h->W * 24;
     if (need + static_smem <= h->smem_optin) {
@@ -177,7 +181,7 @@ static int configure(mpc_handle *h) {
         h->grid_exact = h->sm_count * 2;
     }
     // ---- fast kernel: 16 B per cell (one packed 64-bit word, double buffered) behind a ring window ----
-    const size_t clamp_bytes = 2 * (((size_t)P.num_s_max + 31) / 32) * 4 + 16;   // two bit arrays behind the word buffers
+    const size_t clamp_bytes = (4 * (((size_t)P.num_s_max + 31) / 32) + 4) * 4 + 16;   // behind the word buffers: two clamp bit arrays, two blocked-cell bit arrays (+2 words each)
     // Ring sized for two blocks per SM when that still covers 2/3 of the row (frontier spans measured: <= 0.6 of the row on
     // ordinary traffic; H=50: ring = 0.73 row, 7.7+0.5 ms vs 9.7 ms with one block per SM), else for one block per SM (long horizons).  MPC_FAST_BLOCKS=32|64 overrides (1 | 2 blocks/SM).
     const size_t cap2 = ((h->smem_optin + 1024) / 2 - 1024 - static_smem - clamp_bytes) / 16;

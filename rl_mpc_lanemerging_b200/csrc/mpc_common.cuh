@@ -37,6 +37,8 @@ struct DevParams {
     unsigned vtab[256], atab[32], jtab[16];
     unsigned long long bound_fx;   // first-pass cost bound of the fast kernel in label units (0 = none), see mpc_fast.cu
     int zone_cells;                // cells next to a band that are certainly inside its penalty zone (>= 0)
+    int zone_ok;                   // LayerDesc::blk (band + exact penalty zone per car) is one interval per car: lean bounded pass allowed
+    float kw;                      // (float)(d_weight * 2^MPC_FX_FRAC): 1/d penalty in label units = rint(kw * (1.0f / (float)d))
 };
 #define MPC_FX_FRAC 18
 #define MPC_FX_ONE 262144.0
@@ -86,7 +88,7 @@ struct LayerDesc {
     int n_act;                   // cars in reference order (exact kernel, rasteriser)
     int n_edge;                  // sorted distance-field edges (= 2 * n_act)
     int n_band;                  // obstacle bands merged into disjoint intervals
-    int pad;
+    int n_blk;                   // blocked intervals (see blk)
     double ef[MPC_NMAX];
     double eb[MPC_NMAX];
     int2 band[MPC_NMAX];
@@ -95,15 +97,20 @@ struct LayerDesc {
     int2 mband[MPC_NMAX];                    // disjoint [x, y), ascending
     unsigned char bucket_edge[MPC_MAX_BUCKETS];   // #edges  <  s_values[64*j]
     unsigned char bucket_band[MPC_MAX_BUCKETS];   // #merged bands with y <= 64*j
+    // cells a bounded plan can never use: in an obstacle band, or closer than MIN_ALLOWED_DISTANCE to a distance-field
+    // edge (penalty 1e6/max(d,1), st_cy.pyx:34-38).  Per car one interval [first cell with |s-ef| < m, last cell with
+    // |s-eb| < m] (exact fp64 tests) joined with its band; merged into disjoint [x, y), ascending.
+    int2 blk[MPC_NMAX];
 };
 
 // the part of a LayerDesc the fast kernel stages in shared memory
 struct LayerSearch {
-    int n_edge, n_band, pad0, pad1;
+    int n_edge, n_band, n_blk, pad1;
     double edge[2 * MPC_NMAX];
     int2 mband[MPC_NMAX];
     unsigned char bucket_edge[MPC_MAX_BUCKETS];
     unsigned char bucket_band[MPC_MAX_BUCKETS];
+    int2 blk[MPC_NMAX];
 };
 
 // distance-field value / obstacle flag through the sorted structure: bit-identical to cell_distance()

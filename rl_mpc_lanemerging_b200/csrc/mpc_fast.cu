@@ -25,7 +25,7 @@
 #define EMPTY_LAB 0x7ff0000000000000ULL      // +inf
 
 struct __align__(16) FastShared {
-    LayerSearch layer[3];        // first: staged with 16-byte vector stores; layer t lives in slot t % 3
+    LayerSearch layer[4];        // first: staged with 16-byte vector stores; layer t lives in slot t & 3
     BlockShared S;
 };
 static_assert(sizeof(LayerSearch) % 16 == 0, "LayerSearch buffers must stay 16-byte aligned");
@@ -33,25 +33,25 @@ static_assert(sizeof(LayerSearch) % 16 == 0, "LayerSearch buffers must stay 16-b
 // cell providers for the fast kernel ------------------------------------------------------------------
 struct FastDescProv {
     const LayerDesc *base;      // desc + b*num_t
-    LayerSearch *sm;            // two staging buffers in shared memory
+    LayerSearch *sm;            // four staging buffers in shared memory
     int4 pre;                   // prefetch register
     // a LayerSearch is a contiguous tail of LayerDesc except for its 16-byte header
     static constexpr int kTail = (int)(sizeof(LayerSearch) - 16) / 16;
     __device__ __forceinline__ void load(int t) {          // issue the global loads of layer t (no wait)
         const LayerDesc *src = base + t;
         if (threadIdx.x < kTail) pre = reinterpret_cast<const int4 *>(reinterpret_cast<const char *>(src) + offsetof(LayerDesc, edge))[threadIdx.x];
-        else if (threadIdx.x == kTail) pre = make_int4(src->n_edge, src->n_band, 0, 0);
+        else if (threadIdx.x == kTail) pre = make_int4(src->n_edge, src->n_band, src->n_blk, 0);
     }
-    __device__ __forceinline__ void store(int t) {         // park them in slot t % 3
-        LayerSearch *dst = sm + (t % 3);
+    __device__ __forceinline__ void store(int t) {         // park them in slot t & 3
+        LayerSearch *dst = sm + (t & 3);
         if (threadIdx.x < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(dst) + 16)[threadIdx.x] = pre;
         else if (threadIdx.x == kTail) *reinterpret_cast<int4 *>(dst) = pre;
     }
     static constexpr bool kClipAtPush = true;               // successors are tested against the next layer's bands before the push
-    __device__ __forceinline__ double eval_staged(int t, int k, double s, bool &ob) const { return cell_distance_sorted(sm[t % 3], s, k, ob); }
+    __device__ __forceinline__ double eval_staged(int t, int k, double s, bool &ob) const { return cell_distance_sorted(sm[t & 3], s, k, ob); }
     // distance only (the caller knows the cell is not in a band)
     __device__ __forceinline__ double distance_staged(int t, int k, double s) const {
-        const LayerSearch &L = sm[t % 3];
+        const LayerSearch &L = sm[t & 3];
         int e = L.bucket_edge[k >> MPC_BUCKET_SHIFT], M = L.n_edge;
         while (e < M && L.edge[e] < s) e++;
         double d = 1E10;
@@ -61,17 +61,24 @@ struct FastDescProv {
     }
     // the (at most two) merged bands of layer t that can intersect the short cell window starting at k
     __device__ __forceinline__ void bands_near(int t, int k, int2 &b0, int2 &b1) const {
-        const LayerSearch &L = sm[t % 3];
+        const LayerSearch &L = sm[t & 3];
         int i = L.bucket_band[k >> MPC_BUCKET_SHIFT], m = L.n_band;
         while (i < m && L.mband[i].y <= k) i++;
         b0 = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX);
         b1 = i + 1 < m ? L.mband[i + 1] : make_int2(INT_MAX, INT_MAX);
     }
     __device__ __forceinline__ bool is_obstacle(int t, int k, int j) const {
-        const LayerSearch &L = sm[t % 3];
+        const LayerSearch &L = sm[t & 3];
         int i = L.bucket_band[j], m = L.n_band;
         while (i < m && L.mband[i].y <= k) i++;
         return i < m && L.mband[i].x <= k;
+    }
+    // in a band or inside a penalty zone (LayerDesc::blk); a handful of calls per problem
+    __device__ __forceinline__ bool is_blocked(int t, int k) const {
+        const LayerSearch &L = sm[t & 3];
+        bool b = false;
+        for (int i = 0; i < L.n_blk; i++) b = b || (k >= L.blk[i].x && k < L.blk[i].y);
+        return b;
     }
     __device__ __forceinline__ double eval_global(int t, int k, double s, bool &ob) const { return cell_distance(base[t], s, k, ob); }
 };
@@ -97,6 +104,7 @@ struct FastDenseProv {
     __device__ __forceinline__ double distance_staged(int t, int k, double s) const { bool ob; return eval_staged(t, k, s, ob); }
     __device__ __forceinline__ void bands_near(int, int, int2 &b0, int2 &b1) const { b0 = make_int2(INT_MAX, INT_MAX); b1 = b0; }
     __device__ __forceinline__ bool is_obstacle(int t, int k, int) const { return ob_base[(size_t)t * stride + k] != 0; }
+    __device__ __forceinline__ bool is_blocked(int t, int k) const { return is_obstacle(t, k, 0); }
 };
 
 #define FX_EMPTY 0xffffffffffffffffULL
@@ -136,26 +144,55 @@ __device__ __forceinline__ void int_window(const DevParams &P, const SGrid &g, c
     n = whi - wlo + 1; n = n < 0 ? 0 : n;
 }
 
+// Shared-memory words are addressed by their 32-bit shared-window address and accessed with explicit
+// ld/st/atom.shared: through a generic pointer that nvcc cannot prove to be shared (the two label buffers
+// are selected by layer parity) it emits generic LD.E / ATOM.E.CAS plus the software fall-back of generic
+// atomics on shared memory, several times the cost of LDS / ATOMS.CAS (seen in the SASS of the v8 kernel).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long lds_u64(unsigned a) {
+    unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_u64(unsigned a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long atoms_cas_u64(unsigned a, unsigned long long cmp, unsigned long long val) {
+    unsigned long long old; asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory"); return old;
+}
+
 // min-combine into shared memory; the CAS is only issued when the candidate beats the stored word.
-// Returns true when this call turned an EMPTY cell into a node (exactly one caller per cell sees that).
-__device__ __forceinline__ bool smem_min64(unsigned long long *addr, unsigned long long val) {
-    unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(addr);
+__device__ __forceinline__ void smem_min64(unsigned addr, unsigned long long val) {
+    unsigned long long old = lds_u64(addr);
     while (val < old) {
         unsigned long long assumed = old;
-        old = atomicCAS(addr, assumed, val);
-        if (old == assumed) return assumed == 0xffffffffffffffffULL;
+        old = atoms_cas_u64(addr, assumed, val);
+        if (old == assumed) return;
     }
-    return false;
 }
 
 __device__ __forceinline__ unsigned long long fx_from_double(double x) { return (unsigned long long)__double2ll_rn(__dmul_rn(x, MPC_FX_ONE)); }
 
-// distance penalty d_w * pen(d) in fixed point (st_cy.pyx:34-38,50); the threshold test is exact fp64
+// distance penalty d_w * pen(d) in label units (st_cy.pyx:34-38,50); the threshold test is exact fp64.  Outside the
+// penalty zone d_w / d is evaluated in fp32 -- rint(kw * (1.0f / (float)d)), kw = (float)(d_w * 2^18) -- (relative error
+// 1e-7 of a term <= d_w / m); the CPU model orc_solve_fast_model does the same three IEEE operations.
+__device__ __forceinline__ unsigned fx_inv_penalty(float kw, double d) { return __float2uint_rn(__fmul_rn(kw, __frcp_rn((float)d))); }
 __device__ __forceinline__ unsigned long long fx_penalty(const DevParams &P, double d) {
-    double pen;
-    if (d < P.p.min_allowed_distance) pen = __ddiv_rn(1000000.0, d > 1.0 ? d : 1.0);
-    else pen = (double)__fdiv_rn(1.0f, (float)d);
-    return fx_from_double(__dmul_rn(P.p.d_weight, pen));
+    if (d < P.p.min_allowed_distance) return fx_from_double(__dmul_rn(P.p.d_weight, __ddiv_rn(1000000.0, d > 1.0 ? d : 1.0)));
+    return (unsigned long long)fx_inv_penalty(P.kw, d);
+}
+
+// Lean bounded pass: bit w*32+j of the array = cell is blocked in the layer (LayerDesc::blk).  Only the words that
+// the layer's nodes can occupy, [klo, khi], are rebuilt.
+__device__ __forceinline__ void build_blocked_bits(const LayerSearch &L, unsigned *bits, int klo, int khi, int tid, int nth) {
+    const int w1 = khi >> 5, nb = L.n_blk;
+    for (int w = (klo >> 5) + tid; w <= w1; w += nth) {
+        const int c0 = w << 5;
+        unsigned m = 0;
+        for (int i = 0; i < nb; i++) {
+            const int2 b = L.blk[i];
+            if (b.x >= c0 + 32) break;
+            const int lo = max(b.x - c0, 0), hi = min(b.y - c0, 32);
+            if (hi > lo) m |= (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        }
+        bits[w] = m;
+    }
 }
 
 // Cost bound.  Labels only grow along a path (every term of st_cy.pyx:46-50 is >= 0) and a cell keeps the arrival with
@@ -178,16 +215,18 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
     __shared__ unsigned long long s_layer_best[2];
     __shared__ int s_chunk[3];          // dense traversal: next 32-cell chunk of a pass
     BlockShared &S = FS.S;
-    unsigned long long *buf[2];
-    buf[0] = reinterpret_cast<unsigned long long *>(smem_raw); buf[1] = buf[0] + Wc;
+    // two label buffers of Wc 64-bit words (layer parity), addressed in the shared window
+    const unsigned sb0 = smem_u32(smem_raw), sb1 = sb0 + 8u * (unsigned)Wc;
     ClampBits CB;
-    CB.lo = reinterpret_cast<unsigned *>(buf[1] + Wc); CB.hi = CB.lo + ((P.num_s_max + 31) >> 5);
+    const int NW = (P.num_s_max + 31) >> 5;
+    CB.lo = reinterpret_cast<unsigned *>(smem_raw + (size_t)16 * Wc); CB.hi = CB.lo + NW;
+    unsigned *const blkbits[2] = {CB.hi + NW, CB.hi + 2 * NW + 2};       // lean pass: blocked cells of layer t in blkbits[t & 1] (NW + 2 words each)
     uint16_t *bp = io.bp + (size_t)blockIdx.x * P.num_t * io.bp_stride;
     const int T = P.num_t, tid = threadIdx.x, nth = blockDim.x;
     auto ring = [Wc](int k) -> int { return WRAP ? (k >= Wc ? k - Wc : k) : k; };
     for (int i = tid; i < 256; i += nth) TB.v[i] = P.vtab[i];
     for (int i = tid; i < 512; i += nth) TB.aj[i] = P.atab[i >> 4] + P.jtab[i & 15];
-    for (int k = tid; k < 2 * Wc; k += nth) buf[0][k] = FX_EMPTY;       // both buffers; every pass leaves them empty again
+    for (int k = tid; k < 2 * Wc; k += nth) sts_u64(sb0 + 8u * k, FX_EMPTY);       // both buffers; every pass leaves them empty again
     if (io.B_dev) B = *io.B_dev;
     for (;;) {
         if (tid == 0) S.b = atomicAdd(io.work_counter, 1);
@@ -212,6 +251,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         // first attempt under the cost bound (and with its penalty zones closed), second attempt without -- see the note above
         unsigned long long bnd = bound;
         int zone = (Prov::kClipAtPush && bound != FX_EMPTY) ? P.zone_cells : 0;
+        // lean first attempt (descriptor-fed, bounded): see the note above the kernel
+        bool lean = DESC && Prov::kClipAtPush && bound != FX_EMPTY && P.zone_ok;
       for (;;) {
         prov.load(1);
         bt = 0; best_word = 0ULL; dlo = 0; dhi = -1;
@@ -231,7 +272,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             if (!ob && kk >= 256) S.need_fallback = 1;
             else if (!ob) {
                 unsigned long long l1 = fx_from_double(exact_cost(P, sn, g.s0, est_prev, est_second, d));
-                buf[1][ring(kk)] = (l1 << 16) | ((unsigned long long)(255 - kk) << 8) | 128ULL;
+                sts_u64(sb1 + 8u * ring(kk), (l1 << 16) | ((unsigned long long)(255 - kk) << 8) | 128ULL);
                 bp[(size_t)1 * io.bp_stride + kk] = 0;
                 atomicMin(&s_layer_best[1], (l1 << 16) | (unsigned long long)kk);
                 atomicMin(&S.nlo[1], kk); atomicMax(&S.nhi[1], kk);
@@ -241,6 +282,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         if (T > 3) prov.load(3);
         __syncthreads();
         if (T > 3) prov.store(3);
+        if (T > 4) prov.load(4);
         bool done = false;
         if (S.nhi[1] < 0) done = true;                        // nothing reachable at layer 1: best node is (0,0)
         else {
@@ -251,32 +293,143 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             int mylo = INT_MAX, myhi = -1;
             for (int e = tid; e < (hi1 - lo1 + 1) * lme; e += nth) {
                 int k1 = lo1 + e / lme, j = e % lme;
-                unsigned long long w1 = buf[1][ring(k1)];
+                unsigned long long w1 = lds_u64(sb1 + 8u * ring(k1));
                 if (w1 == FX_EMPTY) continue;
                 double s = g.sval(k1);
                 int imin, imax;
                 exact_window(P, g.s0, g.ds, s, g.s0, est_prev, imin, imax);
                 int kk = imin + j;
                 if (kk >= imax || kk >= g.num_s) continue;
-                if (prov.is_obstacle(2, kk, kk >> MPC_BUCKET_SHIFT)) continue;          // st_cy.pyx:383-384
+                if (lean ? prov.is_blocked(2, kk) : prov.is_obstacle(2, kk, kk >> MPC_BUCKET_SHIFT)) {               // st_cy.pyx:383-384
+                    if (lean) S.bound_hit = 1;                // (a zone cell: if the plan ends here it is repeated without the bound)
+                    continue;
+                }
                 int vn = kk - k1, an = vn - k1;
                 if (vn > 255 || an < -16 || an > 15) { S.need_fallback = 1; continue; }
                 unsigned long long tot = (w1 >> 16) + fx_from_double(exact_kin(P, g.sval(kk), s, g.s0, est_prev));
-                smem_min64(&buf[0][ring(kk)], (tot << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128));
+                smem_min64(sb0 + 8u * ring(kk), (tot << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128));
                 mylo = min(mylo, kk); myhi = max(myhi, kk);
             }
             mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
             if ((tid & 31) == 0 && myhi >= 0) { atomicMin(&S.nlo[2], mylo); atomicMax(&S.nhi[2], myhi); }
             __syncthreads();
-            for (int k1 = lo1 + tid; k1 <= hi1; k1 += nth) buf[1][ring(k1)] = FX_EMPTY;     // layer 1 is consumed
+            for (int k1 = lo1 + tid; k1 <= hi1; k1 += nth) sts_u64(sb1 + 8u * ring(k1), FX_EMPTY);     // layer 1 is consumed
             dlo = S.nlo[2]; dhi = S.nhi[2];
             if (dhi < 0) done = true;                         // layer-1 nodes have no successors
         }
-        // ---- main loop: pass t finalises the nodes of layer t (buffer t&1) and pushes their successors ----
+        if (T > 4) prov.store(4);
         const int lane = tid & 31;
+        if (lean && !done) {
+            // ---- lean bounded pass.  Every cell that is inside an obstacle band or a penalty zone of layer t is marked in a bit
+            // array one iteration ahead; successors are tested against it at push time, so every node that is finalised has
+            // d >= MIN_ALLOWED_DISTANCE: its penalty is the 1/d branch, and (being the complement of what the bound drops) the
+            // surviving nodes are exactly those of the unbounded pass.  One barrier per layer; the layer's best label is only
+            // tracked at the horizon -- a pass that does not get there is repeated without the bound. ----
+            if (T > 3) build_blocked_bits(FS.layer[3], blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), tid, nth);
+            if (tid == 0) { s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; }      // (layer 1's best is in registers by now)
+            const float kw = P.kw;
+            for (int t = 2; t < T; t++) {
+                const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
+                const unsigned cur = par ? sb1 : sb0, nxt = par ? sb0 : sb1;
+                __syncthreads();                              // pushes into layer t, its span, staging of layer t+2 and bits of t+1 are complete
+                dlo = S.nlo[s3]; dhi = S.nhi[s3];
+                if (dhi < 0) break;                           // no successors
+                if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
+                if (tid == 0) { S.nlo[(t + 2) % 3] = INT_MAX; S.nhi[(t + 2) % 3] = -1; s_chunk[n3] = 0; }    // what iteration t+1 accumulates into
+                if (t + 3 < T) prov.load(t + 3);
+                const bool last = (t == T - 1);
+                if (t + 2 < T) build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[par], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
+                const LayerSearch &L = FS.layer[t & 3];
+                const int M = L.n_edge;
+                const unsigned *bw = blkbits[par ^ 1];
+                uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
+                unsigned long long mybest = FX_EMPTY;
+                int mylo = INT_MAX, myhi = -1;
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_chunk[s3], 1);
+                c = __shfl_sync(FULL, c, 0);
+                for (;;) {
+                    const int base = dlo + (c << 5);
+                    if (base > dhi) break;
+                    int cn = 0;                               // next chunk: fetched before this one is processed
+                    if (lane == 0) cn = atomicAdd(&s_chunk[s3], 1);
+                    const int k = base + lane, rk = ring(k);
+                    unsigned long long w = FX_EMPTY;
+                    if (k <= dhi) w = lds_u64(cur + 8u * rk);
+                    if (w != FX_EMPTY) {
+                        sts_u64(cur + 8u * rk, FX_EMPTY);     // this buffer receives layer t+2
+                        unsigned pen = 0;
+                        if (M) {
+                            const double sv = g.sval(k);
+                            int e = L.bucket_edge[k >> MPC_BUCKET_SHIFT];
+                            while (e < M && L.edge[e] < sv) e++;
+                            double d = 1E10;
+                            if (e > 0) { double x = __dsub_rn(sv, L.edge[e - 1]); d = x < d ? x : d; }
+                            if (e < M) { double x = fabs(__dsub_rn(sv, L.edge[e])); d = x < d ? x : d; }
+                            pen = fx_inv_penalty(kw, d);
+                        }
+                        const unsigned long long label = (w >> 16) + pen;
+                        if (label <= bnd) {                   // (only a layer-1 node inside a zone can push a label above the bound)
+                            const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
+                            bp_row[k] = (uint16_t)(k - v);
+                            if (last) {
+                                const unsigned long long key = (label << 16) | (unsigned long long)k;
+                                mybest = key < mybest ? key : mybest;
+                            } else {
+                                int wlo, n;
+                                int_window(P, g, CB, k, v, a, wlo, n);
+                                if (n > 0) {
+                                    const int vn = wlo - k, an = vn - v, jn = an - a;
+                                    const int wi = wlo >> 5;
+                                    const unsigned open = ~__funnelshift_r(bw[wi], bw[wi + 1], wlo & 31) & ((1u << n) - 1u);
+                                    mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
+                                    unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
+                                    const unsigned *tv = TB.v + vn, *taj = TB.aj + (an + 16) * 16 + (jn + 8);
+                                    const int r0 = ring(wlo);
+                                    const unsigned ra = nxt + 8u * r0;
+                                    if (!WRAP || r0 + n <= Wc) {                // the window does not cross the end of the ring
+#pragma unroll
+                                        for (int e = 0; e < 5; e++)
+                                            if ((open >> e) & 1u) smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                                        for (int e = 5; e < n; e++)
+                                            if ((open >> e) & 1u) smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                                    } else {
+                                        for (int e = 0; e < n; e++) {
+                                            const int r = r0 + e >= Wc ? r0 + e - Wc : r0 + e;
+                                            if ((open >> e) & 1u) smem_min64(nxt + 8u * r, word - 255ULL * e + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    c = __shfl_sync(FULL, cn, 0);
+                }
+                mylo = __reduce_min_sync(FULL, mylo); myhi = __reduce_max_sync(FULL, myhi);
+                if (last) for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, mybest, o); mybest = x < mybest ? x : mybest; }
+                if (lane == 0) {
+                    if (mybest != FX_EMPTY) atomicMin(&s_layer_best[par], mybest);
+                    if (myhi >= 0) { atomicMin(&S.nlo[n3], mylo); atomicMax(&S.nhi[n3], myhi); }
+                }
+                if (t + 3 < T) prov.store(t + 3);
+                if (last) {
+                    __syncthreads();
+                    if (s_layer_best[par] != FX_EMPTY) { bt = t; best_word = s_layer_best[par]; }
+                }
+            }
+            __syncthreads();
+            if (bt < T - 1 && !S.need_fallback) {             // the bound (or a blocked zone) cut the plan short: repeat without
+                for (int k = tid; k < 2 * Wc; k += nth) sts_u64(sb0 + 8u * k, FX_EMPTY);
+                bnd = FX_EMPTY; zone = 0; lean = false;
+                __syncthreads();
+                continue;
+            }
+            break;
+        }
+        // ---- main loop: pass t finalises the nodes of layer t (buffer t&1) and pushes their successors ----
         for (int t = 2; !done && t < T; t++) {
             const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
-            unsigned long long *cur = buf[par], *nxt = buf[par ^ 1];
+            const unsigned cur = par ? sb1 : sb0, nxt = par ? sb0 : sb1;
             if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
             if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; s_chunk[n3] = 0; }
             __syncthreads();                                  // pushes into layer t complete; staging of layers t, t+1 visible
@@ -287,7 +440,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             bool hit = false;                                 // this thread dropped a node / closed a zone cell under the bound
             const bool last = (t == T - 1);
             auto process = [&](const int k, const int rk, const unsigned long long w) {
-                cur[rk] = FX_EMPTY;                           // this buffer receives layer t+2
+                sts_u64(cur + 8u * rk, FX_EMPTY);             // this buffer receives layer t+2
                 double s = g.sval(k);
                 double d;
                 if (Prov::kClipAtPush) d = prov.distance_staged(t, k, s);      // pushes never land in a band
@@ -318,19 +471,20 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                     if (zone && open != (1u << n) - 1) hit = true;          // (counts real band cells too: only costs a spare retry)
                 }
                 mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
-                int r = ring(wlo);
+                unsigned ra = nxt + 8u * ring(wlo);
+                const unsigned ra_end = nxt + 8u * (unsigned)Wc;
                 unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
                 const unsigned *tv = TB.v + vn, *taj = TB.aj + (an + 16) * 16 + (jn + 8);
 #pragma unroll
                 for (int e = 0; e < 5; e++) {                               // the common window has 5 cells: unrolled, predicated
-                    if ((open >> e) & 1u) smem_min64(&nxt[r], word + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                    if ((open >> e) & 1u) smem_min64(ra, word + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
                     word = word - 255ULL;                                   // v' + 1 (bits 8..15 hold 255 - v'), a' + 1 (bits 0..7)
-                    r = (WRAP && r + 1 == Wc) ? 0 : r + 1;
+                    ra += 8u; if (WRAP && ra == ra_end) ra = nxt;
                 }
                 for (int e = 5; e < n; e++) {                               // longer windows (other Settings)
-                    if ((open >> e) & 1u) smem_min64(&nxt[r], word + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                    if ((open >> e) & 1u) smem_min64(ra, word + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
                     word = word - 255ULL;
-                    r = (WRAP && r + 1 == Wc) ? 0 : r + 1;
+                    ra += 8u; if (WRAP && ra == ra_end) ra = nxt;
                 }
             };
             // dense traversal of the layer's cell span: warps take 32-cell chunks from a shared counter (obstacle bands leave
@@ -343,7 +497,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 const int base = dlo + (c << 5);
                 if (base > dhi) break;
                 const int k = base + lane;
-                if (k <= dhi) { const int rk = ring(k); const unsigned long long w = cur[rk]; if (w != FX_EMPTY) process(k, rk, w); }
+                if (k <= dhi) { const int rk = ring(k); const unsigned long long w = lds_u64(cur + 8u * rk); if (w != FX_EMPTY) process(k, rk, w); }
             }
             for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, mybest, o); mybest = x < mybest ? x : mybest; }
             mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
@@ -364,23 +518,23 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
         // nodes were dropped by the cost bound and the horizon was not reached: the bound was too low for this problem
         // (its best path crosses a penalty zone, or it has no full-horizon path at all) -> solve it again without
         if (bnd != FX_EMPTY && S.bound_hit && bt < T - 1 && !S.need_fallback) {
-            for (int k = tid; k < 2 * Wc; k += nth) buf[0][k] = FX_EMPTY;
-            bnd = FX_EMPTY; zone = 0;
+            for (int k = tid; k < 2 * Wc; k += nth) sts_u64(sb0 + 8u * k, FX_EMPTY);
+            bnd = FX_EMPTY; zone = 0; lean = false;
             __syncthreads();
             continue;
         }
         break;
       }
         if (S.need_fallback) {        // saturated label / out-of-range code / ring too small / bound too low: hand the problem on
-            for (int k = tid; k < 2 * Wc; k += nth) buf[0][k] = FX_EMPTY;
+            for (int k = tid; k < 2 * Wc; k += nth) sts_u64(sb0 + 8u * k, FX_EMPTY);
             if (tid == 0) { int p = atomicAdd(io.fallback_count, 1); io.fallback_list[p] = b; }
             __syncthreads();
             continue;
         }
         // an early exit leaves pushed-but-unprocessed words of layer bt+1 behind: clear them
         if (bt < T - 1 && bt >= 1) {
-            const int q = (bt + 1) & 1; unsigned long long *nb = buf[q];
-            if (dhi >= 0) { for (int k = dlo + tid; k <= dhi; k += nth) nb[ring(k)] = FX_EMPTY; }
+            const unsigned nb = ((bt + 1) & 1) ? sb1 : sb0;
+            if (dhi >= 0) { for (int k = dlo + tid; k <= dhi; k += nth) sts_u64(nb + 8u * ring(k), FX_EMPTY); }
         }
         int fbk = (int)(best_word & 0xffff);
         double best_cost = (double)(best_word >> 16) * (1.0 / MPC_FX_ONE);

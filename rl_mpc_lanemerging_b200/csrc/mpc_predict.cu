@@ -81,6 +81,26 @@ __device__ __forceinline__ void warp_predict_without_ego(const DevParams &P, int
     ego = out; x = nx; v = nv;
 }
 
+// Merge intervals sorted by start (lane r reads sorted interval r of sb[0..nb)) into disjoint ones, overlapping or
+// touching intervals joined; writes them back to sb[0..n) and returns n.  One warp.
+__device__ __forceinline__ int merge_sorted_intervals(int lane, int nb, int2 *sb) {
+    int2 mine = lane < nb ? sb[lane] : make_int2(INT_MAX, INT_MIN);
+    int pm = lane < nb ? mine.y : INT_MIN;                                          // inclusive prefix max of interval ends
+    for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(FULL, pm, o); if (lane >= o) pm = max(pm, x); }
+    int pm_excl = __shfl_up_sync(FULL, pm, 1);
+    bool start = lane < nb && (lane == 0 || mine.x > pm_excl);
+    unsigned sm = __ballot_sync(FULL, start);
+    int gid = __popc(sm & ((2u << lane) - 1)) - 1;                                  // group of this interval
+    unsigned below = sm & ((2u << lane) - 1);
+    int first = below ? 31 - __clz(below) : 0;                                      // lane that opened my group
+    int gstart = __shfl_sync(FULL, mine.x, first);
+    bool last = lane < nb && (lane == nb - 1 || ((sm >> (lane + 1)) & 1u));
+    __syncwarp();                                                                   // every lane has read sb[lane]
+    if (last) sb[gid] = make_int2(gstart, pm);
+    __syncwarp();
+    return __popc(sm);
+}
+
 // ---- K1a -----------------------------------------------------------------------------------------
 // desc[B][num_t]; hdr_s0/ds/num_s per problem.
 __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B, const double *__restrict__ ego,
@@ -90,7 +110,7 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
                                                             LayerDesc *__restrict__ desc, double *__restrict__ o_s0,
                                                             double *__restrict__ o_ds, int32_t *__restrict__ o_num_s) {
     __shared__ double s_edge[4][2 * MPC_NMAX];
-    __shared__ int2 s_band[4][MPC_NMAX];
+    __shared__ int2 s_band[4][MPC_NMAX], s_blk[4][MPC_NMAX];
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (warp >= B) return;
     int b = warp;
@@ -126,43 +146,53 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
             if (!(imin < g.num_s && imax > 0)) { imin = 0; imax = 0; }               // 63
             L->ef[slot] = ef; L->eb[slot] = eb; L->band[slot] = make_int2(imin, imax);
         }
+        // ---- blocked interval of this car: its band joined with the cells closer than MIN_ALLOWED_DISTANCE to its two
+        //      distance-field edges, the tests being the reference's own fp64 expression |s_k - edge| < m (st.py:52-53,
+        //      st_cy.pyx:34-38).  s_k is increasing in k, so each end is a monotone predicate: estimate, then fix up. ----
+        int zlo = 0, zhi = 0;                                                        // [zlo, zhi)
+        if (act) {
+            const double m = P.p.min_allowed_distance;
+            int k = (int)floor(__ddiv_rn(__dsub_rn(__dsub_rn(ef, m), g.s0), g.ds));
+            k = k < 0 ? 0 : (k > g.num_s ? g.num_s : k);
+            // first k with s_k >= ef or ef - s_k < m
+            while (k > 0 && !(fabs(__dsub_rn(g.sval(k - 1), ef)) >= m && g.sval(k - 1) < ef)) k--;
+            while (k < g.num_s && (fabs(__dsub_rn(g.sval(k), ef)) >= m && g.sval(k) < ef)) k++;
+            zlo = k;
+            k = (int)floor(__ddiv_rn(__dsub_rn(__dadd_rn(eb, m), g.s0), g.ds)) + 1;
+            k = k < 0 ? 0 : (k > g.num_s ? g.num_s : k);
+            // one past the last k with s_k <= eb or s_k - eb < m
+            while (k < g.num_s && !(fabs(__dsub_rn(g.sval(k), eb)) >= m && g.sval(k) > eb)) k++;
+            while (k > 0 && (fabs(__dsub_rn(g.sval(k - 1), eb)) >= m && g.sval(k - 1) > eb)) k--;
+            zhi = k;
+            if (imin < imax) { zlo = min(zlo, imin); zhi = max(zhi, imax); }
+            if (zhi < zlo) zhi = zlo;
+        }
         // ---- the same information sorted, for the fast kernel's O(1) lookups ----
-        // rank of each edge among all 2*n_act edges (ties by edge id) and of each band by start cell
-        int r_f = 0, r_b = 0, r_band = 0;
-        bool hasband = act && imin < imax;
-        unsigned bm = __ballot_sync(FULL, hasband);
+        // rank of each edge among all 2*n_act edges (ties by edge id), of each band by start cell, of each blocked interval
+        int r_f = 0, r_b = 0, r_band = 0, r_blk = 0;
+        bool hasband = act && imin < imax, hasblk = act && zlo < zhi;
+        unsigned bm = __ballot_sync(FULL, hasband), zm = __ballot_sync(FULL, hasblk);
         for (int j = 0; j < 32; j++) {
             if (!((am >> j) & 1u)) continue;                                        // warp-uniform
             double fj = __shfl_sync(FULL, ef, j), bj = __shfl_sync(FULL, eb, j);
-            int ij = __shfl_sync(FULL, imin, j);
+            int ij = __shfl_sync(FULL, imin, j), zj = __shfl_sync(FULL, zlo, j);
             r_f += (fj < ef || (fj == ef && 2 * j < 2 * lane)) + (bj < ef || (bj == ef && 2 * j + 1 < 2 * lane));
             r_b += (fj < eb || (fj == eb && 2 * j < 2 * lane + 1)) + (bj < eb || (bj == eb && 2 * j + 1 < 2 * lane + 1));
             if ((bm >> j) & 1u) r_band += (ij < imin || (ij == imin && j < lane));
+            if ((zm >> j) & 1u) r_blk += (zj < zlo || (zj == zlo && j < lane));
         }
-        double *se = s_edge[wib]; int2 *sb = s_band[wib];
+        double *se = s_edge[wib]; int2 *sb = s_band[wib], *sz = s_blk[wib];
         if (act) { se[r_f] = ef; se[r_b] = eb; }
         if (hasband) sb[r_band] = make_int2(imin, imax);
+        if (hasblk) sz[r_blk] = make_int2(zlo, zhi);
         __syncwarp();
-        int n_edge = 2 * n_act, nb = __popc(bm);
-        // merge overlapping / touching bands (sorted by start): lane r holds sorted band r
-        int2 mine = lane < nb ? sb[lane] : make_int2(INT_MAX, INT_MIN);
-        int pm = lane < nb ? mine.y : INT_MIN;                                      // inclusive prefix max of band ends
-        for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(FULL, pm, o); if (lane >= o) pm = max(pm, x); }
-        int pm_excl = __shfl_up_sync(FULL, pm, 1);
-        bool start = lane < nb && (lane == 0 || mine.x > pm_excl);
-        unsigned sm = __ballot_sync(FULL, start);
-        int gid = __popc(sm & ((2u << lane) - 1)) - 1;                              // group of this band
-        unsigned below = sm & ((2u << lane) - 1);
-        int first = below ? 31 - __clz(below) : 0;                                  // lane that opened my group
-        int gstart = __shfl_sync(FULL, mine.x, first);
-        bool last = lane < nb && (lane == nb - 1 || ((sm >> (lane + 1)) & 1u));
-        __syncwarp();                                                               // every lane has read sb[lane]
-        if (last) sb[gid] = make_int2(gstart, pm);                                  // sb now holds the merged bands
-        int n_band = __popc(sm);
-        __syncwarp();
+        int n_edge = 2 * n_act;
+        const int n_band = merge_sorted_intervals(lane, __popc(bm), sb);             // sb / sz now hold disjoint intervals
+        const int n_blk = merge_sorted_intervals(lane, __popc(zm), sz);
         for (int i = lane; i < n_edge; i += 32) L->edge[i] = se[i];
         if (lane < n_band) L->mband[lane] = sb[lane];
-        if (lane == 0) { L->n_act = n_act; L->n_edge = n_edge; L->n_band = n_band; L->pad = 0; }
+        if (lane < n_blk) L->blk[lane] = sz[lane];
+        if (lane == 0) { L->n_act = n_act; L->n_edge = n_edge; L->n_band = n_band; L->n_blk = n_blk; }
         __syncwarp();
         // bucket tables: bucket j starts at cell 64*j
         int nbuck = (g.num_s + (1 << MPC_BUCKET_SHIFT) - 1) >> MPC_BUCKET_SHIFT;

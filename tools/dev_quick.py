@@ -6,9 +6,9 @@ from rl_mpc_lanemerging_b200 import synthetic, _lib
 from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
 
 def run(H, B, mode, reps=3, threads=None, blocks=None, lst=0):
-    os.environ["MPC_FAST_LIST"] = str(lst)
-    if threads: os.environ["MPC_FAST_THREADS"] = str(threads)
-    os.environ["MPC_FAST_BLOCKS"] = str(blocks or 32)
+    for k, v in (("MPC_FAST_THREADS", threads), ("MPC_FAST_BLOCKS", blocks)):      # 0 / None = the library's default
+        if v: os.environ[k] = str(v)
+        else: os.environ.pop(k, None)
     p = _lib.default_params()
     p.future_t, p.future_s = synthetic.horizon_settings(H)
     eng = MpcEngine(p, 0, max_batch=B)
@@ -25,7 +25,7 @@ def run(H, B, mode, reps=3, threads=None, blocks=None, lst=0):
         t = ev[0].elapsed_time(ev[1])
         if t < best: best, km = t, eng.last_kernel_ms()
     c = eng.counters()
-    print(f"H={H} B={B} mode={mode} threads={threads or 'default'} blocks/SM={(blocks or 32)//32} list={lst}: {best:.3f} ms -> {B/best*1e3:.0f} gap-evals/s  kernels(pred,dp,fb)={tuple(round(x,3) for x in km)} fallback={c['fallback_problems']}", flush=True)
+    print(f"H={H} B={B} mode={mode} threads={threads or 'default'} blocks={blocks or 'default'}: {best:.3f} ms -> {B/best*1e3:.0f} gap-evals/s  kernels(pred,dp,fb)={tuple(round(x,3) for x in km)} fallback={c['fallback_problems']}", flush=True)
     eng.close()
 
 if __name__ == "__main__":
