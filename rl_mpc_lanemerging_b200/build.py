@@ -37,7 +37,8 @@ def stale() -> bool:
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("MPC_NVCC_EXTRA", "").split()          # dev only (e.g. -DMPC_ABLATE=1)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
     subprocess.check_call(cmd)
     return LIB

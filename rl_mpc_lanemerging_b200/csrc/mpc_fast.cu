@@ -21,6 +21,9 @@
 // orc_solve_fast_model (oracle/mpc_oracle.c).  Quantisation (<= 1.9e-6 per edge) keeps the cost within
 // ~1e-8 rel of the reference; fp32 labels were tried first and rejected.
 #include "mpc_solve_common.cuh"
+#ifndef MPC_ABLATE
+#define MPC_ABLATE 0      // dev-only timing ablations (wrong results when != 0)
+#endif
 
 #define EMPTY_LAB 0x7ff0000000000000ULL      // +inf
 
@@ -155,6 +158,16 @@ __device__ __forceinline__ unsigned long long lds_u64(unsigned a) {
 __device__ __forceinline__ void sts_u64(unsigned a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ unsigned long long atoms_cas_u64(unsigned a, unsigned long long cmp, unsigned long long val) {
     unsigned long long old; asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory"); return old;
+}
+
+// same, without the compiler-level memory barrier: several of them may be scheduled back to back (the caller orders them
+// against the other accesses of the same words with the barrier variants / __syncthreads)
+__device__ __forceinline__ unsigned long long lds_u64_nc(unsigned a) {
+    unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ unsigned lds_u32_nc(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned long long atoms_cas_u64_nc(unsigned a, unsigned long long cmp, unsigned long long val) {
+    unsigned long long old; asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val)); return old;
 }
 
 // min-combine into shared memory; the CAS is only issued when the candidate beats the stored word.
@@ -328,6 +341,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             if (T > 3) build_blocked_bits(FS.layer[3], blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), tid, nth);
             if (tid == 0) { s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; }      // (layer 1's best is in registers by now)
             const float kw = P.kw;
+            const unsigned tbv = smem_u32(TB.v), tbaj = smem_u32(TB.aj);
             for (int t = 2; t < T; t++) {
                 const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
                 const unsigned cur = par ? sb1 : sb0, nxt = par ? sb0 : sb1;
@@ -359,7 +373,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                     if (w != FX_EMPTY) {
                         sts_u64(cur + 8u * rk, FX_EMPTY);     // this buffer receives layer t+2
                         unsigned pen = 0;
-                        if (M) {
+                        if (M && MPC_ABLATE != 3) {
                             const double sv = g.sval(k);
                             int e = L.bucket_edge[k >> MPC_BUCKET_SHIFT];
                             while (e < M && L.edge[e] < sv) e++;
@@ -371,7 +385,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                         const unsigned long long label = (w >> 16) + pen;
                         if (label <= bnd) {                   // (only a layer-1 node inside a zone can push a label above the bound)
                             const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
-                            bp_row[k] = (uint16_t)(k - v);
+                            if (MPC_ABLATE != 4) bp_row[k] = (uint16_t)(k - v);
                             if (last) {
                                 const unsigned long long key = (label << 16) | (unsigned long long)k;
                                 mybest = key < mybest ? key : mybest;
@@ -381,23 +395,50 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                                 if (n > 0) {
                                     const int vn = wlo - k, an = vn - v, jn = an - a;
                                     const int wi = wlo >> 5;
-                                    const unsigned open = ~__funnelshift_r(bw[wi], bw[wi + 1], wlo & 31) & ((1u << n) - 1u);
+                                    const unsigned open = ~__funnelshift_r(bw[wi], bw[wi + 1], wlo & 31) & ((1u << n) - 1u);      // bits >= n are 0
                                     mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
-                                    unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
-                                    const unsigned *tv = TB.v + vn, *taj = TB.aj + (an + 16) * 16 + (jn + 8);
+                                    const unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
+                                    const unsigned tva = tbv + 4u * vn, taja = tbaj + 4u * ((an + 16) * 16 + (jn + 8));    // V[v'], A[a'] + J[j'] of successor 0
                                     const int r0 = ring(wlo);
                                     const unsigned ra = nxt + 8u * r0;
                                     if (!WRAP || r0 + n <= Wc) {                // the window does not cross the end of the ring
-#pragma unroll
-                                        for (int e = 0; e < 5; e++)
-                                            if ((open >> e) & 1u) smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
-                                        for (int e = 5; e < n; e++)
-                                            if ((open >> e) & 1u) smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
-                                    } else {
-                                        for (int e = 0; e < n; e++) {
-                                            const int r = r0 + e >= Wc ? r0 + e - Wc : r0 + e;
-                                            if ((open >> e) & 1u) smem_min64(nxt + 8u * r, word - 255ULL * e + ((unsigned long long)(tv[e] + taj[17 * e]) << 16));
+                                        // Five independent min-combines (five different cells), offered best-first (zero jerk, then outwards) and
+                                        // software-pipelined: the pre-read of the next cell is in flight while this one's CAS is, and a CAS
+                                        // that lost a race is not retried in place but noted and redone after the window (no loop, no branch).
+                                        unsigned redo = 0;
+                                        unsigned long long oldA, oldB, resA, resB, valA, valB;
+#define MPC_PREREAD(E, OLD) OLD = lds_u64_nc(ra + 8u * (E))
+#define MPC_OFFER(E, OLD, RES, VAL)                                                                                         \
+                                        VAL = word - 255ULL * (E) + ((unsigned long long)(lds_u32_nc(tva + 4u * (E)) + lds_u32_nc(taja + 68u * (E))) << 16); \
+                                        RES = OLD;                                                                          \
+                                        if (((open >> (E)) & 1u) && VAL < OLD) RES = atoms_cas_u64_nc(ra + 8u * (E), OLD, VAL)
+#define MPC_CHECK(E, OLD, RES, VAL) redo |= (RES != OLD && VAL < RES) ? (1u << (E)) : 0u
+                                        MPC_PREREAD(2, oldA); MPC_PREREAD(3, oldB);
+                                        MPC_OFFER(2, oldA, resA, valA);
+                                        MPC_OFFER(3, oldB, resB, valB);
+                                        MPC_CHECK(2, oldA, resA, valA); MPC_PREREAD(1, oldA);
+                                        MPC_CHECK(3, oldB, resB, valB); MPC_PREREAD(4, oldB);
+                                        MPC_OFFER(1, oldA, resA, valA);
+                                        MPC_OFFER(4, oldB, resB, valB);
+                                        MPC_CHECK(1, oldA, resA, valA); MPC_PREREAD(0, oldA);
+                                        MPC_CHECK(4, oldB, resB, valB);
+                                        MPC_OFFER(0, oldA, resA, valA);
+                                        MPC_CHECK(0, oldA, resA, valA);
+#undef MPC_PREREAD
+#undef MPC_OFFER
+#undef MPC_CHECK
+                                        for (int e = 5; e < n; e++)                 // (windows longer than 5 cells: other Settings)
+                                            if ((open >> e) & 1u) smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(lds_u32_nc(tva + 4u * e) + lds_u32_nc(taja + 68u * e)) << 16));
+                                        while (redo) {                              // rare: another lane / warp changed the cell between pre-read and CAS
+                                            const int e = __ffs(redo) - 1; redo &= redo - 1;
+                                            smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(lds_u32_nc(tva + 4u * e) + lds_u32_nc(taja + 68u * e)) << 16));
                                         }
+                                    } else {
+                                        for (int e = 0; e < n; e++)
+                                            if ((open >> e) & 1u) {
+                                                const unsigned r = nxt + 8u * (r0 + e >= Wc ? r0 + e - Wc : r0 + e);
+                                                smem_min64(r, word - 255ULL * e + ((unsigned long long)(lds_u32_nc(tva + 4u * e) + lds_u32_nc(taja + 68u * e)) << 16));
+                                            }
                                     }
                                 }
                             }
