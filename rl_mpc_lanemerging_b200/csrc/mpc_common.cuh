@@ -93,7 +93,7 @@ struct LayerDesc {
     double eb[MPC_NMAX];
     int2 band[MPC_NMAX];
     // ---- search structure for the fast kernel (same information, sorted) ----
-    double edge[2 * MPC_NMAX];               // ascending
+    double edge[2 * MPC_NMAX + 2];           // ascending; edge[n_edge] = +1e300 (sentinel for the branch-free lookup)
     int2 mband[MPC_NMAX];                    // disjoint [x, y), ascending
     unsigned char bucket_edge[MPC_MAX_BUCKETS];   // #edges  <  s_values[64*j]
     unsigned char bucket_band[MPC_MAX_BUCKETS];   // #merged bands with y <= 64*j
@@ -106,7 +106,8 @@ struct LayerDesc {
 // the part of a LayerDesc the fast kernel stages in shared memory
 struct LayerSearch {
     int n_edge, n_band, n_blk, pad1;
-    double edge[2 * MPC_NMAX];
+    double pad2, edge_lo;        // edge_lo = edge[-1] = -1e300 (sentinel)
+    double edge[2 * MPC_NMAX + 2];
     int2 mband[MPC_NMAX];
     unsigned char bucket_edge[MPC_MAX_BUCKETS];
     unsigned char bucket_band[MPC_MAX_BUCKETS];

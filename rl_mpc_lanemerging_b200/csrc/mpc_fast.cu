@@ -38,8 +38,9 @@ struct FastDescProv {
     const LayerDesc *base;      // desc + b*num_t
     LayerSearch *sm;            // four staging buffers in shared memory
     int4 pre;                   // prefetch register
-    // a LayerSearch is a contiguous tail of LayerDesc except for its 16-byte header
-    static constexpr int kTail = (int)(sizeof(LayerSearch) - 16) / 16;
+    // a LayerSearch is a contiguous tail of LayerDesc behind its 32-byte header (counts, lower sentinel edge)
+    static constexpr int kHead = (int)offsetof(LayerSearch, edge);
+    static constexpr int kTail = (int)(sizeof(LayerSearch) - kHead) / 16;
     __device__ __forceinline__ void load(int t) {          // issue the global loads of layer t (no wait)
         const LayerDesc *src = base + t;
         if (threadIdx.x < kTail) pre = reinterpret_cast<const int4 *>(reinterpret_cast<const char *>(src) + offsetof(LayerDesc, edge))[threadIdx.x];
@@ -47,8 +48,8 @@ struct FastDescProv {
     }
     __device__ __forceinline__ void store(int t) {         // park them in slot t & 3
         LayerSearch *dst = sm + (t & 3);
-        if (threadIdx.x < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(dst) + 16)[threadIdx.x] = pre;
-        else if (threadIdx.x == kTail) *reinterpret_cast<int4 *>(dst) = pre;
+        if (threadIdx.x < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(dst) + kHead)[threadIdx.x] = pre;
+        else if (threadIdx.x == kTail) { *reinterpret_cast<int4 *>(dst) = pre; dst->edge_lo = -1e300; }
     }
     static constexpr bool kClipAtPush = true;               // successors are tested against the next layer's bands before the push
     __device__ __forceinline__ double eval_staged(int t, int k, double s, bool &ob) const { return cell_distance_sorted(sm[t & 3], s, k, ob); }
@@ -86,7 +87,9 @@ struct FastDescProv {
     __device__ __forceinline__ double eval_global(int t, int k, double s, bool &ob) const { return cell_distance(base[t], s, k, ob); }
 };
 static_assert(offsetof(LayerDesc, edge) % 16 == 0 && sizeof(LayerSearch) % 16 == 0, "LayerSearch must be int4-copyable");
-static_assert(offsetof(LayerDesc, bucket_band) - offsetof(LayerDesc, edge) == offsetof(LayerSearch, bucket_band) - 16, "layout mismatch");
+static_assert(offsetof(LayerDesc, bucket_band) - offsetof(LayerDesc, edge) == offsetof(LayerSearch, bucket_band) - offsetof(LayerSearch, edge), "layout mismatch");
+static_assert(offsetof(LayerDesc, blk) - offsetof(LayerDesc, edge) == offsetof(LayerSearch, blk) - offsetof(LayerSearch, edge), "layout mismatch");
+static_assert(offsetof(LayerSearch, edge) % 16 == 0 && offsetof(LayerSearch, edge_lo) + 8 == offsetof(LayerSearch, edge), "edge[-1] must be the sentinel");
 
 template <typename DT>
 struct FastDenseProv {
@@ -165,9 +168,30 @@ __device__ __forceinline__ unsigned long long atoms_cas_u64(unsigned a, unsigned
 __device__ __forceinline__ unsigned long long lds_u64_nc(unsigned a) {
     unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v;
 }
+__device__ __forceinline__ unsigned lds_u8_nc(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_f64_nc(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+// predicated CAS: returns `cmp` when `doit` is false (no branch around the atomic)
+__device__ __forceinline__ unsigned long long atoms_cas_u64_if(unsigned a, unsigned long long cmp, unsigned long long val, bool doit) {
+    unsigned long long old;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\tmov.b64 %0, %2;\n\t@p atom.shared.cas.b64 %0, [%1], %2, %3;\n\t}"
+                 : "=&l"(old) : "r"(a), "l"(cmp), "l"(val), "r"((unsigned)doit));
+    return old;
+}
 __device__ __forceinline__ unsigned lds_u32_nc(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ unsigned long long atoms_cas_u64_nc(unsigned a, unsigned long long cmp, unsigned long long val) {
     unsigned long long old; asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val)); return old;
+}
+
+// int_window with the clamp bit arrays addressed in the shared window (lo at cba, hi at cba + 4 * NW)
+__device__ __forceinline__ void int_window_sa(const DevParams &P, int num_s, unsigned cba, int NW, int k, int v, int a, int &wlo, int &n) {
+    int alo = max(a + P.jlo_c, P.alo_c), ahi = min(a + P.jhi_c, P.ahi_c);
+    int vlo = v + alo, vhi = v + ahi;
+    if (vlo <= 0) vlo = (lds_u32_nc(cba + 4u * (unsigned)(k >> 5)) >> (k & 31)) & 1;
+    bool clamp_hi = P.vmax_is_int ? (vhi >= P.vmax_c) : ((double)v + fmin((double)a + P.jhi_r, P.ahi_r) > P.vmax_r);
+    if (clamp_hi) vhi = P.vmax_c - (P.vmax_is_int ? (int)((lds_u32_nc(cba + 4u * (unsigned)(NW + (k >> 5))) >> (k & 31)) & 1) : 0);
+    wlo = k + vlo;
+    int whi = min(k + vhi, num_s - 1);
+    n = whi - wlo + 1; n = n < 0 ? 0 : n;
 }
 
 // min-combine into shared memory; the CAS is only issued when the candidate beats the stored word.
@@ -219,7 +243,7 @@ __device__ __forceinline__ void build_blocked_bits(const LayerSearch &L, unsigne
 struct FxTables { unsigned v[256], aj[32 * 16]; };     // aj[(a'+16)*16 + (j'+8)] = A[a'] + J[j']: one lookup, stride 17 along a window
 
 template <class Prov, bool DESC, bool WRAP, int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
                                                                               const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc,
                                                                               unsigned long long bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -341,7 +365,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
             if (T > 3) build_blocked_bits(FS.layer[3], blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), tid, nth);
             if (tid == 0) { s_layer_best[0] = FX_EMPTY; s_layer_best[1] = FX_EMPTY; }      // (layer 1's best is in registers by now)
             const float kw = P.kw;
-            const unsigned tbv = smem_u32(TB.v), tbaj = smem_u32(TB.aj);
+            const unsigned tbv = smem_u32(TB.v), tbaj = smem_u32(TB.aj), cba = smem_u32(CB.lo);
             for (int t = 2; t < T; t++) {
                 const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
                 const unsigned cur = par ? sb1 : sb0, nxt = par ? sb0 : sb1;
@@ -353,10 +377,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                 if (t + 3 < T) prov.load(t + 3);
                 const bool last = (t == T - 1);
                 if (t + 2 < T) build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[par], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
-                const LayerSearch &L = FS.layer[t & 3];
-                const int M = L.n_edge;
-                const unsigned *bw = blkbits[par ^ 1];
+                const unsigned edge0 = smem_u32(FS.layer[t & 3].edge), bucket0 = smem_u32(FS.layer[t & 3].bucket_edge);
+                const unsigned bwa = smem_u32(blkbits[0]) + (par ? 0u : 4u * (unsigned)(NW + 2));      // blocked bits of layer t+1
                 uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
+                asm volatile("" : "+l"(bp_row));              // keep the row pointer in registers (else it is rebuilt per node)
                 unsigned long long mybest = FX_EMPTY;
                 int mylo = INT_MAX, myhi = -1;
                 int c = 0;
@@ -373,14 +397,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                     if (w != FX_EMPTY) {
                         sts_u64(cur + 8u * rk, FX_EMPTY);     // this buffer receives layer t+2
                         unsigned pen = 0;
-                        if (M && MPC_ABLATE != 3) {
+                        if (MPC_ABLATE != 3) {                // nearest distance-field edge on either side; edge[-1] / edge[n_edge] are -/+1e300
                             const double sv = g.sval(k);
-                            int e = L.bucket_edge[k >> MPC_BUCKET_SHIFT];
-                            while (e < M && L.edge[e] < sv) e++;
-                            double d = 1E10;
-                            if (e > 0) { double x = __dsub_rn(sv, L.edge[e - 1]); d = x < d ? x : d; }
-                            if (e < M) { double x = fabs(__dsub_rn(sv, L.edge[e])); d = x < d ? x : d; }
-                            pen = fx_inv_penalty(kw, d);
+                            unsigned ea = edge0 + 8u * lds_u8_nc(bucket0 + (k >> MPC_BUCKET_SHIFT));
+                            double hi = lds_f64_nc(ea);
+                            while (hi < sv) { ea += 8u; hi = lds_f64_nc(ea); }
+                            const double dl = __dsub_rn(sv, lds_f64_nc(ea - 8u)), dr = __dsub_rn(hi, sv);
+                            pen = fx_inv_penalty(kw, dr < dl ? dr : dl);
                         }
                         const unsigned long long label = (w >> 16) + pen;
                         if (label <= bnd) {                   // (only a layer-1 node inside a zone can push a label above the bound)
@@ -391,11 +414,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
                                 mybest = key < mybest ? key : mybest;
                             } else {
                                 int wlo, n;
-                                int_window(P, g, CB, k, v, a, wlo, n);
+                                int_window_sa(P, g.num_s, cba, NW, k, v, a, wlo, n);
                                 if (n > 0) {
                                     const int vn = wlo - k, an = vn - v, jn = an - a;
-                                    const int wi = wlo >> 5;
-                                    const unsigned open = ~__funnelshift_r(bw[wi], bw[wi + 1], wlo & 31) & ((1u << n) - 1u);      // bits >= n are 0
+                                    const unsigned wa = bwa + 4u * (unsigned)(wlo >> 5);
+                                    const unsigned open = ~__funnelshift_r(lds_u32_nc(wa), lds_u32_nc(wa + 4u), wlo & 31) & ((1u << n) - 1u);      // bits >= n are 0
                                     mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
                                     const unsigned long long word = (label << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128);
                                     const unsigned tva = tbv + 4u * vn, taja = tbaj + 4u * ((an + 16) * 16 + (jn + 8));    // V[v'], A[a'] + J[j'] of successor 0
@@ -410,8 +433,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) fast_pull_kernel(
 #define MPC_PREREAD(E, OLD) OLD = lds_u64_nc(ra + 8u * (E))
 #define MPC_OFFER(E, OLD, RES, VAL)                                                                                         \
                                         VAL = word - 255ULL * (E) + ((unsigned long long)(lds_u32_nc(tva + 4u * (E)) + lds_u32_nc(taja + 68u * (E))) << 16); \
-                                        RES = OLD;                                                                          \
-                                        if (((open >> (E)) & 1u) && VAL < OLD) RES = atoms_cas_u64_nc(ra + 8u * (E), OLD, VAL)
+                                        RES = atoms_cas_u64_if(ra + 8u * (E), OLD, VAL, ((open >> (E)) & 1u) && VAL < OLD)
 #define MPC_CHECK(E, OLD, RES, VAL) redo |= (RES != OLD && VAL < RES) ? (1u << (E)) : 0u
                                         MPC_PREREAD(2, oldA); MPC_PREREAD(3, oldB);
                                         MPC_OFFER(2, oldA, resA, valA);
@@ -589,7 +611,7 @@ static cudaError_t set_smem(K kernel, size_t smem) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-// two register budgets are compiled: <= 512 threads/block (128 registers) and <= 1024 (64 registers)
+// four launch shapes are compiled: <= 256 threads x 4 blocks/SM, <= 384 x 3, <= 512 x 2, <= 1024 x 1
 template <class Prov, bool DESC>
 static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, const uint8_t *ob,
                                  const void *dist, int stride, cudaStream_t st) {
@@ -600,7 +622,9 @@ static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;                                            \
         k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, desc, ob, dist, stride, L.W, L.bound);                     \
     } while (0)
-    if (L.threads <= 512) { if (L.wrap) MPC_LAUNCH_FAST(true, 512); else MPC_LAUNCH_FAST(false, 512); }
+    if (L.threads <= 256) { if (L.wrap) MPC_LAUNCH_FAST(true, 256); else MPC_LAUNCH_FAST(false, 256); }
+    else if (L.threads <= 384) { if (L.wrap) MPC_LAUNCH_FAST(true, 384); else MPC_LAUNCH_FAST(false, 384); }
+    else if (L.threads <= 512) { if (L.wrap) MPC_LAUNCH_FAST(true, 512); else MPC_LAUNCH_FAST(false, 512); }
     else { if (L.wrap) MPC_LAUNCH_FAST(true, 1024); else MPC_LAUNCH_FAST(false, 1024); }
 #undef MPC_LAUNCH_FAST
     return cudaGetLastError();
@@ -627,7 +651,9 @@ int fast_occupancy(int threads, size_t smem, int wrap) {
         if (set_smem(k, smem) != cudaSuccess) { cudaGetLastError(); return 0; }                            \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem);                           \
     } while (0)
-    if (threads <= 512) { if (wrap) MPC_OCC(true, 512); else MPC_OCC(false, 512); }
+    if (threads <= 256) { if (wrap) MPC_OCC(true, 256); else MPC_OCC(false, 256); }
+    else if (threads <= 384) { if (wrap) MPC_OCC(true, 384); else MPC_OCC(false, 384); }
+    else if (threads <= 512) { if (wrap) MPC_OCC(true, 512); else MPC_OCC(false, 512); }
     else { if (wrap) MPC_OCC(true, 1024); else MPC_OCC(false, 1024); }
 #undef MPC_OCC
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
         for (int i = lane; i < n_edge; i += 32) L->edge[i] = se[i];
         if (lane < n_band) L->mband[lane] = sb[lane];
         if (lane < n_blk) L->blk[lane] = sz[lane];
-        if (lane == 0) { L->n_act = n_act; L->n_edge = n_edge; L->n_band = n_band; L->n_blk = n_blk; }
+        if (lane == 0) { L->n_act = n_act; L->n_edge = n_edge; L->n_band = n_band; L->n_blk = n_blk; L->edge[n_edge] = 1e300; }
         __syncwarp();
         // bucket tables: bucket j starts at cell 64*j
         int nbuck = (g.num_s + (1 << MPC_BUCKET_SHIFT) - 1) >> MPC_BUCKET_SHIFT;
@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int 
     const int bt = blockIdx.x, b = bt / P.num_t;
     {
         const char *src = reinterpret_cast<const char *>(desc + bt);
-        constexpr int kTail = (int)(sizeof(LayerSearch) - 16) / 16;
-        if (threadIdx.x < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(&L) + 16)[threadIdx.x] =
+        constexpr int kTail = (int)(sizeof(LayerSearch) - offsetof(LayerSearch, edge)) / 16;
+        if (threadIdx.x < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(&L) + offsetof(LayerSearch, edge))[threadIdx.x] =
             reinterpret_cast<const int4 *>(src + offsetof(LayerDesc, edge))[threadIdx.x];
         else if (threadIdx.x == kTail) *reinterpret_cast<int4 *>(&L) = make_int4(desc[bt].n_edge, desc[bt].n_band, 0, 0);
     }
