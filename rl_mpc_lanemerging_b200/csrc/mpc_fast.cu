@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
         if (T > 4) prov.store(4);
         const int lane = tid & 31;
         if (lean && !done) {
+            if (T > 5) prov.load(5);
             // ---- lean bounded pass.  Every cell that is inside an obstacle band or a penalty zone of layer t is marked in a bit
             // array one iteration ahead; successors are tested against it at push time, so every node that is finalised has
             // d >= MIN_ALLOWED_DISTANCE: its penalty is the 1/d branch, and (being the complement of what the bound drops) the
@@ -374,7 +375,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
                 if (dhi < 0) break;                           // no successors
                 if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
                 if (tid == 0) { S.nlo[(t + 2) % 3] = INT_MAX; S.nhi[(t + 2) % 3] = -1; s_chunk[n3] = 0; }    // what iteration t+1 accumulates into
-                if (t + 3 < T) prov.load(t + 3);
+                if (t + 3 < T) prov.store(t + 3);             // loaded during iteration t-1; first read in iteration t+1
+                if (t + 4 < T) prov.load(t + 4);
                 const bool last = (t == T - 1);
                 if (t + 2 < T) build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[par], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
                 const unsigned edge0 = smem_u32(FS.layer[t & 3].edge), bucket0 = smem_u32(FS.layer[t & 3].bucket_edge);
@@ -383,14 +385,14 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
                 asm volatile("" : "+l"(bp_row));              // keep the row pointer in registers (else it is rebuilt per node)
                 unsigned long long mybest = FX_EMPTY;
                 int mylo = INT_MAX, myhi = -1;
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&s_chunk[s3], 1);
-                c = __shfl_sync(FULL, c, 0);
+                // 32-cell chunks of the layer's span: the first one per warp is static, the rest come from a shared counter
+                const int nwarp = nth >> 5;
+                int c = tid >> 5;
                 for (;;) {
                     const int base = dlo + (c << 5);
                     if (base > dhi) break;
                     int cn = 0;                               // next chunk: fetched before this one is processed
-                    if (lane == 0) cn = atomicAdd(&s_chunk[s3], 1);
+                    if (lane == 0) cn = nwarp + atomicAdd(&s_chunk[s3], 1);
                     const int k = base + lane, rk = ring(k);
                     unsigned long long w = FX_EMPTY;
                     if (k <= dhi) w = lds_u64(cur + 8u * rk);
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
 #undef MPC_CHECK
                                         for (int e = 5; e < n; e++)                 // (windows longer than 5 cells: other Settings)
                                             if ((open >> e) & 1u) smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(lds_u32_nc(tva + 4u * e) + lds_u32_nc(taja + 68u * e)) << 16));
-                                        while (redo) {                              // rare: another lane / warp changed the cell between pre-read and CAS
+                                        while (redo) {                              // a CAS lost a race (two nodes of the warp with the same window, or another warp)
                                             const int e = __ffs(redo) - 1; redo &= redo - 1;
                                             smem_min64(ra + 8u * e, word - 255ULL * e + ((unsigned long long)(lds_u32_nc(tva + 4u * e) + lds_u32_nc(taja + 68u * e)) << 16));
                                         }
@@ -474,7 +476,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
                     if (mybest != FX_EMPTY) atomicMin(&s_layer_best[par], mybest);
                     if (myhi >= 0) { atomicMin(&S.nlo[n3], mylo); atomicMax(&S.nhi[n3], myhi); }
                 }
-                if (t + 3 < T) prov.store(t + 3);
                 if (last) {
                     __syncthreads();
                     if (s_layer_best[par] != FX_EMPTY) { bt = t; best_word = s_layer_best[par]; }
