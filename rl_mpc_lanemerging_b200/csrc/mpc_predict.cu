@@ -275,6 +275,13 @@ __global__ void __launch_bounds__(256) check_sorted_kernel(DevParams P, int B, c
         double s = g.sval(k);
         double d1 = cell_distance(L, s, k, o1), d2 = cell_distance_sorted(L, s, k, o2);
         if (o1 != o2 || d1 != d2) bad++;
+        // blocked intervals (lean bounded pass) == in a band, or closer than MIN_ALLOWED_DISTANCE to a distance-field edge
+        double dn = 1E10;
+        for (int c = 0; c < L.n_act; c++) { dn = fmin(dn, fabs(__dsub_rn(s, L.ef[c]))); dn = fmin(dn, fabs(__dsub_rn(s, L.eb[c]))); }
+        bool blocked = false;
+        for (int i = 0; i < L.n_blk; i++) blocked = blocked || (k >= L.blk[i].x && k < L.blk[i].y);
+        if (P.zone_ok && blocked != (o1 || dn < P.p.min_allowed_distance)) bad++;
+        if (k == 0 && L.edge[L.n_edge] != 1e300) bad++;                     // upper sentinel of the sorted edge list
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -117,10 +117,36 @@ def test_build_grid_matches_oracle(oracle, engines, torch_mod, traffic, kind):
 @pytest.mark.parametrize("H", [17, 50])
 @pytest.mark.parametrize("traffic,kind", CASES)
 def test_sorted_search_structure_is_exact(engines, torch_mod, H, traffic, kind):
-    """The fast kernel's O(1) obstacle/distance lookup equals the reference-order evaluation on every cell."""
+    """The fast kernel's O(1) obstacle/distance lookup equals the reference-order evaluation on every cell, and the
+    blocked intervals of the lean bounded pass are exactly the cells in a band or inside a penalty zone (device self-test)."""
     _, eng = engines[H]
     D = _dev(_states(traffic, kind, 64, seed=16), torch_mod)
     assert eng.selftest_search(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"]) == 0
+
+
+@pytest.mark.parametrize("H,env", [(17, {"MPC_FAST_BOUND": "0"}), (17, {"MPC_FAST_BLOCKS": "64", "MPC_FAST_THREADS": "512"}),
+                                   (17, {"MPC_FAST_BLOCKS": "32", "MPC_FAST_THREADS": "1024"}), (50, {"MPC_FAST_BOUND": "0"}),
+                                   (50, {"MPC_FAST_BLOCKS": "96", "MPC_FAST_THREADS": "384"})])
+def test_fast_result_does_not_depend_on_bound_or_launch_shape(oracle, engines, torch_mod, monkeypatch, H, env):
+    """The lean bounded first pass (blocked-cell bit arrays, retry without the bound inside the kernel), the plain unbounded
+    pass (MPC_FAST_BOUND=0) and every launch shape / ring size (H=50 with 3 blocks per SM overflows the ring for some problems:
+    they are re-solved with a full row) give bit-identical plans."""
+    from rl_mpc_lanemerging_b200.engine import MpcEngine
+    op, eng = engines[H]
+    S = _states("moderate", "mixed", 64, seed=21)
+    D = _dev(S, torch_mod)
+    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
+    ref = {k: v.cpu().numpy() for k, v in eng.plan(*a, mode="fast").items()}
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    other = MpcEngine(helpers.mpc_params_from_oracle(op), device=0, max_batch=64, nmax=32)   # reads the overrides at create time
+    try:
+        out = {k: v.cpu().numpy() for k, v in other.plan(*a, mode="fast").items()}
+    finally:
+        other.close()
+    for k in ("idx", "s_seq", "cost", "reached_t", "crash", "min_dist"):
+        assert np.array_equal(out[k], ref[k]), k
+    assert (ref["reached_t"] < H).any() and (ref["reached_t"] == H).any()
 
 
 @pytest.mark.parametrize("mode", ["exact", "fast"])
