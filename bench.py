@@ -306,6 +306,18 @@ def run_ours(args):
                        "world_model": "reference predictor as dynamics (SUMO-free, parity vs SUMO unpinned)"}
         except Exception as e:          # noqa: BLE001  -- the secondary figure must never break the headline line
             env_res = {"error": repr(e)}
+    train_res = None
+    if args.train_ticks > 0:            # DDPG training: envs sharded over the ranks, one NCCL all-reduce of the flat gradient per step
+        try:
+            frames, gsteps, nbytes = train_steps_per_sec(local, world, args.env_envs, args.train_ticks, args.seed + rank)
+            r = sharding.reduce_sum([frames], dev)
+            g = sharding.reduce_max([gsteps], dev)
+            train_res = {"value": float(r[0]), "unit": "env-frames/s", "grad_steps_per_s": float(g[0]), "envs_per_gpu": args.env_envs,
+                         "ticks": args.train_ticks, "minibatch_per_gpu": 4096, "allreduce_bytes_per_step": nbytes if world > 1 else 0,
+                         "collective": "NCCL all-reduce of ONE flat fp32 gradient (actor + critic)" if world > 1 else "none (1 rank)",
+                         "config": "train_medium_1.json semantics (DDPG, traffic 7 m/s / 1.8 s); library hyper-parameters unpinned"}
+        except Exception as e:          # noqa: BLE001
+            train_res = {"error": repr(e)}
     if rank == 0:
         num_s = eng.num_s_max - 1
         ms_per_step = step_ms / K
@@ -343,6 +355,8 @@ def run_ours(args):
             line["grid_build"] = grid_res
         if env_res is not None:
             line["env_steps"] = env_res
+        if train_res is not None:
+            line["train"] = train_res
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             probe = cpu_port_rate(H, args.traffic, args.seed, cores * 2, cores)
@@ -391,6 +405,32 @@ def env_steps_per_sec(local, world, n_envs, ticks, seed):
     return n_envs * ticks / (ms * 1e-3), float(take) / ticks
 
 
+def train_steps_per_sec(local, world, n_envs, ticks, seed):
+    """BASELINE.json configs[3] (train_medium_1.json): DDPG training, environments sharded over the ranks, ONE NCCL all-reduce
+    of the flat actor+critic gradient per step.  Returns this rank's env-frames/s incl. the gradient steps, grad steps/s
+    and the all-reduce payload."""
+    import torch
+    from rl_mpc_lanemerging_b200 import merge_gym, st, trainer
+    from rl_mpc_lanemerging_b200.config import Settings
+    Settings.reset()
+    Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL, Settings.CUDA_DEVICE = 20, 7.0, 1.8, local   # train_medium_1.json
+    st.refresh_engine()
+    env = merge_gym.MergeEnv(n_envs, seed=seed)
+    tr = trainer.DDPGTrainer(env, device=f"cuda:{local}", lr=2e-4, seed=0, minibatch_size=4096, replay_start_size=n_envs,
+                             replay_buffer_size=max(4 * n_envs, 65536))
+    tr.train(n_envs * 3)                                          # warm-up: fills the replay ring, first updates
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0 = tr.grad_steps
+    torch.cuda.synchronize(); e0.record()
+    tr.train(n_envs * ticks)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = (n_envs * ticks / (ms * 1e-3), (tr.grad_steps - g0) / (ms * 1e-3), tr.allreduce_bytes)
+    st.refresh_engine()
+    Settings.reset()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -405,6 +445,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--env-ticks", type=int, default=20, help="ticks of the closed-loop env-steps/s measurement (0 = skip)")
     ap.add_argument("--env-envs", type=int, default=8192, help="environments per GPU for it (BASELINE configs[2])")
+    ap.add_argument("--train-ticks", type=int, default=10, help="ticks of the DDPG training throughput figure (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -37,6 +37,8 @@ _HOT_PATH_DEFAULTS = {
     "TEST_ROLLOUT_STATE": True, "CHECK_ROLLOUT_CRASH": True, "COMBINATION_MIN_DISTANCE": 5.1, "STOP_X": 65,
     "REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED": False, "LEARNING_RATE": 2e-4,
     # this implementation only
+    # training (reference ddpg.py:46-117; per-rank environment count and update cadence are this implementation's)
+    "TRAIN_NUM_ENVS": 8192, "TRAIN_UPDATES_PER_TICK": 1, "TRAIN_MINIBATCH": 4096, "EVAL_NUM_ENVS": 4096,
     "ST_MODE": "exact",       # arithmetic of the single-state drop-in calls: "exact" (fp64, st_cy-identical) or "fast"
     "CUDA_DEVICE": 0,
 }
@@ -60,6 +62,24 @@ class Settings(metaclass=_SettingsMeta):
             if isinstance(value, dict):
                 value = {int(k): v for k, v in value.items()}
             setattr(cls, key, value)
+
+    @classmethod
+    def setup_logging(cls):
+        """runs/<LOG_DIR>/ with settings.json and out.log (reference config.py:179-193; the source snapshot is not copied)."""
+        import logging
+        import os
+        logdir = os.path.join(getattr(cls, "RUNS_DIR", "runs"), str(cls.LOG_DIR))
+        os.makedirs(logdir, exist_ok=True)
+        with open(os.path.join(logdir, "settings.json"), "w") as f:
+            json.dump({k: v for k, v in cls.export_settings().items() if isinstance(v, (str, int, float, bool, list, dict))},
+                      f, indent=4, sort_keys=True, default=str)
+        for h in list(logging.getLogger().handlers):
+            if isinstance(h, logging.FileHandler):
+                logging.getLogger().removeHandler(h)
+        logging.getLogger().addHandler(logging.FileHandler(os.path.join(logdir, "out.log")))
+        logging.getLogger().setLevel(logging.INFO)
+        cls.FULL_LOG_DIR = logdir
+        return logdir
 
     @classmethod
     def reset(cls):

@@ -72,3 +72,121 @@ def get_ego_start_speed(n=None, generator=None):
         return Settings.START_SPEED if n is None else np.full(n, float(Settings.START_SPEED))
     v = rng.normal(Settings.START_SPEED, Settings.START_SPEED_VARIANCE, size=n)
     return np.clip(v, Settings.MIN_START_SPEED, Settings.MAX_START_SPEED)
+
+
+# ---- batched episode loop: reference control.py:229-363 (run_episode / evaluate_control) --------------------------
+class EpisodeTracker:
+    """Per-episode running reductions of the metrics reference run_episode records tick by tick (control.py:269-318):
+    speed, |jerk| from the acceleration differences, distance to the closest vehicle once on the highway, deceleration
+    forced on the car behind ("disruption"), per-segment histograms, planner take-overs.  All on the device."""
+
+    def __init__(self, num_envs: int, device):
+        f = dict(dtype=torch.float64, device=device)
+        self.B, self.device = num_envs, device
+        names = ("steps", "sum_speed", "max_speed", "sum_abs_jerk", "prev_acc", "min_closest", "sum_closest", "n_closest",
+                 "sum_disr", "max_disr", "n_disr", "nz_disr", "takeovers")
+        self.v = {n: torch.zeros(num_envs, **f) for n in names}
+        self.v["min_closest"].fill_(float("inf"))
+        self.bins = torch.arange(-220, 61, 20, **f)
+        self.seg_counts = torch.zeros(len(self.bins) - 1, **f)
+        self.seg_jerks, self.seg_speeds = torch.zeros_like(self.seg_counts), torch.zeros_like(self.seg_counts)
+
+    def reset_where(self, mask):
+        for n, t in self.v.items():
+            t.masked_fill_(mask, float("inf") if n == "min_closest" else 0.0)
+
+    def record(self, state, takeover=None):
+        """Called with the state the controller sees (before the tick), like the reference loop."""
+        from . import dqn
+        S, V, tick = Settings, self.v, float(Settings.TICK_LENGTH)
+        ex, speed, acc = state.ego[:, 0], state.ego[:, 2], state.ego[:, 3]
+        jerk = torch.where(V["steps"] > 0, (acc - V["prev_acc"]) / tick, torch.zeros_like(acc))       # control.py:286-289
+        V["steps"] += 1; V["sum_speed"] += speed; V["max_speed"] = torch.maximum(V["max_speed"], speed)
+        V["sum_abs_jerk"] += jerk.abs(); V["prev_acc"] = acc.clone()
+        ego_s = dqn._ego_s(state.ego)
+        valid = torch.arange(state.cars_x.shape[1], device=self.device).unsqueeze(0) < state.n_cars.unsqueeze(1)
+        dx = state.cars_x - ex.unsqueeze(1)
+        inf = torch.full_like(dx, float("inf"))
+        ahead = torch.where(valid & (dx >= 0), dx, inf).min(1).values                                   # prediction.py:162-182
+        behind_d, behind_i = torch.where(valid & (dx < 0), -dx, inf).min(1)
+        behind_acc = state.cars_a.gather(1, behind_i.unsqueeze(1)).squeeze(1)
+        on_highway = ego_s > float(S.MERGE_POINT_X)                                                    # control.py:292
+        min_d = torch.minimum(torch.minimum(ahead, behind_d), torch.full_like(ahead, 100.0))           # 305
+        m_close = on_highway & (ego_s > float(S.CRASH_MIN_S))                                          # 306-307
+        V["min_closest"] = torch.where(m_close, torch.minimum(V["min_closest"], min_d), V["min_closest"])
+        V["sum_closest"] += torch.where(m_close, min_d, torch.zeros_like(min_d)); V["n_closest"] += m_close.double()
+        disr = torch.where(on_highway & torch.isfinite(behind_d), (-behind_acc).clamp(min=0), torch.zeros_like(behind_acc))   # 300-304, 308
+        V["sum_disr"] += disr; V["max_disr"] = torch.maximum(V["max_disr"], disr)
+        V["n_disr"] += on_highway.double(); V["nz_disr"] += (disr != 0).double()
+        if takeover is not None:
+            V["takeovers"] += takeover.double()
+        seg = torch.bucketize(ex.contiguous(), self.bins, right=False) - 1                                          # stats.py:44-52
+        ok = (seg >= 0) & (seg < self.seg_counts.numel())
+        seg = seg.clamp(0, self.seg_counts.numel() - 1)
+        self.seg_counts.index_add_(0, seg, ok.double()); self.seg_jerks.index_add_(0, seg, jerk.abs() * ok)
+        self.seg_speeds.index_add_(0, seg, speed.abs() * ok)
+
+    def finished(self, done, crashed, merged, wall_per_env_tick: float):
+        """Episode dicts (host floats) for the rows where `done`."""
+        idx = done.nonzero().squeeze(1)
+        if idx.numel() == 0:
+            return []
+        tick = float(Settings.TICK_LENGTH)
+        rows = {n: t[idx].cpu().numpy() for n, t in self.v.items()}
+        cr, mg = crashed[idx].cpu().numpy(), merged[idx].cpu().numpy()
+        out = []
+        for i in range(idx.numel()):
+            n = max(rows["steps"][i], 1.0)
+            out.append(dict(
+                crashed=bool(cr[i]), merged=bool(mg[i]), mean_speed=rows["sum_speed"][i] / n, max_speed=rows["max_speed"][i],
+                mean_abs_jerk=rows["sum_abs_jerk"][i] / n, time_taken=rows["steps"][i] * tick,
+                clock_time_per_episode=wall_per_env_tick * n, clock_time_per_step=wall_per_env_tick,
+                n_closest=int(rows["n_closest"][i]), closest_distance=rows["min_closest"][i],
+                mean_closest_distance=rows["sum_closest"][i] / max(rows["n_closest"][i], 1.0),
+                n_disruption=int(rows["n_disr"][i]), mean_disruption=rows["sum_disr"][i] / max(rows["n_disr"][i], 1.0),
+                max_disruption=rows["max_disr"][i], total_disruption=rows["sum_disr"][i] * tick,
+                disruption_time=rows["nz_disr"][i] * tick, steps=int(rows["steps"][i]), takeovers=int(rows["takeovers"][i])))
+        return out
+
+
+def evaluate_control(control_function, num_episodes=1000, state_function=None, custom_stats_function=None,
+                     end_episode_callback=None, max_episode_length=100, start_velocity=None, wait_before_start=50,
+                     save_state_on_crash=False, verbose=False, crash_callback=None, num_envs=None, seed=0):
+    """Run `num_episodes` lane-merging episodes under `control_function` and aggregate the reference's statistics
+    (reference control.py:343-363).  Episodes run `num_envs` at a time in merge_gym.MergeEnv.
+
+    control_function(BatchedState) -> commanded speed [B], or (speed [B], takeover mask [B]) for the combined controller.
+    end_episode_callback(done_mask) is called after every tick that finished episodes.  state_function,
+    wait_before_start, start_velocity, crash_callback exist for signature parity (the batched world has no SUMO warm-up).
+    clock_time_per_step is the wall time of a batched tick divided by the number of environments."""
+    import time
+    from . import merge_gym, stats
+    B = int(num_envs or min(max(num_episodes, 1), 4096))
+    Settings.MAX_EPISODE_LENGTH = max_episode_length
+    env = merge_gym.MergeEnv(B, seed=seed)
+    agg = stats.StatsAggregator(save_state_on_crash)
+    if custom_stats_function is not None:
+        agg.add_custom_stat_callback(custom_stats_function)
+    tracker = EpisodeTracker(B, env.device)
+    env.reset()
+    tick = float(Settings.TICK_LENGTH)
+    t_prev, wall = time.perf_counter(), 0.0
+    while agg.episodes < num_episodes:
+        out = control_function(env.state)
+        speed, takeover = out if isinstance(out, tuple) else (out, None)
+        tracker.record(env.state, takeover)
+        jerk = ((speed - env.state.ego[:, 2]) / tick - env.state.ego[:, 3]) / tick
+        _obs, _reward, done, info = env.step(jerk)
+        if bool(done.any()):                                   # (host sync: evaluation bookkeeping, not the hot path)
+            now = time.perf_counter(); wall = 0.9 * wall + 0.1 * (now - t_prev) if wall else now - t_prev
+            for ep in tracker.finished(done, info["crashed"], info["merged"], wall / B):
+                if agg.episodes < num_episodes:
+                    agg.add_episode_stats(ep)
+                    if verbose and ep["crashed"]:
+                        print("crashed")
+            tracker.reset_where(done)
+            if end_episode_callback is not None:
+                end_episode_callback(done)
+        t_prev = time.perf_counter()
+    agg.add_segment_histograms(tracker.seg_counts.cpu().numpy(), tracker.seg_jerks.cpu().numpy(), tracker.seg_speeds.cpu().numpy())
+    return agg

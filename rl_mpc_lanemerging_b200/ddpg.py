@@ -101,4 +101,51 @@ class DDPGAgent(dqn.RLAgent):
         return float(jerk.item()) if single else jerk
 
     def end_episode_callback(self, last_state=None):
-        self.reset_time()
+        """Reference ddpg.py:89-90.  In the batched loops `last_state` is the mask of the episodes that just ended."""
+        self.reset_time(last_state if torch.is_tensor(last_state) else None)
+
+    # ---- training entry points with the reference's names (ddpg.py:46-81) ----
+    @classmethod
+    def _trainer(cls, seed=0, num_envs=None):
+        from . import merge_gym, trainer
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        dev = int(os.environ.get("LOCAL_RANK", getattr(Settings, "CUDA_DEVICE", 0)))
+        Settings.CUDA_DEVICE = dev
+        st.refresh_engine()
+        env = merge_gym.MergeEnv(int(num_envs or Settings.TRAIN_NUM_ENVS), seed=seed + 104729 * rank)
+        return trainer.DDPGTrainer(env, device=f"cuda:{dev}", lr=Settings.LEARNING_RATE, seed=seed,
+                                   minibatch_size=int(Settings.TRAIN_MINIBATCH), updates_per_tick=int(Settings.TRAIN_UPDATES_PER_TICK))
+
+    @classmethod
+    def train(cls, num_frames: int, num_envs=None):
+        """Train from scratch for `num_frames` frames per rank and leave policy.pt / q.pt in Settings.FULL_LOG_DIR."""
+        tr = cls._trainer(num_envs=num_envs).train(int(num_frames))
+        tr.save(Settings.FULL_LOG_DIR)
+        return tr
+
+    @classmethod
+    def resume_training(cls, path, num_frames: int, num_envs=None):
+        tr = cls._trainer(num_envs=num_envs).load(path)
+        tr.train(int(num_frames))
+        tr.save(Settings.FULL_LOG_DIR)
+        return tr
+
+
+def train_ddpg_all_with_lr_drop(num_frames, third=False, num_envs=None):
+    """Reference ddpg.py:96-117: train, divide the learning rate by 10, train again from the first run's weights
+    (optionally a third time), then evaluate NUM_EPISODES episodes with the result."""
+    if not hasattr(Settings, "FULL_LOG_DIR"):
+        Settings.setup_logging()
+    DDPGAgent.train(num_frames, num_envs)
+    stages = 2 if third else 1
+    for i in range(stages):
+        Settings.LEARNING_RATE /= 10
+        old_log_dir = Settings.FULL_LOG_DIR
+        Settings.LOG_DIR = Settings.LOG_DIR + ("_extended" if i == 0 else "2")
+        Settings.setup_logging()
+        DDPGAgent.resume_training(old_log_dir, num_frames, num_envs)
+    Settings.TASK = "EVALUATE_DDPG"
+    Settings.MODEL_NAME = Settings.FULL_LOG_DIR
+    eval_agent = DDPGAgent.load(Settings.FULL_LOG_DIR)
+    return eval_agent.evaluate(Settings.NUM_EPISODES)

@@ -64,6 +64,41 @@ class RLAgent:
     def _setup(self):
         self.takeover_history = []
 
+    def _cleanup(self):
+        pass
+
+    def do_control(self, state):
+        """Apply the agent's jerk: the commanded speed after one tick (reference dqn.py:99-100 -> control.set_ego_jerk)."""
+        jerk = self.get_control(state)
+        if isinstance(state, HighwayState):
+            return control.get_ego_speed_from_jerk(state.ego_speed, state.ego_acceleration, jerk)
+        return control.get_ego_speed_from_jerk(state.ego[:, 2].contiguous(), state.ego[:, 3].contiguous(), jerk.double())
+
+    def end_episode_callback(self, last_state=None):
+        pass
+
+    def combined_stats_callback(self, episode_stats):
+        """Share of the ticks on which the planner took over (reference dqn.py:102-115)."""
+        return {"percent st solver": episode_stats.get("takeovers", 0) / max(episode_stats.get("steps", 0), 1)}
+
+    # ---- reference dqn.py:202-241 ----
+    def evaluate(self, num_episodes, num_envs=None, csv_path="run_data.csv"):
+        self._setup()
+        output = control.evaluate_control(control_function=self.do_control, num_episodes=num_episodes,
+                                          end_episode_callback=self.end_episode_callback, num_envs=num_envs or Settings.EVAL_NUM_ENVS)
+        output.print_stats(csv_path)
+        self._cleanup()
+        return output
+
+    def evaluate_combined(self, num_episodes, num_envs=None, csv_path="run_data.csv"):
+        self._setup()
+        output = control.evaluate_control(control_function=self.do_combined_control, num_episodes=num_episodes,
+                                          end_episode_callback=self.end_episode_callback,
+                                          custom_stats_function=self.combined_stats_callback, num_envs=num_envs or Settings.EVAL_NUM_ENVS)
+        self._cleanup()
+        output.print_stats(csv_path)
+        return output
+
     # ---- reference dqn.py:117-200 ----------------------------------------------------------------
     def do_combined_control(self, state):
         """RL proposes a jerk, a short policy rollout and the MPC planner decide whether the planner takes over.

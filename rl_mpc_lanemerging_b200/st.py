@@ -159,3 +159,12 @@ def get_path_mean_abs_jerk(s_sequence, ego_start_speed, ego_start_acceleration, 
     for x in j:                       # sequential accumulation like the reference's loop
         total += abs(float(x))
     return total / (len(s) - 1)
+
+
+def evaluate_st_and_dump_crash(num_episodes=1000, num_envs=None, csv_path="run_data.csv"):
+    """Reference st.py:822-824: closed-loop evaluation of the pure MPC controller; prints the statistics and appends the
+    run_data.csv row.  (The crash replay pickle of the reference is debug tooling and not reproduced.)"""
+    from . import control
+    output = control.evaluate_control(do_st_control, num_episodes=num_episodes, num_envs=num_envs or Settings.EVAL_NUM_ENVS)
+    output.print_stats(csv_path)
+    return output

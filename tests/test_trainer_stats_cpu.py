@@ -1,0 +1,108 @@
+"""-m "not gpu": host logic of the "next" rows on CPU -- the data-parallel DDPG step with its single
+flat-gradient all-reduce (gloo, world_size 2), and the StatsAggregator / run_data.csv contract."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _ToyEnv:
+    """Stands in for merge_gym.MergeEnv (which needs the GPU): B independent 20-dim random walks, reward = -|action|."""
+
+    def __init__(self, B, seed):
+        self.B, self.device = B, torch.device("cpu")
+        self.g = torch.Generator().manual_seed(seed)
+        self.obs = torch.zeros(B, 20)
+
+    def reset(self):
+        self.obs = torch.rand(self.B, 20, generator=self.g)
+        return self.obs
+
+    def step(self, action):
+        self.obs = (self.obs + 0.01 * torch.randn(self.B, 20, generator=self.g)).clamp(0, 1)
+        done = torch.rand(self.B, generator=self.g) < 0.05
+        return self.obs, -action.abs().double(), done, {}
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rl_mpc_lanemerging_b200 import trainer
+    tr = trainer.DDPGTrainer(_ToyEnv(16, seed=rank), device="cpu", lr=1e-3, seed=3, minibatch_size=32, replay_start_size=64,
+                             replay_buffer_size=4096)
+    p0 = torch.nn.utils.parameters_to_vector(tr.policy.parameters()).clone()
+    tr.train(16 * 12)
+    vec = torch.cat([torch.nn.utils.parameters_to_vector(m.parameters()) for m in (tr.policy, tr.q, tr.policy_target, tr.q_target)])
+    q.put((rank, vec.detach().numpy(), float((vec[:p0.numel()] - p0).abs().max()), tr.grad_steps, tr.allreduce_bytes,
+           float(tr.replay.obs[:tr.replay.size].sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ddpg_replicas_stay_identical():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, v0, moved0, steps0, nbytes, rep0), (_, v1, _moved1, steps1, _, rep1) = res
+    assert steps0 == steps1 and steps0 >= 8
+    assert nbytes == (129401 + 129801) * 4                       # one fp32 bucket: policy + critic
+    assert np.array_equal(v0, v1)                                # replicas bit-identical after averaged-gradient steps
+    assert moved0 > 0 and rep0 != rep1                           # they learned, from different experience
+
+
+def test_flat_gradient_bucket_and_checkpoint_layout(tmp_path):
+    from rl_mpc_lanemerging_b200 import ddpg, trainer
+    tr = trainer.DDPGTrainer(_ToyEnv(8, seed=0), device="cpu", lr=1e-3, seed=1, minibatch_size=16, replay_start_size=16,
+                             replay_buffer_size=256)
+    tr.train(8 * 6)
+    lo, hi = tr.flat_grad.data_ptr(), tr.flat_grad.data_ptr() + tr.flat_grad.numel() * 4
+    for p in list(tr.policy.parameters()) + list(tr.q.parameters()):
+        assert lo <= p.grad.data_ptr() < hi                      # autograd accumulated in place: still views of the bucket
+    assert float(tr.flat_grad.abs().sum()) > 0
+    tr.save(str(tmp_path))
+    sd = torch.load(os.path.join(tmp_path, "policy.pt"))
+    assert sorted(sd) == ["model.0.bias", "model.0.weight", "model.2.bias", "model.2.weight", "model.4.bias", "model.4.weight"]
+    assert sd["model.0.weight"].shape == (400, 21) and torch.load(os.path.join(tmp_path, "q.pt"))["model.0.weight"].shape == (400, 22)
+    pol = ddpg.PolicyNet()
+    pol.load_state_dict(ddpg._load_legacy_state_dict(os.path.join(tmp_path, "policy.pt")))
+    x = torch.rand(5, 21)
+    assert torch.equal(pol(x), tr.policy(x))
+    tr2 = trainer.DDPGTrainer(_ToyEnv(8, seed=0), device="cpu", seed=9).load(str(tmp_path))       # resume_training path
+    assert torch.equal(tr2.q(x, x[:, 0]), tr.q(x, x[:, 0]))
+
+
+def test_stats_row_has_the_reference_columns(tmp_path):
+    from rl_mpc_lanemerging_b200 import stats
+    from rl_mpc_lanemerging_b200.config import Settings
+    Settings.reset()
+    agg = stats.StatsAggregator()
+    agg.add_custom_stat_callback(lambda ep: {"percent st solver": ep["takeovers"] / ep["steps"]})
+    rng = np.random.default_rng(0)
+    for i in range(12):
+        merged = i % 4 != 0
+        agg.add_episode_stats(dict(crashed=not merged and i % 8 == 0, merged=merged, mean_speed=12 + rng.random(), max_speed=20.0,
+                                   mean_abs_jerk=0.5 + rng.random(), time_taken=20.0 + i, clock_time_per_episode=0.1,
+                                   clock_time_per_step=1e-3, n_closest=5 if merged else 0, closest_distance=7.0,
+                                   mean_closest_distance=9.0, n_disruption=5, mean_disruption=0.1, max_disruption=0.5,
+                                   total_disruption=0.3, disruption_time=0.6, steps=100, takeovers=3))
+    row = agg.get_stat_report_row_dict()
+    for name in ("crashed", "merged", "mean_abs_jerk_merged", "time_to_merge", "clock_time_per_step", "closest_distance_merged",
+                 "total_disruption", "percent st solver"):
+        assert name in row and name + "_std" in row
+    assert row["merged"] == 9 / 12 and abs(row["percent st solver"] - 0.03) < 1e-12
+    assert row["time_to_merge"] == np.mean([20.0 + i for i in range(12) if i % 4 != 0])
+    assert row["ST_DESCRIPTION"] == "st-0.5-10.0-10.0-10.0-5-12-0.0-0.0" and row["TRAFFIC_DESCRIPTION"] == "uniform-7.0-1.2-varying"
+    assert row["OTHER_CAR_SPEED"] == 7.0 and row["TASK"] == "ST"          # scalar Settings ride along as columns
+    csv = os.path.join(tmp_path, "run_data.csv")
+    agg.add_csv_data(csv); agg.add_csv_data(csv)
+    import pandas as pd
+    assert len(pd.read_csv(csv)) == 2
