@@ -437,17 +437,19 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
                                         VAL = word - 255ULL * (E) + ((unsigned long long)(lds_u32_nc(tva + 4u * (E)) + lds_u32_nc(taja + 68u * (E))) << 16); \
                                         RES = atoms_cas_u64_if(ra + 8u * (E), OLD, VAL, ((open >> (E)) & 1u) && VAL < OLD)
 #define MPC_CHECK(E, OLD, RES, VAL) redo |= (RES != OLD && VAL < RES) ? (1u << (E)) : 0u
-                                        MPC_PREREAD(2, oldA); MPC_PREREAD(3, oldB);
+                                        // Cells offered while another pre-read is in flight are 3 apart: neighbouring nodes have windows
+                                        // shifted by 1-2 cells, so their CAS rarely lands on a cell this lane has already pre-read.
+                                        MPC_PREREAD(2, oldA);
                                         MPC_OFFER(2, oldA, resA, valA);
+                                        MPC_PREREAD(3, oldB); MPC_CHECK(2, oldA, resA, valA); MPC_PREREAD(0, oldA);
                                         MPC_OFFER(3, oldB, resB, valB);
-                                        MPC_CHECK(2, oldA, resA, valA); MPC_PREREAD(1, oldA);
-                                        MPC_CHECK(3, oldB, resB, valB); MPC_PREREAD(4, oldB);
-                                        MPC_OFFER(1, oldA, resA, valA);
-                                        MPC_OFFER(4, oldB, resB, valB);
-                                        MPC_CHECK(1, oldA, resA, valA); MPC_PREREAD(0, oldA);
-                                        MPC_CHECK(4, oldB, resB, valB);
                                         MPC_OFFER(0, oldA, resA, valA);
-                                        MPC_CHECK(0, oldA, resA, valA);
+                                        MPC_CHECK(3, oldB, resB, valB); MPC_PREREAD(1, oldB);
+                                        MPC_CHECK(0, oldA, resA, valA); MPC_PREREAD(4, oldA);
+                                        MPC_OFFER(1, oldB, resB, valB);
+                                        MPC_OFFER(4, oldA, resA, valA);
+                                        MPC_CHECK(1, oldB, resB, valB);
+                                        MPC_CHECK(4, oldA, resA, valA);
 #undef MPC_PREREAD
 #undef MPC_OFFER
 #undef MPC_CHECK
