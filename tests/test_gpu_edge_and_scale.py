@@ -156,3 +156,35 @@ def test_horizon_and_density_sweep(oracle, H, traffic, B):
     assert np.all(helpers.rel(fa["cost"].cpu().numpy()[ok], ref["cost"][ok]) < 1e-6)
     assert (fa["idx"].cpu().numpy() == ref["idx"]).all(1).sum() >= B - 1
     eng.close()
+
+
+@pytest.mark.parametrize("over", [dict(start_uncertainty=0.5, uncertainty_per_second=0.3), dict(min_allowed_distance=6.0, crash_min_s=15.0),
+                                  dict(d_weight=100.0, v_weight=1.0), dict(car_length=4.0, min_allowed_distance=3.0)])
+def test_other_settings_keep_parity(oracle, over):
+    """Settings away from the published configs (prediction uncertainty widens the bands, other safety distances / weights --
+    the reference's grid-search ranges, main.py:43-52): exact mode index-identical, fast mode bit-identical to its CPU model, and
+    the blocked intervals of the lean bounded pass still equal 'in a band or inside a penalty zone' on every cell."""
+    import torch
+    from rl_mpc_lanemerging_b200 import synthetic
+    from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
+    op = oracle.horizon_params(17, **over)
+    B = 48
+    eng = MpcEngine(helpers.mpc_params_from_oracle(op), device=0, max_batch=B)
+    S = synthetic.make_states(B, "moderate", seed=41, kind="mixed")
+    ref = helpers.oracle_plan_batch(oracle, op, S, 18)
+    D = states_to_device(S, "cuda:0")
+    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
+    assert eng.selftest_search(*a) == 0
+    ex = eng.plan(*a, mode="exact")
+    assert np.array_equal(ex["idx"].cpu().numpy(), ref["idx"]) and np.array_equal(ex["cost"].cpu().numpy(), ref["cost"])
+    fa = {k: v.cpu().numpy() for k, v in eng.plan(*a, mode="fast").items()}
+    torch.cuda.synchronize()
+    assert np.array_equal(fa["reached_t"], ref["reached_t"])
+    ok = ref["cost"] > 0
+    assert np.all(helpers.rel(fa["cost"][ok], ref["cost"][ok]) <= 1e-4)
+    for b in range(0, B, 5):
+        st = helpers.oracle_state(oracle, S, b)
+        obst, dist, sv = oracle.build_grid(op, st)
+        m = oracle.solve_fast_model(op, obst, dist, sv, op.t_disc, st.ego_v, st.ego_a)
+        assert np.array_equal(m["idx"], fa["idx"][b]) and m["cost"] == fa["cost"][b], (b, m["cost"], fa["cost"][b])
+    eng.close()
