@@ -185,20 +185,20 @@ static int configure(mpc_handle *h) {
     // Ring sized for two blocks per SM when that still covers 2/3 of the row (frontier spans measured: <= 0.6 of the row on
     // ordinary traffic; H=50: ring = 0.73 row, 7.7+0.5 ms vs 9.7 ms with one block per SM), else for one block per SM (long horizons).  MPC_FAST_BLOCKS=32|64 overrides (1 | 2 blocks/SM).
     // MPC_FAST_BLOCKS = 32 * (blocks per SM, 1..4) and MPC_FAST_THREADS override the shape (dev sweeps).
-    // Blocks per SM: as many (<= 4) as still leave a ring of 2/3 of the row -- the barrier per layer makes a block latency bound,
-    // more resident blocks hide it (H=17: 4 x 256 threads, H=25: 3 x 384, H=50: 2 x 512, H=100: 1 x 1024).
+    // Blocks per SM: as many (<= 5) as still leave a ring of 2/3 of the row -- the barrier per layer makes a block latency bound,
+    // more resident blocks hide it (H=17: 5 x 192 threads, H=25: 3 x 384, H=50: 2 x 512, H=100: 1 x 1024).
     int auto_blocks = 1;
-    for (int nb = 2; nb <= 4; nb++) {
+    for (int nb = 2; nb <= 5; nb++) {
         const size_t per = (h->smem_optin + 1024) / nb;
         if (per > 1024 + static_smem + clamp_bytes && ((per - 1024 - static_smem - clamp_bytes) / 16) * 3 >= (size_t)h->W * 2) auto_blocks = nb;
     }
-    int fast_blocks = env_int("MPC_FAST_BLOCKS", 32, 128, 32 * auto_blocks) / 32;
+    int fast_blocks = env_int("MPC_FAST_BLOCKS", 32, 160, 32 * auto_blocks) / 32;
     size_t cap = ((h->smem_optin + 1024) / fast_blocks - 1024 - static_smem - clamp_bytes) / 16;
     h->wrap_fast = (size_t)h->W > cap;
     h->Wc = h->wrap_fast ? (int)(cap & ~(size_t)7) : h->W;
     h->smem_fast = (size_t)h->Wc * 16 + clamp_bytes;
     int bps = (int)(h->smem_optin / (h->smem_fast + static_smem));
-    h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 4 ? 256 : (bps >= 3 ? 384 : (bps >= 2 ? 512 : 1024)));
+    h->threads_fast = env_int("MPC_FAST_THREADS", 64, 1024, bps >= 5 ? 192 : (bps >= 4 ? 256 : (bps >= 3 ? 384 : (bps >= 2 ? 512 : 1024))));
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;

@@ -243,7 +243,7 @@ __device__ __forceinline__ void build_blocked_bits(const LayerSearch &L, unsigne
 struct FxTables { unsigned v[256], aj[32 * 16]; };     // aj[(a'+16)*16 + (j'+8)] = A[a'] + J[j']: one lookup, stride 17 along a window
 
 template <class Prov, bool DESC, bool WRAP, int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
+__global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
                                                                               const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc,
                                                                               unsigned long long bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
                 __syncthreads();                              // pushes into layer t, its span, staging of layer t+2 and bits of t+1 are complete
                 dlo = S.nlo[s3]; dhi = S.nhi[s3];
                 if (dhi < 0) break;                           // no successors
-                if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
+                if (WRAP && dhi - dlo + 1 + (t == T - 1 ? 0 : P.vmax_c + 8) > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier (and, but for the last layer, its successors) may outgrow the ring
                 if (tid == 0) { S.nlo[(t + 2) % 3] = INT_MAX; S.nhi[(t + 2) % 3] = -1; s_chunk[n3] = 0; }    // what iteration t+1 accumulates into
                 if (t + 3 < T) prov.store(t + 3);             // loaded during iteration t-1; first read in iteration t+1
                 if (t + 4 < T) prov.load(t + 4);
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAX
         for (int t = 2; !done && t < T; t++) {
             const int par = t & 1, s3 = t % 3, n3 = (t + 1) % 3;
             const unsigned cur = par ? sb1 : sb0, nxt = par ? sb0 : sb1;
-            if (WRAP && dhi - dlo + 1 + P.vmax_c + 8 > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
+            if (WRAP && dhi - dlo + 1 + (t == T - 1 ? 0 : P.vmax_c + 8) > Wc) { if (tid == 0) S.need_fallback = 1; break; }   // frontier may outgrow the ring
             if (tid == 0) { S.nlo[n3] = INT_MAX; S.nhi[n3] = -1; s_layer_best[par] = FX_EMPTY; s_chunk[n3] = 0; }
             __syncthreads();                                  // pushes into layer t complete; staging of layers t, t+1 visible
             if (t + 2 < T) prov.load(t + 2);                  // prefetch the search structure of layer t+2
@@ -625,7 +625,8 @@ static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;                                            \
         k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, desc, ob, dist, stride, L.W, L.bound);                     \
     } while (0)
-    if (L.threads <= 256) { if (L.wrap) MPC_LAUNCH_FAST(true, 256); else MPC_LAUNCH_FAST(false, 256); }
+    if (L.threads <= 192) { if (L.wrap) MPC_LAUNCH_FAST(true, 192); else MPC_LAUNCH_FAST(false, 192); }
+    else if (L.threads <= 256) { if (L.wrap) MPC_LAUNCH_FAST(true, 256); else MPC_LAUNCH_FAST(false, 256); }
     else if (L.threads <= 384) { if (L.wrap) MPC_LAUNCH_FAST(true, 384); else MPC_LAUNCH_FAST(false, 384); }
     else if (L.threads <= 512) { if (L.wrap) MPC_LAUNCH_FAST(true, 512); else MPC_LAUNCH_FAST(false, 512); }
     else { if (L.wrap) MPC_LAUNCH_FAST(true, 1024); else MPC_LAUNCH_FAST(false, 1024); }
@@ -654,7 +655,8 @@ int fast_occupancy(int threads, size_t smem, int wrap) {
         if (set_smem(k, smem) != cudaSuccess) { cudaGetLastError(); return 0; }                            \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem);                           \
     } while (0)
-    if (threads <= 256) { if (wrap) MPC_OCC(true, 256); else MPC_OCC(false, 256); }
+    if (threads <= 192) { if (wrap) MPC_OCC(true, 192); else MPC_OCC(false, 192); }
+    else if (threads <= 256) { if (wrap) MPC_OCC(true, 256); else MPC_OCC(false, 256); }
     else if (threads <= 384) { if (wrap) MPC_OCC(true, 384); else MPC_OCC(false, 384); }
     else if (threads <= 512) { if (wrap) MPC_OCC(true, 512); else MPC_OCC(false, 512); }
     else { if (wrap) MPC_OCC(true, 1024); else MPC_OCC(false, 1024); }
