@@ -12,7 +12,7 @@
 // iterates are not reproducible bit for bit; here the same convex QP is solved by a Mehrotra predictor-corrector
 // primal-dual interior-point method (the same family, ~12 iterations to 1e-9): with G = [A; -A] the Newton system
 // reduces to (I + A^T diag(w) A) dx = g, which is banded (half-bandwidth 3) and is factorised in place per iteration.
-// One thread per episode (m <= 25 unknowns at the published discretisation).  Parity vs cvxopt is UNPINNED (SURVEY.md
+// One warp per episode (m <= 25 unknowns at the published discretisation).  Parity vs cvxopt is UNPINNED (SURVEY.md
 // §8c); the tests check the KKT conditions and agreement with an independent CPU solve (scipy SLSQP).
 #include "mpc_common.cuh"
 
@@ -74,13 +74,48 @@ __device__ __forceinline__ void qp_solve(int m, const double (*Lb)[4], double *g
     }
 }
 
-__global__ void __launch_bounds__(64) finer_fit_kernel(DevParams P, int B, int T, const double *__restrict__ s_seq,
-                                                       const int32_t *__restrict__ reached, const double *__restrict__ ego,
-                                                       int max_iter, double tol, double *__restrict__ fine, int fine_stride,
-                                                       int32_t *__restrict__ n_fine, double *__restrict__ speed,
-                                                       int32_t *__restrict__ iters_out) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// ---- one WARP per episode ------------------------------------------------------------------------------------------
+// The rows of A (<= 117) are spread over the lanes, the vectors live in shared memory; only the banded Cholesky factorisation
+// and the two triangular solves (m <= 39 steps, half-bandwidth 3) are sequential and done by lane 0.  (The first version ran one
+// THREAD per episode with ~13 KB of local-memory arrays: 7.2 ms for the ~1200 take-over episodes of a closed-loop tick, 70 % of
+// the tick; this one takes tens of microseconds.)
+#define QP_WARPS 2
+struct QpWarpShared {
+    double x[QP_MAXN], g[QP_MAXN], rd[QP_MAXN], bv[QP_MAXN];
+    double r[QP_R], w[QP_R], ax[QP_R], su[QP_R], sl[QP_R], zu[QP_R], zl[QP_R], lb[QP_R], ub[QP_R];
+    double dsu[QP_R], dsl[QP_R], dzu[QP_R], dzl[QP_R], tcu[QP_R], tcl[QP_R];
+    double Mb[QP_M][4];
+};
+__device__ __forceinline__ double wsum(double v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+__device__ __forceinline__ double wmax(double v) { for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ double wmin(double v) { for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+
+// row rr = (family f, position i) of A applied to u (see qp_apply_A)
+__device__ __forceinline__ double qp_row(int m, int rr, const double *u) {
+    const int f = rr / m, i = rr - f * m;
+    const double u0 = u[i], u1 = i >= 1 ? u[i - 1] : 0.0, u2 = i >= 2 ? u[i - 2] : 0.0, u3 = i >= 3 ? u[i - 3] : 0.0;
+    return f == 0 ? u0 - u1 : (f == 1 ? u0 - 2.0 * u1 + u2 : u0 - 3.0 * u1 + 3.0 * u2 - u3);
+}
+// (A^T w)[i]  (see qp_apply_AT)
+__device__ __forceinline__ double qp_col(int m, int i, const double *w) {
+    const double *w1 = w, *w2 = w + m, *w3 = w + 2 * m;
+    double s = w1[i] + w2[i] + w3[i];
+    if (i + 1 < m) s += -w1[i + 1] - 2.0 * w2[i + 1] - 3.0 * w3[i + 1];
+    if (i + 2 < m) s += w2[i + 2] + 3.0 * w3[i + 2];
+    if (i + 3 < m) s += -w3[i + 3];
+    return s;
+}
+
+__global__ void __launch_bounds__(32 * QP_WARPS) finer_fit_kernel(DevParams P, int B, int T, const double *__restrict__ s_seq,
+                                                                 const int32_t *__restrict__ reached, const double *__restrict__ ego,
+                                                                 int max_iter, double tol, double *__restrict__ fine, int fine_stride,
+                                                                 int32_t *__restrict__ n_fine, double *__restrict__ speed,
+                                                                 int32_t *__restrict__ iters_out) {
+    __shared__ QpWarpShared SH[QP_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int b = blockIdx.x * QP_WARPS + wib;
+    if (b >= B) return;                                          // (whole warp)
+    QpWarpShared &S = SH[wib];
     const double dt = P.p.tick_length, dtc = P.p.t_disc;
     const int Lc = reached[b] + 1;                               // coarse points that exist (st.py:762-768 trims the 0.0 tail)
     const double *sc = s_seq + (size_t)b * T;
@@ -96,112 +131,155 @@ __global__ void __launch_bounds__(64) finer_fit_kernel(DevParams P, int B, int T
     }
     const int m = n - 1;
     if (m <= 0) {                                                // st.py:587-588, 775-777: keep the current speed
-        out[0] = sc[0]; n_fine[b] = 1; if (speed) speed[b] = v0; if (iters_out) iters_out[b] = 0;
+        if (lane == 0) { out[0] = sc[0]; n_fine[b] = 1; if (speed) speed[b] = v0; if (iters_out) iters_out[b] = 0; }
         return;
     }
+    const int R = 3 * m;
     // st.py:597-598: linear interpolation (scipy interp1d: slope * (x - x_lo) + y_lo on the bracketing interval)
-    double bv[QP_M];
-    for (int i = 1; i < n; i++) {
+    for (int i = 1 + lane; i < n; i += 32) {
         double tf = (double)i * dt;
         int hi = 1;
         while (hi < Lc - 1 && (double)hi * dtc < tf) hi++;
         int lo = hi - 1;
         double xl = (double)lo * dtc, xh = (double)hi * dtc;
-        bv[i - 1] = (sc[hi] - sc[lo]) / (xh - xl) * (tf - xl) + sc[lo];
+        S.bv[i - 1] = (sc[hi] - sc[lo]) / (xh - xl) * (tf - xl) + sc[lo];
+        S.x[i - 1] = S.bv[i - 1];
     }
     // bounds of the rows with the fixed history (x_{-2}, x_{-1}, x_0; st.py:626-668) folded in
     const double f2 = sc[0], f1 = f2 - v0 * dt, f0 = f1 - (v0 - a0 * dt) * dt;
-    double lb[QP_R], ub[QP_R];
     {
         const double lo1 = 0.0, hi1 = P.p.max_speed * dt, lo2 = P.p.a_min * dt * dt, hi2 = P.p.a_max * dt * dt;
         const double lo3 = P.p.j_min * dt * dt * dt, hi3 = P.p.j_max * dt * dt * dt;
-        for (int i = 0; i < m; i++) {
-            double k1 = (i == 0) ? -f2 : 0.0;
-            double k2 = (i == 0) ? (-2.0 * f2 + f1) : (i == 1 ? f2 : 0.0);
-            double k3 = (i == 0) ? (-3.0 * f2 + 3.0 * f1 - f0) : (i == 1 ? (3.0 * f2 - f1) : (i == 2 ? -f2 : 0.0));
-            lb[i] = lo1 - k1; ub[i] = hi1 - k1; lb[m + i] = lo2 - k2; ub[m + i] = hi2 - k2; lb[2 * m + i] = lo3 - k3; ub[2 * m + i] = hi3 - k3;
+        for (int rr = lane; rr < R; rr += 32) {
+            const int f = rr / m, i = rr - f * m;
+            double k, lo, hi;
+            if (f == 0) { k = (i == 0) ? -f2 : 0.0; lo = lo1; hi = hi1; }
+            else if (f == 1) { k = (i == 0) ? (-2.0 * f2 + f1) : (i == 1 ? f2 : 0.0); lo = lo2; hi = hi2; }
+            else { k = (i == 0) ? (-3.0 * f2 + 3.0 * f1 - f0) : (i == 1 ? (3.0 * f2 - f1) : (i == 2 ? -f2 : 0.0)); lo = lo3; hi = hi3; }
+            S.lb[rr] = lo - k; S.ub[rr] = hi - k;
         }
     }
-    const int R = 3 * m;
-    double x[QP_M], r[QP_R], su[QP_R], sl[QP_R], zu[QP_R], zl[QP_R], w[QP_R], dsu[QP_R], dsl[QP_R], dzu[QP_R], dzl[QP_R], g[QP_M], tcu[QP_R], tcl[QP_R];
-    double Mb[QP_M][4];
-    for (int i = 0; i < m; i++) x[i] = bv[i];
-    qp_apply_A(m, x, r);
-    for (int i = 0; i < R; i++) { su[i] = fmax(ub[i] - r[i], 0.1); sl[i] = fmax(r[i] - lb[i], 0.1); zu[i] = 1.0; zl[i] = 1.0; }
+    __syncwarp();
+    for (int rr = lane; rr < R; rr += 32) {
+        const double rv = qp_row(m, rr, S.x);
+        S.su[rr] = fmax(S.ub[rr] - rv, 0.1); S.sl[rr] = fmax(rv - S.lb[rr], 0.1); S.zu[rr] = 1.0; S.zl[rr] = 1.0;
+    }
+    __syncwarp();
     int it = 0;
     for (; it < max_iter; it++) {
-        qp_apply_A(m, x, r);
         double mu = 0.0, res = 0.0;
-        for (int i = 0; i < R; i++) { mu += su[i] * zu[i] + sl[i] * zl[i]; res = fmax(res, fmax(fabs(r[i] + su[i] - ub[i]), fabs(-r[i] + sl[i] + lb[i]))); }
-        mu /= (double)(2 * R);
-        // rd = x - b + A^T (zu - zl)
-        double rd[QP_M];
-        for (int i = 0; i < m; i++) rd[i] = x[i] - bv[i];
-        for (int i = 0; i < R; i++) w[i] = zu[i] - zl[i];
-        qp_apply_AT(m, w, rd);
-        for (int i = 0; i < m; i++) res = fmax(res, fabs(rd[i]));
-        if ((res < tol && mu < tol) || mu < 1e-13) break;
-        for (int i = 0; i < R; i++) w[i] = zu[i] / su[i] + zl[i] / sl[i];
-        qp_factor(m, w, Mb);
+        for (int rr = lane; rr < R; rr += 32) {
+            const double rv = qp_row(m, rr, S.x);
+            S.r[rr] = rv;
+            mu += S.su[rr] * S.zu[rr] + S.sl[rr] * S.zl[rr];
+            res = fmax(res, fmax(fabs(rv + S.su[rr] - S.ub[rr]), fabs(-rv + S.sl[rr] + S.lb[rr])));
+            S.w[rr] = S.zu[rr] - S.zl[rr];
+        }
+        __syncwarp();
+        mu = wsum(mu) / (double)(2 * R);
+        for (int i = lane; i < m; i += 32) {                    // rd = x - b + A^T (zu - zl)
+            const double v = S.x[i] - S.bv[i] + qp_col(m, i, S.w);
+            S.rd[i] = v; res = fmax(res, fabs(v));
+        }
+        res = wmax(res);
+        if ((res < tol && mu < tol) || mu < 1e-13) break;        // (uniform)
+        __syncwarp();
+        for (int rr = lane; rr < R; rr += 32) S.w[rr] = S.zu[rr] / S.su[rr] + S.zl[rr] / S.sl[rr];
+        __syncwarp();
+        // M = I + A^T diag(w) A, band storage Mb[i][d] = M(i, i-d)
+        for (int i = lane; i < m; i += 32) {
+            const double c1[2] = {1, -1}, c2[3] = {1, -2, 1}, c3[4] = {1, -3, 3, -1};
+            for (int d = 0; d < 4; d++) {
+                double v = (d == 0) ? 1.0 : 0.0;
+                if (i - d >= 0)
+                    for (int p = 0; p + d < 4 && i + p < m; p++) {
+                        v += S.w[2 * m + i + p] * c3[p] * c3[p + d];
+                        if (p + d < 3) v += S.w[m + i + p] * c2[p] * c2[p + d];
+                        if (p + d < 2) v += S.w[i + p] * c1[p] * c1[p + d];
+                    }
+                S.Mb[i][d] = v;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {                                        // banded Cholesky in place (sequential)
+            for (int i = 0; i < m; i++)
+                for (int d = 3; d >= 0; d--) {
+                    const int j = i - d;
+                    if (j < 0) { S.Mb[i][d] = 0.0; continue; }
+                    double sv = S.Mb[i][d];
+                    for (int k = (i - 3 > 0 ? i - 3 : 0); k < j; k++) sv -= S.Mb[i][i - k] * S.Mb[j][j - k];
+                    S.Mb[i][d] = (d == 0) ? sqrt(sv) : sv / S.Mb[j][0];
+                }
+        }
+        __syncwarp();
         double sigma_mu = 0.0;
         for (int pass = 0; pass < 2; pass++) {
             // complementarity targets: predictor su*zu ; corrector su*zu + dsu*dzu - sigma*mu
-            for (int i = 0; i < m; i++) g[i] = rd[i];
-            for (int i = 0; i < R; i++) {
-                double rpu = r[i] + su[i] - ub[i], rpl = -r[i] + sl[i] + lb[i];
-                double rcu = su[i] * zu[i], rcl = sl[i] * zl[i];
-                if (pass) { rcu += dsu[i] * dzu[i] - sigma_mu; rcl += dsl[i] * dzl[i] - sigma_mu; }
-                w[i] = (-rcu + zu[i] * rpu) / su[i] - (-rcl + zl[i] * rpl) / sl[i];
-                tcu[i] = rcu; tcl[i] = rcl;
+            for (int rr = lane; rr < R; rr += 32) {
+                const double rv = S.r[rr];
+                const double rpu = rv + S.su[rr] - S.ub[rr], rpl = -rv + S.sl[rr] + S.lb[rr];
+                double rcu = S.su[rr] * S.zu[rr], rcl = S.sl[rr] * S.zl[rr];
+                if (pass) { rcu += S.dsu[rr] * S.dzu[rr] - sigma_mu; rcl += S.dsl[rr] * S.dzl[rr] - sigma_mu; }
+                S.w[rr] = (-rcu + S.zu[rr] * rpu) / S.su[rr] - (-rcl + S.zl[rr] * rpl) / S.sl[rr];
+                S.tcu[rr] = rcu; S.tcl[rr] = rcl;
             }
-            qp_apply_AT(m, w, g);
-            for (int i = 0; i < m; i++) g[i] = -g[i];
-            qp_solve(m, Mb, g);                                // g = dx
-            double ax_tmp[QP_R];
-            qp_apply_A(m, g, ax_tmp);
+            __syncwarp();
+            for (int i = lane; i < m; i += 32) S.g[i] = -(S.rd[i] + qp_col(m, i, S.w));
+            __syncwarp();
+            if (lane == 0) qp_solve(m, S.Mb, S.g);              // g = dx
+            __syncwarp();
             double ap = 1.0, ad = 1.0;
-            for (int i = 0; i < R; i++) {
-                double rpu = r[i] + su[i] - ub[i], rpl = -r[i] + sl[i] + lb[i];
-                double d_su = -rpu - ax_tmp[i], d_sl = -rpl + ax_tmp[i];
-                double d_zu = -(tcu[i] + zu[i] * d_su) / su[i], d_zl = -(tcl[i] + zl[i] * d_sl) / sl[i];
-                dsu[i] = d_su; dsl[i] = d_sl; dzu[i] = d_zu; dzl[i] = d_zl;
-                if (d_su < 0.0) ap = fmin(ap, -su[i] / d_su);
-                if (d_sl < 0.0) ap = fmin(ap, -sl[i] / d_sl);
-                if (d_zu < 0.0) ad = fmin(ad, -zu[i] / d_zu);
-                if (d_zl < 0.0) ad = fmin(ad, -zl[i] / d_zl);
+            for (int rr = lane; rr < R; rr += 32) {
+                const double rv = S.r[rr], axv = qp_row(m, rr, S.g);
+                const double rpu = rv + S.su[rr] - S.ub[rr], rpl = -rv + S.sl[rr] + S.lb[rr];
+                const double d_su = -rpu - axv, d_sl = -rpl + axv;
+                const double d_zu = -(S.tcu[rr] + S.zu[rr] * d_su) / S.su[rr], d_zl = -(S.tcl[rr] + S.zl[rr] * d_sl) / S.sl[rr];
+                S.dsu[rr] = d_su; S.dsl[rr] = d_sl; S.dzu[rr] = d_zu; S.dzl[rr] = d_zl;
+                if (d_su < 0.0) ap = fmin(ap, -S.su[rr] / d_su);
+                if (d_sl < 0.0) ap = fmin(ap, -S.sl[rr] / d_sl);
+                if (d_zu < 0.0) ad = fmin(ad, -S.zu[rr] / d_zu);
+                if (d_zl < 0.0) ad = fmin(ad, -S.zl[rr] / d_zl);
             }
+            ap = wmin(ap); ad = wmin(ad);
             if (pass == 0) {
                 double mu_aff = 0.0;
-                for (int i = 0; i < R; i++) mu_aff += (su[i] + ap * dsu[i]) * (zu[i] + ad * dzu[i]) + (sl[i] + ap * dsl[i]) * (zl[i] + ad * dzl[i]);
-                mu_aff /= (double)(2 * R);
-                double sg = mu_aff / mu; sigma_mu = sg * sg * sg * mu;
+                for (int rr = lane; rr < R; rr += 32)
+                    mu_aff += (S.su[rr] + ap * S.dsu[rr]) * (S.zu[rr] + ad * S.dzu[rr]) + (S.sl[rr] + ap * S.dsl[rr]) * (S.zl[rr] + ad * S.dzl[rr]);
+                mu_aff = wsum(mu_aff) / (double)(2 * R);
+                const double sg = mu_aff / mu; sigma_mu = sg * sg * sg * mu;
             } else {
                 // fraction to the boundary 0.995 (the unit step is kept when no slack / multiplier blocks it)
                 double apf = 1.0e9, adf = 1.0e9;
-                for (int i = 0; i < R; i++) {
-                    if (dsu[i] < 0.0) apf = fmin(apf, -su[i] / dsu[i]);
-                    if (dsl[i] < 0.0) apf = fmin(apf, -sl[i] / dsl[i]);
-                    if (dzu[i] < 0.0) adf = fmin(adf, -zu[i] / dzu[i]);
-                    if (dzl[i] < 0.0) adf = fmin(adf, -zl[i] / dzl[i]);
+                for (int rr = lane; rr < R; rr += 32) {
+                    if (S.dsu[rr] < 0.0) apf = fmin(apf, -S.su[rr] / S.dsu[rr]);
+                    if (S.dsl[rr] < 0.0) apf = fmin(apf, -S.sl[rr] / S.dsl[rr]);
+                    if (S.dzu[rr] < 0.0) adf = fmin(adf, -S.zu[rr] / S.dzu[rr]);
+                    if (S.dzl[rr] < 0.0) adf = fmin(adf, -S.zl[rr] / S.dzl[rr]);
                 }
+                apf = wmin(apf); adf = wmin(adf);
                 ap = fmin(1.0, 0.995 * apf); ad = fmin(1.0, 0.995 * adf);
-                for (int i = 0; i < m; i++) x[i] += ap * g[i];
-                for (int i = 0; i < R; i++) { su[i] += ap * dsu[i]; sl[i] += ap * dsl[i]; zu[i] += ad * dzu[i]; zl[i] += ad * dzl[i]; }
+                __syncwarp();
+                for (int i = lane; i < m; i += 32) S.x[i] += ap * S.g[i];
+                for (int rr = lane; rr < R; rr += 32) { S.su[rr] += ap * S.dsu[rr]; S.sl[rr] += ap * S.dsl[rr]; S.zu[rr] += ad * S.dzu[rr]; S.zl[rr] += ad * S.dzl[rr]; }
             }
+            __syncwarp();
         }
     }
-    out[0] = sc[0];
-    for (int i = 0; i < m; i++) out[i + 1] = x[i];
-    n_fine[b] = n;
-    if (speed) speed[b] = (out[1] - out[0]) / dt;                  // st.py:780-781
-    if (iters_out) iters_out[b] = it;
+    __syncwarp();
+    if (lane == 0) out[0] = sc[0];
+    for (int i = lane; i < m; i += 32) out[i + 1] = S.x[i];
+    if (lane == 0) {
+        n_fine[b] = n;
+        if (speed) speed[b] = (S.x[0] - sc[0]) / dt;              // st.py:780-781
+        if (iters_out) iters_out[b] = it;
+    }
 }
 
 cudaError_t launch_finer_fit(const DevParams &P, int B, int T, const double *s_seq, const int32_t *reached, const double *ego,
                              int max_iter, double tol, double *fine, int fine_stride, int32_t *n_fine, double *speed,
                              int32_t *iters, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    finer_fit_kernel<<<(B + 63) / 64, 64, 0, st>>>(P, B, T, s_seq, reached, ego, max_iter, tol, fine, fine_stride, n_fine, speed, iters);
+    finer_fit_kernel<<<(B + QP_WARPS - 1) / QP_WARPS, 32 * QP_WARPS, 0, st>>>(P, B, T, s_seq, reached, ego, max_iter, tol, fine, fine_stride, n_fine, speed, iters);
     return cudaGetLastError();
 }
 
