@@ -88,12 +88,16 @@ class EpisodeTracker:
         self.v = {n: torch.zeros(num_envs, **f) for n in names}
         self.v["min_closest"].fill_(float("inf"))
         self.bins = torch.arange(-220, 61, 20, **f)
-        self.seg_counts = torch.zeros(len(self.bins) - 1, **f)
+        nb = len(self.bins) - 1
+        self.seg = {n: torch.zeros((num_envs, nb), **f) for n in ("counts", "jerks", "speeds")}     # per running episode
+        self.seg_counts = torch.zeros(nb, **f)                                                       # finished episodes only
         self.seg_jerks, self.seg_speeds = torch.zeros_like(self.seg_counts), torch.zeros_like(self.seg_counts)
 
     def reset_where(self, mask):
         for n, t in self.v.items():
             t.masked_fill_(mask, float("inf") if n == "min_closest" else 0.0)
+        for t in self.seg.values():
+            t.masked_fill_(mask.unsqueeze(1), 0.0)
 
     def record(self, state, takeover=None):
         """Called with the state the controller sees (before the tick), like the reference loop."""
@@ -122,15 +126,18 @@ class EpisodeTracker:
             V["takeovers"] += takeover.double()
         seg = torch.bucketize(ex.contiguous(), self.bins, right=False) - 1                                          # stats.py:44-52
         ok = (seg >= 0) & (seg < self.seg_counts.numel())
-        seg = seg.clamp(0, self.seg_counts.numel() - 1)
-        self.seg_counts.index_add_(0, seg, ok.double()); self.seg_jerks.index_add_(0, seg, jerk.abs() * ok)
-        self.seg_speeds.index_add_(0, seg, speed.abs() * ok)
+        seg = seg.clamp(0, self.seg_counts.numel() - 1).unsqueeze(1)
+        self.seg["counts"].scatter_add_(1, seg, ok.double().unsqueeze(1))
+        self.seg["jerks"].scatter_add_(1, seg, (jerk.abs() * ok).unsqueeze(1))
+        self.seg["speeds"].scatter_add_(1, seg, (speed.abs() * ok).unsqueeze(1))
 
     def finished(self, done, crashed, merged, wall_per_env_tick: float):
         """Episode dicts (host floats) for the rows where `done`."""
         idx = done.nonzero().squeeze(1)
         if idx.numel() == 0:
             return []
+        self.seg_counts += self.seg["counts"][idx].sum(0); self.seg_jerks += self.seg["jerks"][idx].sum(0)
+        self.seg_speeds += self.seg["speeds"][idx].sum(0)                 # the histograms cover finished episodes (stats.py:43-52)
         tick = float(Settings.TICK_LENGTH)
         rows = {n: t[idx].cpu().numpy() for n, t in self.v.items()}
         cr, mg = crashed[idx].cpu().numpy(), merged[idx].cpu().numpy()
@@ -151,19 +158,22 @@ class EpisodeTracker:
 
 def evaluate_control(control_function, num_episodes=1000, state_function=None, custom_stats_function=None,
                      end_episode_callback=None, max_episode_length=100, start_velocity=None, wait_before_start=50,
-                     save_state_on_crash=False, verbose=False, crash_callback=None, num_envs=None, seed=0):
+                     save_state_on_crash=False, verbose=False, crash_callback=None, num_envs=None, seed=0, env=None):
     """Run `num_episodes` lane-merging episodes under `control_function` and aggregate the reference's statistics
     (reference control.py:343-363).  Episodes run `num_envs` at a time in merge_gym.MergeEnv.
 
     control_function(BatchedState) -> commanded speed [B], or (speed [B], takeover mask [B]) for the combined controller.
     end_episode_callback(done_mask) is called after every tick that finished episodes.  state_function,
     wait_before_start, start_velocity, crash_callback exist for signature parity (the batched world has no SUMO warm-up).
-    clock_time_per_step is the wall time of a batched tick divided by the number of environments."""
+    clock_time_per_step is the wall time of a batched tick divided by the number of environments.  `env` may be any object
+    with MergeEnv's interface (state, device, B, reset(), step(jerk))."""
     import time
     from . import merge_gym, stats
     B = int(num_envs or min(max(num_episodes, 1), 4096))
     Settings.MAX_EPISODE_LENGTH = max_episode_length
-    env = merge_gym.MergeEnv(B, seed=seed)
+    if env is None:
+        env = merge_gym.MergeEnv(B, seed=seed)
+    B = env.B
     agg = stats.StatsAggregator(save_state_on_crash)
     if custom_stats_function is not None:
         agg.add_custom_stat_callback(custom_stats_function)

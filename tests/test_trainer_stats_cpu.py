@@ -106,3 +106,69 @@ def test_stats_row_has_the_reference_columns(tmp_path):
     agg.add_csv_data(csv); agg.add_csv_data(csv)
     import pandas as pd
     assert len(pd.read_csv(csv)) == 2
+
+
+class _ScriptedEnv:
+    """MergeEnv's interface on CPU with scripted dynamics: the ego drives along the highway at the commanded speed, one car
+    10 m ahead and one 8 m behind that brakes at 1.5 m/s^2; episode b ends (merged) after 6 + b ticks; env 1 'crashes'."""
+
+    def __init__(self, B):
+        from rl_mpc_lanemerging_b200.prediction import BatchedState
+        self.B, self.device = B, torch.device("cpu")
+        z = lambda *s: torch.zeros(*s, dtype=torch.float64)                                     # noqa: E731
+        self.state = BatchedState(z(B, 4), z(B, 32), z(B, 32), z(B, 32), torch.full((B,), 2, dtype=torch.int32))
+        self.t = torch.zeros(B, dtype=torch.long)
+
+    def reset(self):
+        self._fresh(torch.ones(self.B, dtype=torch.bool))
+        return None
+
+    def _fresh(self, m):
+        s = self.state
+        s.ego[m] = torch.tensor([30.0, -1.6, 10.0, 0.0], dtype=torch.float64)                   # on the highway: ego_s = 81
+        s.cars_x[m, 0], s.cars_x[m, 1] = 40.0, 22.0
+        s.cars_a[m, 1] = -1.5
+        self.t[m] = 0
+
+    def step(self, jerk):
+        s, tick = self.state, 0.2
+        acc = s.ego[:, 3] + jerk * tick
+        s.ego[:, 2] += acc * tick; s.ego[:, 3] = acc; s.ego[:, 0] += s.ego[:, 2] * tick
+        s.cars_x[:, :2] += 10.0 * tick
+        self.t += 1
+        done = self.t >= 6 + torch.arange(self.B)
+        crashed = done & (torch.arange(self.B) == 1)
+        info = {"crashed": crashed, "merged": done & ~crashed}
+        self._fresh(done)
+        return None, None, done, info
+
+
+def test_evaluate_control_aggregates_like_the_reference_loop():
+    """control.evaluate_control + EpisodeTracker on a scripted CPU world: metrics are recorded before the control of each
+    tick (reference control.py:280-310), jerk is the acceleration difference (0 on the first tick), closest distance /
+    disruption only once on the highway past CRASH_MIN_S, percent st solver from the take-over mask."""
+    from rl_mpc_lanemerging_b200 import control
+    from rl_mpc_lanemerging_b200.config import Settings
+    Settings.reset()
+    env = _ScriptedEnv(3)
+    calls = []
+
+    def controller(state):                       # accelerate by 1 m/s^2 (jerk 5 on the first tick, 0 afterwards); "take over" on env 2
+        calls.append(1)
+        v, a = state.ego[:, 2], state.ego[:, 3]
+        return v + (1.0) * 0.2 + 0 * a, torch.arange(3) == 2
+
+    ended = []
+    agg = control.evaluate_control(controller, num_episodes=3, env=env, end_episode_callback=lambda m: ended.append(int(m.sum())),
+                                   custom_stats_function=lambda ep: {"percent st solver": ep["takeovers"] / ep["steps"]})
+    st = agg.get_stats()
+    assert agg.episodes == 3 and sum(ended) == 3
+    assert st["crashed"] == [0.0, 1.0, 0.0] and st["merged"] == [1.0, 0.0, 1.0]
+    assert st["time_taken"] == [6 * 0.2, 7 * 0.2, 8 * 0.2] and st["time_to_merge"] == [6 * 0.2, 8 * 0.2]
+    # speeds recorded before control: 10, 10.2, ..., so mean over n ticks = 10 + 0.1 (n - 1); first acceleration step 0 -> 1: jerk 5 once
+    for n, ms, mj in zip((6, 7, 8), st["mean_speed"], st["mean_abs_jerk"]):
+        assert abs(ms - (10.0 + 0.1 * (n - 1))) < 1e-9 and abs(mj - 5.0 / n) < 1e-9
+    assert all(abs(d - 8.0) < 1e-9 for d in st["closest_distance"])                              # the car behind, 8 m (first tick)
+    assert all(abs(d - 1.5) < 1e-12 for d in st["mean_disruption"]) and all(abs(d - 1.5) < 1e-12 for d in st["max_disruption"])
+    assert st["percent st solver"] == [0.0, 0.0, 1.0]
+    assert agg.counts.sum() == 6 + 7 + 8                                                          # per-segment histogram of ticks
