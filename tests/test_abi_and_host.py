@@ -96,3 +96,33 @@ def test_fast_arithmetic_model_within_tolerance(oracle, H, n):
                 assert abs(m["cost"] - ref["cost"][b]) <= 1e-6 * ref["cost"][b]
             same64 += np.array_equal(m["idx"], ref["idx"][b]); same32 += np.array_equal(m32["idx"], ref["idx"][b]); tot += 1
     assert same64 >= tot - 1 and same64 >= same32
+
+
+def test_reference_configs_load_unchanged(tmp_path, monkeypatch):
+    """Every configs/*.json of the reference loads through Settings.load_from_file (reference config.py:161-170), yields a
+    parameter snapshot for the library, and names a task the dispatcher knows (or one that is explicitly out of scope).
+    Skipped where the reference tree is not mounted (the GPU box)."""
+    import glob
+    import os
+    import pytest
+    from rl_mpc_lanemerging_b200.config import Settings
+    from rl_mpc_lanemerging_b200.engine import params_from_settings
+    files = sorted(glob.glob("/root/reference/configs/*.json"))
+    if not files:
+        pytest.skip("reference tree not mounted")
+    known = {"ST", "TRAIN_DDPG", "RESUME_DDPG", "EVALUATE_DDPG", "EVALUATE_COMBINED_DDPG", "EVALUATE_COMBINED_DQN"}
+    tasks = set()
+    for f in files:
+        Settings.reset()
+        Settings.load_from_file(f)
+        p = params_from_settings(Settings)
+        assert (p.s_disc, p.t_disc, p.future_s, p.future_t) == (0.05, 0.3, 150.0, 5.0)            # SURVEY.md §2 row 14
+        assert p.min_allowed_distance == 5 and p.d_weight == 10.0
+        tasks.add(Settings.TASK)
+    assert tasks <= known | {"TRAIN_DQN", "EVALUATE_DQN", "RESUME_DQN"}, tasks
+    assert {"ST", "TRAIN_DDPG", "EVALUATE_COMBINED_DDPG"} <= tasks
+    monkeypatch.chdir(tmp_path)
+    Settings.reset(); Settings.LOG_DIR = "unit"
+    d = Settings.setup_logging()
+    assert os.path.exists(os.path.join(d, "settings.json")) and Settings.FULL_LOG_DIR == d
+    Settings.reset()
