@@ -393,7 +393,9 @@ def env_steps_per_sec(local, world, n_envs, ticks, seed):
     # the planner take-over is rare (~1 % of the episodes per tick) and would otherwise first happen inside the timed region
     from rl_mpc_lanemerging_b200.prediction import BatchedState
     st.do_st_control(BatchedState(*(t[:64].contiguous() for t in env.state.args())))
-    for phase, n in (("warm", 8), ("timed", ticks)):
+    # (24 warm ticks: by then the episodes have reached the merge area and take-overs of realistic size have happened; on multi-rank
+    # runs a first-time stall inside the timed region was observed to cost seconds -- profiles/r01_scaling.json)
+    for phase, n in (("warm", 24), ("timed", ticks)):
         if phase == "timed":
             torch.cuda.synchronize(); e0.record()
         for _ in range(n):
