@@ -118,3 +118,32 @@ def test_cost_bound_is_exact_when_the_horizon_is_reached(oracle):
             else:
                 assert (not feasible) or bound < full["cost"]
     assert reached_bounded > 40 and pruned > 20
+
+
+def test_blocked_interval_is_band_plus_penalty_zones():
+    """The lean bounded pass of the fast kernel blocks, per car, ONE interval of cells: from the first cell closer than
+    MIN_ALLOWED_DISTANCE to the car's rear edge to the last cell closer than that to its front edge, joined with the band
+    (mpc_predict.cu).  Claim behind `zone_ok` (mpc_api.cu): for m >= 4 cells that interval is exactly 'in the band, or
+    min(|s - ef|, |s - eb|) < m' -- checked here in numpy on random geometry, with and without prediction uncertainty."""
+    rng = np.random.default_rng(0)
+    for ds, L, m, unc_max in ((0.05, 5.0, 5.0, 0.0), (0.05, 5.0, 5.0, 2.0), (0.05, 5.0, 0.2, 2.0), (0.05, 4.0, 3.0, 1.0),
+                              (0.05, 5.03, 0.2, 1.0), (0.1, 5.0, 6.0, 1.0)):
+        for _ in range(150):
+            s0, num_s = rng.uniform(-200, 80), 3001
+            s = s0 + np.arange(num_s) * ((s0 + ds) - s0)
+            obs, unc = rng.uniform(s0 - 20, s[-1] + 12), rng.uniform(0, unc_max)
+            du, ef, eb = int(unc / ds), obs - L - unc, obs + L + unc
+            si, dl = int((obs - s0) / ds), int(L / ds)
+            imin, imax = max(si - dl - du, 0), min(si + dl + du, num_s)
+            if not (imin < num_s and imax > 0):
+                imin = imax = 0
+            ref = np.minimum(np.abs(s - ef), np.abs(s - eb)) < m
+            ref[imin:imax] = True
+            out_lo, out_hi = (s < ef) & (np.abs(s - ef) >= m), (s > eb) & (np.abs(s - eb) >= m)
+            zlo = int(np.argmin(out_lo)) if not out_lo.all() else num_s
+            zhi = int(num_s - np.argmin(out_hi[::-1])) if not out_hi.all() else 0
+            if imin < imax:
+                zlo, zhi = min(zlo, imin), max(zhi, imax)
+            hull = np.zeros(num_s, bool)
+            hull[zlo:max(zhi, zlo)] = True
+            assert np.array_equal(hull, ref), (ds, L, m, unc, s0, obs)
