@@ -8,18 +8,24 @@
 // (st_cy.pyx:329-330) and are handled in exact fp64, then quantised.
 //
 // Integer DP: a cell's state is ONE 64-bit word  [label : 48 bits fixed point][255 - v : 8][a + 128 : 8].
-// One pass and one __syncthreads per layer; every cell k of layer t is handled by one thread:
+// One pass over the layers; every cell k of layer t is handled by one thread:
 //   1. read + clear its word (the buffer is the destination buffer of layer t+2);
-//   2. obstacle test and distance penalty through the layer's sorted search structure (O(1) lookups,
-//      exact fp64 threshold test), label += penalty; record the layer's best (label, k) for the final arg-min;
+//   2. distance penalty through the layer's sorted search structure (bucket table + sentinel edges), label += penalty;
 //   3. integer successor window [w, w+n); for each successor k' the candidate word
-//      (label + V[v'] + A[a'] + J[j'], v', a') is min-combined into the next layer's buffer with a
-//      compare-and-swap loop that only issues the CAS when the candidate beats the stored word.
+//      (label + V[v'] + A[a'] + J[j'], v', a') is min-combined into the next layer's buffer: plain pre-read, CAS only
+//      where the candidate beats what was read.
 // The unsigned 64-bit order of the word IS the reference's heap order: smaller label first, ties to the
 // larger v' = smaller predecessor index (st_cy.pyx:388).  Integer addition is exact and associative, so the
 // result is independent of thread scheduling and is reproduced bit for bit by the CPU model
 // orc_solve_fast_model (oracle/mpc_oracle.c).  Quantisation (<= 1.9e-6 per edge) keeps the cost within
-// ~1e-8 rel of the reference; fp32 labels were tried first and rejected.
+// ~1e-7 rel of the reference; fp32 labels were tried first and rejected.
+//
+// Two main loops share the prologue (layers 0..2) and the epilogue (back-track, crash test):
+//   * the LEAN bounded pass (descriptor-fed problems, first attempt): cells in a band or a penalty zone are blocked through a
+//     bit array built one layer ahead, one barrier per layer, software-pipelined branch-free min-combine;
+//   * the general loop (dense grids, no bound / retry after a bounded attempt that did not reach the horizon): obstacle bands
+//     clipped at push time, exact fp64 threshold test of the penalty per node, best label tracked per layer.
+// Design history, ablations and what bounds the kernel: profiles/README.md.
 #include "mpc_solve_common.cuh"
 #ifndef MPC_ABLATE
 #define MPC_ABLATE 0      // dev-only timing ablations (wrong results when != 0)
