@@ -121,6 +121,31 @@ int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
              int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
              uint8_t *d_crash, double *d_min_dist, double *d_start_s, void *stream);
 
+/* mpc_plan with a per-problem COST HINT for MPC_MODE_FAST (ignored by MPC_MODE_EXACT): an estimate of each plan's cost
+ * -- the cost of a coarse probe plan (mpc_plan_probed), or of the previous tick's plan when the reference's
+ * control loop re-plans every TICK_LENGTH (control.py:229-340 calls st.do_st_control once per tick).  Problem b
+ * is first solved under the bound hint_scale * d_hint_cost[b] (when d_hint_reached_t == NULL or d_hint_reached_t[b] ==
+ * hint_full_t; a hint that is <= 0, NaN or >= 1e9 is ignored).  The RESULT DOES NOT DEPEND ON THE HINT: a bounded
+ * pass that reaches the horizon returns the unbounded answer, one that does not is repeated under the standard
+ * bound; a hint only changes how many nodes the solve expands.  The hint arrays must not alias the
+ * outputs. */
+int mpc_plan_hinted(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
+                    const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars, int mode,
+                    const double *d_hint_cost, const int32_t *d_hint_reached_t, int hint_full_t,
+                    double hint_scale, int32_t *d_idx, double *d_s_seq, double *d_cost,
+                    int32_t *d_reached_t, uint8_t *d_crash, double *d_min_dist, double *d_start_s,
+                    void *stream);
+
+/* Probe + plan in one call (MPC_MODE_FAST): `probe` is a second handle on the same device, created from the same
+ * Settings with a coarser S_DISCRETIZATION / T_DISCRETIZATION (e.g. 20x / 3x: an 18 x 451 grid instead of 51 x 9001).
+ * The states are planned on the probe grid first; margin * (num_t-1)/(probe num_t-1) * probe cost is the hint of
+ * the real solve.  Outputs as mpc_plan (identical to mpc_plan's, see above). */
+int mpc_plan_probed(mpc_handle *h, mpc_handle *probe, double margin, int B, const double *d_ego,
+                    const double *d_cars_x, const double *d_cars_v, const double *d_cars_a,
+                    const int32_t *d_n_cars, int32_t *d_idx, double *d_s_seq, double *d_cost,
+                    int32_t *d_reached_t, uint8_t *d_crash, double *d_min_dist, double *d_start_s,
+                    void *stream);
+
 /* Same call with HOST buffers: copies the state in, plans, copies the results out and
  * synchronises the stream (the end-to-end path a CPU caller such as the reference's
  * control.run_episode loop uses). */

@@ -382,9 +382,9 @@ int orc_solve_layered(const orc_params *p, int num_t, int num_s, const uint8_t *
 #define FXONE 262144.0
 static uint64_t fx(double x) { return (uint64_t)llrint(x * FXONE); }
 
-int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
                             const double *distances, const double *s_values, double delta_t,
-                            double v0, double a0, int f32_labels, uint64_t prune_fx,
+                            double v0, double a0, int f32_labels, uint64_t prune_fx, const uint64_t *hfx, uint64_t *fmin_out,
                             int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
     /* prune_fx != 0: nodes whose label exceeds it are dropped (the fast kernel's cost bound, mpc_fast.cu);
      * counts[0..1] = nodes expanded, pushes */
@@ -462,8 +462,9 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                 float penf = (d < p->min_allowed_distance) ? 1000000.0f / fmaxf(df, 1.0f) : 1.0f / df;
                 float labelf = fmaf((float)p->d_weight, penf, labf[cur][k]);
                 int v = vv[cur][k], a = aa[cur][k];
-                if (prune_fx && label > prune_fx) continue;
+                if (prune_fx && label + (hfx ? hfx[id] : 0) > prune_fx) continue;
                 previous[id] = k - v; any = 1; n_nodes++;
+                if (fmin_out) { uint64_t f = label + (hfx ? hfx[id] : 0); if (f < fmin_out[t]) fmin_out[t] = f; }
                 int better = bk < 0 || (f32_labels ? labelf < blf : label < bl);
                 if (better) { bk = k; bl = label; blf = labelf; }
                 if (t == num_t - 1) continue;
@@ -497,6 +498,23 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
     for (int b = 0; b < 2; b++) { free(lab[b]); free(labf[b]); free(vv[b]); free(aa[b]); free(has[b]); }
     free(previous);
     return r;
+}
+
+int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+                            const double *distances, const double *s_values, double delta_t,
+                            double v0, double a0, int f32_labels, uint64_t prune_fx,
+                            int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
+    return fast_model_impl(p, num_t, num_s, obstacles, distances, s_values, delta_t, v0, a0, f32_labels, prune_fx, NULL, NULL,
+                           idx_out, s_seq_out, cost_out, counts);
+}
+
+int orc_solve_fast_model_h(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+                           const double *distances, const double *s_values, double delta_t,
+                           double v0, double a0, uint64_t prune_fx, const uint64_t *hfx, uint64_t *fmin_out,
+                           int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
+    if (fmin_out) for (int t = 0; t < num_t; t++) fmin_out[t] = UINT64_MAX;
+    return fast_model_impl(p, num_t, num_s, obstacles, distances, s_values, delta_t, v0, a0, 0, prune_fx, hfx, fmin_out,
+                           idx_out, s_seq_out, cost_out, counts);
 }
 
 int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,

@@ -90,6 +90,14 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                             double v0, double a0, int f32_labels, uint64_t prune_fx,
                             int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts);
 
+/* Same model with a per-cell heuristic table hfx[num_t*num_s] (label units): a node of layer >= 2 is dropped when
+ * label + hfx[cell] > prune_fx.  Checks the exactness of the reachability heuristic (oracle/bound_model.py).
+ * fmin_out (optional, num_t entries): smallest label + h among the surviving nodes of each layer. */
+int orc_solve_fast_model_h(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+                           const double *distances, const double *s_values, double delta_t,
+                           double v0, double a0, uint64_t prune_fx, const uint64_t *hfx, uint64_t *fmin_out,
+                           int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts);
+
 /* Sum of st.cost (st.py:140-144) along an index path with the solver's history convention. */
 double orc_path_cost(const orc_params *p, int n, const int *idx, const double *s_values,
                      const double *distances, int num_s, double delta_t, double v0, double a0);

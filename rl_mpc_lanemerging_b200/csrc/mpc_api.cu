@@ -128,7 +128,8 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     D->dw = (float)p->d_weight;
     // fixed-point cost tables (fast kernel): every entry must fit 32 bits
     double mx = 0.0;
-    for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * ds / dt - p->desired_speed) * (v * ds / dt - p->desired_speed); mx = fmax(mx, x); D->vtab[v] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
+    // (speeds above vmax_c are never looked up: the window clamp of st_cy.pyx:72 keeps v' <= vmax_c; a coarse probe grid has v = 255 far beyond MAX_SPEED)
+    for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * ds / dt - p->desired_speed) * (v * ds / dt - p->desired_speed); if (v <= D->vmax_c + 1) mx = fmax(mx, x); D->vtab[v] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
     for (int i = 0; i < 32; i++) { double acc = (i - 16) * ds / (dt * dt), x = p->a_weight * acc * acc; mx = fmax(mx, x); D->atab[i] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
     for (int i = 0; i < 16; i++) { double jk = (i - 8) * ds / (dt * dt * dt), x = p->j_weight * jk * jk; mx = fmax(mx, x); D->jtab[i] = (unsigned)llrint(fmin(x, 16000.0) * MPC_FX_ONE); }
     if (mx >= 16000.0 || D->jlo_c < -8 || D->jhi_c > 7 || !(p->d_weight >= 0) || p->d_weight > 1e4) D->fast_ok = 0;
@@ -436,14 +437,14 @@ extern "C" int mpc_solve_dense(mpc_handle *h, int B, int num_t, int num_s_stride
     return run_solve(h, B, mode, true, io, d_obstacles, d_distances, dist_f32, num_s_stride, (cudaStream_t)stream);
 }
 
-extern "C" int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v, const double *d_cars_a,
-                        const int32_t *d_n_cars, int mode, int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
-                        uint8_t *d_crash, double *d_min_dist, double *d_start_s, void *stream) {
+// mpc_plan with an optional per-problem cost hint for the fast kernel (hint_cost == NULL: none)
+static int plan_impl(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                     const int32_t *d_n_cars, int mode, const double *hint_cost, const int32_t *hint_reached, int hint_full_t,
+                     double hint_scale, int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
+                     uint8_t *d_crash, double *d_min_dist, double *d_start_s, cudaStream_t st, const char *who) {
     int rc = check_batch(h, B); if (rc) return rc;
     if (B == 0) return MPC_OK;
-    if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars) return mpc_set_error(MPC_E_INVALID, "mpc_plan: null pointer");
-    (void)d_cars_a;
-    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars) return mpc_set_error(MPC_E_INVALID, who);
     h->ev_valid = 0;
     if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[0], st));
     MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, d_start_s ? d_start_s : h->s0, h->ds, h->num_s, st));
@@ -451,7 +452,54 @@ extern "C" int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double 
     SolveIO io; memset(&io, 0, sizeof(io));
     io.ego = d_ego;
     io.idx = d_idx; io.s_seq = d_s_seq; io.cost = d_cost; io.reached = d_reached_t; io.crash = d_crash; io.min_dist = d_min_dist;
+    io.hint_cost = hint_cost; io.hint_reached = hint_reached; io.hint_full_t = hint_full_t; io.hint_scale = hint_scale;
     return run_solve(h, B, mode, false, io, nullptr, nullptr, 0, 0, st);
+}
+
+extern "C" int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v, const double *d_cars_a,
+                        const int32_t *d_n_cars, int mode, int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
+                        uint8_t *d_crash, double *d_min_dist, double *d_start_s, void *stream) {
+    (void)d_cars_a;
+    return plan_impl(h, B, d_ego, d_cars_x, d_cars_v, d_n_cars, mode, nullptr, nullptr, 0, 1.0, d_idx, d_s_seq, d_cost, d_reached_t,
+                     d_crash, d_min_dist, d_start_s, (cudaStream_t)stream, "mpc_plan: null pointer");
+}
+
+extern "C" int mpc_plan_hinted(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                               const double *d_cars_a, const int32_t *d_n_cars, int mode, const double *d_hint_cost,
+                               const int32_t *d_hint_reached_t, int hint_full_t, double hint_scale, int32_t *d_idx, double *d_s_seq,
+                               double *d_cost, int32_t *d_reached_t, uint8_t *d_crash, double *d_min_dist, double *d_start_s,
+                               void *stream) {
+    (void)d_cars_a;
+    if (d_hint_cost && !(hint_scale > 0.0)) return mpc_set_error(MPC_E_INVALID, "mpc_plan_hinted: hint_scale must be positive");
+    if (d_hint_cost && (d_hint_cost == d_cost || (d_hint_reached_t && d_hint_reached_t == d_reached_t)))
+        return mpc_set_error(MPC_E_INVALID, "mpc_plan_hinted: the hint arrays must not alias the outputs");
+    return plan_impl(h, B, d_ego, d_cars_x, d_cars_v, d_n_cars, mode, d_hint_cost, d_hint_reached_t, hint_full_t, hint_scale, d_idx,
+                     d_s_seq, d_cost, d_reached_t, d_crash, d_min_dist, d_start_s, (cudaStream_t)stream, "mpc_plan_hinted: null pointer");
+}
+
+// Probe + plan: `probe` is a second handle on the same device whose Settings differ only in a coarser S/T_DISCRETIZATION
+// (a grid ~100x smaller).  Its plan of the same states costs a few percent of the real one and its cost, scaled by the
+// ratio of the step counts and by `margin`, is the first bound of the real solve.
+extern "C" int mpc_plan_probed(mpc_handle *h, mpc_handle *probe, double margin, int B, const double *d_ego, const double *d_cars_x,
+                               const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars, int32_t *d_idx,
+                               double *d_s_seq, double *d_cost, int32_t *d_reached_t, uint8_t *d_crash, double *d_min_dist,
+                               double *d_start_s, void *stream) {
+    (void)d_cars_a;
+    if (!h || !probe || h == probe) return mpc_set_error(MPC_E_INVALID, "mpc_plan_probed: two distinct handles are required");
+    if (probe->device != h->device) return mpc_set_error(MPC_E_INVALID, "mpc_plan_probed: the handles live on different devices");
+    if (B > probe->max_batch) return mpc_set_error(MPC_E_CAPACITY, "mpc_plan_probed: batch larger than the probe handle's max_batch");
+    if (!(margin > 0.0) || probe->P.num_t < 2) return mpc_set_error(MPC_E_INVALID, "mpc_plan_probed: bad margin / probe horizon");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = plan_impl(probe, B, d_ego, d_cars_x, d_cars_v, d_n_cars, MPC_MODE_FAST, nullptr, nullptr, 0, 1.0, nullptr, nullptr,
+                       probe->st_cost, probe->st_reached, nullptr, nullptr, nullptr, st, "mpc_plan_probed: null pointer");
+    if (rc) return rc;
+    const int64_t probe_launches = probe->kernels_launched;
+    // every step costs about the same in both grids (the cost is a sum over steps of the same rates): scale by the step counts
+    const double scale = margin * (double)(h->P.num_t - 1) / (double)(probe->P.num_t - 1);
+    rc = plan_impl(h, B, d_ego, d_cars_x, d_cars_v, d_n_cars, MPC_MODE_FAST, probe->st_cost, probe->st_reached, probe->P.num_t - 1,
+                   scale, d_idx, d_s_seq, d_cost, d_reached_t, d_crash, d_min_dist, d_start_s, st, "mpc_plan_probed: null pointer");
+    if (rc == MPC_OK) h->kernels_launched += probe_launches;
+    return rc;
 }
 
 extern "C" int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const double *h_cars_x, const double *h_cars_v, const double *h_cars_a,

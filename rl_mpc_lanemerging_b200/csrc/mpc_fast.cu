@@ -248,7 +248,7 @@ __device__ __forceinline__ void build_blocked_bits(const LayerSearch &L, unsigne
 // ~30 % of all nodes at H=50 (oracle model counts).
 struct FxTables { unsigned v[256], aj[32 * 16]; };     // aj[(a'+16)*16 + (j'+8)] = A[a'] + J[j']: one lookup, stride 17 along a window
 
-template <class Prov, bool DESC, bool WRAP, int MAXT>
+template <class Prov, bool DESC, bool WRAP, int MAXT, bool HINT>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
                                                                               const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc,
                                                                               unsigned long long bound) {
@@ -296,6 +296,19 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
         int zone = (Prov::kClipAtPush && bound != FX_EMPTY) ? P.zone_cells : 0;
         // lean first attempt (descriptor-fed, bounded): see the note above the kernel
         bool lean = DESC && Prov::kClipAtPush && bound != FX_EMPTY && P.zone_ok;
+        // Per-problem cost hint (mpc_plan_hinted: a coarse probe plan, or the previous tick's plan in closed loop): an
+        // ESTIMATE of the plan's cost, used as a tighter first bound.  Any bound is exact when the pass reaches the
+        // horizon (note above the kernel), so a hint can only cost time: too low -> the attempt is repeated under the
+        // standard bound; at or above the standard bound (the plan is expected to cross a penalty zone) -> the
+        // zone-closed attempts, which could not succeed, are skipped.
+        // (HINT is a template parameter so that the code of the un-hinted kernel does not change.)
+        if (HINT && DESC && bound != FX_EMPTY && (io.hint_reached == nullptr || io.hint_reached[b] == io.hint_full_t)) {
+            const double hc = __dmul_rn(io.hint_cost[b], io.hint_scale);
+            if (hc > 0.0 && hc < 1.0e9) {                      // (a NaN fails both tests)
+                bnd = fx_from_double(hc);
+                if (bnd >= bound) { zone = 0; lean = false; }
+            }
+        }
       for (;;) {
         prov.load(1);
         bt = 0; best_word = 0ULL; dlo = 0; dhi = -1;
@@ -492,7 +505,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
             __syncthreads();
             if (bt < T - 1 && !S.need_fallback) {             // the bound (or a blocked zone) cut the plan short: repeat without
                 for (int k = tid; k < 2 * Wc; k += nth) sts_u64(sb0 + 8u * k, FX_EMPTY);
-                bnd = FX_EMPTY; zone = 0; lean = false;
+                if (HINT && bnd < bound) bnd = bound;         // (a cost hint that was too low: once more under the standard bound)
+                else { bnd = FX_EMPTY; zone = 0; lean = false; }
                 __syncthreads();
                 continue;
             }
@@ -620,14 +634,14 @@ static cudaError_t set_smem(K kernel, size_t smem) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-// four launch shapes are compiled: <= 256 threads x 4 blocks/SM, <= 384 x 3, <= 512 x 2, <= 1024 x 1
-template <class Prov, bool DESC>
+// five launch shapes are compiled: <= 192 threads x 5 blocks/SM, <= 256 x 4, <= 384 x 3, <= 512 x 2, <= 1024 x 1
+template <class Prov, bool DESC, bool HINT>
 static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, const uint8_t *ob,
                                  const void *dist, int stride, cudaStream_t st) {
     cudaError_t e;
 #define MPC_LAUNCH_FAST(WRAPV, MAXTV)                                                                      \
     do {                                                                                                   \
-        auto k = fast_pull_kernel<Prov, DESC, WRAPV, MAXTV>;                                               \
+        auto k = fast_pull_kernel<Prov, DESC, WRAPV, MAXTV, HINT>;                                         \
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;                                            \
         k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, desc, ob, dist, stride, L.W, L.bound);                     \
     } while (0)
@@ -642,14 +656,15 @@ static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const
 
 cudaError_t launch_fast_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st) {
     if (L.B <= 0) return cudaSuccess;
-    return launch_fast_t<FastDescProv, true>(P, L, io, desc, nullptr, nullptr, 0, st);
+    if (io.hint_cost != nullptr) return launch_fast_t<FastDescProv, true, true>(P, L, io, desc, nullptr, nullptr, 0, st);
+    return launch_fast_t<FastDescProv, true, false>(P, L, io, desc, nullptr, nullptr, 0, st);
 }
 
 cudaError_t launch_fast_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
                               int dist_f32, int stride, cudaStream_t st) {
     if (L.B <= 0) return cudaSuccess;
-    return dist_f32 ? launch_fast_t<FastDenseProv<float>, false>(P, L, io, nullptr, ob, dist, stride, st)
-                    : launch_fast_t<FastDenseProv<double>, false>(P, L, io, nullptr, ob, dist, stride, st);
+    return dist_f32 ? launch_fast_t<FastDenseProv<float>, false, false>(P, L, io, nullptr, ob, dist, stride, st)
+                    : launch_fast_t<FastDenseProv<double>, false, false>(P, L, io, nullptr, ob, dist, stride, st);
 }
 
 int fast_occupancy(int threads, size_t smem, int wrap) {
@@ -657,7 +672,7 @@ int fast_occupancy(int threads, size_t smem, int wrap) {
     cudaError_t e;
 #define MPC_OCC(WRAPV, MAXTV)                                                                              \
     do {                                                                                                   \
-        auto k = fast_pull_kernel<FastDescProv, true, WRAPV, MAXTV>;                                       \
+        auto k = fast_pull_kernel<FastDescProv, true, WRAPV, MAXTV, false>;                                \
         if (set_smem(k, smem) != cudaSuccess) { cudaGetLastError(); return 0; }                            \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem);                           \
     } while (0)

@@ -140,6 +140,56 @@ class MpcEngine:
                                          _ptr(out["start_s"]), self._stream()))
         return out
 
+    def plan_hinted(self, ego, cars_x, cars_v, cars_a, n_cars, hint_cost, hint_reached=None, hint_full_t=0, hint_scale=1.0,
+                    mode="fast", out: Optional[dict] = None):
+        """plan() with a per-episode cost hint (mpc_plan_hinted): episode b is first solved under the bound
+        hint_scale * hint_cost[b] (when hint_reached is None or hint_reached[b] == hint_full_t).  The hint is an
+        ESTIMATE -- a coarse probe plan, or the previous tick's plan of a closed-loop controller; the outputs are
+        identical to plan()'s whatever the hint, only the number of expanded nodes changes."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        assert hint_cost.dtype == torch.float64 and hint_cost.shape == (B,) and hint_cost.is_contiguous() and hint_cost.is_cuda
+        if hint_reached is not None:
+            assert hint_reached.dtype == torch.int32 and hint_reached.shape == (B,) and hint_reached.is_contiguous() and hint_reached.is_cuda
+        out = self._plan_out(B) if out is None else out
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_plan_hinted(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                                _mode(mode), _ptr(hint_cost), _ptr(hint_reached), int(hint_full_t),
+                                                float(hint_scale), _ptr(out["idx"]), _ptr(out["s_seq"]), _ptr(out["cost"]),
+                                                _ptr(out["reached_t"]), _ptr(out["crash"]), _ptr(out["min_dist"]),
+                                                _ptr(out["start_s"]), self._stream()))
+        return out
+
+    def make_probe(self, s_mult: int = 20, t_mult: int = 3) -> "MpcEngine":
+        """A second engine on the same device whose grid is s_mult x t_mult coarser (same Settings otherwise): its
+        plans are the cost estimates of plan_probed().  20 x 3 keeps the jerk resolution (ds/dt^3) of the published
+        discretisation; H=50 -> an 18 x 451 grid instead of 51 x 9001."""
+        p = MpcParams()
+        for n in _lib.PARAM_FIELDS:
+            setattr(p, n, getattr(self.params, n))
+        p.s_disc, p.t_disc = self.params.s_disc * s_mult, self.params.t_disc * t_mult
+        return MpcEngine(p, device=self.device, max_batch=self.max_batch, nmax=self.nmax)
+
+    def plan_probed(self, probe: "MpcEngine", ego, cars_x, cars_v, cars_a, n_cars, margin: float = 1.1,
+                    out: Optional[dict] = None):
+        """Probe + plan (mpc_plan_probed, fast mode): the states are planned on `probe`'s coarse grid first and
+        margin * (num_t-1)/(probe.num_t-1) * probe cost bounds the first attempt of the real solve.  Same outputs
+        as plan()."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        out = self._plan_out(B) if out is None else out
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_plan_probed(self.h, probe.h, float(margin), B, _ptr(ego), _ptr(cars_x), _ptr(cars_v),
+                                                _ptr(cars_a), _ptr(n_cars), _ptr(out["idx"]), _ptr(out["s_seq"]),
+                                                _ptr(out["cost"]), _ptr(out["reached_t"]), _ptr(out["crash"]),
+                                                _ptr(out["min_dist"]), _ptr(out["start_s"]), self._stream()))
+        return out
+
+    def _plan_out(self, B):
+        o, T = dict(device=self.device), self.num_t
+        return dict(idx=torch.empty((B, T), dtype=torch.int32, **o), s_seq=torch.empty((B, T), dtype=torch.float64, **o),
+                    cost=torch.empty(B, dtype=torch.float64, **o), reached_t=torch.empty(B, dtype=torch.int32, **o),
+                    crash=torch.empty(B, dtype=torch.uint8, **o), min_dist=torch.empty(B, dtype=torch.float64, **o),
+                    start_s=torch.empty(B, dtype=torch.float64, **o))
+
     def _pin(self, name, shape, dtype):
         t = self._pinned.get(name)
         if t is None or t.shape != tuple(shape) or t.dtype != dtype:
