@@ -358,6 +358,8 @@ def run_ours(args):
             line["env_steps"] = env_res
         if train_res is not None:
             line["train"] = train_res
+        if world == 1 and args.mode == "fast" and os.environ.get("MPCB200_BENCH_HINT_LEG", "1") != "0":
+            line["hinted_solve"] = hint_leg_subprocess(args)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             probe = cpu_port_rate(H, args.traffic, args.seed, cores * 2, cores)
@@ -369,6 +371,68 @@ def run_ours(args):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_hint_leg(args):
+    """Child process of the default run (see `hinted_solve` below): the cost-hint entry points on the bench workload.
+    Checks that mpc_plan_probed / mpc_plan_hinted return exactly what mpc_plan returns, then times them the same way
+    the headline is timed (CUDA events around each step, L2 flushed in between).  Prints one JSON object."""
+    import torch
+    from rl_mpc_lanemerging_b200 import synthetic
+    from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
+    torch.cuda.set_device(0)
+    H, B, K = args.horizon, args.batch, max(args.steps, 3)
+    eng = MpcEngine(make_params(H), device=0, max_batch=B)
+    probe = eng.make_probe(20, 3)
+    D = states_to_device(synthetic.make_states(B, args.traffic, seed=args.seed), "cuda:0")
+    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
+    ref = {k: v.clone() for k, v in eng.plan(*a).items()}
+    out, pout = eng.plan(*a), probe.plan(*a)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+
+    def timed(fn):
+        for _ in range(3):
+            fn(); flush.zero_()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        torch.cuda.synchronize()
+        for e0, e1 in ev:
+            e0.record(); fn(); e1.record(); flush.zero_()
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in ev) / K
+
+    def same(got):
+        return bool(all(torch.equal(got[k], ref[k]) for k in ref))
+
+    res = {"workload": f"{B} episodes, {args.traffic} traffic, horizon={H}", "probe_grid": [probe.num_t, probe.num_s_max - 1],
+           "plain_ms": timed(lambda: eng.plan(*a, out=out)), "probe_only_ms": timed(lambda: probe.plan(*a, out=pout)), "probed": {}}
+    for m in (1.1, 1.3):
+        ok = same(eng.plan_probed(probe, *a, margin=m))
+        ms = timed(lambda: eng.plan_probed(probe, *a, margin=m, out=out))
+        res["probed"][str(m)] = {"identical_outputs": ok, "ms": ms, "gap_evals_per_s": B / (ms * 1e-3)}
+    # what a perfect estimate would give (diagnostic only: the hint is the answer's own cost)
+    ok = same(eng.plan_hinted(*a, hint_cost=ref["cost"], hint_scale=1.02))
+    res["oracle_hint_1.02"] = {"identical_outputs": ok, "ms": timed(lambda: eng.plan_hinted(*a, hint_cost=ref["cost"], hint_scale=1.02, out=out))}
+    junk = ref["cost"] * 0.5
+    res["low_hint_0.5"] = {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=junk))}
+    print(json.dumps(res), file=RESULT_OUT, flush=True)
+
+
+def hint_leg_subprocess(args):
+    """Runs run_hint_leg in a child process with a time limit: the cost-hint kernels were written after this round's GPU
+    budget was spent, so their first on-device run must not be able to take the headline line down with it."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--hint-leg", "--horizon", str(args.horizon), "--batch", str(args.batch),
+           "--steps", str(min(args.steps, 10)), "--traffic", args.traffic, "--seed", str(args.seed)]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240, cwd=ROOT)
+        lines = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"exit {r.returncode}: " + r.stderr.decode(errors="replace")[-400:]}
+        res = json.loads(lines[-1])
+    except Exception as e:              # noqa: BLE001
+        return {"error": repr(e)}
+    res["note"] = ("EXPERIMENTAL, not part of `value`: mpc_plan_probed = coarse probe plan (probe_grid) whose scaled cost bounds the first "
+                   "attempt of the real solve; identical_outputs compares every output tensor with mpc_plan's on the same states")
+    return res
 
 
 def env_steps_per_sec(local, world, n_envs, ticks, seed):
@@ -464,8 +528,11 @@ def main():
     ap.add_argument("--env-ticks", type=int, default=40, help="ticks of the closed-loop env-steps/s measurement (0 = skip)")
     ap.add_argument("--env-envs", type=int, default=8192, help="environments per GPU for it (BASELINE configs[2])")
     ap.add_argument("--train-ticks", type=int, default=10, help="ticks of the DDPG training throughput figure (0 = skip)")
+    ap.add_argument("--hint-leg", action="store_true", help="(internal) child process of the default run: cost-hint entry points")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.hint_leg:
+        run_hint_leg(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
