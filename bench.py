@@ -412,6 +412,13 @@ def run_hint_leg(args):
     # what a perfect estimate would give (diagnostic only: the hint is the answer's own cost)
     ok = same(eng.plan_hinted(*a, hint_cost=ref["cost"], hint_scale=1.02))
     res["oracle_hint_1.02"] = {"identical_outputs": ok, "ms": timed(lambda: eng.plan_hinted(*a, hint_cost=ref["cost"], hint_scale=1.02, out=out))}
+    # same without the reachability heuristic (MPC_FAST_HEUR is read when a handle is created): separates the two effects
+    os.environ["MPC_FAST_HEUR"] = "0"
+    eng2 = MpcEngine(make_params(H), device=0, max_batch=B)
+    del os.environ["MPC_FAST_HEUR"]
+    ok = same(eng2.plan_probed(probe, *a, margin=1.1))
+    res["probed_1.1_no_heuristic"] = {"identical_outputs": ok, "ms": timed(lambda: eng2.plan_probed(probe, *a, margin=1.1, out=out))}
+    eng2.close()
     junk = ref["cost"] * 0.5
     res["low_hint_0.5"] = {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=junk))}
     print(json.dumps(res), file=RESULT_OUT, flush=True)

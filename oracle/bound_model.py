@@ -65,7 +65,7 @@ def speed_table(p) -> np.ndarray:
 H_BUCKET = 64        # cells per bucket (MPC_BUCKET_SHIFT of the kernel's per-layer lookup tables)
 
 
-def heuristic_table(p, ob, di, bucket: int = H_BUCKET) -> np.ndarray:
+def heuristic_table(p, ob, di, bucket: int = H_BUCKET, caps_out=None) -> np.ndarray:
     """h in label units for every cell, u64 [T, S]; blocked and dead-end cells get H_INF.
 
     cap is kept per BUCKET of `bucket` cells (what a kernel would stage per layer: one u16 per bucket):
@@ -95,6 +95,8 @@ def heuristic_table(p, ob, di, bucket: int = H_BUCKET) -> np.ndarray:
     h = np.full((T, S), H_INF, dtype=np.uint64)
     cap = free_hi(blocked[T - 1])
     h[T - 1][~blocked[T - 1]] = 0
+    if caps_out is not None:
+        caps_out[T - 1] = cap
     for t in range(T - 2, -1, -1):
         n = T - 1 - t
         row = blocked[t] if t > 0 else np.zeros(S, bool)        # the start cell is never tested (st_cy.pyx:383)
@@ -108,7 +110,39 @@ def heuristic_table(p, ob, di, bucket: int = H_BUCKET) -> np.ndarray:
         q, r = D // n, D % n
         h[t] = np.where(ok, ((n - r) * Vm[q] + r * Vm[q + 1]).astype(np.uint64), H_INF)
         cap = new
+        if caps_out is not None:
+            caps_out[t] = cap
     return h
+
+
+def blocked_intervals(blocked_row: np.ndarray):
+    """Maximal runs of blocked cells as [x, y) -- what LayerDesc::blk holds for a layer."""
+    edges = np.flatnonzero(np.diff(np.concatenate(([0], blocked_row.view(np.int8), [0]))))
+    return [(int(edges[i]), int(edges[i + 1])) for i in range(0, len(edges), 2)]
+
+
+def bucket_caps_like_kernel(p, ob, di) -> np.ndarray:
+    """The loops of reach_caps_kernel (rl_mpc_lanemerging_b200/csrc/mpc_reach.cu) restated step by step on the
+    blocked INTERVALS: i32 [T, NB], -1 = no path.  tests/ compares it with the mask-based caps of heuristic_table."""
+    T, S = ob.shape
+    blocked = (ob != 0) | (di < p.min_allowed_distance)
+    vmax_c = int(np.floor(p.max_speed * p.t_disc / p.s_disc + 1e-9))
+    NB, reach = (S + 63) >> 6, (63 + vmax_c) >> 6
+    caps = np.full((T, NB), -1, np.int64)
+    cap = np.full(NB + 8, -1, np.int64)
+    for t in range(T - 1, -1, -1):
+        blk = [] if t == 0 else blocked_intervals(blocked[t])
+        nv = np.full(NB, -1, np.int64)
+        for j in range(NB):
+            c = min((j << 6) + 63, S - 1)
+            for x, y in reversed(blk):
+                if x <= c < y:
+                    c = x - 1
+            if c >= (j << 6):
+                nv[j] = c if t == T - 1 else max(cap[j + r] for r in range(reach + 1))
+        cap[:NB] = nv
+        caps[t] = nv
+    return caps
 
 
 def solve_with_heuristic(p, ob, di, sv, v0, a0, U, h):

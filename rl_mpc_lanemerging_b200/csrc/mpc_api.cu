@@ -32,6 +32,8 @@ cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const doubl
 cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
                                 const double *ca, const int32_t *n, float *out, int stride, cudaStream_t st);
 cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st);
+cudaError_t launch_reach_caps(const DevParams &P, int B, const LayerDesc *desc, const int32_t *num_s, unsigned short *capb,
+                              int stride, cudaStream_t st);
 cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
                                 const int32_t *n, const double *jerk, double dt, double mcd, double stop_x, int step,
                                 uint8_t *alive, double *sel_speed, double *roll_s, int roll_stride, int32_t *roll_len,
@@ -79,6 +81,8 @@ struct mpc_handle {
     // staging for the host-buffer entry point
     double *st_ego, *st_cx, *st_cv, *st_ca; int32_t *st_n;
     int32_t *st_idx; double *st_seq, *st_cost, *st_mind, *st_s0; int32_t *st_reached; uint8_t *st_crash;
+    unsigned short *capb; int cap_stride;      // reachability caps of hinted solves (allocated on first use)
+    int use_heur;                                // MPC_FAST_HEUR=0 disables the heuristic pruning of hinted solves (dev A/B)
     int64_t kernels_launched;
     // optional per-kernel timing (bench.py roofline): events around [predict | DP | fallback DP]
     int timing; cudaEvent_t ev[4]; int ev_valid;
@@ -147,10 +151,13 @@ static int derive_params(const mpc_params *p, DevParams *D) {
         D->zone_ok = (D->bound_fx && p->min_allowed_distance >= 4.0 * ds && p->min_allowed_distance >= 1.0) ? 1 : 0;
     }
     D->kw = (float)(p->d_weight * MPC_FX_ONE);
+    D->vstar_c = 0;
+    for (int v = 1; v <= D->vmax_c && v < 256; v++) if (D->vtab[v] < D->vtab[D->vstar_c]) D->vstar_c = v;
     return MPC_OK;
 }
 
 static void free_scratch(mpc_handle *h) {
+    if (h->capb) { cudaFree(h->capb); h->capb = nullptr; }
     void *ptrs[] = {h->desc, h->s0, h->ds, h->num_s, h->bp, h->counters, h->fallback_list, h->glab, h->ghist, h->st_ego,
                     h->st_cx, h->st_cv, h->st_ca, h->st_n, h->st_idx, h->st_seq, h->st_cost, h->st_mind, h->st_s0,
                     h->st_reached, h->st_crash};
@@ -204,6 +211,7 @@ static int configure(mpc_handle *h) {
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
     h->use_bound = env_int("MPC_FAST_BOUND", 0, 1, 1) && P.bound_fx != 0;
+    { const char *e = getenv("MPC_FAST_HEUR"); h->use_heur = !(e && e[0] == '0'); }
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     return MPC_OK;
 }
@@ -453,6 +461,17 @@ static int plan_impl(mpc_handle *h, int B, const double *d_ego, const double *d_
     io.ego = d_ego;
     io.idx = d_idx; io.s_seq = d_s_seq; io.cost = d_cost; io.reached = d_reached_t; io.crash = d_crash; io.min_dist = d_min_dist;
     io.hint_cost = hint_cost; io.hint_reached = hint_reached; io.hint_full_t = hint_full_t; io.hint_scale = hint_scale;
+    if (hint_cost && mode == MPC_MODE_FAST && h->P.fast_ok && h->P.zone_ok && h->use_bound && h->use_heur) {
+        // reachability caps for the exact A*-style pruning of the hinted lean pass (mpc_reach.cu)
+        if (!h->capb) {
+            h->cap_stride = ((h->P.num_s_max + 63) / 64 + 7) & ~7;
+            if (h->cap_stride > MPC_MAX_BUCKETS) h->cap_stride = MPC_MAX_BUCKETS;
+            MPC_CUDA_OK(cudaMalloc(&h->capb, (size_t)h->max_batch * h->P.num_t * h->cap_stride * sizeof(unsigned short)));
+        }
+        MPC_CUDA_OK(launch_reach_caps(h->P, B, h->desc, h->num_s, h->capb, h->cap_stride, st));
+        h->kernels_launched++;
+        io.capb = h->capb; io.cap_stride = h->cap_stride;
+    }
     return run_solve(h, B, mode, false, io, nullptr, nullptr, 0, 0, st);
 }
 

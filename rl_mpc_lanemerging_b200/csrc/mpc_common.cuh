@@ -39,6 +39,7 @@ struct DevParams {
     int zone_cells;                // cells next to a band that are certainly inside its penalty zone (>= 0)
     int zone_ok;                   // LayerDesc::blk (band + exact penalty zone per car) is one interval per car: lean bounded pass allowed
     float kw;                      // (float)(d_weight * 2^MPC_FX_FRAC): 1/d penalty in label units = rint(kw * (1.0f / (float)d))
+    int vstar_c;                   // cheapest speed of vtab on [0, vmax_c] (cells/step): vtab is convex and non-increasing up to it
 };
 #define MPC_FX_FRAC 18
 #define MPC_FX_ONE 262144.0
@@ -165,6 +166,8 @@ struct SolveIO {
     // optional per-problem cost hint of the fast kernel (mpc_plan_hinted): first bound = hint_scale * hint_cost[b], used when
     // hint_reached == NULL or hint_reached[b] == hint_full_t
     const double *hint_cost; const int32_t *hint_reached; int hint_full_t; double hint_scale;
+    // hinted solves: per-bucket reachability caps u16 [B][num_t][cap_stride] (mpc_reach.cu), NULL = no heuristic pruning
+    const unsigned short *capb; int cap_stride;
 };
 
 struct SolveLaunch {

@@ -397,6 +397,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
                 if (t + 3 < T) prov.store(t + 3);             // loaded during iteration t-1; first read in iteration t+1
                 if (t + 4 < T) prov.load(t + 4);
                 const bool last = (t == T - 1);
+                // hinted solves: per-bucket reachability caps of layer t (mpc_reach.cu), nrem = steps to the horizon
+                const unsigned short *caprow = (HINT && io.capb != nullptr) ? io.capb + ((size_t)b * T + t) * io.cap_stride : nullptr;
+                const int nrem = T - 1 - t, dmax = P.vstar_c * nrem;
+                const float rcpn = 1.0f / (float)(nrem > 0 ? nrem : 1);
                 if (t + 2 < T) build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[par], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
                 const unsigned edge0 = smem_u32(FS.layer[t & 3].edge), bucket0 = smem_u32(FS.layer[t & 3].bucket_edge);
                 const unsigned bwa = smem_u32(blkbits[0]) + (par ? 0u : 4u * (unsigned)(NW + 2));      // blocked bits of layer t+1
@@ -427,7 +431,19 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
                             pen = fx_inv_penalty(kw, dr < dl ? dr : dl);
                         }
                         const unsigned long long label = (w >> 16) + pen;
-                        if (label <= bnd) {                   // (only a layer-1 node inside a zone can push a label above the bound)
+                        bool keep = label <= bnd;             // (un-hinted: only a layer-1 node inside a zone can push a label above the bound)
+                        if (HINT && caprow != nullptr && !last) {
+                            // exact A*-style pruning (mpc_reach.cu): the rest of the plan costs at least h = (n - r) V[q] + r V[q+1],
+                            // q = D div n, r = D mod n, D = cells the ego can still advance; drop the node when label + h > bound
+                            const unsigned capv = __ldg(caprow + (k >> MPC_BUCKET_SHIFT));
+                            int D = (int)capv - k; D = D < 0 ? 0 : D; D = D > dmax ? dmax : D;
+                            int q = (int)((float)D * rcpn), r = D - q * nrem;              // D < 2^16: the estimate is off by at most one
+                            if (r < 0) { q--; r += nrem; } else if (r >= nrem) { q++; r -= nrem; }
+                            const unsigned long long h = (unsigned long long)(unsigned)(nrem - r) * lds_u32_nc(tbv + 4u * q) +
+                                                         (unsigned long long)(unsigned)r * lds_u32_nc(tbv + 4u * q + 4u);
+                            keep = capv != 0xffffu && label + h <= bnd;
+                        }
+                        if (keep) {
                             const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
                             if (MPC_ABLATE != 4) bp_row[k] = (uint16_t)(k - v);
                             if (last) {

@@ -82,6 +82,19 @@ def test_reachability_heuristic_is_exact_and_prunes(H, traffic):
     assert pruned <= plain and (H < 50 or pruned < 0.9 * plain), (pruned, plain)
 
 
+def test_reach_caps_kernel_algorithm_matches_the_mask_based_caps():
+    """reach_caps_kernel works on the blocked INTERVALS of a layer (LayerDesc::blk); its loops, restated in
+    bound_model.bucket_caps_like_kernel, must give the caps heuristic_table derives from the dense blocked mask."""
+    for H, traffic, kind in ((50, "moderate", "onramp"), (17, "default", "mixed"), (25, "fast", "onramp")):
+        p = O.horizon_params(H)
+        for st in _states(5, traffic, seed=9, kind=kind):
+            ob, di, sv = O.build_grid(p, st)
+            nb = (ob.shape[1] + 63) // 64
+            caps = np.full((ob.shape[0], nb), -1, np.int64)
+            BM.heuristic_table(p, ob, di, caps_out=caps)
+            assert np.array_equal(caps, BM.bucket_caps_like_kernel(p, ob, di))
+
+
 def test_probe_plan_estimates_the_cost():
     H = 50
     p = O.horizon_params(H)
@@ -105,3 +118,17 @@ def test_probe_plan_estimates_the_cost():
     assert 0.9 < np.median(ratios) < 1.1, np.median(ratios)         # measured: 1.00 (IQR 0.97-1.04)
     assert first_ok >= 0.6 * tried, (first_ok, tried)               # measured: ~0.8
     assert hinted_nodes < 0.92 * base_nodes, (hinted_nodes, base_nodes)   # measured: ~0.77 over 150 states
+
+
+def test_kernel_division_by_the_layer_constant_is_exact():
+    """The hinted kernel divides D (<= 250 * 127 cells) by n = steps to the horizon as (int)((float)D * (1.0f / n)) followed by
+    one correction step (mpc_fast.cu); that must equal D div n, D mod n for every D and n it can meet."""
+    D = np.arange(0, 250 * 127 + 1, dtype=np.int64)
+    for n in range(1, 128):
+        rcp = np.float32(1.0) / np.float32(n)
+        q = (D.astype(np.float32) * rcp).astype(np.int64)          # truncation, like the cast in the kernel
+        r = D - q * n
+        lo, hi = r < 0, r >= n
+        q = q - lo + hi
+        r = r + lo * n - hi * n
+        assert np.array_equal(q, D // n) and np.array_equal(r, D % n), n
