@@ -8,7 +8,7 @@ kernel's pruning rests on (rl_mpc_lanemerging_b200/csrc/mpc_fast.cu, DESIGN.md s
    unbounded pass computes them; if the bounded pass reaches the horizon its answer IS the unbounded
    answer.  `solve_with_ladder` mirrors the kernel's retry ladder (hint -> standard zone bound -> none).
 
-2. REACHABILITY HEURISTIC (designed and checked here, not yet in the kernel).  h(t, k) = a lower bound of
+2. REACHABILITY HEURISTIC (hinted solves: mpc_reach.cu + the HINT instances of the fast kernel).  h(t, k) = a lower bound of
    the cost still to pay from cell k of layer t that depends on the CELL ONLY (not on the node's
    history) and is consistent (h(p) <= edge(p -> c) + h(c) for every edge).  Dropping the nodes with
    label + h > U is then exact in the same sense as 1. (proof: DESIGN.md).  The bound used is the

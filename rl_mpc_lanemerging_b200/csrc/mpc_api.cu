@@ -153,6 +153,9 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     D->kw = (float)(p->d_weight * MPC_FX_ONE);
     D->vstar_c = 0;
     for (int v = 1; v <= D->vmax_c && v < 256; v++) if (D->vtab[v] < D->vtab[D->vstar_c]) D->vstar_c = v;
+    // the reachability heuristic of hinted solves (mpc_reach.cu) needs the ROUNDED table to be convex up to vstar_c
+    for (int v = 1; v < D->vstar_c; v++)
+        if ((long long)D->vtab[v - 1] - 2LL * D->vtab[v] + (long long)D->vtab[v + 1] < 0) { D->vstar_c = 0; break; }
     return MPC_OK;
 }
 
@@ -461,7 +464,7 @@ static int plan_impl(mpc_handle *h, int B, const double *d_ego, const double *d_
     io.ego = d_ego;
     io.idx = d_idx; io.s_seq = d_s_seq; io.cost = d_cost; io.reached = d_reached_t; io.crash = d_crash; io.min_dist = d_min_dist;
     io.hint_cost = hint_cost; io.hint_reached = hint_reached; io.hint_full_t = hint_full_t; io.hint_scale = hint_scale;
-    if (hint_cost && mode == MPC_MODE_FAST && h->P.fast_ok && h->P.zone_ok && h->use_bound && h->use_heur) {
+    if (hint_cost && mode == MPC_MODE_FAST && h->P.fast_ok && h->P.zone_ok && h->P.vstar_c > 0 && h->use_bound && h->use_heur) {
         // reachability caps for the exact A*-style pruning of the hinted lean pass (mpc_reach.cu)
         if (!h->capb) {
             h->cap_stride = ((h->P.num_s_max + 63) / 64 + 7) & ~7;
