@@ -359,7 +359,10 @@ def run_ours(args):
         if train_res is not None:
             line["train"] = train_res
         if world == 1 and args.mode == "fast" and os.environ.get("MPCB200_BENCH_HINT_LEG", "1") != "0":
-            line["hinted_solve"] = hint_leg_subprocess(args)
+            aux = hint_leg_subprocess(args)
+            if "dense_solve" in aux:
+                line["dense_solve"] = aux.pop("dense_solve")
+            line["hinted_solve"] = aux
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             probe = cpu_port_rate(H, args.traffic, args.seed, cores * 2, cores)
@@ -421,6 +424,34 @@ def run_hint_leg(args):
     eng2.close()
     junk = ref["cost"] * 0.5
     res["low_hint_0.5"] = {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=junk))}
+    # ---- K2, the st_cy drop-in itself: the DP kernel fed by DENSE grids in HBM (mpc_solve_dense), i.e. the solver boundary of the
+    #      reference (st_cy.pyx:315) with the grid read from memory instead of being evaluated from the layer descriptors ----
+    T, Bg = eng.num_t, min(B, 256)
+    sub = [D[k][:Bg].contiguous() for k in ("ego", "cars_x", "cars_v", "cars_a", "n_cars")]
+    v0, a0 = sub[0][:, 2].contiguous(), sub[0][:, 3].contiguous()
+    dense = {}
+    for name, dt, cell in (("fp32_distances", torch.float32, 5), ("fp64_distances", torch.float64, 9)):
+        try:
+            g_ = eng.build_grid(*sub, dist_dtype=dt)
+            eng.set_timing(True)
+            dms = []
+            for i in range(4):
+                r_ = eng.solve_dense(g_["obstacles"], g_["distances"], g_["start_s"], g_["delta_s"], g_["num_s"], v0, a0, mode="fast")
+                if i:
+                    dms.append(eng.last_kernel_ms()[1])
+                flush.zero_()
+            eng.set_timing(False)
+            dbytes = (T * (eng.num_s_max - 1) * cell + T * 4) * Bg
+            dense[name] = {"ms": min(dms), "gap_evals_per_s": Bg / (min(dms) * 1e-3), "algorithmic_gbs": dbytes / (min(dms) * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": dbytes / (min(dms) * 1e-3) / 1e9 / peak_hbm()[0],
+                           "same_plan_as_fused": bool(torch.equal(r_["idx"], ref["idx"][:Bg]) and torch.equal(r_["cost"], ref["cost"][:Bg]))}
+            del g_, r_
+        except Exception as e:          # noqa: BLE001
+            dense[name] = {"error": repr(e)}
+    dense["note"] = (f"{Bg} episodes; grids (u8 mask + distance, built by mpc_build_grid) resident in HBM, L2 flushed between calls; "
+                     "algorithmic bytes = whole grid once (SURVEY 8d) -- the kernel only touches the cells the DP reaches; fp32 "
+                     "distances may move a near-tie (same_plan_as_fused compares with the descriptor-fed fp64 plan)")
+    res["dense_solve"] = dense
     print(json.dumps(res), file=RESULT_OUT, flush=True)
 
 
