@@ -173,6 +173,15 @@ int mpc_predict_step_with_ego(mpc_handle *h, int B, const double *d_ego, const d
                               double min_crash_distance, double *d_ego_out, double *d_cars_x_out,
                               double *d_cars_v_out, double *d_cars_a_out, uint8_t *d_crashed,
                               void *stream);
+/* HighwayState.predict_step_without_ego (prediction.py:22-44): the traffic-only step the S-T grid builder applies per
+ * layer (st.py:42-43) -- the ego is replaced by a pseudo-ego (stays put before the merge point, ignored when it leads all
+ * cars, otherwise placed CAR_LENGTH + 5 m behind the car ahead of it at that car's speed) and the state advances with
+ * predict_step_with_ego.  Same buffers and aliasing rules as mpc_predict_step_with_ego. */
+int mpc_predict_step_without_ego(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
+                                 const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars,
+                                 double dt, double min_crash_distance, double *d_ego_out,
+                                 double *d_cars_x_out, double *d_cars_v_out, double *d_cars_a_out,
+                                 uint8_t *d_crashed, void *stream);
 /* dqn.get_state_vector_from_base_state (dqn.py:389-446) -> f32 [B][out_stride] (first 20 columns
  * written); control.get_ego_speed_from_jerk (control.py:160-171) -> f64[B]. */
 int mpc_state_vector(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,

@@ -55,6 +55,7 @@ SYMBOLS = {
     "mpc_finer_fit": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mpc_finer_fit_max_points": (_i, []),
     "mpc_predict_step_with_ego": (_i, [_vp, _i] + [_vp] * 6 + [_d, _d] + [_vp] * 5 + [_vp]),
+    "mpc_predict_step_without_ego": (_i, [_vp, _i] + [_vp] * 5 + [_d, _d] + [_vp] * 5 + [_vp]),
     "mpc_state_vector": (_i, [_vp, _i] + [_vp] * 5 + [_vp, _i, _vp]),
     "mpc_speed_from_jerk": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "mpc_rollout_step": (_i, [_vp, _i] + [_vp] * 6 + [_d, _d, _d, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),

@@ -32,6 +32,9 @@ cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const doubl
 cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
                                 const double *ca, const int32_t *n, float *out, int stride, cudaStream_t st);
 cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st);
+cudaError_t launch_predict_step_without_ego(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
+                                            const double *cv, const double *ca, const int32_t *n, double dt, double mcd,
+                                            double *ego_out, double *ox, double *ov, double *oa, uint8_t *crashed, cudaStream_t st);
 cudaError_t launch_reach_caps(const DevParams &P, int B, const LayerDesc *desc, const int32_t *num_s, unsigned short *capb,
                               int stride, cudaStream_t st);
 cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
@@ -578,6 +581,20 @@ extern "C" int mpc_predict_step_with_ego(mpc_handle *h, int B, const double *d_e
         return mpc_set_error(MPC_E_INVALID, "mpc_predict_step_with_ego: null pointer");
     MPC_CUDA_OK(launch_predict_step(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, d_selected_speed, dt,
                                     min_crash_distance, d_ego_out, d_cars_x_out, d_cars_v_out, d_cars_a_out, d_crashed, (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}
+
+extern "C" int mpc_predict_step_without_ego(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
+                                            const double *d_cars_a, const int32_t *d_n_cars, double dt, double min_crash_distance,
+                                            double *d_ego_out, double *d_cars_x_out, double *d_cars_v_out, double *d_cars_a_out,
+                                            uint8_t *d_crashed, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars || !d_ego_out || !d_cars_x_out || !d_cars_v_out)
+        return mpc_set_error(MPC_E_INVALID, "mpc_predict_step_without_ego: null pointer");
+    MPC_CUDA_OK(launch_predict_step_without_ego(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, dt, min_crash_distance,
+                                                d_ego_out, d_cars_x_out, d_cars_v_out, d_cars_a_out, d_crashed, (cudaStream_t)stream));
     h->kernels_launched = 1;
     return MPC_OK;
 }

@@ -322,6 +322,48 @@ __global__ void __launch_bounds__(128) predict_step_with_ego_kernel(DevParams P,
     }
 }
 
+// HighwayState.predict_step_without_ego (prediction.py:22-44) as a public step: the pseudo-ego choice of
+// warp_predict_without_ego, but with the caller's min_crash_distance and with everything predict_step_with_ego returns
+// (new ego incl. its acceleration, car accelerations, crash flag).
+__global__ void __launch_bounds__(128) predict_step_without_ego_kernel(DevParams P, int B, int nmax, const double *ego,
+                                                                      const double *cars_x, const double *cars_v,
+                                                                      const double *cars_a, const int32_t *n_cars, double dt,
+                                                                      double mcd, double *ego_out, double *ox, double *ov,
+                                                                      double *oa, uint8_t *crashed) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    int b = warp;
+    int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
+    EgoState e = {ego[4 * b], ego[4 * b + 1], ego[4 * b + 2], ego[4 * b + 3]}, eo;
+    double x = lane < n ? cars_x[(size_t)b * nmax + lane] : 0.0;
+    double v = lane < n ? cars_v[(size_t)b * nmax + lane] : 0.0;
+    const double ego_s = get_ego_s(e.x, e.y);
+    double sel;
+    const double x0 = __shfl_sync(FULL, x, 0);
+    if (ego_s < 8.0 || n == 0) { sel = 0.0; }                                                 // 26-27: the ego stays put
+    else if (x0 < e.x) { e.x = -20.0; e.y = -10.0; e.v = 0.0; e.a = 0.0; sel = 0.0; }         // 28-31: ego in front of everybody
+    else {                                                                                    // 33-44: ego follows the car ahead
+        const unsigned behind = __ballot_sync(FULL, lane < n && x < e.x);
+        const int first = behind ? __ffs(behind) - 1 : n;                                     // >= 1 here
+        const double lx = __shfl_sync(FULL, x, first - 1), lv = __shfl_sync(FULL, v, first - 1);
+        sel = lv;
+        if (behind) { e.x = __dsub_rn(__dsub_rn(lx, P.p.car_length), 5.0); e.v = lv; e.a = 0.0; }
+    }
+    double nx, nv, na;
+    bool cr = warp_predict_with_ego(P, lane, n, e, x, v, sel, dt, mcd, eo, nx, nv, na);
+    if (lane == 0) {
+        ego_out[4 * b] = eo.x; ego_out[4 * b + 1] = eo.y; ego_out[4 * b + 2] = eo.v; ego_out[4 * b + 3] = eo.a;
+        if (crashed) crashed[b] = cr ? 1 : 0;
+    }
+    if (lane < nmax) {
+        size_t o = (size_t)b * nmax + lane;
+        bool ok = lane < n;
+        ox[o] = ok ? nx : (cars_x == ox ? cars_x[o] : 0.0);
+        ov[o] = ok ? nv : (cars_v == ov ? cars_v[o] : 0.0);
+        if (oa) oa[o] = ok ? na : ((cars_a && cars_a == oa) ? cars_a[o] : 0.0);
+    }
+}
+
 // dqn.py:389-446 with CARS_AHEAD = CARS_BEHIND = 2, acceleration + speed difference, normalised.
 __global__ void __launch_bounds__(128) state_vector_kernel(DevParams P, int B, int nmax, const double *ego,
                                                           const double *cars_x, const double *cars_v,
@@ -434,6 +476,15 @@ cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const doubl
     if (B <= 0) return cudaSuccess;
     int wpb = 4;
     predict_step_with_ego_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, sel, dt, mcd, ego_out, ox, ov, oa, crashed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_predict_step_without_ego(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
+                                            const double *cv, const double *ca, const int32_t *n, double dt, double mcd,
+                                            double *ego_out, double *ox, double *ov, double *oa, uint8_t *crashed, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    int wpb = 4;
+    predict_step_without_ego_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, dt, mcd, ego_out, ox, ov, oa, crashed);
     return cudaGetLastError();
 }
 

@@ -278,6 +278,17 @@ class MpcEngine:
                                                           _ptr(eo), _ptr(xo), _ptr(vo), _ptr(ao), _ptr(crashed), self._stream()))
         return eo, xo, vo, ao, crashed
 
+    def predict_step_without_ego(self, ego, cars_x, cars_v, cars_a, n_cars, dt, min_crash_distance=5.0):
+        """HighwayState.predict_step_without_ego (prediction.py:22-44) for the whole batch: (ego, x, v, a, crashed)."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        eo, xo, vo, ao = torch.empty_like(ego), torch.empty_like(cars_x), torch.empty_like(cars_v), torch.empty_like(cars_x)
+        crashed = torch.empty(B, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.dev_index):
+            _lib.check(self.lib.mpc_predict_step_without_ego(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a),
+                                                             _ptr(n_cars), float(dt), float(min_crash_distance),
+                                                             _ptr(eo), _ptr(xo), _ptr(vo), _ptr(ao), _ptr(crashed), self._stream()))
+        return eo, xo, vo, ao, crashed
+
     def state_vector(self, ego, cars_x, cars_v, cars_a, n_cars, out=None):
         """dqn.get_state_vector_from_base_state -> f32 [B, >=20] (column 20, if present, is left for the time feature)."""
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)

@@ -87,6 +87,15 @@ class HighwayState:
         out = BatchedState(eo, xo, vo, ao, bs.n_cars).to_states()[0]
         return out, bool(cr.item())
 
+    def predict_step_without_ego(self, delta_t, min_crash_distance=5) -> Tuple["HighwayState", bool]:
+        """Reference prediction.py:22-44 (the traffic-only step of the S-T grid builder), batch of one."""
+        from . import st
+        eng = st.get_engine()
+        bs = BatchedState.from_states([self], eng.device, eng.nmax)
+        eo, xo, vo, ao, cr = eng.predict_step_without_ego(*bs.args(), delta_t, min_crash_distance)
+        out = BatchedState(eo, xo, vo, ao, bs.n_cars).to_states()[0]
+        return out, bool(cr.item())
+
     def get_closest_cars(self) -> Tuple[Optional[tuple], Optional[tuple]]:
         """(car directly ahead, car directly behind) as (x, speed, acceleration) tuples or None (host bookkeeping)."""
         behind = next((i for i, x in enumerate(self.other_xs) if x < self.ego_position[0]), None)
