@@ -382,13 +382,16 @@ int orc_solve_layered(const orc_params *p, int num_t, int num_s, const uint8_t *
 #define FXONE 262144.0
 static uint64_t fx(double x) { return (uint64_t)llrint(x * FXONE); }
 
+static int g_last_max_span = 0;      /* widest layer span (cells) the kernel's ring would have had to hold in the last model run */
+int orc_last_max_span(void) { return g_last_max_span; }
+
 static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
                             const double *distances, const double *s_values, double delta_t,
                             double v0, double a0, int f32_labels, uint64_t prune_fx, const uint64_t *hfx, uint64_t *fmin_out,
                             int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
     /* prune_fx != 0: nodes whose label exceeds it are dropped (the fast kernel's cost bound, mpc_fast.cu);
      * counts[0..1] = nodes expanded, pushes */
-    int64_t n_nodes = 0, n_push = 0;
+    int64_t n_nodes = 0, n_push = 0; int max_span_ = 0;
     double dsn = p->s_disc, dt = p->t_disc;
     double jlo = p->j_min * dt * dt * dt / dsn, jhi = p->j_max * dt * dt * dt / dsn;
     double alo_r = p->a_min * dt * dt / dsn, ahi_r = p->a_max * dt * dt / dsn, vmax_r = p->max_speed * dt / dsn;
@@ -448,6 +451,7 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
         /* pass t: finalise layer t (buffer t&1), push into layer t+1 */
         for (int t = 2; t < num_t && dhi >= 0; t++) {
             int cur = t & 1, nxt = cur ^ 1, any = 0, nlo = num_s, nhi = -1, bk = -1; uint64_t bl = 0; float blf = 0;
+            int klo_ = num_s, khi_ = -1;
             for (int k = dlo; k <= dhi; k++) {
                 if (!has[cur][k]) continue;
                 has[cur][k] = 0;
@@ -475,6 +479,7 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
                 int clamp = vmax_is_int ? (vhi >= vmax_c) : ((double)v + fmin((double)a + jhi, ahi_r) > vmax_r);
                 if (clamp) vhi = vmax_is_int ? (int)((s + p->max_speed * dt - start_s) / delta_s) - k : vmax_c;
                 int wlo = k + vlo, whi = k + vhi; if (whi > num_s - 1) whi = num_s - 1;
+                if (whi >= wlo) { if (wlo < klo_) klo_ = wlo; if (whi > khi_) khi_ = whi; }   /* the kernel's span: windows of kept nodes */
                 for (int kk = wlo; kk <= whi; kk++) {
                     int vn = kk - k, an = vn - v, jn = an - a;
                     uint64_t tot = label + vtab[vn] + atab[an + 16] + jtab[jn + 8];
@@ -486,6 +491,7 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
                     if (kk < nlo) nlo = kk; if (kk > nhi) nhi = kk;
                 }
             }
+            if (khi_ - klo_ + 1 > max_span_) max_span_ = khi_ - klo_ + 1;
             if (!any) break;
             best_t = t; best_k = bk; best_lab = bl; best_labf = blf;
             dlo = nlo; dhi = nhi;
@@ -494,6 +500,7 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
 #undef BETTER
     if (cost_out) *cost_out = f32_labels ? (double)best_labf : (double)best_lab * (1.0 / FXONE);
     if (counts) { counts[0] = n_nodes; counts[1] = n_push; }
+    g_last_max_span = max_span_;
     int r = backtrack(num_t, num_s, previous, s_values, best_t, best_k, idx_out, s_seq_out);
     for (int b = 0; b < 2; b++) { free(lab[b]); free(labf[b]); free(vv[b]); free(aa[b]); free(has[b]); }
     free(previous);

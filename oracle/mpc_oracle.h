@@ -98,6 +98,10 @@ int orc_solve_fast_model_h(const orc_params *p, int num_t, int num_s, const uint
                            double v0, double a0, uint64_t prune_fx, const uint64_t *hfx, uint64_t *fmin_out,
                            int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts);
 
+/* widest layer span (cells between the lowest and highest successor of a layer's surviving nodes) of the last
+ * fast-model run on this thread of control: what the fast kernel's label ring must hold (not thread safe; tools only) */
+int orc_last_max_span(void);
+
 /* Sum of st.cost (st.py:140-144) along an index path with the solver's history convention. */
 double orc_path_cost(const orc_params *p, int n, const int *idx, const double *s_values,
                      const double *distances, int num_s, double delta_t, double v0, double a0);
