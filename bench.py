@@ -422,6 +422,14 @@ def run_hint_leg(args):
     ok = same(eng2.plan_probed(probe, *a, margin=1.1))
     res["probed_1.1_no_heuristic"] = {"identical_outputs": ok, "ms": timed(lambda: eng2.plan_probed(probe, *a, margin=1.1, out=out))}
     eng2.close()
+    # the pruned frontier is narrow enough for three resident blocks per SM: same call, other launch shape
+    os.environ["MPC_FAST_BLOCKS"] = "96"
+    eng3 = MpcEngine(make_params(H), device=0, max_batch=B)
+    del os.environ["MPC_FAST_BLOCKS"]
+    ok = same(eng3.plan_probed(probe, *a, margin=1.1))
+    res["probed_1.1_three_blocks_per_sm"] = {"identical_outputs": ok, "ms": timed(lambda: eng3.plan_probed(probe, *a, margin=1.1, out=out)),
+                                             "fallback_problems": eng3.counters()["fallback_problems"]}
+    eng3.close()
     junk = ref["cost"] * 0.5
     res["low_hint_0.5"] = {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=junk))}
     # ---- K2, the st_cy drop-in itself: the DP kernel fed by DENSE grids in HBM (mpc_solve_dense), i.e. the solver boundary of the
