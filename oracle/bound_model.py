@@ -33,15 +33,20 @@ def zone_bound(p) -> float:
     return p.d_weight * 1000000.0 / max(p.min_allowed_distance, 1.0)
 
 
-def solve_with_ladder(p, ob, di, sv, v0, a0, hint=None):
-    """The kernel's attempts for one problem: [hint] -> zone bound -> unbounded.  A hint at or above the
-    zone bound skips the zone-bounded attempt.  Returns (result, nodes expanded over all attempts, attempts)."""
+HINT_RETRY = 1.36       # middle rung of the hinted ladder (mpc_handle::hint_retry)
+
+
+def solve_with_ladder(p, ob, di, sv, v0, a0, hint=None, retry=HINT_RETRY):
+    """The kernel's attempts for one problem: [hint -> retry * hint] -> zone bound -> unbounded.  A hint at or above
+    the zone bound skips the zone-bounded attempts.  Returns (result, nodes expanded over all attempts, attempts)."""
     T = ob.shape[0]
     zb = zone_bound(p)
     ladder = []
     if hint is not None and 0.0 < hint < 1e9:
         ladder.append(hint)
         if hint < zb:
+            if retry > 1.0 and hint * retry < zb:
+                ladder.append(hint * retry)
             ladder.append(zb)
     else:
         ladder.append(zb)

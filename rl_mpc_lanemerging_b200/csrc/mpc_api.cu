@@ -86,6 +86,7 @@ struct mpc_handle {
     int32_t *st_idx; double *st_seq, *st_cost, *st_mind, *st_s0; int32_t *st_reached; uint8_t *st_crash;
     unsigned short *capb; int cap_stride;      // reachability caps of hinted solves (allocated on first use)
     int use_heur;                                // MPC_FAST_HEUR=0 disables the heuristic pruning of hinted solves (dev A/B)
+    double hint_retry;                           // middle rung of the hinted ladder (MPC_HINT_RETRY, default 1.36 = 1.5 / 1.1; <= 1 disables)
     int64_t kernels_launched;
     // optional per-kernel timing (bench.py roofline): events around [predict | DP | fallback DP]
     int timing; cudaEvent_t ev[4]; int ev_valid;
@@ -218,6 +219,7 @@ static int configure(mpc_handle *h) {
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
     h->use_bound = env_int("MPC_FAST_BOUND", 0, 1, 1) && P.bound_fx != 0;
     { const char *e = getenv("MPC_FAST_HEUR"); h->use_heur = !(e && e[0] == '0'); }
+    { const char *e = getenv("MPC_HINT_RETRY"); h->hint_retry = e ? atof(e) : 1.36; if (!(h->hint_retry >= 0.0 && h->hint_retry < 100.0)) h->hint_retry = 1.36; }
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     return MPC_OK;
 }
@@ -467,6 +469,7 @@ static int plan_impl(mpc_handle *h, int B, const double *d_ego, const double *d_
     io.ego = d_ego;
     io.idx = d_idx; io.s_seq = d_s_seq; io.cost = d_cost; io.reached = d_reached_t; io.crash = d_crash; io.min_dist = d_min_dist;
     io.hint_cost = hint_cost; io.hint_reached = hint_reached; io.hint_full_t = hint_full_t; io.hint_scale = hint_scale;
+    io.hint_retry = h->hint_retry;
     if (hint_cost && mode == MPC_MODE_FAST && h->P.fast_ok && h->P.zone_ok && h->P.vstar_c > 0 && h->use_bound && h->use_heur) {
         // reachability caps for the exact A*-style pruning of the hinted lean pass (mpc_reach.cu)
         if (!h->capb) {

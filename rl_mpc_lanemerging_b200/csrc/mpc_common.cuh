@@ -166,6 +166,7 @@ struct SolveIO {
     // optional per-problem cost hint of the fast kernel (mpc_plan_hinted): first bound = hint_scale * hint_cost[b], used when
     // hint_reached == NULL or hint_reached[b] == hint_full_t
     const double *hint_cost; const int32_t *hint_reached; int hint_full_t; double hint_scale;
+    double hint_retry;           // second attempt under hint_retry * first bound (<= 1: straight to the standard bound)
     // hinted solves: per-bucket reachability caps u16 [B][num_t][cap_stride] (mpc_reach.cu), NULL = no heuristic pruning
     const unsigned short *capb; int cap_stride;
 };

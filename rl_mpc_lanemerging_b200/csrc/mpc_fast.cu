@@ -521,7 +521,12 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
             __syncthreads();
             if (bt < T - 1 && !S.need_fallback) {             // the bound (or a blocked zone) cut the plan short: repeat without
                 for (int k = tid; k < 2 * Wc; k += nth) sts_u64(sb0 + 8u * k, FX_EMPTY);
-                if (HINT && bnd < bound) bnd = bound;         // (a cost hint that was too low: once more under the standard bound)
+                // a cost hint that was too low: once more under hint_retry x the hint (CPU model: -2..-9 % nodes against going
+                // straight to the standard bound), then under the standard bound, then without
+                unsigned long long mid = FX_EMPTY;
+                if (HINT && bnd < bound && io.hint_retry > 1.0) mid = fx_from_double(__dmul_rn(__dmul_rn(io.hint_cost[b], io.hint_scale), io.hint_retry));
+                if (HINT && bnd < mid && mid < bound) bnd = mid;
+                else if (HINT && bnd < bound) bnd = bound;
                 else { bnd = FX_EMPTY; zone = 0; lean = false; }
                 __syncthreads();
                 continue;

@@ -46,7 +46,7 @@ def test_any_bound_that_reaches_the_horizon_is_exact(H, traffic, kind):
                 assert ref["reached_t"] < H or U < ref["cost"]
             # the kernel's ladder always ends on the unbounded answer, whatever the hint
             lad, _, tries = BM.solve_with_ladder(p, ob, di, sv, st.ego_v, st.ego_a, hint=U)
-            assert _same(lad, ref) and 1 <= tries <= 3
+            assert _same(lad, ref) and 1 <= tries <= 4
         lad, _, _ = BM.solve_with_ladder(p, ob, di, sv, st.ego_v, st.ego_a, hint=None)
         assert _same(lad, ref)
     assert n_bounded_ok >= 20
