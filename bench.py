@@ -448,6 +448,16 @@ def run_hint_leg(args):
     section("probed_1.1_no_heuristic", lambda: other_engine("MPC_FAST_HEUR", "0", 1.1))
     # the pruned frontier is narrow enough for three resident blocks per SM: same call, other launch shape
     section("probed_1.1_three_blocks_per_sm", lambda: other_engine("MPC_FAST_BLOCKS", "96", 1.1))
+    def other_probe(sm, tm):              # CPU model: 12x2 (26 x 751 cells) misses less often than 20x3 but costs more itself
+        p2 = eng.make_probe(sm, tm)
+        try:
+            ok = same(eng.plan_probed(p2, *a, margin=1.1))
+            ms = timed(lambda: eng.plan_probed(p2, *a, margin=1.1, out=out))
+            return {"identical_outputs": ok, "ms": ms, "probe_grid": [p2.num_t, p2.num_s_max - 1]}
+        finally:
+            p2.close()
+
+    section("probed_1.1_probe_12x2", lambda: other_probe(12, 2))
     section("low_hint_0.5", lambda: {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=ref["cost"] * 0.5))})
     # ---- K2, the st_cy drop-in itself: the DP kernel fed by DENSE grids in HBM (mpc_solve_dense), i.e. the solver boundary of the
     #      reference (st_cy.pyx:315) with the grid read from memory instead of being evaluated from the layer descriptors ----

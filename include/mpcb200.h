@@ -154,6 +154,13 @@ int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const double *h_car
                   int32_t *h_idx, double *h_s_seq, double *h_cost, int32_t *h_reached_t,
                   uint8_t *h_crash, double *h_min_dist, double *h_start_s, void *stream);
 
+/* mpc_plan_probed with HOST buffers (the end-to-end form of the probed solve). */
+int mpc_plan_host_probed(mpc_handle *h, mpc_handle *probe, double margin, int B, const double *h_ego,
+                         const double *h_cars_x, const double *h_cars_v, const double *h_cars_a,
+                         const int32_t *h_n_cars, int32_t *h_idx, double *h_s_seq, double *h_cost,
+                         int32_t *h_reached_t, uint8_t *h_crash, double *h_min_dist, double *h_start_s,
+                         void *stream);
+
 /* ---- finer_fit (st.py:584-723): re-sample each plan from T_DISCRETIZATION to TICK_LENGTH by linear interpolation and
  * project it onto the speed / acceleration / jerk limits (the QP the reference gives to cvxopt; solved here by a
  * primal-dual interior-point method, one thread per episode).  d_s_seq f64[B][num_t] and d_reached_t i32[B] are mpc_plan's

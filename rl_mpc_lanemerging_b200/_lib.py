@@ -52,6 +52,7 @@ SYMBOLS = {
     "mpc_plan_hinted": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp, _vp, _i, _d] + [_vp] * 7 + [_vp]),
     "mpc_plan_probed": (_i, [_vp, _vp, _d, _i] + [_vp] * 5 + [_vp] * 7 + [_vp]),
     "mpc_plan_host": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),
+    "mpc_plan_host_probed": (_i, [_vp, _vp, _d, _i] + [_vp] * 5 + [_vp] * 7 + [_vp]),
     "mpc_finer_fit": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mpc_finer_fit_max_points": (_i, []),
     "mpc_predict_step_with_ego": (_i, [_vp, _i] + [_vp] * 6 + [_d, _d] + [_vp] * 5 + [_vp]),

@@ -530,22 +530,25 @@ extern "C" int mpc_plan_probed(mpc_handle *h, mpc_handle *probe, double margin, 
     return rc;
 }
 
-extern "C" int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const double *h_cars_x, const double *h_cars_v, const double *h_cars_a,
-                             const int32_t *h_n_cars, int mode, int32_t *h_idx, double *h_s_seq, double *h_cost, int32_t *h_reached_t,
-                             uint8_t *h_crash, double *h_min_dist, double *h_start_s, void *stream) {
+// host-buffer variants: copy the state in, plan (plain or probed), copy the results out, synchronise
+static int plan_host_impl(mpc_handle *h, mpc_handle *probe, double margin, int B, const double *h_ego, const double *h_cars_x,
+                          const double *h_cars_v, const int32_t *h_n_cars, int mode, int32_t *h_idx, double *h_s_seq, double *h_cost,
+                          int32_t *h_reached_t, uint8_t *h_crash, double *h_min_dist, double *h_start_s, void *stream, const char *who) {
     int rc = check_batch(h, B); if (rc) return rc;
     if (B == 0) return MPC_OK;
-    if (!h_ego || !h_cars_x || !h_cars_v || !h_n_cars) return mpc_set_error(MPC_E_INVALID, "mpc_plan_host: null pointer");
-    (void)h_cars_a;
+    if (!h_ego || !h_cars_x || !h_cars_v || !h_n_cars) return mpc_set_error(MPC_E_INVALID, who);
     cudaStream_t st = (cudaStream_t)stream;
     size_t N = (size_t)h->nmax, T = (size_t)h->P.num_t, b = (size_t)B;
     MPC_CUDA_OK(cudaMemcpyAsync(h->st_ego, h_ego, b * 32, cudaMemcpyHostToDevice, st));
     MPC_CUDA_OK(cudaMemcpyAsync(h->st_cx, h_cars_x, b * N * 8, cudaMemcpyHostToDevice, st));
     MPC_CUDA_OK(cudaMemcpyAsync(h->st_cv, h_cars_v, b * N * 8, cudaMemcpyHostToDevice, st));
     MPC_CUDA_OK(cudaMemcpyAsync(h->st_n, h_n_cars, b * 4, cudaMemcpyHostToDevice, st));
-    rc = mpc_plan(h, B, h->st_ego, h->st_cx, h->st_cv, nullptr, h->st_n, mode, h_idx ? h->st_idx : nullptr, h_s_seq ? h->st_seq : nullptr,
-                  h_cost ? h->st_cost : nullptr, h_reached_t ? h->st_reached : nullptr, h_crash ? h->st_crash : nullptr,
-                  h_min_dist ? h->st_mind : nullptr, h_start_s ? h->st_s0 : nullptr, stream);
+    int32_t *d_idx = h_idx ? h->st_idx : nullptr; double *d_seq = h_s_seq ? h->st_seq : nullptr, *d_cost = h_cost ? h->st_cost : nullptr;
+    int32_t *d_reached = h_reached_t ? h->st_reached : nullptr; uint8_t *d_crash = h_crash ? h->st_crash : nullptr;
+    double *d_mind = h_min_dist ? h->st_mind : nullptr, *d_s0 = h_start_s ? h->st_s0 : nullptr;
+    if (probe) rc = mpc_plan_probed(h, probe, margin, B, h->st_ego, h->st_cx, h->st_cv, nullptr, h->st_n, d_idx, d_seq, d_cost, d_reached,
+                                    d_crash, d_mind, d_s0, stream);
+    else rc = mpc_plan(h, B, h->st_ego, h->st_cx, h->st_cv, nullptr, h->st_n, mode, d_idx, d_seq, d_cost, d_reached, d_crash, d_mind, d_s0, stream);
     if (rc) return rc;
     if (h_idx) MPC_CUDA_OK(cudaMemcpyAsync(h_idx, h->st_idx, b * T * 4, cudaMemcpyDeviceToHost, st));
     if (h_s_seq) MPC_CUDA_OK(cudaMemcpyAsync(h_s_seq, h->st_seq, b * T * 8, cudaMemcpyDeviceToHost, st));
@@ -556,6 +559,24 @@ extern "C" int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const do
     if (h_start_s) MPC_CUDA_OK(cudaMemcpyAsync(h_start_s, h->st_s0, b * 8, cudaMemcpyDeviceToHost, st));
     MPC_CUDA_OK(cudaStreamSynchronize(st));
     return MPC_OK;
+}
+
+extern "C" int mpc_plan_host(mpc_handle *h, int B, const double *h_ego, const double *h_cars_x, const double *h_cars_v, const double *h_cars_a,
+                             const int32_t *h_n_cars, int mode, int32_t *h_idx, double *h_s_seq, double *h_cost, int32_t *h_reached_t,
+                             uint8_t *h_crash, double *h_min_dist, double *h_start_s, void *stream) {
+    (void)h_cars_a;
+    return plan_host_impl(h, nullptr, 0.0, B, h_ego, h_cars_x, h_cars_v, h_n_cars, mode, h_idx, h_s_seq, h_cost, h_reached_t, h_crash,
+                          h_min_dist, h_start_s, stream, "mpc_plan_host: null pointer");
+}
+
+extern "C" int mpc_plan_host_probed(mpc_handle *h, mpc_handle *probe, double margin, int B, const double *h_ego, const double *h_cars_x,
+                                    const double *h_cars_v, const double *h_cars_a, const int32_t *h_n_cars, int32_t *h_idx,
+                                    double *h_s_seq, double *h_cost, int32_t *h_reached_t, uint8_t *h_crash, double *h_min_dist,
+                                    double *h_start_s, void *stream) {
+    (void)h_cars_a;
+    if (!probe) return mpc_set_error(MPC_E_INVALID, "mpc_plan_host_probed: null probe handle");
+    return plan_host_impl(h, probe, margin, B, h_ego, h_cars_x, h_cars_v, h_n_cars, MPC_MODE_FAST, h_idx, h_s_seq, h_cost, h_reached_t,
+                          h_crash, h_min_dist, h_start_s, stream, "mpc_plan_host_probed: null pointer");
 }
 
 // ---- finer_fit (st.py:584-723): tick-rate re-sampling + speed/accel/jerk projection of the plans ------------------------

@@ -197,9 +197,10 @@ class MpcEngine:
             self._pinned[name] = t
         return t
 
-    def plan_host(self, ego, cars_x, cars_v, cars_a, n_cars, mode="fast"):
+    def plan_host(self, ego, cars_x, cars_v, cars_a, n_cars, mode="fast", probe: Optional["MpcEngine"] = None, margin: float = 1.1):
         """Same through HOST buffers (numpy in, numpy out): the end-to-end call a CPU rollout loop makes.
-        Inputs are staged through pinned memory; results come back in (re-used) pinned arrays."""
+        Inputs are staged through pinned memory; results come back in (re-used) pinned arrays.
+        probe: a make_probe() engine -> mpc_plan_host_probed (fast mode; same outputs)."""
         B, T = int(ego.shape[0]), self.num_t
         f64, i32 = torch.float64, torch.int32
         pe = self._pin("ego", (B, 4), f64); pe.numpy()[...] = ego
@@ -210,9 +211,14 @@ class MpcEngine:
                  reached_t=self._pin("reached", (B,), i32), crash=self._pin("crash", (B,), torch.uint8),
                  min_dist=self._pin("mind", (B,), f64), start_s=self._pin("s0", (B,), f64))
         with torch.cuda.device(self.dev_index):
-            _lib.check(self.lib.mpc_plan_host(self.h, B, _ptr(pe), _ptr(px), _ptr(pv), None, _ptr(pn), _mode(mode),
-                                              _ptr(o["idx"]), _ptr(o["s_seq"]), _ptr(o["cost"]), _ptr(o["reached_t"]),
-                                              _ptr(o["crash"]), _ptr(o["min_dist"]), _ptr(o["start_s"]), self._stream()))
+            if probe is not None:
+                _lib.check(self.lib.mpc_plan_host_probed(self.h, probe.h, float(margin), B, _ptr(pe), _ptr(px), _ptr(pv), None, _ptr(pn),
+                                                         _ptr(o["idx"]), _ptr(o["s_seq"]), _ptr(o["cost"]), _ptr(o["reached_t"]),
+                                                         _ptr(o["crash"]), _ptr(o["min_dist"]), _ptr(o["start_s"]), self._stream()))
+            else:
+                _lib.check(self.lib.mpc_plan_host(self.h, B, _ptr(pe), _ptr(px), _ptr(pv), None, _ptr(pn), _mode(mode),
+                                                  _ptr(o["idx"]), _ptr(o["s_seq"]), _ptr(o["cost"]), _ptr(o["reached_t"]),
+                                                  _ptr(o["crash"]), _ptr(o["min_dist"]), _ptr(o["start_s"]), self._stream()))
         return {k: v.numpy() for k, v in o.items()}
 
     # ------------------------------------------------------------------------------------------

@@ -62,11 +62,16 @@ def test_probed_plan_equals_plain_plan(mult):
     eng = _engine(50, B)
     probe = eng.make_probe(*mult)
     assert probe.num_t < eng.num_t and probe.num_s_max < eng.num_s_max
-    S = E.states_to_device(synthetic.make_states(B, "moderate", seed=0), eng.device)
+    S_np = synthetic.make_states(B, "moderate", seed=0)
+    S = E.states_to_device(S_np, eng.device)
     args = (S["ego"], S["cars_x"], S["cars_v"], S["cars_a"], S["n_cars"])
     ref = {k: v.clone() for k, v in eng.plan(*args).items()}
     _same(eng.plan_probed(probe, *args, margin=1.1), ref)
     _same(eng.plan_probed(probe, *args, margin=0.5), ref)          # every first attempt too low: the ladder recovers
+    if mult == (20, 3):                                            # the host-buffer form of the same call
+        host = eng.plan_host(S_np["ego"], S_np["cars_x"], S_np["cars_v"], S_np["cars_a"], S_np["n_cars"], probe=probe)
+        for k in ("idx", "s_seq", "cost", "reached_t", "crash", "min_dist", "start_s"):
+            assert np.array_equal(host[k], ref[k].cpu().numpy()), k
     # the probe plan is a usable estimate (CPU model: median 1.00, IQR 0.97-1.04 for 20x3)
     pr = probe.plan(*args)
     ok = (pr["reached_t"] == probe.num_t - 1) & (ref["reached_t"] == eng.num_t - 1) & (ref["cost"] < 1e6)
