@@ -27,9 +27,9 @@ def test_unverified_gpu_tests_in_a_child_process(name):
     env = dict(os.environ, MPCB200_RUN_UNVERIFIED="1")
     cmd = [sys.executable, "-m", "pytest", os.path.join(HERE, name), "-q", "-m", "gpu and unverified", "-p", "no:cacheprovider"]
     try:
-        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, cwd=root)
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=240, cwd=root)
     except subprocess.TimeoutExpired:
-        pytest.xfail(f"{name}: did not finish within 600 s in the child process")
+        pytest.xfail(f"{name}: did not finish within 240 s in the child process")
     tail = r.stdout.decode(errors="replace")[-3000:]
     print(tail)
     if r.returncode != 0:
