@@ -38,7 +38,7 @@ enum {
 
 /* arithmetic of the DP solve */
 enum {
-    MPC_MODE_FAST = 0,   /* integer-cell kinematics, fp32 labels (north_star tolerance 1e-4 rel)  */
+    MPC_MODE_FAST = 0,   /* integer-cell kinematics, 2^-18 fixed-point 48-bit labels (cost within 1e-7 rel) */
     MPC_MODE_EXACT = 1   /* fp64, reference operation order: index-identical to st_cy            */
 };
 

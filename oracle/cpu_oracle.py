@@ -154,7 +154,8 @@ def solve(p, obstacles, distances, s_values, delta_t, v0, a0, layered=False):
 
 
 def solve_fast_model(p, obstacles, distances, s_values, delta_t, v0, a0, f32_labels=False):
-    """CPU model of the CUDA fast kernel (integer kinematics, fp32 labels); NOT the reference."""
+    """CPU model of the CUDA fast kernel (integer kinematics, 2^-18 fixed-point labels; f32_labels=True = the rejected
+    fp32-label design, kept to document why); NOT the reference."""
     nt, ns = obstacles.shape
     idx = np.zeros(nt, np.int32)
     seq = np.zeros(nt, np.float64)
