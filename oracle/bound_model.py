@@ -150,8 +150,9 @@ def bucket_caps_like_kernel(p, ob, di) -> np.ndarray:
     return caps
 
 
-def solve_with_heuristic(p, ob, di, sv, v0, a0, U, h):
-    """Fast-kernel model that drops a node when label + h > U (U in cost units, h from heuristic_table)."""
+def solve_with_heuristic(p, ob, di, sv, v0, a0, U, h, U_fx=None):
+    """Fast-kernel model that drops a node when label + h > U (U in cost units or, U_fx, in label units; h from
+    heuristic_table)."""
     import ctypes as C
     T, S = ob.shape
     idx = np.zeros(T, np.int32); seq = np.zeros(T, np.float64); cost = C.c_double(); counts = (C.c_int64 * 2)()
@@ -160,7 +161,7 @@ def solve_with_heuristic(p, ob, di, sv, v0, a0, U, h):
     dp = C.POINTER(C.c_double)
     r = O.lib().orc_solve_fast_model_h(C.byref(p), T, S, ob.ctypes.data_as(C.c_void_p), di.ctypes.data_as(dp),
                                        sv.ctypes.data_as(dp), C.c_double(p.t_disc), C.c_double(v0), C.c_double(a0),
-                                       C.c_uint64(int(round(U * FX_ONE))), h.ctypes.data_as(C.POINTER(C.c_uint64)), None,
+                                       C.c_uint64(int(U_fx) if U_fx is not None else int(round(U * FX_ONE))), h.ctypes.data_as(C.POINTER(C.c_uint64)), None,
                                        idx.ctypes.data_as(C.POINTER(C.c_int)), seq.ctypes.data_as(dp), C.byref(cost), counts)
     return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value, nodes=int(counts[0]), pushes=int(counts[1]))
 

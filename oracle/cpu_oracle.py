@@ -168,15 +168,15 @@ def solve_fast_model(p, obstacles, distances, s_values, delta_t, v0, a0, f32_lab
     return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value)
 
 
-def solve_fast_model_ex(p, obstacles, distances, s_values, delta_t, v0, a0, prune_cost=0.0):
-    """Fast-kernel model with the cost bound (nodes with a label above prune_cost are dropped; 0 = none).
-    Also returns the node / push counts."""
+def solve_fast_model_ex(p, obstacles, distances, s_values, delta_t, v0, a0, prune_cost=0.0, prune_fx=None):
+    """Fast-kernel model with the cost bound (nodes with a label above prune_cost are dropped; 0 = none; prune_fx gives the
+    bound in label units, 2^-18, exactly as the kernel holds it).  Also returns the node / push counts."""
     nt, ns = obstacles.shape
     idx = np.zeros(nt, np.int32); seq = np.zeros(nt, np.float64); cost = C.c_double(); counts = (C.c_int64 * 2)()
     obstacles = np.ascontiguousarray(obstacles, dtype=np.uint8)
     distances = np.ascontiguousarray(distances, dtype=np.float64)
     s_values = np.ascontiguousarray(s_values, dtype=np.float64)
-    fxb = int(round(prune_cost * 262144.0)) if prune_cost else 0
+    fxb = int(prune_fx) if prune_fx is not None else (int(round(prune_cost * 262144.0)) if prune_cost else 0)
     r = lib().orc_solve_fast_model_ex(C.byref(p), nt, ns, obstacles.ctypes.data_as(C.c_void_p), _dp(distances), _dp(s_values),
                                       C.c_double(delta_t), C.c_double(v0), C.c_double(a0), C.c_int(0), C.c_uint64(fxb),
                                       _ip(idx), _dp(seq), C.byref(cost), counts)

@@ -4,7 +4,11 @@
 // multiply-add into an FMA; the library is also compiled with -fmad=false and uses fmaf()
 // explicitly where a fused fp32 multiply-add is wanted.
 #pragma once
+#ifdef MPC_HOST_EMU               // tests/emu: the kernels compiled by g++ and run on fibers (test infrastructure only)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "../../include/mpcb200.h"
 

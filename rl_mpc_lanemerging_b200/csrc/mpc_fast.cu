@@ -32,6 +32,9 @@
 #endif
 
 #define EMPTY_LAB 0x7ff0000000000000ULL      // +inf
+#ifndef MPC_EMU_COUNT_NODE                    // tests/emu counts the nodes each pass finalises (compared with the CPU model)
+#define MPC_EMU_COUNT_NODE()
+#endif
 
 struct __align__(16) FastShared {
     LayerSearch layer[4];        // first: staged with 16-byte vector stores; layer t lives in slot t & 3
@@ -160,6 +163,22 @@ __device__ __forceinline__ void int_window(const DevParams &P, const SGrid &g, c
 // ld/st/atom.shared: through a generic pointer that nvcc cannot prove to be shared (the two label buffers
 // are selected by layer parity) it emits generic LD.E / ATOM.E.CAS plus the software fall-back of generic
 // atomics on shared memory, several times the cost of LDS / ATOMS.CAS (seen in the SASS of the v8 kernel).
+#ifdef MPC_HOST_EMU     // tests/emu: the same accessors on the emulated shared window (plain memory operations)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return emu::to_shared(p); }
+__device__ __forceinline__ unsigned long long lds_u64(unsigned a) { return *emu::from_shared<unsigned long long>(a); }
+__device__ __forceinline__ void sts_u64(unsigned a, unsigned long long v) { *emu::from_shared<unsigned long long>(a) = v; }
+__device__ __forceinline__ unsigned long long atoms_cas_u64(unsigned a, unsigned long long cmp, unsigned long long val) {
+    unsigned long long *p = emu::from_shared<unsigned long long>(a), old = *p; if (old == cmp) *p = val; return old;
+}
+__device__ __forceinline__ unsigned long long lds_u64_nc(unsigned a) { return lds_u64(a); }
+__device__ __forceinline__ unsigned lds_u8_nc(unsigned a) { return *emu::from_shared<unsigned char>(a); }
+__device__ __forceinline__ double lds_f64_nc(unsigned a) { return *emu::from_shared<double>(a); }
+__device__ __forceinline__ unsigned long long atoms_cas_u64_if(unsigned a, unsigned long long cmp, unsigned long long val, bool doit) {
+    return doit ? atoms_cas_u64(a, cmp, val) : cmp;
+}
+__device__ __forceinline__ unsigned lds_u32_nc(unsigned a) { return *emu::from_shared<unsigned>(a); }
+__device__ __forceinline__ unsigned long long atoms_cas_u64_nc(unsigned a, unsigned long long cmp, unsigned long long val) { return atoms_cas_u64(a, cmp, val); }
+#else
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned long long lds_u64(unsigned a) {
     unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v;
@@ -187,6 +206,7 @@ __device__ __forceinline__ unsigned lds_u32_nc(unsigned a) { unsigned v; asm vol
 __device__ __forceinline__ unsigned long long atoms_cas_u64_nc(unsigned a, unsigned long long cmp, unsigned long long val) {
     unsigned long long old; asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val)); return old;
 }
+#endif
 
 // int_window with the clamp bit arrays addressed in the shared window (lo at cba, hi at cba + 4 * NW)
 __device__ __forceinline__ void int_window_sa(const DevParams &P, int num_s, unsigned cba, int NW, int k, int v, int a, int &wlo, int &n) {
@@ -252,7 +272,11 @@ template <class Prov, bool DESC, bool WRAP, int MAXT, bool HINT>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1)) fast_pull_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
                                                                               const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc,
                                                                               unsigned long long bound) {
+#ifdef MPC_HOST_EMU
+    unsigned char *const smem_raw = emu::S().dyn_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     __shared__ FastShared FS;
     __shared__ FxTables TB;
     __shared__ unsigned long long s_layer_best[2];
@@ -405,7 +429,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
                 const unsigned edge0 = smem_u32(FS.layer[t & 3].edge), bucket0 = smem_u32(FS.layer[t & 3].bucket_edge);
                 const unsigned bwa = smem_u32(blkbits[0]) + (par ? 0u : 4u * (unsigned)(NW + 2));      // blocked bits of layer t+1
                 uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
+#ifndef MPC_HOST_EMU
                 asm volatile("" : "+l"(bp_row));              // keep the row pointer in registers (else it is rebuilt per node)
+#endif
                 unsigned long long mybest = FX_EMPTY;
                 int mylo = INT_MAX, myhi = -1;
                 // 32-cell chunks of the layer's span: the first one per warp is static, the rest come from a shared counter
@@ -444,6 +470,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
                             keep = capv != 0xffffu && label + h <= bnd;
                         }
                         if (keep) {
+                            MPC_EMU_COUNT_NODE();
                             const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
                             if (MPC_ABLATE != 4) bp_row[k] = (uint16_t)(k - v);
                             if (last) {
@@ -556,6 +583,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
                 if (label > bnd) { hit = true; return; }                      // cost bound: see the note above the kernel
                 if (label >= FX_LABEL_LIMIT) { S.need_fallback = 1; return; }
                 const int v = 255 - (int)((w >> 8) & 0xff), a = (int)(w & 0xff) - 128;
+                MPC_EMU_COUNT_NODE();
                 bp_row[k] = (uint16_t)(k - v);
                 unsigned long long key = (label << 16) | (unsigned long long)k;
                 mybest = key < mybest ? key : mybest;
@@ -649,6 +677,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
     }
 }
 
+#ifndef MPC_HOST_EMU      // host-side launchers (the emulation harness instantiates the kernel templates itself)
 // ------------------------------------------------------------------------------------------------
 template <class K>
 static cudaError_t set_smem(K kernel, size_t smem) {
@@ -706,3 +735,4 @@ int fast_occupancy(int threads, size_t smem, int wrap) {
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+#endif  // MPC_HOST_EMU

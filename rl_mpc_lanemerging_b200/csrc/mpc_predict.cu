@@ -286,12 +286,14 @@ __global__ void __launch_bounds__(256) check_sorted_kernel(DevParams P, int B, c
     if (bad) atomicAdd(mismatches, bad);
 }
 
+#ifndef MPC_HOST_EMU
 cudaError_t launch_check_sorted(const DevParams &P, int B, const LayerDesc *desc, const double *s0, const double *ds,
                                 const int32_t *ns, unsigned long long *mismatches, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     check_sorted_kernel<<<B * P.num_t, 256, 0, st>>>(P, B, desc, s0, ds, ns, mismatches);
     return cudaGetLastError();
 }
+#endif
 
 // ---- K4 -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) predict_step_with_ego_kernel(DevParams P, int B, int nmax, const double *ego,
@@ -451,6 +453,7 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(DevParams P, int B, i
 }
 
 // ---- host launchers (called from mpc_api.cu) -----------------------------------------------------
+#ifndef MPC_HOST_EMU      // host-side launchers
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
                                   const double *cv, const int32_t *n, LayerDesc *desc, double *s0, double *ds,
                                   int32_t *ns, cudaStream_t st) {
@@ -511,3 +514,4 @@ cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego
                                                      sel_speed, roll_s, roll_stride, roll_len, crash_pred);
     return cudaGetLastError();
 }
+#endif  // MPC_HOST_EMU

@@ -1,0 +1,101 @@
+// Kernel-emulation harness -- TEST INFRASTRUCTURE ONLY (see cuda_emu.h).
+//
+// Compiles the library's kernel sources with g++ against the fiber shim and exposes the fused gap-evaluation
+//   predict_layers_kernel -> [reach_caps_kernel] -> fast_pull_kernel<FastDescProv, DESC, WRAP, MAXT, HINT>
+// as one C function, with the launch shape chosen by the caller.  tests/test_kernel_emulation_cpu.py compares its outputs
+// with the CPU oracle / the C model of the fast kernel.
+#include "cuda_emu.h"
+
+#include "../../rl_mpc_lanemerging_b200/csrc/mpc_common.cuh"
+
+static char g_err[256];
+int mpc_set_error(int code, const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
+int mpc_set_cuda_error(cudaError_t, const char *what) { snprintf(g_err, sizeof(g_err), "%s", what); return MPC_E_CUDA; }
+
+static long long g_nodes = 0;                  // nodes finalised by the fast kernel since the last emu_plan call began
+#define MPC_EMU_COUNT_NODE() (g_nodes++)
+extern "C" long long emu_node_count() { return g_nodes; }
+
+#include "../../rl_mpc_lanemerging_b200/csrc/mpc_derive.h"
+#include "../../rl_mpc_lanemerging_b200/csrc/mpc_predict.cu"
+#undef FULL
+#include "../../rl_mpc_lanemerging_b200/csrc/mpc_reach.cu"
+#include "../../rl_mpc_lanemerging_b200/csrc/mpc_fast.cu"
+
+#include <vector>
+
+extern "C" const char *emu_last_error() { return g_err; }
+
+// One fused gap-evaluation of B states on the emulated device.
+//   threads: block size of the fast kernel (multiple of 32, <= 1024); ring: label ring capacity in cells (0 = full row, no wrap)
+//   hint_cost (nullable) / hint_scale / hint_retry: the cost-hint ladder; use_caps: reachability pruning (hinted solves)
+//   use_bound: 0 = unbounded pass, 1 = standard zone bound
+// Outputs as mpc_plan; fallback[b] = 1 when the kernel handed the problem back (ring overflow / saturation).
+extern "C" int emu_plan(const mpc_params *params, int B, int nmax, const double *ego, const double *cars_x, const double *cars_v,
+                        const int32_t *n_cars, int threads, int ring, int use_bound, const double *hint_cost, double hint_scale,
+                        double hint_retry, int use_caps, int32_t *idx, double *s_seq, double *cost, int32_t *reached,
+                        uint8_t *crash, double *min_dist, double *start_s, uint8_t *fallback, int32_t *num_t_out) {
+    DevParams P;
+    g_nodes = 0;
+    int rc = derive_params(params, &P);
+    if (rc) return rc;
+    if (!P.fast_ok) return mpc_set_error(MPC_E_INVALID, "fast mode not available for these params");
+    const int T = P.num_t;
+    if (num_t_out) *num_t_out = T;
+    std::vector<LayerDesc> desc((size_t)B * T);
+    std::vector<double> s0(B), ds(B);
+    std::vector<int32_t> num_s(B);
+    // K1a
+    emu::launch((B + 3) / 4, 128, 0, [&] { predict_layers_kernel(P, B, ego, cars_x, cars_v, n_cars, nmax, desc.data(), s0.data(), ds.data(), num_s.data()); });
+    if (start_s) for (int b = 0; b < B; b++) start_s[b] = s0[b];
+    // reachability caps
+    const int stride = ((P.num_s_max + 63) / 64 + 7) & ~7;
+    std::vector<unsigned short> capb;
+    const bool hinted = hint_cost != nullptr;
+    if (hinted && use_caps && P.zone_ok && P.vstar_c > 0 && use_bound) {
+        capb.assign((size_t)B * T * stride, 0);
+        emu::launch((B + RC_WARPS - 1) / RC_WARPS, 32 * RC_WARPS, 0, [&] { reach_caps_kernel(P, B, desc.data(), num_s.data(), capb.data(), stride); });
+    }
+    // K3
+    const int W = (P.num_s_max + 7) & ~7;
+    const bool wrap = ring > 0 && ring < W;
+    const int Wc = wrap ? (ring & ~7) : W;
+    const size_t clamp_bytes = (4 * (((size_t)P.num_s_max + 31) / 32) + 4) * 4 + 16;
+    const size_t smem = (size_t)Wc * 16 + clamp_bytes;
+    std::vector<uint16_t> bp((size_t)T * W);
+    std::vector<int> counters(16, 0);
+    std::vector<int32_t> fb_list(2 * (size_t)B + 2, -1);
+    SolveIO io; memset(&io, 0, sizeof(io));
+    io.ego = ego;
+    io.idx = idx; io.s_seq = s_seq; io.cost = cost; io.reached = reached; io.crash = crash; io.min_dist = min_dist;
+    io.bp = bp.data(); io.bp_stride = W;
+    io.work_counter = &counters[0]; io.fallback_list = fb_list.data(); io.fallback_count = &counters[2];
+    io.hint_cost = hint_cost; io.hint_scale = hint_scale; io.hint_retry = hint_retry;
+    io.capb = capb.empty() ? nullptr : capb.data(); io.cap_stride = stride;
+    const unsigned long long bound = use_bound ? P.bound_fx : ~0ULL;
+    const LayerDesc *d = desc.data();
+#define EMU_RUN(WRAPV, MAXTV, HINTV) \
+    emu::launch(1, threads, smem, [&] { fast_pull_kernel<FastDescProv, true, WRAPV, MAXTV, HINTV>(P, B, io, d, nullptr, nullptr, 0, Wc, bound); })
+#define EMU_SHAPE(MAXTV) \
+    do { if (wrap) { if (hinted) EMU_RUN(true, MAXTV, true); else EMU_RUN(true, MAXTV, false); } \
+         else { if (hinted) EMU_RUN(false, MAXTV, true); else EMU_RUN(false, MAXTV, false); } } while (0)
+    if (threads <= 192) EMU_SHAPE(192);
+    else if (threads <= 512) EMU_SHAPE(512);
+    else EMU_SHAPE(1024);
+    if (fallback) {
+        memset(fallback, 0, B);
+        for (int i = 0; i < counters[2]; i++) if (fb_list[i] >= 0 && fb_list[i] < B) fallback[fb_list[i]] = 1;
+    }
+    return MPC_OK;
+}
+
+// HighwayState.predict_step_without_ego through the K4 kernel
+extern "C" int emu_predict_step_without_ego(const mpc_params *params, int B, int nmax, const double *ego, const double *cars_x,
+                                            const double *cars_v, const double *cars_a, const int32_t *n_cars, double dt, double mcd,
+                                            double *ego_out, double *ox, double *ov, double *oa, uint8_t *crashed) {
+    DevParams P;
+    int rc = derive_params(params, &P);
+    if (rc) return rc;
+    emu::launch((B + 3) / 4, 128, 0, [&] { predict_step_without_ego_kernel(P, B, nmax, ego, cars_x, cars_v, cars_a, n_cars, dt, mcd, ego_out, ox, ov, oa, crashed); });
+    return MPC_OK;
+}

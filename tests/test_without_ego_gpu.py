@@ -21,6 +21,8 @@ def test_predict_step_without_ego_matches_oracle(oracle, traffic, kind, dt, mcd)
     eng = MpcEngine(helpers.mpc_params_from_oracle(op), device=0, max_batch=B)
     S = synthetic.make_states(B, traffic, seed=21, kind=kind)
     S["n_cars"][:4] = 0                                       # the "no cars" branch (prediction.py:26)
+    S["ego"][5] = (60.0, -1.6, 12.0, 0.0)                     # the ego leads every car (prediction.py:28-31)
+    S["cars_x"][5, :3] = (40.0, 20.0, 0.0); S["cars_v"][5, :3] = 11.0; S["cars_a"][5, :3] = 0.0; S["n_cars"][5] = 3
     D = states_to_device(S, "cuda:0")
     eo, xo, vo, ao, cr = eng.predict_step_without_ego(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], dt, mcd)
     torch.cuda.synchronize()
