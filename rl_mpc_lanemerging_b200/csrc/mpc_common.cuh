@@ -12,6 +12,13 @@
 #include <stdint.h>
 #include "../../include/mpcb200.h"
 
+// kernel launch: the CUDA launch syntax for nvcc; the fiber scheduler of tests/emu when the sources are compiled by g++
+#ifdef MPC_HOST_EMU
+#define MPC_LAUNCH(kernel, grid, block, smem, st, ...) emu::launch((grid), (block), (smem), [=] { kernel(__VA_ARGS__); })
+#else
+#define MPC_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__)
+#endif
+
 #define MPC_NMAX 32            // cars per problem handled by one warp (lane == car)
 #define MPC_MAX_T 128          // time layers supported (H <= 127)
 

@@ -677,7 +677,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
     }
 }
 
-#ifndef MPC_HOST_EMU      // host-side launchers (the emulation harness instantiates the kernel templates itself)
 // ------------------------------------------------------------------------------------------------
 template <class K>
 static cudaError_t set_smem(K kernel, size_t smem) {
@@ -693,7 +692,7 @@ static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const
     do {                                                                                                   \
         auto k = fast_pull_kernel<Prov, DESC, WRAPV, MAXTV, HINT>;                                         \
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;                                            \
-        k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, desc, ob, dist, stride, L.W, L.bound);                     \
+        MPC_LAUNCH(k, L.grid, L.threads, L.smem, st, P, L.B, io, desc, ob, dist, stride, L.W, L.bound);                     \
     } while (0)
     if (L.threads <= 192) { if (L.wrap) MPC_LAUNCH_FAST(true, 192); else MPC_LAUNCH_FAST(false, 192); }
     else if (L.threads <= 256) { if (L.wrap) MPC_LAUNCH_FAST(true, 256); else MPC_LAUNCH_FAST(false, 256); }
@@ -735,4 +734,3 @@ int fast_occupancy(int threads, size_t smem, int wrap) {
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
-#endif  // MPC_HOST_EMU

@@ -286,14 +286,12 @@ __global__ void __launch_bounds__(256) check_sorted_kernel(DevParams P, int B, c
     if (bad) atomicAdd(mismatches, bad);
 }
 
-#ifndef MPC_HOST_EMU
 cudaError_t launch_check_sorted(const DevParams &P, int B, const LayerDesc *desc, const double *s0, const double *ds,
                                 const int32_t *ns, unsigned long long *mismatches, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    check_sorted_kernel<<<B * P.num_t, 256, 0, st>>>(P, B, desc, s0, ds, ns, mismatches);
+    MPC_LAUNCH(check_sorted_kernel, B * P.num_t, 256, 0, st, P, B, desc, s0, ds, ns, mismatches);
     return cudaGetLastError();
 }
-#endif
 
 // ---- K4 -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) predict_step_with_ego_kernel(DevParams P, int B, int nmax, const double *ego,
@@ -453,13 +451,12 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(DevParams P, int B, i
 }
 
 // ---- host launchers (called from mpc_api.cu) -----------------------------------------------------
-#ifndef MPC_HOST_EMU      // host-side launchers
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
                                   const double *cv, const int32_t *n, LayerDesc *desc, double *s0, double *ds,
                                   int32_t *ns, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     int wpb = 4;
-    predict_layers_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, ego, cx, cv, n, nmax, desc, s0, ds, ns);
+    MPC_LAUNCH(predict_layers_kernel, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, ego, cx, cv, n, nmax, desc, s0, ds, ns);
     return cudaGetLastError();
 }
 
@@ -468,8 +465,8 @@ cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const Laye
                              cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     const int vec_ok = (stride_s % 4 == 0) && ((uintptr_t)obstacles % 4 == 0) && ((uintptr_t)distances % 16 == 0);
-    if (dist_f32) rasterise_kernel<float><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances, vec_ok);
-    else rasterise_kernel<double><<<B * P.num_t, 256, 0, st>>>(P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances, vec_ok);
+    if (dist_f32) MPC_LAUNCH(rasterise_kernel<float>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances, vec_ok);
+    else MPC_LAUNCH(rasterise_kernel<double>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances, vec_ok);
     return cudaGetLastError();
 }
 
@@ -478,7 +475,7 @@ cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const doubl
                                 double *ego_out, double *ox, double *ov, double *oa, uint8_t *crashed, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     int wpb = 4;
-    predict_step_with_ego_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, sel, dt, mcd, ego_out, ox, ov, oa, crashed);
+    MPC_LAUNCH(predict_step_with_ego_kernel, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, nmax, ego, cx, cv, ca, n, sel, dt, mcd, ego_out, ox, ov, oa, crashed);
     return cudaGetLastError();
 }
 
@@ -487,7 +484,7 @@ cudaError_t launch_predict_step_without_ego(const DevParams &P, int B, int nmax,
                                             double *ego_out, double *ox, double *ov, double *oa, uint8_t *crashed, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     int wpb = 4;
-    predict_step_without_ego_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, dt, mcd, ego_out, ox, ov, oa, crashed);
+    MPC_LAUNCH(predict_step_without_ego_kernel, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, nmax, ego, cx, cv, ca, n, dt, mcd, ego_out, ox, ov, oa, crashed);
     return cudaGetLastError();
 }
 
@@ -495,13 +492,13 @@ cudaError_t launch_state_vector(const DevParams &P, int B, int nmax, const doubl
                                 const double *ca, const int32_t *n, float *out, int stride, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     int wpb = 4;
-    state_vector_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, out, stride);
+    MPC_LAUNCH(state_vector_kernel, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, nmax, ego, cx, cv, ca, n, out, stride);
     return cudaGetLastError();
 }
 
 cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego, const double *jerk, double *speed, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    speed_from_jerk_kernel<<<(B + 127) / 128, 128, 0, st>>>(P, B, ego, jerk, speed);
+    MPC_LAUNCH(speed_from_jerk_kernel, (B + 127) / 128, 128, 0, st, P, B, ego, jerk, speed);
     return cudaGetLastError();
 }
 
@@ -510,8 +507,7 @@ cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego
                                 uint8_t *alive, double *sel_speed, double *roll_s, int roll_stride, int32_t *roll_len,
                                 uint8_t *crash_pred, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    rollout_step_kernel<<<(B + 3) / 4, 128, 0, st>>>(P, B, nmax, ego, cx, cv, ca, n, jerk, dt, mcd, stop_x, step, alive,
+    MPC_LAUNCH(rollout_step_kernel, (B + 3) / 4, 128, 0, st, P, B, nmax, ego, cx, cv, ca, n, jerk, dt, mcd, stop_x, step, alive,
                                                      sel_speed, roll_s, roll_stride, roll_len, crash_pred);
     return cudaGetLastError();
 }
-#endif  // MPC_HOST_EMU

@@ -279,7 +279,7 @@ cudaError_t launch_finer_fit(const DevParams &P, int B, int T, const double *s_s
                              int max_iter, double tol, double *fine, int fine_stride, int32_t *n_fine, double *speed,
                              int32_t *iters, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    finer_fit_kernel<<<(B + QP_WARPS - 1) / QP_WARPS, 32 * QP_WARPS, 0, st>>>(P, B, T, s_seq, reached, ego, max_iter, tol, fine, fine_stride, n_fine, speed, iters);
+    MPC_LAUNCH(finer_fit_kernel, (B + QP_WARPS - 1) / QP_WARPS, 32 * QP_WARPS, 0, st, P, B, T, s_seq, reached, ego, max_iter, tol, fine, fine_stride, n_fine, speed, iters);
     return cudaGetLastError();
 }
 

@@ -68,11 +68,9 @@ __global__ void __launch_bounds__(32 * RC_WARPS) reach_caps_kernel(DevParams P, 
     }
 }
 
-#ifndef MPC_HOST_EMU
 cudaError_t launch_reach_caps(const DevParams &P, int B, const LayerDesc *desc, const int32_t *num_s, unsigned short *capb,
                               int stride, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    reach_caps_kernel<<<(B + RC_WARPS - 1) / RC_WARPS, 32 * RC_WARPS, 0, st>>>(P, B, desc, num_s, capb, stride);
+    MPC_LAUNCH(reach_caps_kernel, (B + RC_WARPS - 1) / RC_WARPS, 32 * RC_WARPS, 0, st, P, B, desc, num_s, capb, stride);
     return cudaGetLastError();
 }
-#endif

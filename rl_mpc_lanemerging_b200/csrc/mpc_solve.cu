@@ -28,7 +28,11 @@ template <class Prov, bool DESC>
 __global__ void __launch_bounds__(512) exact_push_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc,
                                                           const uint8_t *dense_ob, const void *dense_d, int dense_stride,
                                                           int W, unsigned long long *glab, unsigned *ghist) {
+#ifdef MPC_HOST_EMU
+    unsigned char *const smem_raw = emu::S().dyn_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     __shared__ BlockShared S;
     __shared__ LayerDesc s_layer;
     unsigned long long *lab[2];
@@ -134,7 +138,7 @@ cudaError_t launch_exact_desc(const DevParams &P, const SolveLaunch &L, const So
     auto k = exact_push_kernel<DescProv, true>;
     cudaError_t e = set_smem(k, L.smem);
     if (e != cudaSuccess) return e;
-    k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, desc, nullptr, nullptr, 0, L.W, L.glab, L.ghist);
+    MPC_LAUNCH(k, L.grid, L.threads, L.smem, st, P, L.B, io, desc, nullptr, nullptr, 0, L.W, L.glab, L.ghist);
     return cudaGetLastError();
 }
 
@@ -145,11 +149,11 @@ cudaError_t launch_exact_dense(const DevParams &P, const SolveLaunch &L, const S
     if (dist_f32) {
         auto k = exact_push_kernel<DenseProv<float>, false>;
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;
-        k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, nullptr, ob, dist, stride, L.W, L.glab, L.ghist);
+        MPC_LAUNCH(k, L.grid, L.threads, L.smem, st, P, L.B, io, nullptr, ob, dist, stride, L.W, L.glab, L.ghist);
     } else {
         auto k = exact_push_kernel<DenseProv<double>, false>;
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;
-        k<<<L.grid, L.threads, L.smem, st>>>(P, L.B, io, nullptr, ob, dist, stride, L.W, L.glab, L.ghist);
+        MPC_LAUNCH(k, L.grid, L.threads, L.smem, st, P, L.B, io, nullptr, ob, dist, stride, L.W, L.glab, L.ghist);
     }
     return cudaGetLastError();
 }

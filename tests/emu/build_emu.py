@@ -20,5 +20,29 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+API_LIB = os.path.join(HERE, "libmpc_emu_api.so")
+API_SOURCES = ["mpc_api.cu", "mpc_predict.cu", "mpc_solve.cu", "mpc_fast.cu", "mpc_qp.cu", "mpc_reach.cu"]
+
+
+def build_api(force: bool = False) -> str:
+    """The WHOLE library (C ABI included) compiled by g++ against the shim: every .cu its own translation unit, the CUDA
+    runtime replaced by the stubs of cuda_emu.h ("device" memory = host memory)."""
+    deps = [os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "mpcb200.h")] + \
+           [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if force or not os.path.exists(API_LIB) or os.path.getmtime(API_LIB) < max(os.path.getmtime(d) for d in deps):
+        objs = []
+        for f in API_SOURCES:
+            o = os.path.join(HERE, "_" + f.replace(".cu", ".emu.o"))
+            subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-c", "-DMPC_HOST_EMU=1",
+                                   "-I", HERE, "-I", os.path.join(ROOT, "include"), "-Wno-unused-function",
+                                   os.path.join(CSRC, f), "-o", o])
+            objs.append(o)
+        subprocess.check_call(["g++", "-shared", "-o", API_LIB] + objs)
+        for o in objs:
+            os.remove(o)
+    return API_LIB
+
+
 if __name__ == "__main__":
+    print(build_api(force=True))
     print(build(force=True))

@@ -54,6 +54,33 @@ static const cudaError_t cudaSuccess = 0;
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 
+// ---- runtime stubs: "device" memory is host memory, streams and events do nothing -------------------------------
+typedef void *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; };
+template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->multiProcessorCount = 2; p->sharedMemPerBlockOptin = 232448; return 0; }   // B200's opt-in limit, two "SMs"
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (void *)1; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return 0; }
+// resident blocks per SM as the shared-memory budget of a B200 SM allows (228 KB, 1 KB reserved per block, ~11 KB static)
+template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int threads, size_t smem) {
+    int by_smem = (int)(233472 / (smem + 11264 + 1024)), by_threads = 2048 / (threads > 0 ? threads : 1);
+    *n = by_smem < by_threads ? by_smem : by_threads;
+    return 0;
+}
+
 namespace emu {
 struct Fiber { ucontext_t ctx; char *stack = nullptr; bool done = false; };
 struct State {
@@ -188,6 +215,8 @@ static inline int __reduce_max_sync(unsigned, int v) { const unsigned long long 
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline unsigned atomicMin(unsigned *p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 

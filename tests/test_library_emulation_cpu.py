@@ -1,0 +1,130 @@
+"""The WHOLE library -- C ABI, handle set-up, launch configuration, the fallback chain, every kernel -- compiled by g++ against
+the CUDA shim of tests/emu and driven with numpy arrays in the place of device pointers (tests/emu/emu_api.py).
+
+Covers on the CPU what otherwise only a device run can: the host-side orchestration of the entry points written without GPU
+access (mpc_plan_hinted, mpc_plan_probed, mpc_plan_host_probed, mpc_predict_step_without_ego), the ring-overflow re-solve
+of hinted problems, the fp32 dense solve.  See tests/emu/cuda_emu.h for what an emulation can and cannot show.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as O
+from rl_mpc_lanemerging_b200 import _lib, synthetic
+from tests import helpers
+from tests.emu import emu_api as EA
+
+KEYS = ("idx", "s_seq", "cost", "reached_t", "crash", "min_dist", "start_s")
+
+
+def _params(H, **over):
+    op = O.horizon_params(H, **over)
+    return op, helpers.mpc_params_from_oracle(op)
+
+
+def _same(a, b, keys=KEYS):
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_plan_exact_and_fast_against_the_oracle():
+    op, p = _params(17)
+    eng = EA.EmuEngine(p, max_batch=16)
+    S = synthetic.make_states(12, "moderate", seed=5, kind="mixed")
+    ref = helpers.oracle_plan_batch(O, op, S, 18)
+    ex = eng.plan(S, mode=_lib.MODE_EXACT)
+    assert np.array_equal(ex["idx"], ref["idx"]) and np.array_equal(ex["cost"], ref["cost"]) and np.array_equal(ex["s_seq"], ref["s_seq"])
+    assert np.array_equal(ex["crash"].astype(bool), ref["crash"]) and np.array_equal(ex["min_dist"], ref["min_path_distance"])
+    fa = eng.plan(S)
+    assert np.array_equal(fa["reached_t"], ref["reached_t"]) and (fa["idx"] == ref["idx"]).all(1).sum() >= 11
+    ok = ref["cost"] > 0
+    assert np.all(helpers.rel(fa["cost"][ok], ref["cost"][ok]) < 1e-6)
+    eng.close()
+
+
+@pytest.mark.parametrize("H,B,mult", [(50, 6, (20, 3)), (17, 10, (8, 2))])
+def test_probed_and_hinted_plans_equal_the_plain_plan(H, B, mult):
+    _op, p = _params(H)
+    eng = EA.EmuEngine(p, max_batch=B)
+    q = _lib.MpcParams()
+    for n in _lib.PARAM_FIELDS:
+        setattr(q, n, getattr(p, n))
+    q.s_disc, q.t_disc = p.s_disc * mult[0], p.t_disc * mult[1]
+    probe = EA.EmuEngine(q, max_batch=B)
+    S = synthetic.make_states(B, "moderate", seed=8, kind="mixed" if H == 17 else "onramp")
+    ref = eng.plan(S)
+    _same(eng.plan_probed(probe, S, margin=1.1), ref)
+    assert eng.counters()["kernels_launched"] >= 7            # probe: predictor + DP (+ re-solves); plan: predictor + caps + DP (+ re-solves)
+    _same(eng.plan_probed(probe, S, margin=0.4), ref)         # every first bound too low
+    _same(eng.plan_probed(probe, S, margin=1.1, host=True), ref)
+    for scale in (1.05, 0.7, 500.0):
+        _same(eng.plan_hinted(S, ref["cost"].copy(), hint_scale=scale), ref)
+    junk = ref["cost"].copy()
+    junk[::3] = np.nan; junk[1::3] = -2.0
+    _same(eng.plan_hinted(S, junk), ref)
+    reached = np.where(np.arange(B) % 2 == 0, H, H - 1).astype(np.int32)
+    _same(eng.plan_hinted(S, ref["cost"] * 0.5, hint_reached=reached, hint_full_t=H), ref)
+    ex = eng.plan(S, mode=_lib.MODE_EXACT)
+    _same(eng.plan_hinted(S, junk, mode=_lib.MODE_EXACT), ex)
+    with pytest.raises(RuntimeError):                          # the hint must not alias the cost output
+        o = eng._out(B)
+        EA.check(eng.L.mpc_plan_hinted(eng.h, B, EA._p(S["ego"]), EA._p(S["cars_x"]), EA._p(S["cars_v"]), None, EA._p(S["n_cars"]), 0,
+                                       EA._p(o["cost"]), None, 0, 1.0, EA._p(o["idx"]), EA._p(o["s_seq"]), EA._p(o["cost"]),
+                                       EA._p(o["reached_t"]), None, None, None, None))
+    probe.close(); eng.close()
+
+
+def test_hinted_problems_that_overflow_the_ring_are_resolved():
+    """Five blocks per SM at H=50 leave a ring of ~2.1 k cells: many frontiers outgrow it and go through the library's re-solve
+    chain (full-row fast kernel -- HINT instance for hinted calls -- then the exact kernel): same answers."""
+    _op, p = _params(50)
+    S = synthetic.make_states(5, "fast", seed=2)
+    wide = EA.EmuEngine(p, max_batch=8)
+    ref = wide.plan(S)
+    assert wide.counters()["fallback_problems"] == 0
+    small = EA.EmuEngine(p, max_batch=8, env={"MPC_FAST_BLOCKS": "160"})
+    got = small.plan(S)
+    assert small.counters()["fallback_problems"] > 0
+    _same(got, ref)
+    got = small.plan_hinted(S, ref["cost"].copy(), hint_scale=0.6)      # low hints: retries under wider bounds overflow the ring
+    assert small.counters()["fallback_problems"] > 0
+    _same(got, ref)
+    _same(small.plan_hinted(S, ref["cost"].copy(), hint_scale=1.1), ref)
+    wide.close(); small.close()
+
+
+def test_dense_solve_on_fp32_and_fp64_grids():
+    """K2 (mpc_solve_dense) fed by mpc_build_grid: fp64 grids give the fused plan exactly, fp32 distances within tolerance."""
+    op, p = _params(17)
+    eng = EA.EmuEngine(p, max_batch=8)
+    S = synthetic.make_states(6, "moderate", seed=6, kind="mixed")
+    ref = eng.plan(S)
+    v0, a0 = S["ego"][:, 2].copy(), S["ego"][:, 3].copy()
+    g64 = eng.build_grid(S)
+    for b in range(6):                                         # the grids themselves: bit-identical to the oracle's
+        ob, di, sv = O.build_grid(op, helpers.oracle_state(O, S, b))
+        n = sv.size
+        assert g64["num_s"][b] == n and np.array_equal(g64["obstacles"][b, :, :n], ob) and np.array_equal(g64["distances"][b, :, :n], di)
+    d64 = eng.solve_dense(g64, v0, a0)
+    _same(d64, ref, ("idx", "cost", "reached_t"))
+    d32 = eng.solve_dense(eng.build_grid(S, f32=True), v0, a0)
+    assert np.array_equal(d32["reached_t"], ref["reached_t"])
+    ok = ref["cost"] > 0
+    assert np.all(helpers.rel(d32["cost"][ok], ref["cost"][ok]) < 1e-4)
+    eng.close()
+
+
+def test_predict_step_without_ego_entry_point():
+    op, p = _params(17)
+    eng = EA.EmuEngine(p, max_batch=64)
+    S = synthetic.make_states(48, "default", seed=12, kind="mixed")
+    eo, xo, vo, ao, cr = eng.predict_step_without_ego(S, 0.3, 5.0)
+    for b in range(48):
+        st = helpers.oracle_state(O, S, b)
+        out, crashed = O.predict_step_without_ego(op, st, 0.3, 5.0)
+        n = st.n
+        assert tuple(eo[b]) == (out.ego_x, out.ego_y, out.ego_v, out.ego_a) and bool(cr[b]) == crashed, b
+        assert np.array_equal(xo[b, :n], np.array(out.x[:n])) and np.array_equal(vo[b, :n], np.array(out.v[:n])), b
+        assert np.array_equal(ao[b, :n], np.array(out.a[:n])), b
+    eng.close()
