@@ -96,10 +96,22 @@ struct State {
     std::function<void()> body;
     unsigned char *dyn_smem = nullptr;
     long progress = 0;                          // barrier releases + finished fibers (deadlock watchdog)
+    long cas_lost = 0;                          // compare-and-swap operations that found another value (only under preemption)
 };
 inline State &S() { static State s; return s; }
 inline void yield() { State &s = S(); swapcontext(&s.fibers[s.cur].ctx, &s.main_ctx); }
 inline void trampoline() { State &s = S(); s.body(); s.fibers[s.cur].done = true; swapcontext(&s.fibers[s.cur].ctx, &s.main_ctx); }
+
+// Optional random preemption at shared-memory accesses (emu::set_preempt(seed)): threads then interleave inside a phase, so a
+// CAS can lose and the retry / redo paths of the lock-free min-combine are exercised.  Results must not depend on it.
+inline unsigned long long &preempt_state() { static unsigned long long x = 0; return x; }
+inline void set_preempt(unsigned long long seed) { preempt_state() = seed; }
+inline void preempt_point() {
+    unsigned long long &x = preempt_state();
+    if (!x || S().cur < 0) return;
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    if ((x & 7) == 0) { S().progress++; yield(); }
+}
 
 inline void warp_barrier() {
     State &s = S();

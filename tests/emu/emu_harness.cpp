@@ -25,6 +25,8 @@ extern "C" long long emu_node_count() { return g_nodes; }
 #include <vector>
 
 extern "C" const char *emu_last_error() { return g_err; }
+extern "C" void emu_set_preempt(unsigned long long seed) { emu::set_preempt(seed); }
+extern "C" long emu_cas_lost() { return emu::S().cas_lost; }
 
 // One fused gap-evaluation of B states on the emulated device.
 //   threads: block size of the fast kernel (multiple of 32, <= 1024); ring: label ring capacity in cells (0 = full row, no wrap)

@@ -157,6 +157,29 @@ def test_emulated_hinted_plan_is_identical_and_expands_what_the_model_says(emu, 
         assert np.array_equal(got[k], plain[k]), k
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_result_does_not_depend_on_thread_interleaving(emu, seed):
+    """With random preemption at every shared-memory access the threads of a block interleave inside a phase: CAS operations
+    lose, the retry / redo paths of the min-combine run, cells are finalised while neighbours still push.  The answer and the
+    number of finalised nodes must not change (integer labels: the min-combine is order independent)."""
+    op = O.horizon_params(17)
+    S = synthetic.make_states(6, "moderate", seed=30 + seed, kind="mixed")
+    emu.emu_set_preempt(C.c_ulonglong(0))
+    plain = _plan(emu, op, S, 192, 1600)
+    hinted = _plan(emu, op, S, 192, 1600, hint=plain["cost"].copy(), scale=0.9)
+    try:
+        emu.emu_set_preempt(C.c_ulonglong(0x9E3779B97F4A7C15 * seed % (1 << 64)))
+        lost0 = emu.emu_cas_lost()
+        for ref, kw in ((plain, {}), (hinted, dict(hint=plain["cost"].copy(), scale=0.9))):
+            got = _plan(emu, op, S, 192, 1600, **kw)
+            for k in ("idx", "s_seq", "cost", "reached_t", "crash", "min_dist", "fallback"):
+                assert np.array_equal(got[k], ref[k]), k
+            assert got["nodes"] == ref["nodes"]
+        assert emu.emu_cas_lost() > lost0                     # races did happen
+    finally:
+        emu.emu_set_preempt(C.c_ulonglong(0))
+
+
 def test_emulated_probe_grid_runs_the_same_kernels(emu):
     """The 20x3 coarse probe grid of mpc_plan_probed is just another Settings snapshot for the same kernels."""
     op = O.horizon_params(50)
