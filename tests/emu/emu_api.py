@@ -120,3 +120,46 @@ class EmuEngine:
                                      _p(g["start_s"]), _p(g["delta_s"]), _p(g["num_s"]), _p(v0), _p(a0), mode,
                                      _p(o["idx"]), _p(o["s_seq"]), _p(o["cost"]), _p(o["reached_t"]), None))
         return o
+
+    def plan_host(self, S, mode=0):
+        B = S["ego"].shape[0]
+        o = self._out(B)
+        check(self.L.mpc_plan_host(self.h, B, _p(S["ego"]), _p(S["cars_x"]), _p(S["cars_v"]), _p(S["cars_a"]), _p(S["n_cars"]), mode,
+                                   *self._outs(o), None))
+        return o
+
+    def selftest_search(self, S):
+        out = C.c_int64(-1)
+        check(self.L.mpc_selftest_search(self.h, S["ego"].shape[0], _p(S["ego"]), _p(S["cars_x"]), _p(S["cars_v"]), _p(S["n_cars"]),
+                                         C.byref(out), None))
+        return int(out.value)
+
+    def predict_step_with_ego(self, S, sel, dt, mcd):
+        B = S["ego"].shape[0]
+        eo, xo, vo, ao = np.zeros((B, 4)), np.zeros((B, self.nmax)), np.zeros((B, self.nmax)), np.zeros((B, self.nmax))
+        cr = np.zeros(B, np.uint8)
+        sel = np.ascontiguousarray(sel, np.float64)
+        check(self.L.mpc_predict_step_with_ego(self.h, B, _p(S["ego"]), _p(S["cars_x"]), _p(S["cars_v"]), _p(S["cars_a"]),
+                                               _p(S["n_cars"]), _p(sel), dt, mcd, _p(eo), _p(xo), _p(vo), _p(ao), _p(cr), None))
+        return eo, xo, vo, ao, cr
+
+    def state_vector(self, S):
+        B = S["ego"].shape[0]
+        out = np.zeros((B, 21), np.float32)
+        check(self.L.mpc_state_vector(self.h, B, _p(S["ego"]), _p(S["cars_x"]), _p(S["cars_v"]), _p(S["cars_a"]), _p(S["n_cars"]),
+                                      _p(out), 21, None))
+        return out
+
+    def speed_from_jerk(self, S, jerk):
+        B = S["ego"].shape[0]
+        out = np.zeros(B)
+        jerk = np.ascontiguousarray(jerk, np.float64)
+        check(self.L.mpc_speed_from_jerk(self.h, B, _p(S["ego"]), _p(jerk), _p(out), None))
+        return out
+
+    def finer_fit(self, s_seq, reached_t, ego):
+        B = s_seq.shape[0]
+        nf = int(self.L.mpc_finer_fit_max_points())
+        fine, n_fine, speed, iters = np.zeros((B, nf)), np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
+        check(self.L.mpc_finer_fit(self.h, B, _p(s_seq), _p(reached_t), _p(ego), _p(fine), nf, _p(n_fine), _p(speed), _p(iters), None))
+        return fine, n_fine, speed, iters

@@ -128,3 +128,41 @@ def test_predict_step_without_ego_entry_point():
         assert np.array_equal(xo[b, :n], np.array(out.x[:n])) and np.array_equal(vo[b, :n], np.array(out.v[:n])), b
         assert np.array_equal(ao[b, :n], np.array(out.a[:n])), b
     eng.close()
+
+
+def test_remaining_entry_points_against_the_oracle():
+    """The rest of the C ABI on the emulated library (all of it verified on a device already): guards the host-side
+    refactors made without GPU access (shared plan / plan_host implementations, derive_params header, launch macro)."""
+    op, p = _params(17)
+    eng = EA.EmuEngine(p, max_batch=32)
+    S = synthetic.make_states(24, "moderate", seed=15, kind="mixed")
+    assert eng.selftest_search(S) == 0
+    _same(eng.plan_host(S), eng.plan(S))
+    rng = np.random.default_rng(0)
+    sel, jerk = rng.uniform(0, 30, 24), rng.uniform(-6, 6, 24)
+    eo, xo, vo, ao, cr = eng.predict_step_with_ego(S, sel, 0.2, 5.1)
+    sv = eng.state_vector(S)
+    sp = eng.speed_from_jerk(S, jerk)
+    for b in range(24):
+        st = helpers.oracle_state(O, S, b)
+        out, crashed = O.predict_step_with_ego(op, st, sel[b], 0.2, 5.1)
+        n = st.n
+        assert tuple(eo[b]) == (out.ego_x, out.ego_y, out.ego_v, out.ego_a) and bool(cr[b]) == crashed
+        assert np.array_equal(xo[b, :n], np.array(out.x[:n])) and np.array_equal(vo[b, :n], np.array(out.v[:n]))
+        assert np.array_equal(ao[b, :n], np.array(out.a[:n]))
+        assert np.allclose(sv[b, :20], O.state_vector(op, st).astype(np.float32), rtol=0, atol=1e-7)
+        assert sp[b] == O.speed_from_jerk(op, st.ego_v, st.ego_a, jerk[b])
+    plan = eng.plan(S)
+    fine, n_fine, speed, iters = eng.finer_fit(plan["s_seq"], plan["reached_t"], S["ego"])
+    tick = op.tick_length
+    for b in range(24):                                        # the projected plan obeys the limits of st.py:608-668
+        n = n_fine[b]
+        if n < 4:
+            continue
+        x = fine[b, :n]
+        v = np.diff(x) / tick
+        assert v.min() > -1e-6 and v.max() < op.max_speed + 1e-6
+        a = np.diff(np.concatenate(([S["ego"][b, 2]], v))) / tick
+        assert a.min() > op.a_min - 1e-5 and a.max() < op.a_max + 1e-5
+        assert abs(speed[b] - (x[1] - x[0]) / tick) < 1e-12
+    eng.close()
