@@ -166,3 +166,23 @@ def test_remaining_entry_points_against_the_oracle():
         assert a.min() > op.a_min - 1e-5 and a.max() < op.a_max + 1e-5
         assert abs(speed[b] - (x[1] - x[0]) / tick) < 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("name,H,n", [("plan_h17.npz", 17, 40), ("plan_h50.npz", 50, 6)])
+def test_emulated_library_against_the_reference_golden_vectors(name, H, n):
+    """The committed outputs of the UNMODIFIED reference (tests/golden/make_golden.py): exact mode reproduces positions, crash
+    verdict and start_s bit for bit, fast mode the same plans with the cost within 1e-6; the hinted path returns the same."""
+    import os
+    G = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+    S = {k: np.ascontiguousarray(G[k][:n]) for k in ("ego", "cars_x", "cars_v", "cars_a", "n_cars")}
+    _op, p = _params(H)
+    eng = EA.EmuEngine(p, max_batch=n)
+    ex = eng.plan(S, mode=_lib.MODE_EXACT)
+    assert np.array_equal(ex["s_seq"], G["s_seq"][:n]) and np.array_equal(ex["crash"].astype(bool), G["crash"][:n])
+    assert np.array_equal(ex["start_s"], G["start_s"][:n])
+    ok = G["cost"][:n] > 0
+    assert np.all(helpers.rel(ex["cost"][ok], G["cost"][:n][ok]) < 1e-12)
+    fa = eng.plan(S)
+    assert (fa["s_seq"] == G["s_seq"][:n]).all(1).sum() >= n - 1 and np.all(helpers.rel(fa["cost"][ok], G["cost"][:n][ok]) < 1e-6)
+    _same(eng.plan_hinted(S, fa["cost"].copy(), hint_scale=1.1), fa)
+    eng.close()
