@@ -54,6 +54,8 @@ class MpcEngine:
     """Owns one mpc_handle.  All tensor arguments live on `device`; states are fp64:
     ego [B,4] = (x, y, speed, acceleration); cars_x/v/a [B,nmax]; n_cars [B] int32."""
 
+    _pin_host = True             # host staging buffers of plan_host are page-locked
+
     def __init__(self, params: Optional[MpcParams] = None, device: int | str | torch.device = 0,
                  max_batch: int = 4096, nmax: int = 32):
         self.lib = _lib.load()
@@ -65,7 +67,7 @@ class MpcEngine:
         self.params = params if params is not None else _lib.default_params()
         self.max_batch, self.nmax = int(max_batch), int(nmax)
         torch.cuda.init()
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             torch.zeros(1, device=dev)            # make sure the primary context exists before the library uses it
             h = C.c_void_p()
             _lib.check(self.lib.mpc_create(C.byref(self.params), self.dev_index, self.max_batch, self.nmax, C.byref(h)))
@@ -91,12 +93,21 @@ class MpcEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    @staticmethod
+    def _is_dev(t) -> bool:
+        """Tensor arguments must live in device memory: the library dereferences their data_ptr() on the GPU."""
+        return t.is_cuda
+
+    def _device_ctx(self):
+        """Context in which the library is called: the handle's device made current."""
+        return torch.cuda.device(self.dev_index)
+
     def _check_state(self, ego, cars_x, cars_v, cars_a, n_cars):
         B = ego.shape[0]
-        assert ego.dtype == torch.float64 and ego.shape == (B, 4) and ego.is_contiguous() and ego.is_cuda
+        assert ego.dtype == torch.float64 and ego.shape == (B, 4) and ego.is_contiguous() and self._is_dev(ego)
         for c in (cars_x, cars_v) + ((cars_a,) if cars_a is not None else ()):
-            assert c.dtype == torch.float64 and c.shape == (B, self.nmax) and c.is_contiguous() and c.is_cuda
-        assert n_cars.dtype == torch.int32 and n_cars.shape == (B,) and n_cars.is_contiguous() and n_cars.is_cuda
+            assert c.dtype == torch.float64 and c.shape == (B, self.nmax) and c.is_contiguous() and self._is_dev(c)
+        assert n_cars.dtype == torch.int32 and n_cars.shape == (B,) and n_cars.is_contiguous() and self._is_dev(n_cars)
         return B
 
     def counters(self):
@@ -108,7 +119,7 @@ class MpcEngine:
         """Cells whose sorted-structure lookup differs from the reference-order evaluation (must be 0)."""
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
         out = C.c_int64(-1)
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_selftest_search(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(n_cars), C.byref(out), self._stream()))
         return int(out.value)
 
@@ -133,7 +144,7 @@ class MpcEngine:
                        cost=torch.empty(B, dtype=torch.float64, **o), reached_t=torch.empty(B, dtype=torch.int32, **o),
                        crash=torch.empty(B, dtype=torch.uint8, **o), min_dist=torch.empty(B, dtype=torch.float64, **o),
                        start_s=torch.empty(B, dtype=torch.float64, **o))
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_plan(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
                                          _mode(mode), _ptr(out["idx"]), _ptr(out["s_seq"]), _ptr(out["cost"]),
                                          _ptr(out["reached_t"]), _ptr(out["crash"]), _ptr(out["min_dist"]),
@@ -147,11 +158,11 @@ class MpcEngine:
         ESTIMATE -- a coarse probe plan, or the previous tick's plan of a closed-loop controller; the outputs are
         identical to plan()'s whatever the hint, only the number of expanded nodes changes."""
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
-        assert hint_cost.dtype == torch.float64 and hint_cost.shape == (B,) and hint_cost.is_contiguous() and hint_cost.is_cuda
+        assert hint_cost.dtype == torch.float64 and hint_cost.shape == (B,) and hint_cost.is_contiguous() and self._is_dev(hint_cost)
         if hint_reached is not None:
-            assert hint_reached.dtype == torch.int32 and hint_reached.shape == (B,) and hint_reached.is_contiguous() and hint_reached.is_cuda
+            assert hint_reached.dtype == torch.int32 and hint_reached.shape == (B,) and hint_reached.is_contiguous() and self._is_dev(hint_reached)
         out = self._plan_out(B) if out is None else out
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_plan_hinted(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
                                                 _mode(mode), _ptr(hint_cost), _ptr(hint_reached), int(hint_full_t),
                                                 float(hint_scale), _ptr(out["idx"]), _ptr(out["s_seq"]), _ptr(out["cost"]),
@@ -176,7 +187,7 @@ class MpcEngine:
         as plan()."""
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
         out = self._plan_out(B) if out is None else out
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_plan_probed(self.h, probe.h, float(margin), B, _ptr(ego), _ptr(cars_x), _ptr(cars_v),
                                                 _ptr(cars_a), _ptr(n_cars), _ptr(out["idx"]), _ptr(out["s_seq"]),
                                                 _ptr(out["cost"]), _ptr(out["reached_t"]), _ptr(out["crash"]),
@@ -193,7 +204,7 @@ class MpcEngine:
     def _pin(self, name, shape, dtype):
         t = self._pinned.get(name)
         if t is None or t.shape != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            t = torch.empty(shape, dtype=dtype, pin_memory=self._pin_host)
             self._pinned[name] = t
         return t
 
@@ -210,7 +221,7 @@ class MpcEngine:
         o = dict(idx=self._pin("idx", (B, T), i32), s_seq=self._pin("seq", (B, T), f64), cost=self._pin("cost", (B,), f64),
                  reached_t=self._pin("reached", (B,), i32), crash=self._pin("crash", (B,), torch.uint8),
                  min_dist=self._pin("mind", (B,), f64), start_s=self._pin("s0", (B,), f64))
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             if probe is not None:
                 _lib.check(self.lib.mpc_plan_host_probed(self.h, probe.h, float(margin), B, _ptr(pe), _ptr(px), _ptr(pv), None, _ptr(pn),
                                                          _ptr(o["idx"]), _ptr(o["s_seq"]), _ptr(o["cost"]), _ptr(o["reached_t"]),
@@ -233,7 +244,7 @@ class MpcEngine:
         s0 = torch.empty(B, dtype=torch.float64, **o)
         ds = torch.empty(B, dtype=torch.float64, **o)
         ns = torch.empty(B, dtype=torch.int32, **o)
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_build_grid(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
                                                _ptr(obstacles), _ptr(distances), int(dist_dtype == torch.float32),
                                                _ptr(s0), _ptr(ds), _ptr(ns), self._stream()))
@@ -247,7 +258,7 @@ class MpcEngine:
         o = dict(device=self.device)
         out = dict(idx=torch.empty((B, T), dtype=torch.int32, **o), s_seq=torch.empty((B, T), dtype=torch.float64, **o),
                    cost=torch.empty(B, dtype=torch.float64, **o), reached_t=torch.empty(B, dtype=torch.int32, **o))
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_solve_dense(self.h, B, T, S, _ptr(obstacles), _ptr(distances),
                                                 int(distances.dtype == torch.float32), _ptr(start_s), _ptr(delta_s),
                                                 _ptr(num_s), _ptr(v0), _ptr(a0), _mode(mode), _ptr(out["idx"]),
@@ -263,7 +274,7 @@ class MpcEngine:
         n_fine = torch.empty(B, dtype=torch.int32, **o)
         speed = torch.empty(B, dtype=torch.float64, **o)
         iters = torch.empty(B, dtype=torch.int32, **o)
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_finer_fit(self.h, B, _ptr(s_seq), _ptr(reached_t), _ptr(ego), _ptr(fine), nf, _ptr(n_fine),
                                               _ptr(speed), _ptr(iters), self._stream()))
         return fine, n_fine, speed, iters
@@ -278,7 +289,7 @@ class MpcEngine:
         else:
             eo, xo, vo, ao = torch.empty_like(ego), torch.empty_like(cars_x), torch.empty_like(cars_v), torch.empty_like(cars_x)
         crashed = torch.empty(B, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_predict_step_with_ego(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a),
                                                           _ptr(n_cars), _ptr(selected_speed), float(dt), float(min_crash_distance),
                                                           _ptr(eo), _ptr(xo), _ptr(vo), _ptr(ao), _ptr(crashed), self._stream()))
@@ -289,7 +300,7 @@ class MpcEngine:
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
         eo, xo, vo, ao = torch.empty_like(ego), torch.empty_like(cars_x), torch.empty_like(cars_v), torch.empty_like(cars_x)
         crashed = torch.empty(B, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_predict_step_without_ego(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a),
                                                              _ptr(n_cars), float(dt), float(min_crash_distance),
                                                              _ptr(eo), _ptr(xo), _ptr(vo), _ptr(ao), _ptr(crashed), self._stream()))
@@ -300,7 +311,7 @@ class MpcEngine:
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
         if out is None:
             out = torch.zeros((B, 21), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_state_vector(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
                                                  _ptr(out), out.shape[1], self._stream()))
         return out
@@ -313,7 +324,7 @@ class MpcEngine:
         assert jerk.dtype == torch.float64 and jerk.is_contiguous() and jerk.numel() == B
         assert alive.dtype == torch.uint8 and crash_predicted.dtype == torch.uint8 and roll_len.dtype == torch.int32
         assert roll_s.dtype == torch.float64 and roll_s.is_contiguous() and roll_s.shape[0] == B
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_rollout_step(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
                                                  _ptr(jerk), float(dt), float(min_crash_distance), float(stop_x), int(step),
                                                  _ptr(alive), _ptr(selected_speed), _ptr(roll_s), roll_s.shape[1], _ptr(roll_len),
@@ -322,7 +333,7 @@ class MpcEngine:
     def speed_from_jerk(self, ego, jerk):
         B = ego.shape[0]
         out = torch.empty(B, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.dev_index):
+        with self._device_ctx():
             _lib.check(self.lib.mpc_speed_from_jerk(self.h, B, _ptr(ego), _ptr(jerk), _ptr(out), self._stream()))
         return out
 

@@ -42,3 +42,21 @@ def oracle():
     from oracle import cpu_oracle
     cpu_oracle.build()
     return cpu_oracle
+
+
+@pytest.fixture
+def emulated_engine(monkeypatch):
+    """The Python host layer on the EMULATED library with CPU tensors (tests/emu/emu_engine.py): st.get_engine() hands out
+    EmuBackedEngine instances for the duration of the test."""
+    from rl_mpc_lanemerging_b200 import st
+    from rl_mpc_lanemerging_b200.config import Settings
+    from tests.emu.emu_engine import EmuBackedEngine
+    st.refresh_engine()
+    Settings.reset()
+    from rl_mpc_lanemerging_b200 import st_cy
+    monkeypatch.setattr(st, "MpcEngine", EmuBackedEngine)
+    monkeypatch.setattr(st_cy, "MpcEngine", EmuBackedEngine)
+    monkeypatch.setattr(st_cy, "_engines", {})
+    yield EmuBackedEngine
+    st.refresh_engine()
+    Settings.reset()

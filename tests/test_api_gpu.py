@@ -20,7 +20,7 @@ def api():
     config.Settings.OTHER_CAR_SPEED = 11.0
     config.Settings.TEST_ST_STRICTLY_BETTER = False
     yield dict(torch=torch, Settings=config.Settings, control=control, ddpg=ddpg, dqn=dqn, merge_gym=merge_gym,
-               prediction=prediction, st=st, st_cy=st_cy)
+               prediction=prediction, st=st, st_cy=st_cy, device="cuda:0")
     st.refresh_engine()
     config.Settings.reset()
 
@@ -116,9 +116,9 @@ def test_combined_control_matches_cpu_chain(api, oracle):
     from rl_mpc_lanemerging_b200.prediction import BatchedState
     S = synthetic.make_states(48, "moderate", seed=17, kind="mixed")
     op = oracle.default_params()
-    agent = api["ddpg"].DDPGAgent(device="cuda:0", seed=3)
+    agent = api["ddpg"].DDPGAgent(device=api["device"], seed=3)
     cpu_policy = copy.deepcopy(agent.policy).cpu()
-    batch = BatchedState.from_numpy(S, "cuda:0")
+    batch = BatchedState.from_numpy(S, api["device"])
     speed, takeover = agent.do_combined_control(batch)
     takeover = takeover.cpu().numpy(); speed = speed.cpu().numpy()
     agree = 0
@@ -136,7 +136,7 @@ def test_merge_env_steps(api):
     env = api["merge_gym"].MergeEnv(64, seed=1)
     obs = env.reset()
     assert obs.shape == (64, 20) and obs.dtype == torch.float32
-    agent = api["ddpg"].DDPGAgent(device="cuda:0", seed=0)
+    agent = api["ddpg"].DDPGAgent(device=api["device"], seed=0)
     done_total = 0
     for _ in range(40):
         jerk = agent.get_control(env.state)
