@@ -1,0 +1,48 @@
+"""The closed loops around the hot path on the EMULATED library (small sizes): TASK ST evaluation with its run_data.csv
+row, the combined controller through the task dispatcher, a few DDPG training ticks with save / load.  Same code paths as
+tests/test_train_eval_gpu.py (which stays the device gate), sized for the CPU suite."""
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture
+def settings(emulated_engine):
+    from rl_mpc_lanemerging_b200.config import Settings
+    Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL = 20, 11.0, 1.2     # the "moderate" configs
+    Settings.ST_MODE = "fast"
+    return Settings
+
+
+def test_st_and_combined_evaluation_loops(settings, tmp_path):
+    """control.evaluate_control (the reference's episode loop, control.py:343-363, batched) under the ST planner and under
+    the RL-proposes / MPC-vetoes controller; episodes cut at 3 s / 2 s so that the emulation finishes in seconds."""
+    from rl_mpc_lanemerging_b200 import control, ddpg, st
+    out = control.evaluate_control(st.do_st_control, num_episodes=6, max_episode_length=3, num_envs=8, seed=1)
+    avg = out.get_stat_averages()
+    assert out.episodes >= 6 and avg["crashed"] == 0.0 and avg["mean_speed"] > 5.0 and np.isfinite(avg["mean_abs_jerk"])
+    assert avg["time_taken"] <= 3.0 + 0.2 + 1e-9 and avg["clock_time_per_step"] > 0
+    out.print_stats = getattr(out, "print_stats", None)
+    settings.TEST_ST_STRICTLY_BETTER = False
+    agent = ddpg.DDPGAgent(device="cpu", seed=1)
+    out2 = control.evaluate_control(agent.do_combined_control, num_episodes=4, max_episode_length=2, num_envs=8, seed=2,
+                                    end_episode_callback=agent.reset_time)
+    assert out2.episodes >= 4 and np.isfinite(out2.get_stat_averages()["mean_speed"])
+    assert len(agent.takeover_history) > 0
+
+
+def test_ddpg_training_ticks_save_load(settings, tmp_path):
+    import torch
+    from rl_mpc_lanemerging_b200 import ddpg, merge_gym, trainer
+    env = merge_gym.MergeEnv(16, seed=3)
+    tr = trainer.DDPGTrainer(env, lr=2e-4, seed=0, minibatch_size=32, replay_start_size=48, replay_buffer_size=1024)
+    w0 = torch.nn.utils.parameters_to_vector(tr.policy.parameters()).detach().clone()
+    tr.train(16 * 8)
+    assert tr.frames == 16 * 8 and tr.grad_steps >= 3
+    assert torch.isfinite(tr.last["q_loss"]) and torch.isfinite(tr.last["pi_loss"])
+    assert float((torch.nn.utils.parameters_to_vector(tr.policy.parameters()).detach() - w0).abs().max()) > 0
+    tr.save(str(tmp_path))
+    agent = ddpg.DDPGAgent.load(str(tmp_path), device="cpu")
+    x = torch.rand(7, 21)
+    assert torch.equal(agent.policy(x), tr.policy(x))
