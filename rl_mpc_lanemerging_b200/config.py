@@ -41,6 +41,9 @@ _HOT_PATH_DEFAULTS = {
     "TRAIN_NUM_ENVS": 8192, "TRAIN_UPDATES_PER_TICK": 1, "TRAIN_MINIBATCH": 4096, "EVAL_NUM_ENVS": 4096,
     "ST_MODE": "exact",       # arithmetic of the single-state drop-in calls: "exact" (fp64, st_cy-identical) or "fast"
     "CUDA_DEVICE": 0,
+    # closed loop: bound each episode's plan by PLAN_HINT_SCALE x the cost of its previous plan (mpc_plan_hinted; the plans are
+    # identical either way, DESIGN.md §3 "Cost hints").  Off until the hinted kernels have run on a device.
+    "PLAN_COST_HINTS": False, "PLAN_HINT_SCALE": 1.15,
 }
 
 

@@ -138,7 +138,9 @@ class RLAgent:
         if Settings.LIMIT_DQN_SPEED:                                                # 148-151
             takeover |= selected_speed > Settings.DESIRED_SPEED
         if Settings.TEST_ROLLOUT_STATE:                                             # 152-155: full gap-evaluation from the rollout state
-            takeover |= st.test_guaranteed_crash_from_state(test)
+            if getattr(self, "_plan_hint", None) is None:
+                self._plan_hint = st.PlanHint()                                      # episode b's rollout state is re-planned every tick
+            takeover |= st.test_guaranteed_crash_from_state(test, hint=self._plan_hint)
         speed = rl_speed
         if Settings.TEST_ST_STRICTLY_BETTER:                                        # 156-197 ("b" configs)
             if Settings.REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED:

@@ -70,10 +70,33 @@ def find_s_t_obstacles_from_state(current_state: HighwayState, *_ignored, **_kw)
     return obstacles, s_values, _t_values(eng), current_state.ego_speed, distances
 
 
-def plan_batch(batch: BatchedState, mode: Optional[str] = None, out: Optional[dict] = None) -> dict:
+class PlanHint:
+    """Cost and reached_t of the previous plan of the SAME episodes (row b = episode b), kept by a closed-loop caller that
+    re-plans every tick like the reference's control.run_episode (control.py:229-340).  With Settings.PLAN_COST_HINTS the next
+    plan_batch(..., hint=h) bounds each episode's first attempt by PLAN_HINT_SCALE x its previous cost (mpc_plan_hinted).
+    Plans do not depend on the hint -- a stale row (episode reset, other batch) only costs that episode a retry."""
+
+    def __init__(self):
+        self.cost: Optional[torch.Tensor] = None
+        self.reached: Optional[torch.Tensor] = None
+
+
+def plan_batch(batch: BatchedState, mode: Optional[str] = None, out: Optional[dict] = None, hint: Optional[PlanHint] = None) -> dict:
     """Fused gap-evaluation for a batch: dict(idx, s_seq, cost, reached_t, crash, min_dist, start_s) of device tensors."""
     eng = get_engine(batch.batch)
-    return eng.plan(*batch.args(), mode=mode or "fast", out=out)
+    mode = mode or "fast"
+    hinted = hint is not None and mode == "fast" and bool(getattr(Settings, "PLAN_COST_HINTS", False))
+    if hinted and hint.cost is not None and hint.cost.shape[0] == batch.batch:
+        r = eng.plan_hinted(*batch.args(), hint_cost=hint.cost, hint_reached=hint.reached, hint_full_t=eng.num_t - 1,
+                            hint_scale=float(getattr(Settings, "PLAN_HINT_SCALE", 1.15)), mode=mode, out=out)
+    else:
+        r = eng.plan(*batch.args(), mode=mode, out=out)
+    if hinted:                                      # remember this plan for the next tick (own tensors: never alias the outputs)
+        if hint.cost is None or hint.cost.shape != r["cost"].shape:
+            hint.cost, hint.reached = r["cost"].clone(), r["reached_t"].clone()
+        else:
+            hint.cost.copy_(r["cost"]); hint.reached.copy_(r["reached_t"])
+    return r
 
 
 def get_appropriate_base_st_path_and_obstacles(state):
@@ -91,11 +114,11 @@ def get_appropriate_base_st_path_and_obstacles(state):
 solve = get_appropriate_base_st_path_and_obstacles          # the name BASELINE.json's north_star uses
 
 
-def test_guaranteed_crash_from_state(state):
+def test_guaranteed_crash_from_state(state, hint: Optional[PlanHint] = None):
     """Reference st.py:790-802: True when the plan is incomplete or touches a cell closer than
-    COMBINATION_MIN_DISTANCE - CAR_LENGTH to traffic.  BatchedState -> bool tensor [B]."""
+    COMBINATION_MIN_DISTANCE - CAR_LENGTH to traffic.  BatchedState -> bool tensor [B] (hint: see PlanHint)."""
     if isinstance(state, BatchedState):
-        return plan_batch(state)["crash"].bool()
+        return plan_batch(state, hint=hint)["crash"].bool()
     eng = get_engine()
     bs = BatchedState.from_states([state], eng.device, eng.nmax)
     return bool(eng.plan(*bs.args(), mode=getattr(Settings, "ST_MODE", "exact"))["crash"].item())
@@ -139,10 +162,11 @@ def smoothed_speed(batch: BatchedState, plan: dict):
     return torch.where(plan["reached_t"] >= 1, v, batch.ego[:, 2]), s, plan["reached_t"] + 1
 
 
-def do_st_control(state):
-    """Reference st.py:757-783.  Returns the commanded ego speed (float, or tensor [B] for a BatchedState)."""
+def do_st_control(state, hint: Optional[PlanHint] = None):
+    """Reference st.py:757-783.  Returns the commanded ego speed (float, or tensor [B] for a BatchedState).
+    hint: see PlanHint (batched closed-loop callers)."""
     if isinstance(state, BatchedState):
-        return smoothed_speed(state, plan_batch(state))[0]
+        return smoothed_speed(state, plan_batch(state, hint=hint))[0]
     eng = get_engine()
     bs = BatchedState.from_states([state], eng.device, eng.nmax)
     plan = eng.plan(*bs.args(), mode=getattr(Settings, "ST_MODE", "exact"))
@@ -165,6 +189,8 @@ def evaluate_st_and_dump_crash(num_episodes=1000, num_envs=None, csv_path="run_d
     """Reference st.py:822-824: closed-loop evaluation of the pure MPC controller; prints the statistics and appends the
     run_data.csv row.  (The crash replay pickle of the reference is debug tooling and not reproduced.)"""
     from . import control
-    output = control.evaluate_control(do_st_control, num_episodes=num_episodes, num_envs=num_envs or Settings.EVAL_NUM_ENVS)
+    hint = PlanHint()                               # the same environments are re-planned every tick
+    output = control.evaluate_control(lambda state: do_st_control(state, hint=hint), num_episodes=num_episodes,
+                                      num_envs=num_envs or Settings.EVAL_NUM_ENVS)
     output.print_stats(csv_path)
     return output

@@ -46,3 +46,33 @@ def test_ddpg_training_ticks_save_load(settings, tmp_path):
     agent = ddpg.DDPGAgent.load(str(tmp_path), device="cpu")
     x = torch.rand(7, 21)
     assert torch.equal(agent.policy(x), tr.policy(x))
+
+
+def test_plan_cost_hints_do_not_change_the_closed_loop(settings):
+    """Settings.PLAN_COST_HINTS: every tick's plans are bounded by the previous tick's costs (mpc_plan_hinted).  The closed
+    loop -- commanded speeds, take-over decisions, episode statistics -- must be the same with and without."""
+    import torch
+    from rl_mpc_lanemerging_b200 import ddpg, merge_gym, st
+    settings.TEST_ST_STRICTLY_BETTER = False
+    runs = {}
+    for hints in (False, True):
+        settings.PLAN_COST_HINTS = hints
+        env = merge_gym.MergeEnv(8, seed=5)
+        env.reset()
+        agent = ddpg.DDPGAgent(device="cpu", seed=2)
+        hint = st.PlanHint()
+        log = []
+        for tick in range(12):
+            if tick % 2 == 0:                                              # alternate the two closed-loop callers
+                speed = st.do_st_control(env.state, hint=hint)
+            else:
+                speed, take = agent.do_combined_control(env.state)
+                log.append(take.clone())
+            jerk = ((speed - env.state.ego[:, 2]) / settings.TICK_LENGTH - env.state.ego[:, 3]) / settings.TICK_LENGTH
+            _obs, _r, done, _info = env.step(jerk)
+            agent.reset_time(done)
+            log.append(speed.clone())
+        assert (hint.cost is not None) == hints
+        runs[hints] = log
+    for a, b in zip(runs[False], runs[True]):
+        assert torch.equal(a, b)
