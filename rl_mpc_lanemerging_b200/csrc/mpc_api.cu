@@ -50,6 +50,9 @@ int mpc_set_cuda_error(cudaError_t e, const char *what) {
     return MPC_E_CUDA;
 }
 extern "C" const char *mpc_last_error(void) { return g_err; }
+#ifdef MPC_HOST_EMU      // tests/emu only: nodes the fast kernel has finalised so far
+extern "C" long long mpc_emu_nodes(void) { return emu::S().nodes; }
+#endif
 extern "C" int mpc_abi_version(void) { return MPC_ABI_VERSION; }
 extern "C" int mpc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 

@@ -33,7 +33,11 @@
 
 #define EMPTY_LAB 0x7ff0000000000000ULL      // +inf
 #ifndef MPC_EMU_COUNT_NODE                    // tests/emu counts the nodes each pass finalises (compared with the CPU model)
+#ifdef MPC_HOST_EMU
+#define MPC_EMU_COUNT_NODE() (emu::S().nodes++)
+#else
 #define MPC_EMU_COUNT_NODE()
+#endif
 #endif
 
 struct __align__(16) FastShared {

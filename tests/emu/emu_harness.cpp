@@ -12,9 +12,7 @@ static char g_err[256];
 int mpc_set_error(int code, const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
 int mpc_set_cuda_error(cudaError_t, const char *what) { snprintf(g_err, sizeof(g_err), "%s", what); return MPC_E_CUDA; }
 
-static long long g_nodes = 0;                  // nodes finalised by the fast kernel since the last emu_plan call began
-#define MPC_EMU_COUNT_NODE() (g_nodes++)
-extern "C" long long emu_node_count() { return g_nodes; }
+extern "C" long long emu_node_count() { return emu::S().nodes; }   // nodes finalised by the fast kernel since emu_plan began
 
 #include "../../rl_mpc_lanemerging_b200/csrc/mpc_derive.h"
 #include "../../rl_mpc_lanemerging_b200/csrc/mpc_predict.cu"
@@ -38,7 +36,7 @@ extern "C" int emu_plan(const mpc_params *params, int B, int nmax, const double 
                         double hint_retry, int use_caps, int32_t *idx, double *s_seq, double *cost, int32_t *reached,
                         uint8_t *crash, double *min_dist, double *start_s, uint8_t *fallback, int32_t *num_t_out) {
     DevParams P;
-    g_nodes = 0;
+    emu::S().nodes = 0;
     int rc = derive_params(params, &P);
     if (rc) return rc;
     if (!P.fast_ok) return mpc_set_error(MPC_E_INVALID, "fast mode not available for these params");
