@@ -207,6 +207,28 @@ int mpc_rollout_step(mpc_handle *h, int B, double *d_ego, double *d_cars_x, doub
                      double stop_x, int step, uint8_t *d_alive, double *d_selected_speed, double *d_roll_s,
                      int roll_stride, int32_t *d_roll_len, uint8_t *d_crash_predicted, void *stream);
 
+/* ---- one tick of the batched lane-merging environment, fused (the per-tick body of the reference's
+ * ContinuousJerkEnv.step, merge_gym.py:83-162, on the SUMO-free world of rl_mpc_lanemerging_b200/merge_gym.py): invalid-action
+ * clipping (merge_gym.py:83-96), the world step (predict_step_with_ego as dynamics), recycling of the front car beyond
+ * sensor range, entry of a new car every BASE_TRAFFIC_INTERVAL + U[0,1) s (control.py:215-226), termination (arrived /
+ * collision / timeout), the Slotted-Jerk reward (dqn.py:557-563) and, with auto_reset, fresh initial conditions for the
+ * finished episodes.  One warp per episode, everything in place.  Random numbers are INPUTS (the caller draws them with its
+ * own generator): d_u_spawn f64[B] (U[0,1), NULL = 0), and for auto_reset d_fresh_gap_u f64[B][nmax], d_fresh_first_u f64[B],
+ * d_fresh_speed_z f64[B] (N(0,1); NULL = no start-speed randomisation), d_fresh_delay_u f64[B].
+ * Outputs: d_reward f64[B], d_flags u8[4][B] = (done, crashed, arrived, timeout), d_projected_jerk f64[B]. */
+typedef struct mpc_env_params {
+    double tick, a_min, a_max, max_speed, min_crash_distance, sensor_radius, spawn_x, other_speed, interval, arrival_x;
+    double ego_start_x, ego_start_y, start_speed, start_speed_var, min_start_speed, max_start_speed;
+    double time_reward_step;        /* TIME_REWARD * TICK_LENGTH */
+    double jerk_weight, crash_reward, success_reward;
+    int32_t max_ticks, auto_reset;
+} mpc_env_params;
+int mpc_env_step(mpc_handle *h, const mpc_env_params *ep, int B, double *d_ego, double *d_cars_x, double *d_cars_v,
+                 double *d_cars_a, int32_t *d_n_cars, double *d_prev_acc, double *d_delay, int32_t *d_ticks,
+                 const double *d_jerk, const double *d_u_spawn, const double *d_fresh_gap_u,
+                 const double *d_fresh_first_u, const double *d_fresh_speed_z, const double *d_fresh_delay_u,
+                 double *d_reward, uint8_t *d_flags, double *d_projected_jerk, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

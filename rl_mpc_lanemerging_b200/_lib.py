@@ -24,6 +24,15 @@ class MpcParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in PARAM_FIELDS]
 
 
+ENV_PARAM_FIELDS = ("tick", "a_min", "a_max", "max_speed", "min_crash_distance", "sensor_radius", "spawn_x", "other_speed", "interval",
+                    "arrival_x", "ego_start_x", "ego_start_y", "start_speed", "start_speed_var", "min_start_speed", "max_start_speed",
+                    "time_reward_step", "jerk_weight", "crash_reward", "success_reward")
+
+
+class MpcEnvParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ENV_PARAM_FIELDS] + [("max_ticks", C.c_int32), ("auto_reset", C.c_int32)]
+
+
 class MpcError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libmpcb200 error {code}: {msg}")
@@ -59,6 +68,7 @@ SYMBOLS = {
     "mpc_predict_step_without_ego": (_i, [_vp, _i] + [_vp] * 5 + [_d, _d] + [_vp] * 5 + [_vp]),
     "mpc_state_vector": (_i, [_vp, _i] + [_vp] * 5 + [_vp, _i, _vp]),
     "mpc_speed_from_jerk": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "mpc_env_step": (_i, [_vp, C.POINTER(MpcEnvParams), _i] + [_vp] * 17 + [_vp]),
     "mpc_rollout_step": (_i, [_vp, _i] + [_vp] * 6 + [_d, _d, _d, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
 }
 

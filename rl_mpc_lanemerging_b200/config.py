@@ -44,6 +44,9 @@ _HOT_PATH_DEFAULTS = {
     # closed loop: bound each episode's plan by PLAN_HINT_SCALE x the cost of its previous plan (mpc_plan_hinted; the plans are
     # identical either way, DESIGN.md §3 "Cost hints").  Off until the hinted kernels have run on a device.
     "PLAN_COST_HINTS": False, "PLAN_HINT_SCALE": 1.15,
+    # MergeEnv.step as ONE kernel (mpc_env_step) instead of ~150 tensor operations; same random numbers, same trajectories
+    # (bit-identical under the CPU emulation of tests/emu).  Off until it has run on a device.
+    "FUSED_ENV_STEP": False,
 }
 
 

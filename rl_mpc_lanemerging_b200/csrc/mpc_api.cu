@@ -35,6 +35,10 @@ cudaError_t launch_speed_from_jerk(const DevParams &P, int B, const double *ego,
 cudaError_t launch_predict_step_without_ego(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
                                             const double *cv, const double *ca, const int32_t *n, double dt, double mcd,
                                             double *ego_out, double *ox, double *ov, double *oa, uint8_t *crashed, cudaStream_t st);
+cudaError_t launch_env_step(const DevParams &P, const mpc_env_params &E, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
+                            int32_t *n, double *prev_acc, double *delay, int32_t *ticks, const double *jerk, const double *u_spawn,
+                            const double *gap_u, const double *first_u, const double *speed_z, const double *delay_u, double *reward,
+                            uint8_t *flags, double *proj_jerk, cudaStream_t st);
 cudaError_t launch_reach_caps(const DevParams &P, int B, const LayerDesc *desc, const int32_t *num_s, unsigned short *capb,
                               int stride, cudaStream_t st);
 cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
@@ -589,6 +593,26 @@ extern "C" int mpc_rollout_step(mpc_handle *h, int B, double *d_ego, double *d_c
     MPC_CUDA_OK(launch_rollout_step(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, d_jerk, dt, min_crash_distance,
                                     stop_x, step, d_alive, d_selected_speed, d_roll_s, roll_stride, d_roll_len, d_crash_predicted,
                                     (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}
+
+extern "C" int mpc_env_step(mpc_handle *h, const mpc_env_params *ep, int B, double *d_ego, double *d_cars_x, double *d_cars_v,
+                            double *d_cars_a, int32_t *d_n_cars, double *d_prev_acc, double *d_delay, int32_t *d_ticks,
+                            const double *d_jerk, const double *d_u_spawn, const double *d_fresh_gap_u, const double *d_fresh_first_u,
+                            const double *d_fresh_speed_z, const double *d_fresh_delay_u, double *d_reward, uint8_t *d_flags,
+                            double *d_projected_jerk, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!ep || !d_ego || !d_cars_x || !d_cars_v || !d_cars_a || !d_n_cars || !d_prev_acc || !d_delay || !d_ticks || !d_jerk || !d_reward ||
+        !d_flags || !d_projected_jerk)
+        return mpc_set_error(MPC_E_INVALID, "mpc_env_step: null pointer");
+    if (ep->auto_reset && (!d_fresh_gap_u || !d_fresh_first_u || !d_fresh_delay_u))
+        return mpc_set_error(MPC_E_INVALID, "mpc_env_step: auto_reset needs the fresh-episode random numbers");
+    if (!(ep->tick > 0)) return mpc_set_error(MPC_E_INVALID, "mpc_env_step: tick must be positive");
+    MPC_CUDA_OK(launch_env_step(h->P, *ep, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, d_prev_acc, d_delay, d_ticks, d_jerk,
+                                d_u_spawn, d_fresh_gap_u, d_fresh_first_u, d_fresh_speed_z, d_fresh_delay_u, d_reward, d_flags,
+                                d_projected_jerk, (cudaStream_t)stream));
     h->kernels_launched = 1;
     return MPC_OK;
 }

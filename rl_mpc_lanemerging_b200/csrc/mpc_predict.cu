@@ -451,6 +451,96 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(DevParams P, int B, i
 }
 
 // ---- host launchers (called from mpc_api.cu) -----------------------------------------------------
+// ---- fused environment tick (mpc_env_step): see include/mpcb200.h.  One warp per episode, lane == car slot; registers and
+// shuffles only.  Every fp64 operation is written in the order the tensor expressions of merge_gym.MergeEnv.step evaluate
+// them, so the fused tick is bit-identical to the unfused one given the same random numbers. ----
+__global__ void __launch_bounds__(128) env_step_kernel(DevParams P, mpc_env_params E, int B, int nmax, double *ego, double *cars_x,
+                                                      double *cars_v, double *cars_a, int32_t *n_cars, double *prev_acc,
+                                                      double *delay, int32_t *ticks, const double *jerk, const double *u_spawn,
+                                                      const double *gap_u, const double *first_u, const double *speed_z,
+                                                      const double *delay_u, double *reward, uint8_t *flags, double *proj_jerk) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int b = warp;
+    int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
+    EgoState e = {ego[4 * b], ego[4 * b + 1], ego[4 * b + 2], ego[4 * b + 3]}, eo;
+    const size_t o = (size_t)b * nmax + lane;
+    const bool slot_ok = lane < nmax;
+    double x = slot_ok ? cars_x[o] : 0.0, v = slot_ok ? cars_v[o] : 0.0, a = slot_ok ? cars_a[o] : 0.0;
+    // merge_gym.py:83-96: clip the projected acceleration / speed, remember the realised jerk
+    // every per-episode scalar is read here, before the first collective: lane 0 overwrites them at the end of the kernel
+    const double pa = prev_acc[b], delay_in = delay[b];
+    const int ticks_in = ticks[b];
+    double acc = __dadd_rn(pa, __dmul_rn(jerk[b], E.tick));
+    acc = acc < E.a_min ? E.a_min : (acc > E.a_max ? E.a_max : acc);
+    double spd = __dadd_rn(e.v, __dmul_rn(acc, E.tick));
+    const bool clipped = spd > E.max_speed || spd < 0.0;
+    spd = spd < 0.0 ? 0.0 : (spd > E.max_speed ? E.max_speed : spd);
+    if (clipped) acc = __ddiv_rn(__dsub_rn(spd, e.v), E.tick);
+    const double pj = __ddiv_rn(__dsub_rn(acc, pa), E.tick);
+    // world step: the reference predictor as dynamics (cars beyond n keep their values, like the in-place K4 call)
+    double nx, nv, na;
+    const bool crashed = warp_predict_with_ego(P, lane, n, e, x, v, spd, E.tick, E.min_crash_distance, eo, nx, nv, na);
+    if (lane < n) { x = nx; v = nv; a = na; }
+    double new_prev_acc = eo.a;
+    // recycle the front car once it is out of sensor range ahead (all slots shift), enter a new car at the back
+    const double x0 = __shfl_sync(FULL, x, 0);
+    const bool gone = n > 0 && __dsub_rn(x0, eo.x) > E.sensor_radius;
+    {
+        const double sx = __shfl_down_sync(FULL, x, 1), sv = __shfl_down_sync(FULL, v, 1), sa = __shfl_down_sync(FULL, a, 1);
+        if (gone) { const bool last = lane >= nmax - 1; x = last ? 0.0 : sx; v = last ? 0.0 : sv; a = last ? 0.0 : sa; }
+    }
+    n -= gone ? 1 : 0;
+    double dl = __dsub_rn(delay_in, E.tick);
+    const bool spawn = dl <= 0.0 && n < nmax;
+    if (spawn && lane == n) { x = E.spawn_x; v = E.other_speed; a = 0.0; }
+    n += spawn ? 1 : 0;
+    if (spawn) dl = __dadd_rn(u_spawn ? u_spawn[b] : 0.0, E.interval);
+    int tk = ticks_in + 1;
+    const bool arrived = eo.x > E.arrival_x && !crashed;
+    const bool timeout = tk >= E.max_ticks && !crashed && !arrived;
+    const bool done = crashed || arrived || timeout;
+    // dqn.py:557-563
+    double r = __dsub_rn(E.time_reward_step, __dmul_rn(__dmul_rn(E.jerk_weight, __dmul_rn(pj, pj)), E.tick));
+    if (arrived) r = E.success_reward;
+    if (crashed) r = E.crash_reward;
+    if (E.auto_reset && done) {
+        // fresh initial conditions: spawner-spaced traffic (control.py:215-226), ego at the ramp start (control.py:41-44, 198-204)
+        double g = slot_ok ? __dmul_rn(E.other_speed, __dadd_rn(E.interval, gap_u[o])) : 0.0;
+        if (lane == 0) g = __dmul_rn(__dmul_rn(first_u[b], E.other_speed), __dadd_rn(E.interval, 0.5));
+        double cs = 0.0;                                       // cumulative sum, left to right like a sequential scan
+        for (int j = 0; j < 32; j++) { const double gj = __shfl_sync(FULL, g, j); if (j <= lane) cs = j == 0 ? gj : __dadd_rn(cs, gj); }
+        const double xs = __dsub_rn(__dadd_rn(E.ego_start_x, E.sensor_radius), cs);
+        const bool keep = slot_ok && xs >= E.spawn_x;
+        n = __popc(__ballot_sync(FULL, keep));
+        x = keep ? xs : 0.0; v = keep ? E.other_speed : 0.0; a = 0.0;
+        double v0 = E.start_speed;
+        if (speed_z) { v0 = __dadd_rn(E.start_speed, __dmul_rn(E.start_speed_var, speed_z[b])); v0 = v0 < E.min_start_speed ? E.min_start_speed : (v0 > E.max_start_speed ? E.max_start_speed : v0); }
+        eo.x = E.ego_start_x; eo.y = E.ego_start_y; eo.v = v0; eo.a = 0.0;
+        dl = __dadd_rn(E.interval, delay_u[b]);
+        tk = 0; new_prev_acc = 0.0;
+    }
+    __syncwarp();                                              // all lanes are done reading the episode's inputs
+    if (slot_ok) { cars_x[o] = x; cars_v[o] = v; cars_a[o] = a; }
+    if (lane == 0) {
+        ego[4 * b] = eo.x; ego[4 * b + 1] = eo.y; ego[4 * b + 2] = eo.v; ego[4 * b + 3] = eo.a;
+        n_cars[b] = n; prev_acc[b] = new_prev_acc; delay[b] = dl; ticks[b] = tk;
+        reward[b] = r; proj_jerk[b] = pj;
+        flags[b] = done ? 1 : 0; flags[(size_t)B + b] = crashed ? 1 : 0; flags[2 * (size_t)B + b] = arrived ? 1 : 0;
+        flags[3 * (size_t)B + b] = timeout ? 1 : 0;
+    }
+}
+
+cudaError_t launch_env_step(const DevParams &P, const mpc_env_params &E, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
+                            int32_t *n, double *prev_acc, double *delay, int32_t *ticks, const double *jerk, const double *u_spawn,
+                            const double *gap_u, const double *first_u, const double *speed_z, const double *delay_u, double *reward,
+                            uint8_t *flags, double *proj_jerk, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    MPC_LAUNCH(env_step_kernel, (B + 3) / 4, 128, 0, st, P, E, B, nmax, ego, cx, cv, ca, n, prev_acc, delay, ticks, jerk, u_spawn, gap_u,
+               first_u, speed_z, delay_u, reward, flags, proj_jerk);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
                                   const double *cv, const int32_t *n, LayerDesc *desc, double *s0, double *ds,
                                   int32_t *ns, cudaStream_t st) {

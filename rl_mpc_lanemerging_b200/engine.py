@@ -330,6 +330,20 @@ class MpcEngine:
                                                  _ptr(alive), _ptr(selected_speed), _ptr(roll_s), roll_s.shape[1], _ptr(roll_len),
                                                  _ptr(crash_predicted), self._stream()))
 
+    def env_step(self, ep, state_args, prev_acc, delay, ticks, jerk, u_spawn, fresh, reward, flags, projected_jerk):
+        """mpc_env_step: one fused, in-place tick of merge_gym.MergeEnv.  fresh = (gap_u [B,nmax], first_u [B], speed_z [B] or
+        None, delay_u [B]) or None (no auto-reset); flags u8 [4,B] = (done, crashed, arrived, timeout)."""
+        ego, cars_x, cars_v, cars_a, n_cars = state_args
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        for t in (prev_acc, delay, jerk, reward, projected_jerk):
+            assert t.dtype == torch.float64 and t.shape == (B,) and t.is_contiguous() and self._is_dev(t)
+        assert ticks.dtype == torch.int32 and flags.dtype == torch.uint8 and flags.shape == (4, B) and flags.is_contiguous()
+        g, f, z, d = fresh if fresh is not None else (None, None, None, None)
+        with self._device_ctx():
+            _lib.check(self.lib.mpc_env_step(self.h, C.byref(ep), B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                             _ptr(prev_acc), _ptr(delay), _ptr(ticks), _ptr(jerk), _ptr(u_spawn), _ptr(g), _ptr(f),
+                                             _ptr(z), _ptr(d), _ptr(reward), _ptr(flags), _ptr(projected_jerk), self._stream()))
+
     def speed_from_jerk(self, ego, jerk):
         B = ego.shape[0]
         out = torch.empty(B, dtype=torch.float64, device=self.device)

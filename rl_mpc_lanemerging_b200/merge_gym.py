@@ -90,8 +90,45 @@ class MergeEnv:
         return dqn.get_state_vector_from_base_state(self.state)[:, :20]
 
     # ---- one tick ------------------------------------------------------------------------------------
+    def _step_fused(self, action: torch.Tensor):
+        """step() as one kernel (mpc_env_step).  The random numbers are drawn here, in the order step() draws them, so both
+        paths walk through the same trajectories."""
+        from ._lib import MpcEnvParams
+        S, B, dev = Settings, self.B, self.device
+        jerk = action.to(dev, torch.float64).reshape(B).contiguous()
+        ep = MpcEnvParams()
+        ep.tick, ep.a_min, ep.a_max, ep.max_speed = float(S.TICK_LENGTH), float(S.MAX_NEGATIVE_ACCELERATION), float(S.MAX_POSITIVE_ACCELERATION), float(S.MAX_SPEED)
+        ep.min_crash_distance, ep.sensor_radius, ep.spawn_x = float(S.CAR_LENGTH), float(S.SENSOR_RADIUS), SPAWN_X
+        ep.other_speed, ep.interval, ep.arrival_x = float(S.OTHER_CAR_SPEED), float(S.BASE_TRAFFIC_INTERVAL), ARRIVAL_X
+        ep.ego_start_x, ep.ego_start_y = EGO_START_X, float(self._ego_y0)
+        ep.start_speed, ep.start_speed_var = float(S.START_SPEED), float(S.START_SPEED_VARIANCE)
+        ep.min_start_speed, ep.max_start_speed = float(S.MIN_START_SPEED), float(S.MAX_START_SPEED)
+        ep.time_reward_step = S.TIME_REWARD * S.TICK_LENGTH
+        ep.jerk_weight, ep.crash_reward, ep.success_reward = float(S.ALT_J_WEIGHT), float(S.CRASH_REWARD), float(S.SUCCESS_REWARD)
+        ep.max_ticks, ep.auto_reset = int(self.max_ticks), int(bool(self.auto_reset))
+        u = self._rand(B) if S.VARY_TRAFFIC_START_TIMES else None
+        fresh = None
+        if self.auto_reset:                                   # the draws of _fresh(), in its order
+            gap_u, first_u = self._rand(B, self.N), self._rand(B)
+            z = torch.randn(B, generator=self.gen, dtype=torch.float64, device=dev) if S.RANDOMIZE_START_SPEED else None
+            fresh = (gap_u, first_u, z, self._rand(B))
+        if getattr(self, "_fused_out", None) is None:
+            self._fused_out = (torch.empty(B, dtype=torch.float64, device=dev), torch.empty((4, B), dtype=torch.uint8, device=dev),
+                               torch.empty(B, dtype=torch.float64, device=dev))
+        reward, flags, pj = self._fused_out
+        self.eng.env_step(ep, self.state.args(), self.prev_acc, self.delay, self.ticks, jerk, u, fresh, reward, flags, pj)
+        fb = flags.view(torch.bool)
+        done, crashed, arrived, timeout = fb[0], fb[1], fb[2], fb[3]
+        info = {"crashed": crashed.clone(), "merged": arrived.clone(), "timeout": timeout.clone(), "projected_jerk": pj.clone()}
+        obs = self._obs()
+        if not self.auto_reset:
+            obs = torch.where(done.unsqueeze(1), torch.zeros_like(obs), obs)
+        return obs, reward.clone(), done.clone(), info
+
     def step(self, action: torch.Tensor):
         """action: jerk [B] (continuous, reference ContinuousJerkEnv).  Finished episodes restart when auto_reset."""
+        if getattr(Settings, "FUSED_ENV_STEP", False):
+            return self._step_fused(action)
         S, tick, st8 = Settings, float(Settings.TICK_LENGTH), self.state
         jerk = action.to(self.device, torch.float64).reshape(self.B)
         # merge_gym.py:83-96: clip the projected acceleration / speed, remember the realised jerk

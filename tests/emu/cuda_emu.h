@@ -211,6 +211,11 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d) {
     const int l = emu_lane();
     return l >= (int)d ? emu_unbits<T>(b[l - (int)d]) : v;
 }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
+    const unsigned long long *b = emu::exchange(emu_bits(v));
+    const int l = emu_lane();
+    return l + (int)d < 32 ? emu_unbits<T>(b[l + (int)d]) : v;
+}
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_unbits<T>(emu::exchange(emu_bits(v))[(emu_lane() ^ m) & 31]); }
 static inline unsigned __ballot_sync(unsigned, bool p) {
     const unsigned long long *b = emu::exchange(p ? 1ull : 0ull);

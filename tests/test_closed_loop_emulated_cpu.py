@@ -76,3 +76,45 @@ def test_plan_cost_hints_do_not_change_the_closed_loop(settings):
         runs[hints] = log
     for a, b in zip(runs[False], runs[True]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("auto_reset,randomize", [(True, True), (True, False), (False, True)])
+def test_fused_env_step_equals_the_tensor_version(settings, auto_reset, randomize):
+    """Settings.FUSED_ENV_STEP: MergeEnv.step as one kernel (mpc_env_step).  Two environments with the same seed, one stepped
+    by the kernel, one by the ~150 tensor operations, fed the same jerks: states, rewards, flags and observations must stay
+    bit-identical over resets, recycled and entering cars, clipped actions, crashes and timeouts."""
+    import torch
+    from rl_mpc_lanemerging_b200 import merge_gym
+    settings.MAX_EPISODE_LENGTH = 2.4                            # 12 ticks: timeouts (and their resets) inside the run
+    settings.RANDOMIZE_START_SPEED = randomize
+    envs = {}
+    for fused in (False, True):
+        e = merge_gym.MergeEnv(12, seed=9, auto_reset=auto_reset)
+        e.reset()
+        envs[fused] = e
+    g = torch.Generator().manual_seed(4)
+    seen = dict(crashed=0, timeout=0, clipped=0, spawned=0, recycled=0)
+    for tick in range(45):
+        jerk = (torch.rand(12, generator=g, dtype=torch.float64) - 0.45) * 14.0
+        if tick > 30:
+            jerk = jerk.abs() + 3.0                              # floor it: run into the traffic ahead
+        n_before = envs[True].state.n_cars.clone()
+        outs = {}
+        for fused in (False, True):
+            settings.FUSED_ENV_STEP = fused
+            outs[fused] = envs[fused].step(jerk.clone())
+        settings.FUSED_ENV_STEP = False
+        (o0, r0, d0, i0), (o1, r1, d1, i1) = outs[False], outs[True]
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1), tick
+        for k in ("crashed", "merged", "timeout", "projected_jerk"):
+            assert torch.equal(i0[k], i1[k]), (tick, k)
+        a, b = envs[False], envs[True]
+        for x, y in zip(a.state.args(), b.state.args()):
+            assert torch.equal(x, y), tick
+        assert torch.equal(a.prev_acc, b.prev_acc) and torch.equal(a.delay, b.delay) and torch.equal(a.ticks, b.ticks), tick
+        seen["crashed"] += int(i1["crashed"].sum()); seen["timeout"] += int(i1["timeout"].sum())
+        seen["clipped"] += int((i1["projected_jerk"] != jerk).sum())
+        seen["spawned"] += int((b.state.n_cars > n_before).sum()); seen["recycled"] += int((b.state.n_cars < n_before).sum())
+    assert seen["timeout"] > 0 and seen["clipped"] > 0 and seen["spawned"] > 0
+    if auto_reset:
+        assert seen["crashed"] > 0 or seen["timeout"] > 12
