@@ -487,6 +487,17 @@ def run_hint_leg(args):
                      "algorithmic bytes = whole grid once (SURVEY 8d) -- the kernel only touches the cells the DP reaches; fp32 "
                      "distances may move a near-tie (same_plan_as_fused compares with the descriptor-fed fp64 plan)")
     res["dense_solve"] = dense
+    # ---- closed loop with the two switches that are off by default until they have run on a device ----
+    def closed_loop(extra):
+        rate, take = env_steps_per_sec(0, 1, args.env_envs, args.env_ticks, args.seed, extra)
+        return {"env_steps_per_s": rate, "planner_takeover_fraction": take}
+
+    eng.close()
+    if probe is not None:
+        probe.close()
+    section("closed_loop_default", lambda: closed_loop({}))
+    section("closed_loop_fused_env_step", lambda: closed_loop({"FUSED_ENV_STEP": True}))
+    section("closed_loop_fused_env_step_and_cost_hints", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True}))
     print(json.dumps(res), file=RESULT_OUT, flush=True)
 
 
@@ -494,9 +505,10 @@ def hint_leg_subprocess(args):
     """Runs run_hint_leg in a child process with a time limit: the cost-hint kernels were written after this round's GPU
     budget was spent, so their first on-device run must not be able to take the headline line down with it."""
     cmd = [sys.executable, os.path.abspath(__file__), "--hint-leg", "--horizon", str(args.horizon), "--batch", str(args.batch),
-           "--steps", str(min(args.steps, 10)), "--traffic", args.traffic, "--seed", str(args.seed)]
+           "--steps", str(min(args.steps, 10)), "--traffic", args.traffic, "--seed", str(args.seed),
+           "--env-envs", str(args.env_envs), "--env-ticks", str(max(args.env_ticks, 10))]
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240, cwd=ROOT)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, cwd=ROOT)
         lines = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": f"exit {r.returncode}: " + r.stderr.decode(errors="replace")[-400:]}
@@ -508,7 +520,7 @@ def hint_leg_subprocess(args):
     return res
 
 
-def env_steps_per_sec(local, world, n_envs, ticks, seed):
+def env_steps_per_sec(local, world, n_envs, ticks, seed, extra=None):
     """Secondary figure of BASELINE.json's metric: closed-loop env-steps/s of the combined controller
     (configs/combined_moderate_1.json semantics: 5 policy forwards + 5 predictor steps + 1 gap-evaluation per tick,
     + a second gap-evaluation for the episodes the planner takes over; reference dqn.py:117-200) on the published
@@ -520,6 +532,8 @@ def env_steps_per_sec(local, world, n_envs, ticks, seed):
     Settings.reset()
     Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL = 20, 11.0, 1.2      # combined_moderate_1.json
     Settings.TEST_ST_STRICTLY_BETTER, Settings.CUDA_DEVICE, Settings.ALT_J_WEIGHT = False, local, 0.1
+    for k, v in (extra or {}).items():          # (hint leg: FUSED_ENV_STEP / PLAN_COST_HINTS)
+        setattr(Settings, k, v)
     st.refresh_engine()
     env = merge_gym.MergeEnv(n_envs, seed=seed)
     agent = ddpg.DDPGAgent(device=f"cuda:{local}", seed=seed)
