@@ -160,9 +160,8 @@ class RLAgent:
             takeover_b = better
         else:
             takeover_b = None
-        n_take = int(takeover.sum().item())
-        if n_take:                                                                  # planner takes over: st.do_st_control(start_state)
-            idx = takeover.nonzero().squeeze(1)
+        idx = takeover.nonzero().squeeze(1)                                        # (the tick's one host sync: the list's length)
+        if idx.numel():                                                             # planner takes over: st.do_st_control(start_state)
             sub = BatchedState(*(t[idx].contiguous() for t in start.args()))
             speed = speed.clone()
             speed[idx] = st.do_st_control(sub)
