@@ -476,6 +476,8 @@ def run_hint_leg(args):
                     dms.append(eng.last_kernel_ms()[1])
                 flush.zero_()
             eng.set_timing(False)
+            if not min(dms) > 0:
+                raise RuntimeError(f"no kernel time measured ({dms})")
             dbytes = (T * (eng.num_s_max - 1) * cell + T * 4) * Bg
             dense[name] = {"ms": min(dms), "gap_evals_per_s": Bg / (min(dms) * 1e-3), "algorithmic_gbs": dbytes / (min(dms) * 1e-3) / 1e9,
                            "frac_of_hbm_peak": dbytes / (min(dms) * 1e-3) / 1e9 / peak_hbm()[0],
