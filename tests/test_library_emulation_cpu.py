@@ -186,3 +186,35 @@ def test_emulated_library_against_the_reference_golden_vectors(name, H, n):
     assert (fa["s_seq"] == G["s_seq"][:n]).all(1).sum() >= n - 1 and np.all(helpers.rel(fa["cost"][ok], G["cost"][:n][ok]) < 1e-6)
     _same(eng.plan_hinted(S, fa["cost"].copy(), hint_scale=1.1), fa)
     eng.close()
+
+
+def test_error_conventions_and_set_params():
+    """Status codes of the C ABI (include/mpcb200.h) and a Settings refresh through mpc_set_params (scratch re-allocated,
+    incl. the reachability caps of hinted solves)."""
+    _op, p = _params(17)
+    eng = EA.EmuEngine(p, max_batch=4)
+    L = eng.L
+    S = synthetic.make_states(4, "moderate", seed=1, kind="mixed")
+    o = eng._out(4)
+    a = (EA._p(S["cars_x"]), EA._p(S["cars_v"]), None, EA._p(S["n_cars"]))
+    assert L.mpc_plan(eng.h, 0, EA._p(S["ego"]), *a, 0, *eng._outs(o), None) == _lib.MODE_FAST        # B = 0 is not an error
+    assert L.mpc_plan(eng.h, 5, EA._p(S["ego"]), *a, 0, *eng._outs(o), None) == _lib.E_CAPACITY
+    assert L.mpc_plan(eng.h, -1, EA._p(S["ego"]), *a, 0, *eng._outs(o), None) == _lib.E_INVALID
+    assert L.mpc_plan(eng.h, 4, None, *a, 0, *eng._outs(o), None) == _lib.E_INVALID and b"null pointer" in L.mpc_last_error()
+    assert L.mpc_plan(eng.h, 4, EA._p(S["ego"]), *a, 7, *eng._outs(o), None) == _lib.E_INVALID
+    assert L.mpc_plan_hinted(eng.h, 4, EA._p(S["ego"]), *a, 0, EA._p(np.ones(4)), None, 0, -1.0, *eng._outs(o), None) == _lib.E_INVALID
+    assert L.mpc_plan_probed(eng.h, eng.h, 1.1, 4, EA._p(S["ego"]), *a, *eng._outs(o), None) == _lib.E_INVALID
+    ref = eng.plan(S)
+    _same(eng.plan_hinted(S, ref["cost"].copy(), hint_scale=1.1), ref)
+    p2 = _lib.MpcParams()
+    for n in _lib.PARAM_FIELDS:
+        setattr(p2, n, getattr(p, n))
+    p2.crash_min_s = 12.0                                       # the reference's default (config.py:110)
+    EA.check(L.mpc_set_params(eng.h, C.byref(p2)))
+    ref2 = eng.plan(S)
+    assert not np.array_equal(ref2["cost"], ref["cost"])        # other Settings, other plans
+    _same(eng.plan_hinted(S, ref2["cost"].copy(), hint_scale=1.1), ref2)
+    lone = {k: v[:1].copy() for k, v in S.items()}
+    lone["n_cars"][0] = 0                                       # an empty road
+    assert eng.plan(lone)["reached_t"][0] == 17
+    eng.close()
