@@ -121,6 +121,14 @@ int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x,
              int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
              uint8_t *d_crash, double *d_min_dist, double *d_start_s, void *stream);
 
+/* mpc_plan for the episodes with d_mask[b] != 0 only; the outputs of the other episodes are left untouched (d_start_s is
+ * not available: pass NULL).  The masked episodes are listed and counted on the device, so the call involves no host round
+ * trip: the combined controller (dqn.py:144-155) hands the vetoed episodes to st.do_st_control without synchronising. */
+int mpc_plan_masked(mpc_handle *h, int B, const uint8_t *d_mask, const double *d_ego, const double *d_cars_x,
+                    const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars, int mode,
+                    int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t, uint8_t *d_crash,
+                    double *d_min_dist, double *d_start_s, void *stream);
+
 /* mpc_plan with a per-problem COST HINT for MPC_MODE_FAST (ignored by MPC_MODE_EXACT): an estimate of each plan's cost
  * -- the cost of a coarse probe plan (mpc_plan_probed), or of the previous tick's plan when the reference's
  * control loop re-plans every TICK_LENGTH (control.py:229-340 calls st.do_st_control once per tick).  Problem b
@@ -169,6 +177,10 @@ int mpc_plan_host_probed(mpc_handle *h, mpc_handle *probe, double margin, int B,
  * st.py:780-781 (the current ego speed when the plan has a single point, st.py:775-777), d_iterations i32[B] (optional). */
 int mpc_finer_fit(mpc_handle *h, int B, const double *d_s_seq, const int32_t *d_reached_t, const double *d_ego,
                   double *d_fine, int fine_stride, int32_t *d_n_fine, double *d_speed, int32_t *d_iterations, void *stream);
+/* the same for the episodes with d_mask[b] != 0 only (rows of the others untouched, no host round trip) */
+int mpc_finer_fit_masked(mpc_handle *h, int B, const uint8_t *d_mask, const double *d_s_seq, const int32_t *d_reached_t,
+                         const double *d_ego, double *d_fine, int fine_stride, int32_t *d_n_fine, double *d_speed,
+                         int32_t *d_iterations, void *stream);
 int mpc_finer_fit_max_points(void);
 
 /* ---- K4: rollout tick pieces ------------------------------------------------------------------

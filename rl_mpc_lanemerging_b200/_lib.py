@@ -58,6 +58,8 @@ SYMBOLS = {
     "mpc_build_grid": (_i, [_vp, _i] + [_vp] * 5 + [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mpc_solve_dense": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mpc_plan": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),
+    "mpc_plan_masked": (_i, [_vp, _i, _vp] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),
+    "mpc_finer_fit_masked": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mpc_plan_hinted": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp, _vp, _i, _d] + [_vp] * 7 + [_vp]),
     "mpc_plan_probed": (_i, [_vp, _vp, _d, _i] + [_vp] * 5 + [_vp] * 7 + [_vp]),
     "mpc_plan_host": (_i, [_vp, _i] + [_vp] * 5 + [_i] + [_vp] * 7 + [_vp]),

@@ -47,6 +47,9 @@ _HOT_PATH_DEFAULTS = {
     # MergeEnv.step as ONE kernel (mpc_env_step) instead of ~150 tensor operations; same random numbers, same trajectories
     # (bit-identical under the CPU emulation of tests/emu).  Off until it has run on a device.
     "FUSED_ENV_STEP": False,
+    # combined controller: hand the vetoed episodes to the planner through mpc_plan_masked / mpc_finer_fit_masked (episode list
+    # built and counted on the device) instead of nonzero() + gather on the host side: no host sync in the tick.  Same speeds.
+    "SYNC_FREE_TAKEOVER": False,
 }
 
 

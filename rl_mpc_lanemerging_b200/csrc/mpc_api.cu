@@ -18,12 +18,12 @@ cudaError_t launch_check_sorted(const DevParams &P, int B, const LayerDesc *desc
                                 const int32_t *ns, unsigned long long *mismatches, cudaStream_t st);
 cudaError_t launch_finer_fit(const DevParams &P, int B, int T, const double *s_seq, const int32_t *reached, const double *ego,
                              int max_iter, double tol, double *fine, int fine_stride, int32_t *n_fine, double *speed,
-                             int32_t *iters, cudaStream_t st);
+                             int32_t *iters, cudaStream_t st, const int32_t *subset = nullptr, const int *count = nullptr);
 int qp_max_fine();
 int exact_occupancy(int threads, size_t smem);
 int fast_occupancy(int threads, size_t smem, int wrap);
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
-                                  const int32_t *n, LayerDesc *desc, double *s0, double *ds, int32_t *ns, cudaStream_t st);
+                                  const int32_t *n, LayerDesc *desc, double *s0, double *ds, int32_t *ns, cudaStream_t st, const int32_t *subset = nullptr, const int *count = nullptr);
 cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const LayerDesc *desc, const double *s0, const double *ds,
                              const int32_t *ns, uint8_t *obstacles, void *distances, int dist_f32, cudaStream_t st);
 cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
@@ -39,6 +39,7 @@ cudaError_t launch_env_step(const DevParams &P, const mpc_env_params &E, int B, 
                             int32_t *n, double *prev_acc, double *delay, int32_t *ticks, const double *jerk, const double *u_spawn,
                             const double *gap_u, const double *first_u, const double *speed_z, const double *delay_u, double *reward,
                             uint8_t *flags, double *proj_jerk, cudaStream_t st);
+cudaError_t launch_compact_mask(const uint8_t *mask, int B, int32_t *subset, int *count, cudaStream_t st);
 cudaError_t launch_reach_caps(const DevParams &P, int B, const LayerDesc *desc, const int32_t *num_s, unsigned short *capb,
                               int stride, cudaStream_t st);
 cudaError_t launch_rollout_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca,
@@ -92,6 +93,7 @@ struct mpc_handle {
     double *st_ego, *st_cx, *st_cv, *st_ca; int32_t *st_n;
     int32_t *st_idx; double *st_seq, *st_cost, *st_mind, *st_s0; int32_t *st_reached; uint8_t *st_crash;
     unsigned short *capb; int cap_stride;      // reachability caps of hinted solves (allocated on first use)
+    int32_t *mask_list; int *mask_count;        // masked calls: compacted episode list + its length (allocated on first use)
     int use_heur;                                // MPC_FAST_HEUR=0 disables the heuristic pruning of hinted solves (dev A/B)
     double hint_retry;                           // middle rung of the hinted ladder (MPC_HINT_RETRY, default 1.36 = 1.5 / 1.1; <= 1 disables)
     int64_t kernels_launched;
@@ -103,6 +105,8 @@ struct mpc_handle {
 
 static void free_scratch(mpc_handle *h) {
     if (h->capb) { cudaFree(h->capb); h->capb = nullptr; }
+    if (h->mask_list) { cudaFree(h->mask_list); h->mask_list = nullptr; }
+    if (h->mask_count) { cudaFree(h->mask_count); h->mask_count = nullptr; }
     void *ptrs[] = {h->desc, h->s0, h->ds, h->num_s, h->bp, h->counters, h->fallback_list, h->glab, h->ghist, h->st_ego,
                     h->st_cx, h->st_cv, h->st_ca, h->st_n, h->st_idx, h->st_seq, h->st_cost, h->st_mind, h->st_s0,
                     h->st_reached, h->st_crash};
@@ -323,7 +327,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
     MPC_CUDA_OK(cudaMemsetAsync(h->counters, 0, 16 * sizeof(int), st));
     io.bp = h->bp; io.bp_stride = h->W;
     io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
-    io.subset = nullptr; io.B_dev = nullptr;
+    // (io.subset / io.B_dev as passed: masked plans list the episodes to solve, everybody else passes NULL)
     SolveLaunch X;                                   // exact-kernel launch shape
     X.B = B; X.threads = h->threads; X.smem = h->smem; X.W = h->W; X.wrap = 0; X.bound = ~0ULL;
     X.glab = h->smem ? nullptr : h->glab; X.ghist = h->smem ? nullptr : h->ghist;
@@ -392,18 +396,34 @@ extern "C" int mpc_solve_dense(mpc_handle *h, int B, int num_t, int num_s_stride
 }
 
 // mpc_plan with an optional per-problem cost hint for the fast kernel (hint_cost == NULL: none)
+// builds the compacted list of the episodes with mask[b] != 0 in h->mask_list / h->mask_count (no host round trip)
+static int build_mask_list(mpc_handle *h, int B, const uint8_t *d_mask, cudaStream_t st) {
+    if (!h->mask_list) {
+        MPC_CUDA_OK(cudaMalloc(&h->mask_list, (size_t)h->max_batch * sizeof(int32_t)));
+        MPC_CUDA_OK(cudaMalloc(&h->mask_count, sizeof(int)));
+    }
+    MPC_CUDA_OK(launch_compact_mask(d_mask, B, h->mask_list, h->mask_count, st));
+    return MPC_OK;
+}
+
 static int plan_impl(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
                      const int32_t *d_n_cars, int mode, const double *hint_cost, const int32_t *hint_reached, int hint_full_t,
                      double hint_scale, int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
-                     uint8_t *d_crash, double *d_min_dist, double *d_start_s, cudaStream_t st, const char *who) {
+                     uint8_t *d_crash, double *d_min_dist, double *d_start_s, cudaStream_t st, const char *who,
+                     const uint8_t *d_mask = nullptr) {
     int rc = check_batch(h, B); if (rc) return rc;
     if (B == 0) return MPC_OK;
     if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars) return mpc_set_error(MPC_E_INVALID, who);
     h->ev_valid = 0;
     if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[0], st));
-    MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, d_start_s ? d_start_s : h->s0, h->ds, h->num_s, st));
-    h->kernels_launched = 1;
+    h->kernels_launched = 0;
+    const int32_t *subset = nullptr; const int *count = nullptr;
+    if (d_mask) { rc = build_mask_list(h, B, d_mask, st); if (rc) return rc; subset = h->mask_list; count = h->mask_count; h->kernels_launched++; }
+    MPC_CUDA_OK(launch_predict_layers(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_n_cars, h->desc, d_start_s ? d_start_s : h->s0, h->ds, h->num_s, st,
+                                      subset, count));
+    h->kernels_launched++;
     SolveIO io; memset(&io, 0, sizeof(io));
+    io.subset = subset; io.B_dev = count;
     io.ego = d_ego;
     io.idx = d_idx; io.s_seq = d_s_seq; io.cost = d_cost; io.reached = d_reached_t; io.crash = d_crash; io.min_dist = d_min_dist;
     io.hint_cost = hint_cost; io.hint_reached = hint_reached; io.hint_full_t = hint_full_t; io.hint_scale = hint_scale;
@@ -428,6 +448,20 @@ extern "C" int mpc_plan(mpc_handle *h, int B, const double *d_ego, const double 
     (void)d_cars_a;
     return plan_impl(h, B, d_ego, d_cars_x, d_cars_v, d_n_cars, mode, nullptr, nullptr, 0, 1.0, d_idx, d_s_seq, d_cost, d_reached_t,
                      d_crash, d_min_dist, d_start_s, (cudaStream_t)stream, "mpc_plan: null pointer");
+}
+
+// Masked plan: only the episodes with d_mask[b] != 0 are planned; the outputs of the others are left untouched.  The list of
+// masked episodes is compacted on the device and its length is read there, so the call needs no host round trip -- what the
+// combined controller's take-over (dqn.py:148-155: st.do_st_control for the episodes the planner vetoed) needs to stay asynchronous.
+extern "C" int mpc_plan_masked(mpc_handle *h, int B, const uint8_t *d_mask, const double *d_ego, const double *d_cars_x,
+                               const double *d_cars_v, const double *d_cars_a, const int32_t *d_n_cars, int mode, int32_t *d_idx,
+                               double *d_s_seq, double *d_cost, int32_t *d_reached_t, uint8_t *d_crash, double *d_min_dist,
+                               double *d_start_s, void *stream) {
+    (void)d_cars_a;
+    if (!d_mask) return mpc_set_error(MPC_E_INVALID, "mpc_plan_masked: null mask");
+    if (d_start_s) return mpc_set_error(MPC_E_INVALID, "mpc_plan_masked: start_s is not available for masked plans (pass NULL)");
+    return plan_impl(h, B, d_ego, d_cars_x, d_cars_v, d_n_cars, mode, nullptr, nullptr, 0, 1.0, d_idx, d_s_seq, d_cost, d_reached_t, d_crash,
+                     d_min_dist, nullptr, (cudaStream_t)stream, "mpc_plan_masked: null pointer", d_mask);
 }
 
 extern "C" int mpc_plan_hinted(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
@@ -527,6 +561,21 @@ extern "C" int mpc_finer_fit(mpc_handle *h, int B, const double *d_s_seq, const 
     MPC_CUDA_OK(launch_finer_fit(h->P, B, h->P.num_t, d_s_seq, d_reached_t, d_ego, 40, 1e-9, d_fine, fine_stride, d_n_fine, d_speed,
                                  d_iterations, (cudaStream_t)stream));
     h->kernels_launched = 1;
+    return MPC_OK;
+}
+
+// mpc_finer_fit for the episodes with d_mask[b] != 0 only (rows of the others untouched); no host round trip
+extern "C" int mpc_finer_fit_masked(mpc_handle *h, int B, const uint8_t *d_mask, const double *d_s_seq, const int32_t *d_reached_t,
+                                    const double *d_ego, double *d_fine, int fine_stride, int32_t *d_n_fine, double *d_speed,
+                                    int32_t *d_iterations, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_mask || !d_s_seq || !d_reached_t || !d_ego || !d_fine || !d_n_fine || fine_stride < 2) return mpc_set_error(MPC_E_INVALID, "mpc_finer_fit_masked: bad argument");
+    if (!(h->P.p.tick_length > 0)) return mpc_set_error(MPC_E_INVALID, "mpc_finer_fit_masked: tick_length must be positive");
+    rc = build_mask_list(h, B, d_mask, (cudaStream_t)stream); if (rc) return rc;
+    MPC_CUDA_OK(launch_finer_fit(h->P, B, h->P.num_t, d_s_seq, d_reached_t, d_ego, 40, 1e-9, d_fine, fine_stride, d_n_fine, d_speed,
+                                 d_iterations, (cudaStream_t)stream, h->mask_list, h->mask_count));
+    h->kernels_launched = 2;
     return MPC_OK;
 }
 

@@ -103,17 +103,21 @@ __device__ __forceinline__ int merge_sorted_intervals(int lane, int nb, int2 *sb
 
 // ---- K1a -----------------------------------------------------------------------------------------
 // desc[B][num_t]; hdr_s0/ds/num_s per problem.
+// SUBSET: only the episodes listed in subset[0 .. *count) are predicted (masked plans; the default instance is unchanged)
+template <bool SUBSET>
 __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B, const double *__restrict__ ego,
                                                             const double *__restrict__ cars_x,
                                                             const double *__restrict__ cars_v,
                                                             const int32_t *__restrict__ n_cars, int nmax,
                                                             LayerDesc *__restrict__ desc, double *__restrict__ o_s0,
-                                                            double *__restrict__ o_ds, int32_t *__restrict__ o_num_s) {
+                                                            double *__restrict__ o_ds, int32_t *__restrict__ o_num_s,
+                                                            const int32_t *__restrict__ subset, const int *__restrict__ count) {
     __shared__ double s_edge[4][2 * MPC_NMAX];
     __shared__ int2 s_band[4][MPC_NMAX], s_blk[4][MPC_NMAX];
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (warp >= B) return;
     int b = warp;
+    if (SUBSET) { if (warp >= *count) return; b = subset[warp]; }
     int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
     EgoState e = {ego[4 * b], ego[4 * b + 1], ego[4 * b + 2], ego[4 * b + 3]};
     double x = lane < n ? cars_x[(size_t)b * nmax + lane] : 0.0;
@@ -543,10 +547,11 @@ cudaError_t launch_env_step(const DevParams &P, const mpc_env_params &E, int B, 
 
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx,
                                   const double *cv, const int32_t *n, LayerDesc *desc, double *s0, double *ds,
-                                  int32_t *ns, cudaStream_t st) {
+                                  int32_t *ns, cudaStream_t st, const int32_t *subset, const int *count) {
     if (B <= 0) return cudaSuccess;
     int wpb = 4;
-    MPC_LAUNCH(predict_layers_kernel, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, ego, cx, cv, n, nmax, desc, s0, ds, ns);
+    if (subset) MPC_LAUNCH(predict_layers_kernel<true>, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, ego, cx, cv, n, nmax, desc, s0, ds, ns, subset, count);
+    else MPC_LAUNCH(predict_layers_kernel<false>, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, ego, cx, cv, n, nmax, desc, s0, ds, ns, subset, count);
     return cudaGetLastError();
 }
 

@@ -106,15 +106,20 @@ __device__ __forceinline__ double qp_col(int m, int i, const double *w) {
     return s;
 }
 
+// SUBSET: only the episodes listed in subset[0 .. *count) are fitted (masked calls; the default instance is unchanged)
+template <bool SUBSET>
 __global__ void __launch_bounds__(32 * QP_WARPS) finer_fit_kernel(DevParams P, int B, int T, const double *__restrict__ s_seq,
                                                                  const int32_t *__restrict__ reached, const double *__restrict__ ego,
                                                                  int max_iter, double tol, double *__restrict__ fine, int fine_stride,
                                                                  int32_t *__restrict__ n_fine, double *__restrict__ speed,
-                                                                 int32_t *__restrict__ iters_out) {
+                                                                 int32_t *__restrict__ iters_out, const int32_t *__restrict__ subset,
+                                                                 const int *__restrict__ count) {
     __shared__ QpWarpShared SH[QP_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int b = blockIdx.x * QP_WARPS + wib;
-    if (b >= B) return;                                          // (whole warp)
+    const int w = blockIdx.x * QP_WARPS + wib;
+    if (w >= B) return;                                          // (whole warp)
+    if (SUBSET && w >= *count) return;
+    const int b = SUBSET ? subset[w] : w;
     QpWarpShared &S = SH[wib];
     const double dt = P.p.tick_length, dtc = P.p.t_disc;
     const int Lc = reached[b] + 1;                               // coarse points that exist (st.py:762-768 trims the 0.0 tail)
@@ -277,9 +282,10 @@ __global__ void __launch_bounds__(32 * QP_WARPS) finer_fit_kernel(DevParams P, i
 
 cudaError_t launch_finer_fit(const DevParams &P, int B, int T, const double *s_seq, const int32_t *reached, const double *ego,
                              int max_iter, double tol, double *fine, int fine_stride, int32_t *n_fine, double *speed,
-                             int32_t *iters, cudaStream_t st) {
+                             int32_t *iters, cudaStream_t st, const int32_t *subset, const int *count) {
     if (B <= 0) return cudaSuccess;
-    MPC_LAUNCH(finer_fit_kernel, (B + QP_WARPS - 1) / QP_WARPS, 32 * QP_WARPS, 0, st, P, B, T, s_seq, reached, ego, max_iter, tol, fine, fine_stride, n_fine, speed, iters);
+    if (subset) MPC_LAUNCH(finer_fit_kernel<true>, (B + QP_WARPS - 1) / QP_WARPS, 32 * QP_WARPS, 0, st, P, B, T, s_seq, reached, ego, max_iter, tol, fine, fine_stride, n_fine, speed, iters, subset, count);
+    else MPC_LAUNCH(finer_fit_kernel<false>, (B + QP_WARPS - 1) / QP_WARPS, 32 * QP_WARPS, 0, st, P, B, T, s_seq, reached, ego, max_iter, tol, fine, fine_stride, n_fine, speed, iters, subset, count);
     return cudaGetLastError();
 }
 

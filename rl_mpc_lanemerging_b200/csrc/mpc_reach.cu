@@ -68,6 +68,36 @@ __global__ void __launch_bounds__(32 * RC_WARPS) reach_caps_kernel(DevParams P, 
     }
 }
 
+// Ordered compaction of a byte mask: subset[0 .. *count) = the indices b with mask[b] != 0, ascending.  One block.
+__global__ void __launch_bounds__(1024) compact_mask_kernel(const uint8_t *__restrict__ mask, int B, int32_t *__restrict__ subset,
+                                                           int *__restrict__ count) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < B; start += blockDim.x) {
+        const int b = start + tid;
+        const bool on = b < B && mask[b] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int i = 0; i < w; i++) off += s_warp[i];
+        if (on) subset[off + __popc(bal & ((1u << lane) - 1u))] = b;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int i = 0; i < nw; i++) t += s_warp[i]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) *count = s_base;
+}
+
+cudaError_t launch_compact_mask(const uint8_t *mask, int B, int32_t *subset, int *count, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    MPC_LAUNCH(compact_mask_kernel, 1, 1024, 0, st, mask, B, subset, count);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_reach_caps(const DevParams &P, int B, const LayerDesc *desc, const int32_t *num_s, unsigned short *capb,
                               int stride, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;

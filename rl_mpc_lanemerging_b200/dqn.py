@@ -160,7 +160,12 @@ class RLAgent:
             takeover_b = better
         else:
             takeover_b = None
-        idx = takeover.nonzero().squeeze(1)                                        # (the tick's one host sync: the list's length)
+        if getattr(Settings, "SYNC_FREE_TAKEOVER", False):                         # planner takes over, episode list kept on the device
+            speed = speed.clone()
+            self._takeover_scratch = st.do_st_control_masked(start, takeover, speed, getattr(self, "_takeover_scratch", None))
+            idx = takeover[:0]
+        else:
+            idx = takeover.nonzero().squeeze(1)                                    # (the tick's one host sync: the list's length)
         if idx.numel():                                                             # planner takes over: st.do_st_control(start_state)
             sub = BatchedState(*(t[idx].contiguous() for t in start.args()))
             speed = speed.clone()

@@ -151,6 +151,27 @@ class MpcEngine:
                                          _ptr(out["start_s"]), self._stream()))
         return out
 
+    def plan_masked(self, mask, ego, cars_x, cars_v, cars_a, n_cars, out: dict, mode="fast"):
+        """mpc_plan_masked: plans only the episodes with mask[b] != 0 (u8 / bool [B]); rows of `out` (idx, s_seq, cost, reached_t,
+        crash, min_dist) of the other episodes are left untouched.  No host round trip."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        assert m.dtype == torch.uint8 and m.shape == (B,) and m.is_contiguous() and self._is_dev(m)
+        with self._device_ctx():
+            _lib.check(self.lib.mpc_plan_masked(self.h, B, _ptr(m), _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                                _mode(mode), _ptr(out["idx"]), _ptr(out["s_seq"]), _ptr(out["cost"]),
+                                                _ptr(out["reached_t"]), _ptr(out["crash"]), _ptr(out["min_dist"]), None, self._stream()))
+        return out
+
+    def finer_fit_masked(self, mask, s_seq, reached_t, ego, fine, n_fine, speed):
+        """mpc_finer_fit_masked: st.finer_fit for the episodes with mask[b] != 0; rows of fine / n_fine / speed of the others untouched."""
+        B = s_seq.shape[0]
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        assert m.dtype == torch.uint8 and m.shape == (B,) and m.is_contiguous() and fine.is_contiguous()
+        with self._device_ctx():
+            _lib.check(self.lib.mpc_finer_fit_masked(self.h, B, _ptr(m), _ptr(s_seq), _ptr(reached_t), _ptr(ego), _ptr(fine),
+                                                     fine.shape[1], _ptr(n_fine), _ptr(speed), None, self._stream()))
+
     def plan_hinted(self, ego, cars_x, cars_v, cars_a, n_cars, hint_cost, hint_reached=None, hint_full_t=0, hint_scale=1.0,
                     mode="fast", out: Optional[dict] = None):
         """plan() with a per-episode cost hint (mpc_plan_hinted): episode b is first solved under the bound

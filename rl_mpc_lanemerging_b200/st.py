@@ -173,6 +173,26 @@ def do_st_control(state, hint: Optional[PlanHint] = None):
     return float(smoothed_speed(bs, plan)[0].item())
 
 
+def do_st_control_masked(batch: BatchedState, mask: torch.Tensor, speed: torch.Tensor, scratch: Optional[dict] = None) -> dict:
+    """do_st_control for the episodes with mask[b] set, written into speed[b] in place; the other rows of `speed` keep their
+    values.  Nothing is read back to the host (mpc_plan_masked + mpc_finer_fit_masked).  Returns the scratch tensors for re-use."""
+    eng = get_engine(batch.batch)
+    B = batch.batch
+    if scratch is None or scratch["cost"].shape[0] != B:
+        scratch = eng._plan_out(B)
+        scratch["fine"] = torch.zeros((B, int(eng.lib.mpc_finer_fit_max_points())), dtype=torch.float64, device=eng.device)
+        scratch["n_fine"] = torch.zeros(B, dtype=torch.int32, device=eng.device)
+    m = mask.contiguous()
+    eng.plan_masked(m, *batch.args(), out=scratch)
+    if float(Settings.TICK_LENGTH) < float(Settings.T_DISCRETIZATION):
+        eng.finer_fit_masked(m, scratch["s_seq"], scratch["reached_t"], batch.ego, scratch["fine"], scratch["n_fine"], speed)
+    else:
+        s = scratch["s_seq"]
+        v = torch.where(scratch["reached_t"] >= 1, (s[:, 1] - s[:, 0]) / float(Settings.TICK_LENGTH), batch.ego[:, 2])
+        speed.copy_(torch.where(m.bool(), v, speed))
+    return scratch
+
+
 def get_path_mean_abs_jerk(s_sequence, ego_start_speed, ego_start_acceleration, delta_t):
     """Reference st.py:274-288 (host bookkeeping on a short path)."""
     s = np.asarray(s_sequence, dtype=np.float64)

@@ -163,3 +163,14 @@ class EmuEngine:
         fine, n_fine, speed, iters = np.zeros((B, nf)), np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
         check(self.L.mpc_finer_fit(self.h, B, _p(s_seq), _p(reached_t), _p(ego), _p(fine), nf, _p(n_fine), _p(speed), _p(iters), None))
         return fine, n_fine, speed, iters
+
+    def plan_masked(self, S, mask, out, mode=0):
+        B = S["ego"].shape[0]
+        check(self.L.mpc_plan_masked(self.h, B, _p(mask), _p(S["ego"]), _p(S["cars_x"]), _p(S["cars_v"]), _p(S["cars_a"]), _p(S["n_cars"]),
+                                     mode, _p(out["idx"]), _p(out["s_seq"]), _p(out["cost"]), _p(out["reached_t"]), _p(out["crash"]),
+                                     _p(out["min_dist"]), None, None))
+        return out
+
+    def finer_fit_masked(self, mask, s_seq, reached_t, ego, fine, n_fine, speed):
+        check(self.L.mpc_finer_fit_masked(self.h, s_seq.shape[0], _p(mask), _p(s_seq), _p(reached_t), _p(ego), _p(fine), fine.shape[1],
+                                          _p(n_fine), _p(speed), None, None))

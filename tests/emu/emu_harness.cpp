@@ -46,7 +46,7 @@ extern "C" int emu_plan(const mpc_params *params, int B, int nmax, const double 
     std::vector<double> s0(B), ds(B);
     std::vector<int32_t> num_s(B);
     // K1a
-    emu::launch((B + 3) / 4, 128, 0, [&] { predict_layers_kernel(P, B, ego, cars_x, cars_v, n_cars, nmax, desc.data(), s0.data(), ds.data(), num_s.data()); });
+    emu::launch((B + 3) / 4, 128, 0, [&] { predict_layers_kernel<false>(P, B, ego, cars_x, cars_v, n_cars, nmax, desc.data(), s0.data(), ds.data(), num_s.data(), nullptr, nullptr); });
     if (start_s) for (int b = 0; b < B; b++) start_s[b] = s0[b];
     // reachability caps
     const int stride = ((P.num_s_max + 63) / 64 + 7) & ~7;

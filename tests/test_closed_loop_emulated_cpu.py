@@ -118,3 +118,25 @@ def test_fused_env_step_equals_the_tensor_version(settings, auto_reset, randomiz
     assert seen["timeout"] > 0 and seen["clipped"] > 0 and seen["spawned"] > 0
     if auto_reset:
         assert seen["crashed"] > 0 or seen["timeout"] > 12
+
+
+def test_sync_free_takeover_gives_the_same_decisions(settings):
+    """Settings.SYNC_FREE_TAKEOVER: the vetoed episodes go to the planner through the masked entry points (no nonzero(), no
+    gather, no host sync).  Speeds and take-over masks of the combined controller must not change."""
+    import torch
+    from rl_mpc_lanemerging_b200 import ddpg, synthetic
+    from rl_mpc_lanemerging_b200.prediction import BatchedState
+    settings.TEST_ST_STRICTLY_BETTER = False
+    S = synthetic.make_states(32, "moderate", seed=17, kind="mixed")
+    runs = {}
+    for flag in (False, True):
+        settings.SYNC_FREE_TAKEOVER = flag
+        agent = ddpg.DDPGAgent(device="cpu", seed=3)
+        out = []
+        for rep in range(2):                                     # twice: the second call re-uses the scratch tensors
+            speed, take = agent.do_combined_control(BatchedState.from_numpy(S, "cpu"))
+            out += [speed.clone(), take.clone()]
+        runs[flag] = out
+        assert 0 < int(out[1].sum()) < 32                        # some episodes were taken over, some not
+    for a, b in zip(runs[False], runs[True]):
+        assert torch.equal(a, b)

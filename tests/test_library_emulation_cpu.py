@@ -218,3 +218,43 @@ def test_error_conventions_and_set_params():
     lone["n_cars"][0] = 0                                       # an empty road
     assert eng.plan(lone)["reached_t"][0] == 17
     eng.close()
+
+
+@pytest.mark.parametrize("mode", [_lib.MODE_FAST, _lib.MODE_EXACT])
+def test_masked_plan_and_fit_touch_only_the_masked_episodes(mode):
+    """mpc_plan_masked / mpc_finer_fit_masked: the masked rows equal the plain calls, every other row keeps its contents;
+    empty and full masks; 1100 episodes so that the one-block compaction loops."""
+    _op, p = _params(17)
+    eng = EA.EmuEngine(p, max_batch=64)
+    S = synthetic.make_states(40, "moderate", seed=19, kind="mixed")
+    ref = eng.plan(S, mode=mode)
+    fine_ref, n_ref, speed_ref, _ = eng.finer_fit(ref["s_seq"], ref["reached_t"], S["ego"])
+    rng = np.random.default_rng(3)
+    for mask in (rng.random(40) < 0.3, np.zeros(40, bool), np.ones(40, bool)):
+        m = mask.astype(np.uint8)
+        out = eng._out(40)
+        for k in ("idx", "s_seq", "cost", "reached_t", "crash", "min_dist"):
+            out[k][...] = 77
+        eng.plan_masked(S, m, out, mode=mode)
+        for k in ("idx", "s_seq", "cost", "reached_t", "crash", "min_dist"):
+            assert np.array_equal(out[k][mask], ref[k][mask]), k
+            assert np.all(out[k][~mask] == 77), k
+        fine, n_fine, speed = np.full_like(fine_ref, -5.0), np.full_like(n_ref, -5), np.full_like(speed_ref, -5.0)
+        sseq, reached = np.where(mask[:, None], ref["s_seq"], 1e9), np.where(mask, ref["reached_t"], 999).astype(np.int32)   # junk in unmasked rows
+        eng.finer_fit_masked(m, sseq, reached, S["ego"], fine, n_fine, speed)
+        assert np.array_equal(speed[mask], speed_ref[mask]) and np.array_equal(n_fine[mask], n_ref[mask])
+        for b in np.flatnonzero(mask):
+            assert np.array_equal(fine[b, :n_ref[b]], fine_ref[b, :n_ref[b]])
+        assert np.all(speed[~mask] == -5.0) and np.all(n_fine[~mask] == -5) and np.all(fine[~mask] == -5.0)
+    eng.close()
+    if mode == _lib.MODE_FAST:                                   # the compaction itself, across several 1024-thread rounds
+        big = EA.EmuEngine(p, max_batch=1100)
+        Sb = synthetic.make_states(1100, "moderate", seed=2, kind="mixed")
+        mask = np.zeros(1100, np.uint8); mask[[3, 500, 1023, 1024, 1099]] = 1
+        out = big._out(1100)
+        out["reached_t"][...] = -9
+        big.plan_masked(Sb, mask, out)
+        assert set(np.flatnonzero(out["reached_t"] != -9)) == {3, 500, 1023, 1024, 1099}
+        sub = {k: np.ascontiguousarray(v[[3, 500, 1023, 1024, 1099]]) for k, v in Sb.items()}
+        assert np.array_equal(out["cost"][[3, 500, 1023, 1024, 1099]], big.plan(sub)["cost"])
+        big.close()
