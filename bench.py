@@ -500,6 +500,8 @@ def run_hint_leg(args):
     section("closed_loop_default", lambda: closed_loop({}))
     section("closed_loop_fused_env_step", lambda: closed_loop({"FUSED_ENV_STEP": True}))
     section("closed_loop_fused_env_step_and_cost_hints", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True}))
+    section("closed_loop_sync_free_takeover", lambda: closed_loop({"SYNC_FREE_TAKEOVER": True}))
+    section("closed_loop_all_three", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True, "SYNC_FREE_TAKEOVER": True}))
     print(json.dumps(res), file=RESULT_OUT, flush=True)
 
 
@@ -510,7 +512,7 @@ def hint_leg_subprocess(args):
            "--steps", str(min(args.steps, 10)), "--traffic", args.traffic, "--seed", str(args.seed),
            "--env-envs", str(args.env_envs), "--env-ticks", str(max(args.env_ticks, 10))]
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, cwd=ROOT)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=360, cwd=ROOT)
         lines = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": f"exit {r.returncode}: " + r.stderr.decode(errors="replace")[-400:]}
