@@ -458,6 +458,8 @@ def run_hint_leg(args):
             p2.close()
 
     section("probed_1.1_probe_12x2", lambda: other_probe(12, 2))
+    # the probe plan on a second stream, next to the real predictor (MPC_PROBE_OVERLAP)
+    section("probed_1.1_probe_overlapped", lambda: other_engine("MPC_PROBE_OVERLAP", "1", 1.1))
     section("low_hint_0.5", lambda: {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=ref["cost"] * 0.5))})
     # ---- K2, the st_cy drop-in itself: the DP kernel fed by DENSE grids in HBM (mpc_solve_dense), i.e. the solver boundary of the
     #      reference (st_cy.pyx:315) with the grid read from memory instead of being evaluated from the layer descriptors ----

@@ -95,6 +95,8 @@ struct mpc_handle {
     unsigned short *capb; int cap_stride;      // reachability caps of hinted solves (allocated on first use)
     int32_t *mask_list; int *mask_count;        // masked calls: compacted episode list + its length (allocated on first use)
     int use_heur;                                // MPC_FAST_HEUR=0 disables the heuristic pruning of hinted solves (dev A/B)
+    int probe_overlap;                           // MPC_PROBE_OVERLAP=1: mpc_plan_probed runs the probe plan on a second stream, next to the real predictor
+    cudaStream_t aux; cudaEvent_t ev_fork, ev_join;
     double hint_retry;                           // middle rung of the hinted ladder (MPC_HINT_RETRY, default 1.36 = 1.5 / 1.1; <= 1 disables)
     int64_t kernels_launched;
     // optional per-kernel timing (bench.py roofline): events around [predict | DP | fallback DP]
@@ -161,6 +163,7 @@ static int configure(mpc_handle *h) {
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
     h->use_bound = env_int("MPC_FAST_BOUND", 0, 1, 1) && P.bound_fx != 0;
     { const char *e = getenv("MPC_FAST_HEUR"); h->use_heur = !(e && e[0] == '0'); }
+    { const char *e = getenv("MPC_PROBE_OVERLAP"); h->probe_overlap = (e && e[0] == '1'); }
     { const char *e = getenv("MPC_HINT_RETRY"); h->hint_retry = e ? atof(e) : 1.36; if (!(h->hint_retry >= 0.0 && h->hint_retry < 100.0)) h->hint_retry = 1.36; }
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     return MPC_OK;
@@ -224,6 +227,7 @@ extern "C" int mpc_destroy(mpc_handle *h) {
     if (!h) return MPC_OK;
     cudaSetDevice(h->device);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->aux) { cudaStreamDestroy(h->aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     free_scratch(h);
     free(h);
     return MPC_OK;
@@ -410,7 +414,7 @@ static int plan_impl(mpc_handle *h, int B, const double *d_ego, const double *d_
                      const int32_t *d_n_cars, int mode, const double *hint_cost, const int32_t *hint_reached, int hint_full_t,
                      double hint_scale, int32_t *d_idx, double *d_s_seq, double *d_cost, int32_t *d_reached_t,
                      uint8_t *d_crash, double *d_min_dist, double *d_start_s, cudaStream_t st, const char *who,
-                     const uint8_t *d_mask = nullptr) {
+                     const uint8_t *d_mask = nullptr, cudaEvent_t wait_before_solve = nullptr) {
     int rc = check_batch(h, B); if (rc) return rc;
     if (B == 0) return MPC_OK;
     if (!d_ego || !d_cars_x || !d_cars_v || !d_n_cars) return mpc_set_error(MPC_E_INVALID, who);
@@ -439,6 +443,7 @@ static int plan_impl(mpc_handle *h, int B, const double *d_ego, const double *d_
         h->kernels_launched++;
         io.capb = h->capb; io.cap_stride = h->cap_stride;
     }
+    if (wait_before_solve) MPC_CUDA_OK(cudaStreamWaitEvent(st, wait_before_solve, 0));     // (the hints come from another stream)
     return run_solve(h, B, mode, false, io, nullptr, nullptr, 0, 0, st);
 }
 
@@ -489,15 +494,31 @@ extern "C" int mpc_plan_probed(mpc_handle *h, mpc_handle *probe, double margin, 
     if (probe->device != h->device) return mpc_set_error(MPC_E_INVALID, "mpc_plan_probed: the handles live on different devices");
     if (B > probe->max_batch) return mpc_set_error(MPC_E_CAPACITY, "mpc_plan_probed: batch larger than the probe handle's max_batch");
     if (!(margin > 0.0) || probe->P.num_t < 2) return mpc_set_error(MPC_E_INVALID, "mpc_plan_probed: bad margin / probe horizon");
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc = plan_impl(probe, B, d_ego, d_cars_x, d_cars_v, d_n_cars, MPC_MODE_FAST, nullptr, nullptr, 0, 1.0, nullptr, nullptr,
-                       probe->st_cost, probe->st_reached, nullptr, nullptr, nullptr, st, "mpc_plan_probed: null pointer");
+    cudaStream_t st = (cudaStream_t)stream, pst = st;
+    cudaEvent_t join = nullptr;
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (h->probe_overlap) {
+        // the probe plan and the real predictor (+ reachability caps) are independent: run the probe on a second stream and join
+        // before the real DP reads its costs.  The fork event also orders this probe after the previous call's DP (same scratch).
+        if (!h->aux) {
+            MPC_CUDA_OK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+            MPC_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            MPC_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        MPC_CUDA_OK(cudaEventRecord(h->ev_fork, st));
+        MPC_CUDA_OK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+        pst = h->aux; join = h->ev_join;
+    }
+    rc = plan_impl(probe, B, d_ego, d_cars_x, d_cars_v, d_n_cars, MPC_MODE_FAST, nullptr, nullptr, 0, 1.0, nullptr, nullptr,
+                   probe->st_cost, probe->st_reached, nullptr, nullptr, nullptr, pst, "mpc_plan_probed: null pointer");
     if (rc) return rc;
+    if (join) MPC_CUDA_OK(cudaEventRecord(join, pst));
     const int64_t probe_launches = probe->kernels_launched;
     // every step costs about the same in both grids (the cost is a sum over steps of the same rates): scale by the step counts
     const double scale = margin * (double)(h->P.num_t - 1) / (double)(probe->P.num_t - 1);
     rc = plan_impl(h, B, d_ego, d_cars_x, d_cars_v, d_n_cars, MPC_MODE_FAST, probe->st_cost, probe->st_reached, probe->P.num_t - 1,
-                   scale, d_idx, d_s_seq, d_cost, d_reached_t, d_crash, d_min_dist, d_start_s, st, "mpc_plan_probed: null pointer");
+                   scale, d_idx, d_s_seq, d_cost, d_reached_t, d_crash, d_min_dist, d_start_s, st, "mpc_plan_probed: null pointer",
+                   nullptr, join);
     if (rc == MPC_OK) h->kernels_launched += probe_launches;
     return rc;
 }

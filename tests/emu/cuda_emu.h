@@ -73,6 +73,11 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) {
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)2; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (void *)1; return 0; }
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return 0; }
 // resident blocks per SM as the shared-memory budget of a B200 SM allows (228 KB, 1 KB reserved per block, ~11 KB static)
 template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int threads, size_t smem) {
