@@ -157,7 +157,7 @@ def test_emulated_hinted_plan_is_identical_and_expands_what_the_model_says(emu, 
         assert np.array_equal(got[k], plain[k]), k
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("seed", [1, 2])
 def test_result_does_not_depend_on_thread_interleaving(emu, seed):
     """With random preemption at every shared-memory access the threads of a block interleave inside a phase: CAS operations
     lose, the retry / redo paths of the min-combine run, cells are finalised while neighbours still push.  The answer and the

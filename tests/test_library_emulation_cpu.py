@@ -43,7 +43,7 @@ def test_plan_exact_and_fast_against_the_oracle():
     eng.close()
 
 
-@pytest.mark.parametrize("H,B,mult", [(50, 6, (20, 3)), (17, 10, (8, 2))])
+@pytest.mark.parametrize("H,B,mult", [(50, 4, (20, 3)), (17, 8, (8, 2))])
 def test_probed_and_hinted_plans_equal_the_plain_plan(H, B, mult):
     _op, p = _params(H)
     eng = EA.EmuEngine(p, max_batch=B)
