@@ -169,10 +169,11 @@ __device__ __forceinline__ void int_window(const DevParams &P, const SGrid &g, c
 // atomics on shared memory, several times the cost of LDS / ATOMS.CAS (seen in the SASS of the v8 kernel).
 #ifdef MPC_HOST_EMU     // tests/emu: the same accessors on the emulated shared window (plain memory operations)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return emu::to_shared(p); }
-__device__ __forceinline__ unsigned long long lds_u64(unsigned a) { emu::preempt_point(); return *emu::from_shared<unsigned long long>(a); }
+__device__ __forceinline__ unsigned long long lds_u64(unsigned a) { emu::preempt_point(); emu::S().cell_reads++; return *emu::from_shared<unsigned long long>(a); }
 __device__ __forceinline__ void sts_u64(unsigned a, unsigned long long v) { emu::preempt_point(); *emu::from_shared<unsigned long long>(a) = v; }
 __device__ __forceinline__ unsigned long long atoms_cas_u64(unsigned a, unsigned long long cmp, unsigned long long val) {
     emu::preempt_point();
+    emu::S().cas_issued++;
     unsigned long long *p = emu::from_shared<unsigned long long>(a), old = *p; if (old == cmp) *p = val; else emu::S().cas_lost++; return old;
 }
 __device__ __forceinline__ unsigned long long lds_u64_nc(unsigned a) { return lds_u64(a); }

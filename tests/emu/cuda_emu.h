@@ -102,6 +102,7 @@ struct State {
     unsigned char *dyn_smem = nullptr;
     long progress = 0;                          // barrier releases + finished fibers (deadlock watchdog)
     long long nodes = 0;                        // nodes finalised by the fast kernel (MPC_EMU_COUNT_NODE)
+    long long cas_issued = 0, cell_reads = 0;   // shared-memory traffic of the fast kernel's label ring (accessor counters)
     long cas_lost = 0;                          // compare-and-swap operations that found another value (only under preemption)
 };
 inline State &S() { static State s; return s; }

@@ -25,6 +25,7 @@ extern "C" long long emu_node_count() { return emu::S().nodes; }   // nodes fina
 extern "C" const char *emu_last_error() { return g_err; }
 extern "C" void emu_set_preempt(unsigned long long seed) { emu::set_preempt(seed); }
 extern "C" long emu_cas_lost() { return emu::S().cas_lost; }
+extern "C" void emu_ring_traffic(long long *out2) { out2[0] = emu::S().cell_reads; out2[1] = emu::S().cas_issued; }
 
 // One fused gap-evaluation of B states on the emulated device.
 //   threads: block size of the fast kernel (multiple of 32, <= 1024); ring: label ring capacity in cells (0 = full row, no wrap)
