@@ -218,3 +218,24 @@ def test_emulated_predict_step_without_ego_matches_oracle(emu, traffic, kind, dt
         es = O.get_ego_s(st.ego_x, st.ego_y)
         branches.add("stay" if (es < 8 or n == 0) else ("lead" if st.x[0] < st.ego_x else "follow"))
     assert branches == {"stay", "lead", "follow"}
+
+
+@pytest.mark.parametrize("over", [dict(desired_speed=20.0), dict(start_uncertainty=1.0, uncertainty_per_second=0.5),
+                                  dict(max_speed=27.3), dict(min_allowed_distance=3.0, v_weight=0.1, d_weight=50.0)])
+def test_hinted_kernel_over_other_settings(emu, over):
+    """Settings away from the published ones (cheapest speed below MAX_SPEED, growing uncertainty, a non-integer speed clamp,
+    other weights / safety distance): the un-hinted kernel still equals the C model, hints still change nothing."""
+    op = O.horizon_params(17, **over)
+    S = synthetic.make_states(6, "moderate", seed=41, kind="mixed")
+    plain = _plan(emu, op, S, 192)
+    for b in range(6):
+        st = _state(S, b)
+        ob, di, sv = O.build_grid(op, st)
+        ref = O.solve_fast_model(op, ob, di, sv, op.t_disc, st.ego_v, st.ego_a)
+        assert plain["reached_t"][b] == ref["reached_t"] and np.array_equal(plain["idx"][b], ref["idx"]) and plain["cost"][b] == ref["cost"]
+    for scale in (1.1, 0.8, 50.0):
+        got = _plan(emu, op, S, 192, hint=plain["cost"].copy(), scale=scale)
+        for k in ("idx", "cost", "reached_t", "crash", "min_dist"):
+            assert np.array_equal(got[k], plain[k]), (scale, k)
+        if scale == 1.1:
+            assert got["nodes"] < plain["nodes"]
