@@ -499,7 +499,23 @@ def run_hint_leg(args):
     eng.close()
     if probe is not None:
         probe.close()
+    # the reference's own grid (H=17, 18 x 3001): plain vs probed on the same batch
+    def h17():
+        e17 = MpcEngine(make_params(17), device=0, max_batch=B)
+        p17 = e17.make_probe(20, 3)
+        try:
+            o17 = e17.plan(*a)
+            r17 = {k: v.clone() for k, v in o17.items()}
+            ok = bool(all(torch.equal(e17.plan_probed(p17, *a, margin=1.1)[k], r17[k]) for k in r17))
+            return {"plain_ms": timed(lambda: e17.plan(*a, out=o17)), "probed_1.1_ms": timed(lambda: e17.plan_probed(p17, *a, margin=1.1, out=o17)),
+                    "oracle_hint_1.02_ms": timed(lambda: e17.plan_hinted(*a, hint_cost=r17["cost"], hint_scale=1.02, out=o17)),
+                    "identical_outputs": ok, "probe_grid": [p17.num_t, p17.num_s_max - 1]}
+        finally:
+            p17.close(); e17.close()
+
+    section("horizon_17", h17)
     section("closed_loop_default", lambda: closed_loop({}))
+    section("closed_loop_cost_hints", lambda: closed_loop({"PLAN_COST_HINTS": True}))
     section("closed_loop_fused_env_step", lambda: closed_loop({"FUSED_ENV_STEP": True}))
     section("closed_loop_fused_env_step_and_cost_hints", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True}))
     section("closed_loop_sync_free_takeover", lambda: closed_loop({"SYNC_FREE_TAKEOVER": True}))
@@ -514,7 +530,7 @@ def hint_leg_subprocess(args):
            "--steps", str(min(args.steps, 10)), "--traffic", args.traffic, "--seed", str(args.seed),
            "--env-envs", str(args.env_envs), "--env-ticks", str(max(args.env_ticks, 10))]
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=360, cwd=ROOT)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=420, cwd=ROOT)
         lines = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": f"exit {r.returncode}: " + r.stderr.decode(errors="replace")[-400:]}
