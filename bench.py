@@ -520,7 +520,63 @@ def run_hint_leg(args):
     section("closed_loop_fused_env_step_and_cost_hints", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True}))
     section("closed_loop_sync_free_takeover", lambda: closed_loop({"SYNC_FREE_TAKEOVER": True}))
     section("closed_loop_all_three", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True, "SYNC_FREE_TAKEOVER": True}))
+    # ---- last (a failed capture can leave the context unusable): the whole tick -- no host sync left with the three switches on --
+    #      captured ONCE in a CUDA graph and replayed, i.e. one launch per tick instead of ~100 ----
+    def closed_loop_graph():
+        from rl_mpc_lanemerging_b200 import ddpg, merge_gym, st
+        from rl_mpc_lanemerging_b200.config import Settings
+        Settings.reset()
+        Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL = 20, 11.0, 1.2
+        Settings.TEST_ST_STRICTLY_BETTER, Settings.CUDA_DEVICE, Settings.ALT_J_WEIGHT = False, 0, 0.1
+        Settings.FUSED_ENV_STEP = Settings.PLAN_COST_HINTS = Settings.SYNC_FREE_TAKEOVER = True
+        st.refresh_engine()
+        try:
+            env = merge_gym.MergeEnv(args.env_envs, seed=args.seed)
+            agent = ddpg.DDPGAgent(device="cuda:0", seed=args.seed)
+            env.reset()
+            agent.takeover_history = _Sink()
+
+            def tick():
+                speed, _take = agent.do_combined_control(env.state)
+                jerk = ((speed - env.state.ego[:, 2]) / Settings.TICK_LENGTH - env.state.ego[:, 3]) / Settings.TICK_LENGTH
+                _o, _r, done, _i = env.step(jerk)
+                agent.reset_time(done)
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(30):
+                    tick()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            if hasattr(g, "register_generator_state"):
+                g.register_generator_state(env.gen)
+            with torch.cuda.graph(g):
+                tick()
+            t_before = env.ticks.clone()
+            n = max(args.env_ticks, 10)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(n):
+                g.replay()
+            e1.record(); torch.cuda.synchronize()
+            moved = bool((env.ticks != t_before).any()) and bool(torch.isfinite(env.state.ego).all())
+            return {"env_steps_per_s": args.env_envs * n / (e0.elapsed_time(e1) * 1e-3), "state_advanced_and_finite": moved,
+                    "note": "one graph launch per tick; the random numbers of the environment are drawn inside the graph"}
+        finally:
+            Settings.reset()
+            st.refresh_engine()
+
+    section("closed_loop_all_three_cuda_graph", closed_loop_graph)
     print(json.dumps(res), file=RESULT_OUT, flush=True)
+
+
+class _Sink(list):
+    """takeover_history stand-in that keeps nothing (a captured tick must not accumulate references on the host)."""
+
+    def append(self, _x):
+        pass
 
 
 def hint_leg_subprocess(args):
