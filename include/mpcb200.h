@@ -77,6 +77,12 @@ int mpc_grid_stride(const mpc_handle *h);
 /* counters of the last call on this handle: [0] kernels launched, [1] problems that overflowed
  * the fast kernel's shared-memory window / bucket capacity and were re-solved by the exact kernel */
 int mpc_last_counters(const mpc_handle *h, int64_t *out2);
+/* The 32-bit-key DP kernel that makes the first (bounded) attempt of mpc_plan in MPC_MODE_FAST (csrc/mpc_fast32.cuh):
+ * out6 = {in use (0/1), fraction bits of its fixed-point labels, its cost bound in label units, ring capacity in cells of its
+ * first launch shape, problems of the last call it handed to the 64-bit kernel, problems of the last call its first launch
+ * shape handed on (to its wide-ring shape or the 64-bit kernel)}.  The CPU model of the kernel (oracle/) takes the second
+ * and third entry. */
+int mpc_fast32_info(const mpc_handle *h, int64_t *out6);
 
 /* Optional per-kernel device timing (used by bench.py for the roofline of the dominant kernel):
  * after mpc_set_timing(h,1), mpc_last_kernel_ms returns {traffic-predictor ms, DP-kernel ms,

@@ -183,6 +183,34 @@ def solve_fast_model_ex(p, obstacles, distances, s_values, delta_t, v0, a0, prun
     return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value, nodes=int(counts[0]), pushes=int(counts[1]))
 
 
+def solve_fast_model_q(p, obstacles, distances, s_values, delta_t, v0, a0, frac_bits, key_shift, prune_fx=0):
+    """Model of the 32-bit-key fast kernel: 2^-frac_bits labels, min-combine on (label >> key_shift, larger v')."""
+    nt, ns = obstacles.shape
+    idx = np.zeros(nt, np.int32); seq = np.zeros(nt, np.float64); cost = C.c_double(); counts = (C.c_int64 * 2)()
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.uint8)
+    distances = np.ascontiguousarray(distances, dtype=np.float64)
+    s_values = np.ascontiguousarray(s_values, dtype=np.float64)
+    r = lib().orc_solve_fast_model_q(C.byref(p), nt, ns, obstacles.ctypes.data_as(C.c_void_p), _dp(distances), _dp(s_values),
+                                     C.c_double(delta_t), C.c_double(v0), C.c_double(a0), C.c_int(frac_bits), C.c_int(key_shift),
+                                     C.c_uint64(int(prune_fx)), _ip(idx), _dp(seq), C.byref(cost), counts)
+    return dict(reached_t=r, idx=idx, s_seq=seq, cost=cost.value, nodes=int(counts[0]), pushes=int(counts[1]))
+
+
+def solve_fast_ladder(p, obstacles, distances, s_values, delta_t, v0, a0, frac_bits, bound_fx):
+    """The fast mode of mpc_plan as the device runs it (run_solve, mpc_api.cu): the 32-bit-key kernel's bounded attempt
+    (2^-frac_bits labels under bound_fx; both from mpc_fast32_info / derive_params); when that does not reach the horizon,
+    the 64-bit kernel's unbounded pass (2^-18 labels).  Returns the model's answer plus `stage` (32 or 64)."""
+    H = obstacles.shape[0] - 1
+    if frac_bits:
+        r = solve_fast_model_q(p, obstacles, distances, s_values, delta_t, v0, a0, frac_bits, 0, bound_fx)
+        if r["reached_t"] == H:
+            r["stage"] = 32
+            return r
+    r = solve_fast_model(p, obstacles, distances, s_values, delta_t, v0, a0)
+    r["stage"] = 64
+    return r
+
+
 def path_cost(p, idx, s_values, distances, delta_t, v0, a0):
     idx = np.ascontiguousarray(idx, np.int32)
     distances = np.ascontiguousarray(distances, np.float64)

@@ -380,18 +380,26 @@ int orc_solve_layered(const orc_params *p, int num_t, int num_s, const uint8_t *
  * label_bits: 0 = the kernel's arithmetic; 32 = (rejected design) fp32 labels, kept to document why. */
 #include <float.h>
 #define FXONE 262144.0
-static uint64_t fx(double x) { return (uint64_t)llrint(x * FXONE); }
 
+
+static int64_t g_last_collisions = 0; /* pushes that met a candidate of the same (label >> coll_shift) bucket in their cell (32-bit-key kernel: overflow-list entries) */
+static int g_coll_shift = 8;
+int64_t orc_last_collisions(void) { return g_last_collisions; }
+void orc_set_coll_shift(int s) { g_coll_shift = s; }
 static int g_last_max_span = 0;      /* widest layer span (cells) the kernel's ring would have had to hold in the last model run */
 int orc_last_max_span(void) { return g_last_max_span; }
 
 static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
                             const double *distances, const double *s_values, double delta_t,
                             double v0, double a0, int f32_labels, uint64_t prune_fx, const uint64_t *hfx, uint64_t *fmin_out,
-                            int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
+                            int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts, int frac_bits, int key_shift) {
+    /* frac_bits: fixed-point precision of the labels (18 = the 64-bit kernel); key_shift: low label bits that do not take part in
+     * the min-combine (candidates whose labels agree above them are ordered by v' alone) -- the 32-bit-key kernel, mpc_fast32.cu */
+    const double FX1 = ldexp(1.0, frac_bits);
+#define FXQ(x) ((uint64_t)llrint((x) * FX1))
     /* prune_fx != 0: nodes whose label exceeds it are dropped (the fast kernel's cost bound, mpc_fast.cu);
      * counts[0..1] = nodes expanded, pushes */
-    int64_t n_nodes = 0, n_push = 0; int max_span_ = 0;
+    int64_t n_nodes = 0, n_push = 0, n_coll = 0; int max_span_ = 0;
     double dsn = p->s_disc, dt = p->t_disc;
     double jlo = p->j_min * dt * dt * dt / dsn, jhi = p->j_max * dt * dt * dt / dsn;
     double alo_r = p->a_min * dt * dt / dsn, ahi_r = p->a_max * dt * dt / dsn, vmax_r = p->max_speed * dt / dsn;
@@ -399,10 +407,10 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
     int vmax_is_int = fabs(vmax_r - nearbyint(vmax_r)) < 1e-9;
     int vmax_c = vmax_is_int ? (int)nearbyint(vmax_r) : (int)floor(vmax_r);
     uint32_t vtab[256], atab[32], jtab[16];
-    for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * dsn / dt - p->desired_speed) * (v * dsn / dt - p->desired_speed); vtab[v] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
-    for (int i = 0; i < 32; i++) { double acc = (i - 16) * dsn / (dt * dt), x = p->a_weight * acc * acc; atab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
-    for (int i = 0; i < 16; i++) { double jk = (i - 8) * dsn / (dt * dt * dt), x = p->j_weight * jk * jk; jtab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FXONE); }
-    const float kwf = (float)(p->d_weight * FXONE);
+    for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * dsn / dt - p->desired_speed) * (v * dsn / dt - p->desired_speed); vtab[v] = (uint32_t)llrint(fmin(x, 16000.0) * FX1); }
+    for (int i = 0; i < 32; i++) { double acc = (i - 16) * dsn / (dt * dt), x = p->a_weight * acc * acc; atab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FX1); }
+    for (int i = 0; i < 16; i++) { double jk = (i - 8) * dsn / (dt * dt * dt), x = p->j_weight * jk * jk; jtab[i] = (uint32_t)llrint(fmin(x, 16000.0) * FX1); }
+    const float kwf = (float)(p->d_weight * FX1);
     float cvf = (float)(p->v_weight * (dsn / dt) * (dsn / dt)), caf = (float)(p->a_weight * (dsn / (dt * dt)) * (dsn / (dt * dt)));
     float cjf = (float)(p->j_weight * (dsn / (dt * dt * dt)) * (dsn / (dt * dt * dt))), vdes = (float)(p->desired_speed * dt / dsn);
     double delta_s = s_values[1] - s_values[0], start_s = s_values[0];
@@ -420,10 +428,10 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
     for (int k = imin; k < imax && k < num_s; k++) {
         if (obstacles[(size_t)num_s + k]) continue;
         double c = cost_with_jerk(p, s_values[k], start_s, est_prev, est_second, delta_t, distances[(size_t)num_s + k]);
-        lab[1][k] = fx(c); labf[1][k] = (float)c; vv[1][k] = k; aa[1][k] = 0; has[1][k] = 1; previous[(size_t)num_s + k] = 0;
+        lab[1][k] = FXQ(c); labf[1][k] = (float)c; vv[1][k] = k; aa[1][k] = 0; has[1][k] = 1; previous[(size_t)num_s + k] = 0;
         if (k < lo) lo = k; if (k > hi) hi = k;
     }
-#define BETTER(nl, nlf, nv, kk, buf) (!has[buf][kk] || (f32_labels ? ((nlf) < labf[buf][kk]) : ((nl) < lab[buf][kk] || ((nl) == lab[buf][kk] && (nv) > vv[buf][kk]))))
+#define BETTER(nl, nlf, nv, kk, buf) (!has[buf][kk] || (f32_labels ? ((nlf) < labf[buf][kk]) : (((nl) >> key_shift) < (lab[buf][kk] >> key_shift) || (((nl) >> key_shift) == (lab[buf][kk] >> key_shift) && (nv) > vv[buf][kk]))))
     if (hi >= 0) {
         best_t = 1; best_k = -1;
         for (int k = lo; k <= hi; k++) if (has[1][k]) {
@@ -439,7 +447,7 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
                 double sn = s_values[kk];
                 double v = (sn - s) / delta_t, a = (sn - 2 * s + start_s) / pow(delta_t, 2.0), j = (sn - 3 * s + 3 * start_s - est_prev) / pow(delta_t, 3.0);
                 double kin = p->v_weight * ((v - p->desired_speed) * (v - p->desired_speed)) + p->a_weight * (a * a) + p->j_weight * (j * j);
-                uint64_t tot = lab[1][k1] + fx(kin); float totf = labf[1][k1] + (float)kin;
+                uint64_t tot = lab[1][k1] + FXQ(kin); float totf = labf[1][k1] + (float)kin;
                 int vn = kk - k1;
                 if (prune_fx && tot > prune_fx) continue;
                 n_push++;
@@ -460,7 +468,7 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
                 double d = distances[id];
                 float df = (float)d;
                 /* zone: fp64 as the reference; elsewhere d_w/d in fp32: rint(kw * (1.0f / (float)d)), the kernel's fx_inv_penalty */
-                uint64_t penfx = (d < p->min_allowed_distance) ? fx(p->d_weight * (1000000.0 / (d > 1.0 ? d : 1.0)))
+                uint64_t penfx = (d < p->min_allowed_distance) ? FXQ(p->d_weight * (1000000.0 / (d > 1.0 ? d : 1.0)))
                                                                : (uint64_t)lrintf(kwf * (1.0f / df));
                 uint64_t label = lab[cur][k] + penfx;
                 float penf = (d < p->min_allowed_distance) ? 1000000.0f / fmaxf(df, 1.0f) : 1.0f / df;
@@ -485,6 +493,7 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
                     uint64_t tot = label + vtab[vn] + atab[an + 16] + jtab[jn + 8];
                     if (prune_fx && tot > prune_fx) continue;
                     n_push++;
+                    if (has[nxt][kk] && (tot >> g_coll_shift) == (lab[nxt][kk] >> g_coll_shift)) n_coll++;
                     float fv = (float)vn - vdes, fa = (float)an, fj = (float)jn;
                     float totf = labelf + fmaf(cvf * fv, fv, fmaf(caf * fa, fa, cjf * fj * fj));
                     if (BETTER(tot, totf, vn, kk, nxt)) { lab[nxt][kk] = tot; labf[nxt][kk] = totf; vv[nxt][kk] = vn; aa[nxt][kk] = an; has[nxt][kk] = 1; }
@@ -498,9 +507,10 @@ static int fast_model_impl(const orc_params *p, int num_t, int num_s, const uint
         }
     }
 #undef BETTER
-    if (cost_out) *cost_out = f32_labels ? (double)best_labf : (double)best_lab * (1.0 / FXONE);
+#undef FXQ
+    if (cost_out) *cost_out = f32_labels ? (double)best_labf : (double)best_lab * (1.0 / FX1);
     if (counts) { counts[0] = n_nodes; counts[1] = n_push; }
-    g_last_max_span = max_span_;
+    g_last_max_span = max_span_; g_last_collisions = n_coll;
     int r = backtrack(num_t, num_s, previous, s_values, best_t, best_k, idx_out, s_seq_out);
     for (int b = 0; b < 2; b++) { free(lab[b]); free(labf[b]); free(vv[b]); free(aa[b]); free(has[b]); }
     free(previous);
@@ -512,7 +522,7 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                             double v0, double a0, int f32_labels, uint64_t prune_fx,
                             int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
     return fast_model_impl(p, num_t, num_s, obstacles, distances, s_values, delta_t, v0, a0, f32_labels, prune_fx, NULL, NULL,
-                           idx_out, s_seq_out, cost_out, counts);
+                           idx_out, s_seq_out, cost_out, counts, 18, 0);
 }
 
 int orc_solve_fast_model_h(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
@@ -521,7 +531,16 @@ int orc_solve_fast_model_h(const orc_params *p, int num_t, int num_s, const uint
                            int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
     if (fmin_out) for (int t = 0; t < num_t; t++) fmin_out[t] = UINT64_MAX;
     return fast_model_impl(p, num_t, num_s, obstacles, distances, s_values, delta_t, v0, a0, 0, prune_fx, hfx, fmin_out,
-                           idx_out, s_seq_out, cost_out, counts);
+                           idx_out, s_seq_out, cost_out, counts, 18, 0);
+}
+
+/* the 32-bit-key kernel's arithmetic: labels in 2^-frac_bits fixed point, min-combine on (label >> key_shift, larger v') */
+int orc_solve_fast_model_q(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+                           const double *distances, const double *s_values, double delta_t,
+                           double v0, double a0, int frac_bits, int key_shift, uint64_t prune_fx,
+                           int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts) {
+    return fast_model_impl(p, num_t, num_s, obstacles, distances, s_values, delta_t, v0, a0, 0, prune_fx, NULL, NULL,
+                           idx_out, s_seq_out, cost_out, counts, frac_bits, key_shift);
 }
 
 int orc_solve_fast_model(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,

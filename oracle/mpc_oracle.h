@@ -90,6 +90,13 @@ int orc_solve_fast_model_ex(const orc_params *p, int num_t, int num_s, const uin
                             double v0, double a0, int f32_labels, uint64_t prune_fx,
                             int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts);
 
+/* The 32-bit-key kernel's arithmetic (mpc_fast32.cu): labels in 2^-frac_bits fixed point; the min-combine orders candidates by
+ * (label >> key_shift, larger v'), i.e. the low key_shift bits of a label are carried exactly but do not take part in comparisons. */
+int orc_solve_fast_model_q(const orc_params *p, int num_t, int num_s, const uint8_t *obstacles,
+                           const double *distances, const double *s_values, double delta_t,
+                           double v0, double a0, int frac_bits, int key_shift, uint64_t prune_fx,
+                           int *idx_out, double *s_seq_out, double *cost_out, int64_t *counts);
+
 /* Same model with a per-cell heuristic table hfx[num_t*num_s] (label units): a node of layer >= 2 is dropped when
  * label + hfx[cell] > prune_fx.  Checks the exactness of the reachability heuristic (oracle/bound_model.py).
  * fmin_out (optional, num_t entries): smallest label + h among the surviving nodes of each layer. */

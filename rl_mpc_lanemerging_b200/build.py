@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpcb200.so")
 SOURCES = ["mpc_api.cu", "mpc_predict.cu", "mpc_solve.cu", "mpc_fast.cu", "mpc_qp.cu", "mpc_reach.cu"]
-HEADERS = ["mpc_common.cuh", "mpc_solve_common.cuh", "mpc_derive.h", os.path.join("..", "..", "include", "mpcb200.h")]
+HEADERS = ["mpc_common.cuh", "mpc_solve_common.cuh", "mpc_derive.h", "mpc_fast32.cuh", os.path.join("..", "..", "include", "mpcb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false",            # fp64 parity paths must not contract a*b+c; fused ops are written as fmaf()
               "-Xcompiler", "-fPIC", "-shared"]

@@ -11,6 +11,7 @@ import math
 import torch
 
 from .config import Settings
+from .prediction import tdiv
 
 merge_point = (-50.9, 1.72)
 merge_point2 = (1.5, -1.5)
@@ -185,7 +186,7 @@ def evaluate_control(control_function, num_episodes=1000, state_function=None, c
         out = control_function(env.state)
         speed, takeover = out if isinstance(out, tuple) else (out, None)
         tracker.record(env.state, takeover)
-        jerk = ((speed - env.state.ego[:, 2]) / tick - env.state.ego[:, 3]) / tick
+        jerk = tdiv(tdiv(speed - env.state.ego[:, 2], tick) - env.state.ego[:, 3], tick)
         _obs, _reward, done, info = env.step(jerk)
         if bool(done.any()):                                   # (host sync: evaluation bookkeeping, not the hot path)
             now = time.perf_counter(); wall = 0.9 * wall + 0.1 * (now - t_prev) if wall else now - t_prev

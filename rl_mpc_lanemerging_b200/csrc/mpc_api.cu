@@ -22,6 +22,8 @@ cudaError_t launch_finer_fit(const DevParams &P, int B, int T, const double *s_s
 int qp_max_fine();
 int exact_occupancy(int threads, size_t smem);
 int fast_occupancy(int threads, size_t smem, int wrap);
+cudaError_t launch_fast32_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
+int fast32_occupancy(int threads, size_t smem, int wrap);
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
                                   const int32_t *n, LayerDesc *desc, double *s0, double *ds, int32_t *ns, cudaStream_t st, const int32_t *subset = nullptr, const int *count = nullptr);
 cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const LayerDesc *desc, const double *s0, const double *ds,
@@ -83,6 +85,8 @@ struct mpc_handle {
     int threads, grid_exact;
     int Wc, wrap_fast, threads_fast, grid_fast; size_t smem_fast;   // fast kernel: ring capacity / launch shape
     size_t smem_fast_big;        // full-row variant used to re-solve ring overflows (0 = does not fit)
+    int Wc32, wrap32, threads32, grid32; size_t smem32;             // 32-bit-key kernel (mpc_fast32.cuh): ring capacity / launch shape; grid32 == 0: not used
+    int Wc32b, wrap32b, threads32b, grid32b; size_t smem32b;        // its second shape (wider ring) for the problems that outgrew the first; grid32b == 0: none
     int use_bound;               // first fast pass runs under DevParams::bound_fx (MPC_FAST_BOUND=0|1 overrides)
     int grid_max;
     // scratch
@@ -162,10 +166,50 @@ static int configure(mpc_handle *h) {
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
     h->use_bound = env_int("MPC_FAST_BOUND", 0, 1, 1) && P.bound_fx != 0;
+    // ---- 32-bit-key kernel: 12 B per cell (three rotating arrays of 32-bit words) behind a ring window ----
+    // Two launch shapes.  A: as many blocks per SM (<= 5) as leave a ring of half the row -- frontier spans at H=50: <= 0.46 of the
+    // row in moderate traffic, but 8-12 % of the problems in low / default / fast traffic need 0.6-0.9 of it.  B: the shape with the
+    // fewest blocks whose ring covers 0.88 of the row; it takes the problems whose frontier outgrew ring A (a device-side list, like
+    // every other hand-over).  MPC_F32_BLOCKS = 32 * blocks per SM and MPC_F32_THREADS override shape A (dev sweeps); MPC_FAST32=0
+    // switches the kernel off (the 64-bit kernel does everything).
+    h->grid32 = 0; h->grid32b = 0;
+    { const char *e = getenv("MPC_FAST32");
+      if (P.fast_ok && P.f32_ok && h->use_bound && !(e && e[0] == '0')) {
+        const size_t static32 = 14336 + 1024;        // static shared of fast32_kernel (13.2 KB) + the per-block reserve
+        auto ring_of = [&](int nb) -> size_t {
+            const size_t per = (h->smem_optin + 1024) / nb;
+            return per > static32 + clamp_bytes ? (per - static32 - clamp_bytes) / 12 : 0;
+        };
+        auto shape = [&](int nb, int threads_override, int *Wc, int *wrap, size_t *smem, int *threads, int *grid) {
+            const size_t cap = ring_of(nb);
+            *grid = 0;
+            *wrap = (size_t)h->W > cap;
+            *Wc = *wrap ? (int)(cap & ~(size_t)7) : h->W;
+            if (*Wc < 1024 || 2 * *Wc < h->W) return;        // prologue scratch row; ring() folds an index once
+            *smem = (size_t)*Wc * 12 + clamp_bytes;
+            const int bps = (int)(h->smem_optin / (*smem + static32 - 1024));
+            *threads = threads_override ? threads_override : (bps >= 5 ? 192 : (bps >= 4 ? 256 : (bps >= 3 ? 384 : (bps >= 2 ? 512 : 1024))));
+            const int occ = fast32_occupancy(*threads, *smem, *wrap);
+            *grid = h->sm_count * (occ < 1 ? 1 : occ);
+        };
+        int autoA = 1, autoB = 1;
+        for (int nb = 2; nb <= 5; nb++) {
+            if (ring_of(nb) * 2 >= (size_t)h->W) autoA = nb;
+            if (ring_of(nb) * 100 >= (size_t)h->W * 88) autoB = nb;
+        }
+        const int nbA = env_int("MPC_F32_BLOCKS", 32, 192, 32 * autoA) / 32;
+        shape(nbA, env_int("MPC_F32_THREADS", 64, 1024, 0), &h->Wc32, &h->wrap32, &h->smem32, &h->threads32, &h->grid32);
+        if (h->grid32 > 0 && h->wrap32 && autoB < nbA) {
+            shape(autoB, 0, &h->Wc32b, &h->wrap32b, &h->smem32b, &h->threads32b, &h->grid32b);
+            if (h->Wc32b <= h->Wc32) h->grid32b = 0;
+        }
+      } }
     { const char *e = getenv("MPC_FAST_HEUR"); h->use_heur = !(e && e[0] == '0'); }
     { const char *e = getenv("MPC_PROBE_OVERLAP"); h->probe_overlap = (e && e[0] == '1'); }
     { const char *e = getenv("MPC_HINT_RETRY"); h->hint_retry = e ? atof(e) : 1.36; if (!(h->hint_retry >= 0.0 && h->hint_retry < 100.0)) h->hint_retry = 1.36; }
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
+    if (h->grid32 > h->grid_max) h->grid_max = h->grid32;
+    if (h->grid32b > h->grid_max) h->grid_max = h->grid32b;
     return MPC_OK;
 }
 
@@ -176,7 +220,7 @@ static int alloc_scratch(mpc_handle *h) {
     MPC_CUDA_OK(cudaMalloc(&h->s0, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->ds, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->num_s, B * 4));
     MPC_CUDA_OK(cudaMalloc(&h->bp, (size_t)h->grid_max * T * h->W * sizeof(uint16_t)));
     MPC_CUDA_OK(cudaMalloc(&h->counters, 16 * sizeof(int)));
-    MPC_CUDA_OK(cudaMalloc(&h->fallback_list, 2 * B * 4));
+    MPC_CUDA_OK(cudaMalloc(&h->fallback_list, 4 * B * 4));
     if (h->smem == 0) {
         MPC_CUDA_OK(cudaMalloc(&h->glab, (size_t)h->grid_exact * 2 * h->W * 8));
         MPC_CUDA_OK(cudaMalloc(&h->ghist, (size_t)h->grid_exact * 2 * h->W * 4));
@@ -249,6 +293,16 @@ extern "C" int mpc_last_counters(const mpc_handle *h, int64_t *out2) {
     MPC_CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
     out2[0] = h->kernels_launched;
     out2[1] = c[2];          // problems the first fast launch handed back (c[4]: of those, the ones that needed the exact kernel)
+    return MPC_OK;
+}
+
+extern "C" int mpc_fast32_info(const mpc_handle *h, int64_t *out6) {
+    if (!h || !out6) return mpc_set_error(MPC_E_INVALID, "null argument");
+    int c[16];
+    MPC_CUDA_OK(cudaSetDevice(h->device));
+    MPC_CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out6[0] = h->grid32 > 0; out6[1] = h->P.f32_frac; out6[2] = h->P.f32_bound; out6[3] = h->Wc32;
+    out6[4] = h->grid32 > 0 ? c[h->grid32b > 0 ? 7 : 5] : 0; out6[5] = h->grid32 > 0 ? c[5] : 0;
     return MPC_OK;
 }
 
@@ -350,11 +404,44 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
         F.glab = nullptr; F.ghist = nullptr;
         F.bound = h->use_bound ? h->P.bound_fx : ~0ULL;
         F.grid = h->grid_fast < B ? h->grid_fast : B;
+        if (!dense && h->grid32 > 0 && io.hint_cost == nullptr) {
+            // First attempt by the 32-bit-key kernel (bounded, zones closed).  What it cannot finish -- plans that cross a penalty
+            // zone or do not reach the horizon (list entries with bit 30: straight to the unbounded pass), frontiers wider than
+            // its ring -- goes to the 64-bit kernel through a device-side list, like that kernel's own hand-backs below.
+            SolveLaunch F3 = F;
+            F3.threads = h->threads32; F3.smem = h->smem32; F3.W = h->Wc32; F3.wrap = h->wrap32;
+            F3.grid = h->grid32 < B ? h->grid32 : B;
+            io.work_counter = h->counters + 0;
+            io.fallback_list = h->fallback_list + 2 * (size_t)h->max_batch; io.fallback_count = h->counters + 5;
+            e = launch_fast32_desc(h->P, F3, io, h->desc, st);
+            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast32 solve launch");
+            h->kernels_launched++;
+            if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
+            const int32_t *handed = h->fallback_list + 2 * (size_t)h->max_batch; const int *handed_n = h->counters + 5;
+            if (h->grid32b > 0) {                    // frontiers wider than ring A: once more with the wide ring (flagged entries pass through)
+                F3.threads = h->threads32b; F3.smem = h->smem32b; F3.W = h->Wc32b; F3.wrap = h->wrap32b;
+                F3.grid = h->grid32b < B ? h->grid32b : B;
+                io.work_counter = h->counters + 8;
+                io.subset = handed; io.B_dev = handed_n;
+                io.fallback_list = h->fallback_list + 3 * (size_t)h->max_batch; io.fallback_count = h->counters + 7;
+                e = launch_fast32_desc(h->P, F3, io, h->desc, st);
+                if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast32 wide-ring launch");
+                h->kernels_launched++;
+                handed = h->fallback_list + 3 * (size_t)h->max_batch; handed_n = h->counters + 7;
+            }
+            io.work_counter = h->counters + 6;
+            io.subset = handed; io.B_dev = handed_n;
+            io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
+            e = launch_fast_desc(h->P, F, io, h->desc, st);
+            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the 32-bit-key kernel)");
+            h->kernels_launched++;
+        } else {
         io.work_counter = h->counters + 0;
         e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
         if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch");
         h->kernels_launched++;
         if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
+        }
         // Problems the fast kernel handed back are re-solved on the device (their count is read on the device):
         // first by the fast kernel with a full-row window (ring overflow), then by the exact kernel (label saturation).
         // (A cost bound that proved too low is handled inside the kernel: the same block repeats the problem without it.)

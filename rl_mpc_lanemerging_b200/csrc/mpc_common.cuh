@@ -51,6 +51,13 @@ struct DevParams {
     int zone_ok;                   // LayerDesc::blk (band + exact penalty zone per car) is one interval per car: lean bounded pass allowed
     float kw;                      // (float)(d_weight * 2^MPC_FX_FRAC): 1/d penalty in label units = rint(kw * (1.0f / (float)d))
     int vstar_c;                   // cheapest speed of vtab on [0, vmax_c] (cells/step): vtab is convex and non-increasing up to it
+    // ---- 32-bit-key kernel (mpc_fast32.cuh): labels in 2^-f32_frac fixed point that fit 32 bits; valid only when f32_ok != 0 ----
+    int f32_ok;
+    int f32_frac;                  // fraction bits of its labels (<= MPC_FX_FRAC: the longer the horizon, the fewer)
+    unsigned f32_bound;            // its cost bound in label units: label + any edge + any penalty stays below 0xff000000
+    float kw32;                    // (float)(d_weight * 2^f32_frac)
+    double f32_one;                // 2^f32_frac
+    unsigned vtab32[256], atab32[32], jtab32[16];   // the kinematic tables in 2^-f32_frac units
 };
 #define MPC_FX_FRAC 18
 #define MPC_FX_ONE 262144.0

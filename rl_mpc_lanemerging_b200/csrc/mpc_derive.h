@@ -20,6 +20,8 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     if (D->num_t < 3 || D->num_t > MPC_MAX_T) return mpc_set_error(MPC_E_INVALID, "num_t must be in [3,128]");
     D->num_s_max = host_arange_len(0.0, p->future_s + p->s_disc, p->s_disc) + 1;
     if (D->num_s_max > 65000) return mpc_set_error(MPC_E_INVALID, "num_s too large for 16-bit back-pointers");
+    if (D->num_s_max > (MPC_MAX_BUCKETS << MPC_BUCKET_SHIFT))        // LayerDesc::bucket_edge / bucket_band hold one entry per 64 cells
+        return mpc_set_error(MPC_E_CAPACITY, "FUTURE_S / S_DISCRETIZATION above 18432 cells: the per-layer lookup tables are too small");
     D->discrete_length = (int)(p->car_length / p->s_disc);
     D->dt2 = pow(p->t_disc, 2.0);
     D->dt3 = pow(p->t_disc, 3.0);
@@ -73,5 +75,31 @@ static int derive_params(const mpc_params *p, DevParams *D) {
     // the reachability heuristic of hinted solves (mpc_reach.cu) needs the ROUNDED table to be convex up to vstar_c
     for (int v = 1; v < D->vstar_c; v++)
         if ((long long)D->vtab[v - 1] - 2LL * D->vtab[v] + (long long)D->vtab[v + 1] < 0) { D->vstar_c = 0; break; }
+    // 32-bit-key kernel (mpc_fast32.cuh): the whole label must stay below 0xff000000.  A plan that never enters a penalty zone
+    // costs at most ~(num_t - 1) * (max V + d_w / m) (standing still all the way; measured maxima are within 5 % of it), so the
+    // label precision is the largest 2^-q (q <= 18) that holds 1.25 x that plus one edge and one penalty.  The bound only decides
+    // which problems the kernel can finish (the others go to the 64-bit kernel), never what the answer is.
+    D->f32_ok = 0;
+    if (D->fast_ok && D->zone_ok && D->bound_fx) {
+        double maxv = 0.0, maxa = 0.0, maxj = 0.0;
+        for (int v = 0; v <= D->vmax_c + 1 && v < 256; v++) maxv = fmax(maxv, p->v_weight * (v * ds / dt - p->desired_speed) * (v * ds / dt - p->desired_speed));
+        // (on-grid edges only use a' in [alo_c, ahi_c] and j' in [jlo_c, jhi_c]: int_window_sa)
+        for (int i = D->alo_c; i <= D->ahi_c; i++) { double acc = i * ds / (dt * dt); maxa = fmax(maxa, p->a_weight * acc * acc); }
+        for (int i = D->jlo_c; i <= D->jhi_c; i++) { double jk = i * ds / (dt * dt * dt); maxj = fmax(maxj, p->j_weight * jk * jk); }
+        const double maxpen = p->d_weight / p->min_allowed_distance, edge = maxv + maxa + maxj;
+        const double need = 1.25 * (D->num_t - 1) * (maxv + maxpen) + 2.0 * (edge + maxpen) + 16.0;
+        int q = MPC_FX_FRAC;
+        while (q >= 12 && ldexp(need, q) >= 4278190080.0) q--;
+        if (q >= 12) {
+            D->f32_ok = 1; D->f32_frac = q; D->f32_one = ldexp(1.0, q);
+            D->kw32 = (float)(p->d_weight * D->f32_one);
+            unsigned mv = 0, ma = 0, mj = 0;
+            for (int v = 0; v < 256; v++) { double x = p->v_weight * (v * ds / dt - p->desired_speed) * (v * ds / dt - p->desired_speed); D->vtab32[v] = (unsigned)llrint(fmin(x, 16000.0) * D->f32_one); if (v <= D->vmax_c + 1 && D->vtab32[v] > mv) mv = D->vtab32[v]; }
+            for (int i = 0; i < 32; i++) { double acc = (i - 16) * ds / (dt * dt), x = p->a_weight * acc * acc; D->atab32[i] = (unsigned)llrint(fmin(x, 16000.0) * D->f32_one); if (i - 16 >= D->alo_c && i - 16 <= D->ahi_c && D->atab32[i] > ma) ma = D->atab32[i]; }
+            for (int i = 0; i < 16; i++) { double jk = (i - 8) * ds / (dt * dt * dt), x = p->j_weight * jk * jk; D->jtab32[i] = (unsigned)llrint(fmin(x, 16000.0) * D->f32_one); if (i - 8 >= D->jlo_c && i - 8 <= D->jhi_c && D->jtab32[i] > mj) mj = D->jtab32[i]; }
+            const double room = 4278190080.0 - 8.0 - (double)mv - (double)ma - (double)mj - ceil(ldexp(maxpen, q) * 1.001);
+            D->f32_bound = (unsigned)room;
+        }
+    }
     return MPC_OK;
 }

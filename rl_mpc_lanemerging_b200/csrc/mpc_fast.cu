@@ -307,6 +307,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
         int wi = S.b;
         if (wi >= B) break;
         int b = io.subset ? io.subset[wi] : wi;
+        // bit 30 of a list entry (set by fast32_kernel): the bounded attempt has already failed for this problem
+        const unsigned long long bound_b = ((b >> 30) & 1) ? FX_EMPTY : bound;
+        b &= 0x3fffffff;
         SGrid g;
         double v0, a0;
         if (DESC) { g = make_sgrid(P, io.ego[4 * b], io.ego[4 * b + 1]); v0 = io.ego[4 * b + 2]; a0 = io.ego[4 * b + 3]; }
@@ -322,21 +325,21 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
         int bt = 0; unsigned long long best_word = 0ULL;      // deepest non-empty layer and its (label << 16 | k)
         int dlo = 0, dhi = -1;
         // first attempt under the cost bound (and with its penalty zones closed), second attempt without -- see the note above
-        unsigned long long bnd = bound;
-        int zone = (Prov::kClipAtPush && bound != FX_EMPTY) ? P.zone_cells : 0;
+        unsigned long long bnd = bound_b;
+        int zone = (Prov::kClipAtPush && bound_b != FX_EMPTY) ? P.zone_cells : 0;
         // lean first attempt (descriptor-fed, bounded): see the note above the kernel
-        bool lean = DESC && Prov::kClipAtPush && bound != FX_EMPTY && P.zone_ok;
+        bool lean = DESC && Prov::kClipAtPush && bound_b != FX_EMPTY && P.zone_ok;
         // Per-problem cost hint (mpc_plan_hinted: a coarse probe plan, or the previous tick's plan in closed loop): an
         // ESTIMATE of the plan's cost, used as a tighter first bound.  Any bound is exact when the pass reaches the
         // horizon (note above the kernel), so a hint can only cost time: too low -> the attempt is repeated under the
         // standard bound; at or above the standard bound (the plan is expected to cross a penalty zone) -> the
         // zone-closed attempts, which could not succeed, are skipped.
         // (HINT is a template parameter so that the code of the un-hinted kernel does not change.)
-        if (HINT && DESC && bound != FX_EMPTY && (io.hint_reached == nullptr || io.hint_reached[b] == io.hint_full_t)) {
+        if (HINT && DESC && bound_b != FX_EMPTY && (io.hint_reached == nullptr || io.hint_reached[b] == io.hint_full_t)) {
             const double hc = __dmul_rn(io.hint_cost[b], io.hint_scale);
             if (hc > 0.0 && hc < 1.0e9) {                      // (a NaN fails both tests)
                 bnd = fx_from_double(hc);
-                if (bnd >= bound) { zone = 0; lean = false; }
+                if (bnd >= bound_b) { zone = 0; lean = false; }
             }
         }
       for (;;) {
@@ -557,9 +560,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
                 // a cost hint that was too low: once more under hint_retry x the hint (CPU model: -2..-9 % nodes against going
                 // straight to the standard bound), then under the standard bound, then without
                 unsigned long long mid = FX_EMPTY;
-                if (HINT && bnd < bound && io.hint_retry > 1.0) mid = fx_from_double(__dmul_rn(__dmul_rn(io.hint_cost[b], io.hint_scale), io.hint_retry));
-                if (HINT && bnd < mid && mid < bound) bnd = mid;
-                else if (HINT && bnd < bound) bnd = bound;
+                if (HINT && bnd < bound_b && io.hint_retry > 1.0) mid = fx_from_double(__dmul_rn(__dmul_rn(io.hint_cost[b], io.hint_scale), io.hint_retry));
+                if (HINT && bnd < mid && mid < bound_b) bnd = mid;
+                else if (HINT && bnd < bound_b) bnd = bound_b;
                 else { bnd = FX_EMPTY; zone = 0; lean = false; }
                 __syncthreads();
                 continue;
@@ -689,6 +692,8 @@ static cudaError_t set_smem(K kernel, size_t smem) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+#include "mpc_fast32.cuh"
+
 // five launch shapes are compiled: <= 192 threads x 5 blocks/SM, <= 256 x 4, <= 384 x 3, <= 512 x 2, <= 1024 x 1
 template <class Prov, bool DESC, bool HINT>
 static cudaError_t launch_fast_t(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, const uint8_t *ob,
@@ -720,6 +725,30 @@ cudaError_t launch_fast_dense(const DevParams &P, const SolveLaunch &L, const So
     if (L.B <= 0) return cudaSuccess;
     return dist_f32 ? launch_fast_t<FastDenseProv<float>, false, false>(P, L, io, nullptr, ob, dist, stride, st)
                     : launch_fast_t<FastDenseProv<double>, false, false>(P, L, io, nullptr, ob, dist, stride, st);
+}
+
+cudaError_t launch_fast32_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st) {
+    if (L.B <= 0) return cudaSuccess;
+    return launch_fast32_desc_impl(P, L, io, desc, st);
+}
+
+int fast32_occupancy(int threads, size_t smem, int wrap) {
+    int n = 0;
+    cudaError_t e;
+#define MPC_OCC(WRAPV, MAXTV)                                                                              \
+    do {                                                                                                   \
+        auto k = fast32_kernel<WRAPV, MAXTV>;                                                              \
+        if (set_smem(k, smem) != cudaSuccess) { cudaGetLastError(); return 0; }                            \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem);                           \
+    } while (0)
+    if (threads <= 192) { if (wrap) MPC_OCC(true, 192); else MPC_OCC(false, 192); }
+    else if (threads <= 256) { if (wrap) MPC_OCC(true, 256); else MPC_OCC(false, 256); }
+    else if (threads <= 384) { if (wrap) MPC_OCC(true, 384); else MPC_OCC(false, 384); }
+    else if (threads <= 512) { if (wrap) MPC_OCC(true, 512); else MPC_OCC(false, 512); }
+    else { if (wrap) MPC_OCC(true, 1024); else MPC_OCC(false, 1024); }
+#undef MPC_OCC
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 int fast_occupancy(int threads, size_t smem, int wrap) {

@@ -1,0 +1,323 @@
+// fast32_kernel: the bounded first attempt of the fused gap-evaluation with 32-bit keys (round 2).  Included by mpc_fast.cu.
+//
+// Why: B200 has a native 32-bit shared-memory min (ATOMS.MIN, 2.3 cycles per warp instruction per SM -- the rate of a plain
+// store; tools/microbench3.cu) but no 64-bit one: the 64-bit word of fast_pull_kernel is min-combined with pre-read + compare +
+// ATOMS.CAS.64 + check + redo, 4x the cost and the source of the divergent lost-race paths (profiles/r01_fast_pull_h50.txt).
+//
+// Same DP, same winner at every cell, different encoding:
+//   * labels are 32-bit fixed point (2^-f32_frac, DevParams) under a cost bound that keeps them below 0xff000000; the bounded
+//     pass is exact for every problem whose answer lies below the bound (mpc_fast.cu, note "Cost bound"), the others -- plans
+//     that cross a penalty zone or do not reach the horizon -- are handed to the 64-bit kernel through the fallback list;
+//   * a successor is offered with ONE atom.shared.min.u32 on the key  [label >> 8 : 24 | 255 - v' : 8];
+//   * the low 8 label bits do not fit the key.  They are carried exactly: the thread that finalises cell k of layer t (it
+//     reads the winning key, so it knows v' and the predecessor cell k - v') rebuilds the full label from the predecessor's
+//     state word -- [0xff | label & 255 | v | a + 128], written over the consumed key -- and the edge tables, adds the cell's
+//     penalty, and leaves its own state word behind.  Keys (< 0xff000000) and state words (>= 0xff000000) share three arrays
+//     that rotate with the layers; a stale state word reads as "empty" to the min, so nothing is ever cleared;
+//   * two candidates whose labels agree in all but the low 8 bits are ordered by v' alone in the key.  The atomic returns the
+//     previous key: when it lies in the same 24-bit bucket, the loser of the two goes to a small per-layer list and the
+//     finalising thread decides between the key holder and the listed candidates on the exact labels (~5 of 2.4e5 offers per
+//     problem at H=50).  Every candidate of the winning bucket is either the final holder or was listed when it lost to /
+//     was displaced by a holder of the same bucket, so the winner is the exact minimum of (label, then larger v').
+// The result equals the CPU model orc_solve_fast_model_q(f32_frac, 0, f32_bound) bit for bit (oracle/mpc_oracle.c).
+#pragma once
+
+#define F32_EMPTY 0xffffffffu
+#define F32_STATE 0xff000000u       // words >= this are state words / empty, words below are keys
+#define F32_OVF 32                  // same-bucket candidates per layer (more: the problem is handed on)
+#define F32_L2 512                  // cells of layers 1 and 2 (off-grid history) the prologue can hold
+
+struct F32Tables { unsigned v[256], aj[8 + 32 * 16 + 8]; };     // aj padded: the state rebuild of layer 2 may look 8 entries outside
+
+#ifdef MPC_HOST_EMU
+__device__ __forceinline__ unsigned lds_u32(unsigned a) { emu::preempt_point(); emu::S().cell_reads++; return *emu::from_shared<unsigned>(a); }
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { emu::preempt_point(); *emu::from_shared<unsigned>(a) = v; }
+__device__ __forceinline__ unsigned atoms_min_u32_if(unsigned a, unsigned val, bool doit) {
+    if (!doit) return F32_EMPTY;
+    emu::preempt_point();
+    emu::S().cas_issued++;
+    unsigned *p = emu::from_shared<unsigned>(a), old = *p; if (val < old) *p = val; return old;
+}
+#else
+__device__ __forceinline__ unsigned lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// predicated min: returns the previous word, or F32_EMPTY when `doit` is false (no branch around the atomic)
+__device__ __forceinline__ unsigned atoms_min_u32_if(unsigned a, unsigned val, bool doit) {
+    unsigned old;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.b32 %0, 0xffffffff;\n\t@p atom.shared.min.u32 %0, [%1], %2;\n\t}"
+                 : "=&r"(old) : "r"(a), "r"(val), "r"((unsigned)doit) : "memory");
+    return old;
+}
+#endif
+
+template <bool WRAP, int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1))
+fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
+#ifdef MPC_HOST_EMU
+    unsigned char *const smem_raw = emu::S().dyn_smem;
+#else
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+    __shared__ FastShared FS;
+    __shared__ F32Tables TB;
+    __shared__ unsigned s_l2full[F32_L2];      // full labels of layer 1, then of layer 2 (their edges are not tabulated)
+    __shared__ uint2 s_ovf[3][F32_OVF];        // layer t % 3: (cell, key) of candidates that lost to a key of their own bucket
+    __shared__ int s_ovfn[3];
+    __shared__ unsigned long long s_best;
+    __shared__ int s_chunk[3];
+    BlockShared &S = FS.S;
+    const unsigned ab = smem_u32(smem_raw);    // three arrays of Wc 32-bit words: layer t lives in array t % 3
+    ClampBits CB;
+    const int NW = (P.num_s_max + 31) >> 5;
+    CB.lo = reinterpret_cast<unsigned *>(smem_raw + (size_t)12 * Wc); CB.hi = CB.lo + NW;
+    unsigned *const blkbits[2] = {CB.hi + NW, CB.hi + 2 * NW + 2};      // blocked cells of layer L in blkbits[L & 1]
+    uint16_t *bp = io.bp + (size_t)blockIdx.x * P.num_t * io.bp_stride;
+    const int T = P.num_t, tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+    auto ring = [Wc](int k) -> int { return WRAP ? (k >= Wc ? k - Wc : k) : k; };
+    for (int i = tid; i < 256; i += nth) TB.v[i] = P.vtab32[i];
+    for (int i = tid; i < 8 + 512 + 8; i += nth) TB.aj[i] = (i >= 8 && i < 520) ? P.atab32[(i - 8) >> 4] + P.jtab32[(i - 8) & 15] : 0u;
+    for (int k = tid; k < 3 * Wc; k += nth) sts_u32(ab + 4u * k, F32_EMPTY);
+    if (io.B_dev) B = *io.B_dev;
+    const unsigned bnd = P.f32_bound;
+    const float kw = P.kw32;
+    const unsigned tbv = smem_u32(TB.v), tbaj = smem_u32(TB.aj + 8), cba = smem_u32(CB.lo);
+    for (;;) {
+        if (tid == 0) S.b = atomicAdd(io.work_counter, 1);
+        __syncthreads();
+        const int wi = S.b;
+        if (wi >= B) break;
+        const int b = io.subset ? io.subset[wi] : wi;
+        if (b & (1 << 30)) {                  // (second shape) the bounded attempt has already failed: pass the entry on
+            if (tid == 0) { const int q = atomicAdd(io.fallback_count, 1); io.fallback_list[q] = b; }
+            __syncthreads();
+            continue;
+        }
+        const SGrid g = make_sgrid(P, io.ego[4 * b], io.ego[4 * b + 1]);
+        const double v0 = io.ego[4 * b + 2], a0 = io.ego[4 * b + 3];
+        FastDescProv prov;
+        prov.base = desc + (size_t)b * T; prov.sm = FS.layer;
+        build_clamp_bits(P, g, CB);
+        const double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
+        const double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
+        prov.load(1);
+        if (tid == 0) {
+            S.need_fallback = 0;
+            for (int i = 0; i < 3; i++) { S.nlo[i] = INT_MAX; S.nhi[i] = -1; s_chunk[i] = 0; s_ovfn[i] = 0; }
+            s_best = FX_EMPTY;
+        }
+        // ---- prologue: layers 0 -> 1 -> 2 have off-grid history (st_cy.pyx:329-330): exact fp64 edges, quantised; the few
+        // layer-2 cells are min-combined as 64-bit words in a scratch row (array 0, not yet in use) and then turned into keys ----
+        for (int k = tid; k < F32_L2; k += nth) { sts_u64(ab + 8u * k, FX_EMPTY); s_l2full[k] = F32_EMPTY; }
+        int imin0, imax0;
+        exact_window(P, g.s0, g.ds, g.s0, est_prev, est_second, imin0, imax0);
+        if (imax0 > g.num_s) imax0 = g.num_s;
+        prov.store(1);
+        prov.load(2);
+        __syncthreads();
+        if (tid < imax0 - imin0) {                                // layer 1 (array 1): state word, v = k, a = 0
+            const int kk = imin0 + tid;
+            const double sn = g.sval(kk);
+            bool ob; const double d = prov.eval_staged(1, kk, sn, ob);
+            if (!ob && kk >= 256) S.need_fallback = 1;
+            else if (!ob) {
+                const unsigned long long l1 = (unsigned long long)__double2ll_rn(__dmul_rn(exact_cost(P, sn, g.s0, est_prev, est_second, d), P.f32_one));
+                if (l1 <= bnd) {                                  // (a layer-1 cell inside a penalty zone is above the bound)
+                    s_l2full[kk] = (unsigned)l1;
+                    sts_u32(ab + 4u * (Wc + ring(kk)), F32_STATE | (((unsigned)l1 & 255u) << 16) | ((unsigned)kk << 8) | 128u);
+                    bp[(size_t)1 * io.bp_stride + kk] = 0;
+                    atomicMin(&S.nlo[1], kk); atomicMax(&S.nhi[1], kk);
+                }
+            }
+        }
+        prov.store(2);
+        if (T > 3) prov.load(3);
+        __syncthreads();
+        if (T > 3) prov.store(3);
+        if (T > 4) prov.load(4);
+        bool fail = false;
+        int dlo = 0, dhi = -1;
+        if (S.nhi[1] < 0) fail = true;
+        else {
+            const int lo1 = S.nlo[1], hi1 = S.nhi[1], lme = P.lmax_exact;
+            int mylo = INT_MAX, myhi = -1;
+            for (int e = tid; e < (hi1 - lo1 + 1) * lme; e += nth) {      // one thread per (layer-1 node, successor)
+                const int k1 = lo1 + e / lme, j = e % lme;
+                const unsigned l1 = s_l2full[k1];
+                if (l1 == F32_EMPTY) continue;
+                const double s = g.sval(k1);
+                int imin, imax;
+                exact_window(P, g.s0, g.ds, s, g.s0, est_prev, imin, imax);
+                const int kk = imin + j;
+                if (kk >= imax || kk >= g.num_s) continue;
+                if (prov.is_blocked(2, kk)) continue;             // band or penalty zone (st_cy.pyx:383-384 / the bound)
+                const int vn = kk - k1, an = vn - k1;
+                if (vn > 255 || an < -16 || an > 15 || kk >= F32_L2) { S.need_fallback = 1; continue; }
+                const unsigned long long tot = (unsigned long long)l1 + (unsigned long long)__double2ll_rn(__dmul_rn(exact_kin(P, g.sval(kk), s, g.s0, est_prev), P.f32_one));
+                if (tot > bnd) continue;
+                smem_min64(ab + 8u * kk, (tot << 16) | ((unsigned long long)(255 - vn) << 8) | (unsigned long long)(an + 128));
+                mylo = min(mylo, kk); myhi = max(myhi, kk);
+            }
+            mylo = warp_min_i(mylo); myhi = warp_max_i(myhi);
+            if (lane == 0 && myhi >= 0) { atomicMin(&S.nlo[2], mylo); atomicMax(&S.nhi[2], myhi); }
+            __syncthreads();
+            dlo = S.nlo[2]; dhi = S.nhi[2];
+            if (dhi < 0) fail = true;
+            else for (int kk = dlo + tid; kk <= dhi; kk += nth) { // winners of layer 2 -> keys in array 2, full labels aside
+                const unsigned long long w2 = lds_u64(ab + 8u * kk);
+                if (w2 != FX_EMPTY) {
+                    const unsigned tot = (unsigned)(w2 >> 16);
+                    s_l2full[kk] = tot;
+                    sts_u32(ab + 4u * (2 * Wc + ring(kk)), (tot & ~255u) | (unsigned)((w2 >> 8) & 255u));
+                    sts_u64(ab + 8u * kk, FX_EMPTY);
+                }
+            }
+        }
+        if (T > 4) prov.store(4);
+        int bt = 0; unsigned long long best_word = 0ULL;
+        if (!fail) {
+            if (T > 5) prov.load(5);
+            if (T > 3) build_blocked_bits(FS.layer[3], blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), tid, nth);
+            // ---- layers 2 .. T-1: one barrier per layer; warps take 32-cell chunks of the layer's span ----
+            for (int t = 2; t < T; t++) {
+                const int s3 = t % 3, n3 = (t + 1) % 3, p3 = (t + 2) % 3;
+                const unsigned cur = ab + 4u * (unsigned)(Wc * s3), nxt = ab + 4u * (unsigned)(Wc * n3), prv = ab + 4u * (unsigned)(Wc * p3);
+                __syncthreads();                                  // offers into layer t, its span and list, staging of layer t+2, bits of t+1 are complete
+                dlo = S.nlo[s3]; dhi = S.nhi[s3];
+                if (dhi < 0) break;
+                if (WRAP && dhi - dlo + 1 + (t == T - 1 ? 0 : P.vmax_c + 8) > Wc) { if (tid == 0) S.need_fallback = 1; break; }
+                const int novf = min(s_ovfn[s3], F32_OVF);
+                if (tid == 0) { S.nlo[p3] = INT_MAX; S.nhi[p3] = -1; s_chunk[n3] = 0; s_ovfn[p3] = 0; }      // what iteration t+1 accumulates into
+                if (t + 3 < T) prov.store(t + 3);
+                if (t + 4 < T) prov.load(t + 4);
+                const bool last = (t == T - 1), first = (t == 2);
+                if (t + 2 < T) build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
+                const unsigned edge0 = smem_u32(FS.layer[t & 3].edge), bucket0 = smem_u32(FS.layer[t & 3].bucket_edge);
+                const unsigned bwa = smem_u32(blkbits[(t + 1) & 1]);
+                uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
+#ifndef MPC_HOST_EMU
+                asm volatile("" : "+l"(bp_row));
+#endif
+                unsigned long long mybest = FX_EMPTY;
+                int mylo = INT_MAX, myhi = -1;
+                const int nwarp = nth >> 5;
+                int c = tid >> 5;
+                for (;;) {
+                    const int base = dlo + (c << 5);
+                    if (base > dhi) break;
+                    int cn = 0;
+                    if (lane == 0) cn = nwarp + atomicAdd(&s_chunk[s3], 1);
+                    const int k = base + lane, rk = ring(k);
+                    unsigned w = F32_EMPTY;
+                    if (k <= dhi) w = lds_u32(cur + 4u * rk);
+                    if (w < F32_STATE) {
+                        // the winning offer: v' from the key, the rest from the predecessor's state word
+                        int v = 255 - (int)(w & 255u);
+                        const unsigned stp = lds_u32(prv + 4u * ring(k - v));
+                        int a = v - (int)((stp >> 8) & 255u);
+                        const int jj = a - ((int)(stp & 255u) - 128);
+                        unsigned low = ((stp >> 16) + lds_u32_nc(tbv + 4u * v) + lds_u32_nc(tbaj + 4u * ((a + 16) * 16 + (jj + 8)))) & 255u;
+                        if (novf) {                               // candidates of the same bucket that lost on v': exact comparison
+                            for (int i = 0; i < novf; i++) {
+                                const uint2 oe = s_ovf[s3][i];
+                                if (oe.x == (unsigned)k && ((oe.y ^ w) < 256u)) {
+                                    const int vx = 255 - (int)(oe.y & 255u);
+                                    const unsigned sx = lds_u32(prv + 4u * ring(k - vx));
+                                    const int ax = vx - (int)((sx >> 8) & 255u), jx = ax - ((int)(sx & 255u) - 128);
+                                    const unsigned lx = ((sx >> 16) + lds_u32_nc(tbv + 4u * vx) + lds_u32_nc(tbaj + 4u * ((ax + 16) * 16 + (jx + 8)))) & 255u;
+                                    if (lx < low || (lx == low && vx > v)) { low = lx; v = vx; a = ax; }
+                                }
+                            }
+                        }
+                        unsigned full = (w & ~255u) | low;
+                        if (first) full = s_l2full[k];
+                        // distance penalty: nearest distance-field edge on either side; edge[-1] / edge[n_edge] are -/+1e300
+                        const double sv = g.sval(k);
+                        unsigned ea = edge0 + 8u * lds_u8_nc(bucket0 + (k >> MPC_BUCKET_SHIFT));
+                        double hi = lds_f64_nc(ea);
+                        while (hi < sv) { ea += 8u; hi = lds_f64_nc(ea); }
+                        const double dl = __dsub_rn(sv, lds_f64_nc(ea - 8u)), dr = __dsub_rn(hi, sv);
+                        const unsigned label = full + fx_inv_penalty(kw, dr < dl ? dr : dl);
+                        if (label <= bnd) {
+                            MPC_EMU_COUNT_NODE();
+                            sts_u32(cur + 4u * rk, F32_STATE | ((label & 255u) << 16) | ((unsigned)v << 8) | (unsigned)(a + 128));
+                            bp_row[k] = (uint16_t)(k - v);
+                            if (last) {
+                                const unsigned long long key = ((unsigned long long)label << 16) | (unsigned long long)k;
+                                mybest = key < mybest ? key : mybest;
+                            } else {
+                                int wlo, n;
+                                int_window_sa(P, g.num_s, cba, NW, k, v, a, wlo, n);
+                                if (n > 0) {
+                                    const int vn = wlo - k, an = vn - v, jn = an - a;
+                                    const unsigned wa = bwa + 4u * (unsigned)(wlo >> 5);
+                                    const unsigned open = ~__funnelshift_r(lds_u32_nc(wa), lds_u32_nc(wa + 4u), wlo & 31) & ((1u << n) - 1u);
+                                    mylo = min(mylo, wlo); myhi = max(myhi, wlo + n - 1);
+                                    const unsigned tva = tbv + 4u * vn, taja = tbaj + 4u * ((an + 16) * 16 + (jn + 8));
+                                    const unsigned tie = 255u - (unsigned)vn;
+                                    const int r0 = ring(wlo);
+                                    const bool flat = !WRAP || r0 + n <= Wc;      // the window does not cross the end of the ring
+                                    const unsigned ra = nxt + 4u * r0;
+                                    // offer e: label + V[v'] + A[a'] + J[j'] with v' = vn + e, a' = an + e, j' = jn + e
+#define F32_OFFER(E)                                                                                                          \
+                                    {                                                                                         \
+                                        const unsigned key = ((label + lds_u32_nc(tva + 4u * (E)) + lds_u32_nc(taja + 68u * (E))) & ~255u) | (tie - (E)); \
+                                        const unsigned adr = flat ? ra + 4u * (E) : nxt + 4u * (unsigned)(r0 + (E) >= Wc ? r0 + (E) - Wc : r0 + (E)); \
+                                        const unsigned old = atoms_min_u32_if(adr, key, (open >> (E)) & 1u);                   \
+                                        if ((old ^ key) < 256u) {                 /* same bucket: list the loser (rare) */      \
+                                            const int oi = atomicAdd(&s_ovfn[n3], 1);                                         \
+                                            if (oi < F32_OVF) s_ovf[n3][oi] = make_uint2((unsigned)(wlo + (E)), old > key ? old : key); \
+                                            else S.need_fallback = 1;                                                         \
+                                        }                                                                                     \
+                                    }
+                                    F32_OFFER(0) F32_OFFER(1) F32_OFFER(2) F32_OFFER(3) F32_OFFER(4)
+                                    for (int e = 5; e < n; e++) F32_OFFER(e)       // (windows longer than 5 cells: other Settings)
+#undef F32_OFFER
+                                }
+                            }
+                        } else sts_u32(cur + 4u * rk, F32_EMPTY);   // dropped by the bound: the key must not be seen again
+                    }
+                    c = __shfl_sync(FULL, cn, 0);
+                }
+                mylo = __reduce_min_sync(FULL, mylo); myhi = __reduce_max_sync(FULL, myhi);
+                if (last) for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, mybest, o); mybest = x < mybest ? x : mybest; }
+                if (lane == 0) {
+                    if (mybest != FX_EMPTY) atomicMin(&s_best, mybest);
+                    if (myhi >= 0) { atomicMin(&S.nlo[n3], mylo); atomicMax(&S.nhi[n3], myhi); }
+                }
+                if (last) {
+                    __syncthreads();
+                    if (s_best != FX_EMPTY) { bt = t; best_word = s_best; }
+                }
+            }
+        }
+        __syncthreads();
+        if (bt < T - 1 || S.need_fallback) {
+            // not finished here: offers that were never finalised may be left behind -> empty the arrays, hand the problem on.
+            // Bit 30 of the list entry: the bounded attempt itself failed (the plan crosses a penalty zone or there is none),
+            // the 64-bit kernel goes straight to its unbounded pass; without it (ring / table overflow) it starts over.
+            const bool overflow = S.need_fallback != 0;
+            for (int k = tid; k < 3 * Wc; k += nth) sts_u32(ab + 4u * k, F32_EMPTY);
+            if (tid == 0) { const int q = atomicAdd(io.fallback_count, 1); io.fallback_list[q] = b | (overflow ? 0 : (1 << 30)); }
+            __syncthreads();
+            continue;
+        }
+        finish_problem(P, io, prov, &S, b, g, bt, (int)(best_word & 0xffff), (double)(best_word >> 16) / P.f32_one, bp, true);
+    }
+}
+
+static cudaError_t launch_fast32_desc_impl(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st) {
+    cudaError_t e;
+#define MPC_LAUNCH_F32(WRAPV, MAXTV)                                                                       \
+    do {                                                                                                   \
+        auto k = fast32_kernel<WRAPV, MAXTV>;                                                              \
+        if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;                                            \
+        MPC_LAUNCH(k, L.grid, L.threads, L.smem, st, P, L.B, io, desc, L.W);                               \
+    } while (0)
+    if (L.threads <= 192) { if (L.wrap) MPC_LAUNCH_F32(true, 192); else MPC_LAUNCH_F32(false, 192); }
+    else if (L.threads <= 256) { if (L.wrap) MPC_LAUNCH_F32(true, 256); else MPC_LAUNCH_F32(false, 256); }
+    else if (L.threads <= 384) { if (L.wrap) MPC_LAUNCH_F32(true, 384); else MPC_LAUNCH_F32(false, 384); }
+    else if (L.threads <= 512) { if (L.wrap) MPC_LAUNCH_F32(true, 512); else MPC_LAUNCH_F32(false, 512); }
+    else { if (L.wrap) MPC_LAUNCH_F32(true, 1024); else MPC_LAUNCH_F32(false, 1024); }
+#undef MPC_LAUNCH_F32
+    return cudaGetLastError();
+}

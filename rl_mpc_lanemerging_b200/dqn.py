@@ -15,7 +15,7 @@ import torch
 
 from . import control, st
 from .config import Settings
-from .prediction import BatchedState, HighwayState
+from .prediction import BatchedState, HighwayState, tdiv
 
 
 def get_state_vector_from_base_state(state, out: Optional[torch.Tensor] = None):
@@ -185,8 +185,8 @@ def _ego_s(ego: torch.Tensor) -> torch.Tensor:
 def _mean_abs_jerk(seq: torch.Tensor, length: torch.Tensor, v0: torch.Tensor, a0: torch.Tensor, dt: float) -> torch.Tensor:
     """st.get_path_mean_abs_jerk (st.py:274-288) over the first `length[b]` points of every row."""
     B, N = seq.shape
-    v = (seq[:, 1:] - seq[:, :-1]) / dt
-    a = (v - torch.cat([v0.unsqueeze(1), v[:, :-1]], 1)) / dt
-    j = (a - torch.cat([a0.unsqueeze(1), a[:, :-1]], 1)) / dt
+    v = tdiv(seq[:, 1:] - seq[:, :-1], dt)
+    a = tdiv(v - torch.cat([v0.unsqueeze(1), v[:, :-1]], 1), dt)
+    j = tdiv(a - torch.cat([a0.unsqueeze(1), a[:, :-1]], 1), dt)
     mask = torch.arange(N - 1, device=seq.device).unsqueeze(0) < (length - 1).unsqueeze(1)
     return (j.abs() * mask).sum(1) / (length - 1).clamp(min=1)

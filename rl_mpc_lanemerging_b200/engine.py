@@ -115,6 +115,14 @@ class MpcEngine:
         _lib.check(self.lib.mpc_last_counters(self.h, out))
         return {"kernels_launched": int(out[0]), "fallback_problems": int(out[1])}
 
+    def fast32_info(self):
+        """The 32-bit-key DP kernel of the fast mode's first attempt: in use?, label fraction bits, cost bound (label units),
+        ring capacity of its first launch shape (cells), problems of the last call it handed to the 64-bit kernel / its first shape handed on."""
+        out = (C.c_int64 * 6)()
+        _lib.check(self.lib.mpc_fast32_info(self.h, out))
+        return {"in_use": bool(out[0]), "frac_bits": int(out[1]), "bound_fx": int(out[2]), "ring_cells": int(out[3]),
+                "handed_on": int(out[4]), "first_shape_handed_on": int(out[5])}
+
     def selftest_search(self, ego, cars_x, cars_v, cars_a, n_cars) -> int:
         """Cells whose sorted-structure lookup differs from the reference-order evaluation (must be 0)."""
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)

@@ -14,7 +14,7 @@ import torch
 
 from . import dqn, st, synthetic
 from .config import Settings
-from .prediction import BatchedState
+from .prediction import BatchedState, tdiv
 
 SPAWN_X = -250.0         # highway entry
 ARRIVAL_X = 75.0         # ego route end on the highway edge (approximate; unpinned)
@@ -136,8 +136,8 @@ class MergeEnv:
         spd = st8.ego[:, 2] + acc * tick
         clipped = (spd > S.MAX_SPEED) | (spd < 0)
         spd = spd.clamp(0, S.MAX_SPEED)
-        acc = torch.where(clipped, (spd - st8.ego[:, 2]) / tick, acc)
-        projected_jerk = (acc - self.prev_acc) / tick
+        acc = torch.where(clipped, tdiv(spd - st8.ego[:, 2], tick), acc)
+        projected_jerk = tdiv(acc - self.prev_acc, tick)
         # world step: the reference predictor as dynamics (K4 kernel, in place)
         for t in st8.args():
             assert t.is_contiguous()

@@ -106,3 +106,12 @@ class HighwayState:
     def __repr__(self):
         return (f"HighwayState(ego={self.ego_position}, v={self.ego_speed}, a={self.ego_acceleration}, "
                 f"cars={len(self.other_xs)})")
+
+
+def tdiv(t, scalar):
+    """IEEE division of a tensor by a Python scalar.  `tensor / scalar` on a CUDA device multiplies by the rounded reciprocal
+    (x / 0.2 becomes x * 5.0), which differs from the reference's numpy / float division in the last bit; dividing by a 0-dim
+    tensor is a true division on every device."""
+    import torch
+    return t / torch.as_tensor(float(scalar), dtype=t.dtype, device=t.device)
+

@@ -17,7 +17,7 @@ import torch
 
 from .config import Settings
 from .engine import MpcEngine, params_from_settings, params_key
-from .prediction import BatchedState, HighwayState
+from .prediction import BatchedState, HighwayState, tdiv
 
 _engine: Optional[MpcEngine] = None
 _engine_key = None
@@ -158,7 +158,7 @@ def smoothed_speed(batch: BatchedState, plan: dict):
         fine, n_fine, speed, _it = eng.finer_fit(plan["s_seq"], plan["reached_t"], batch.ego)
         return speed, fine, n_fine
     s = plan["s_seq"]
-    v = (s[:, 1] - s[:, 0]) / float(Settings.TICK_LENGTH)
+    v = tdiv(s[:, 1] - s[:, 0], Settings.TICK_LENGTH)
     return torch.where(plan["reached_t"] >= 1, v, batch.ego[:, 2]), s, plan["reached_t"] + 1
 
 
@@ -188,7 +188,7 @@ def do_st_control_masked(batch: BatchedState, mask: torch.Tensor, speed: torch.T
         eng.finer_fit_masked(m, scratch["s_seq"], scratch["reached_t"], batch.ego, scratch["fine"], scratch["n_fine"], speed)
     else:
         s = scratch["s_seq"]
-        v = torch.where(scratch["reached_t"] >= 1, (s[:, 1] - s[:, 0]) / float(Settings.TICK_LENGTH), batch.ego[:, 2])
+        v = torch.where(scratch["reached_t"] >= 1, tdiv(s[:, 1] - s[:, 0], Settings.TICK_LENGTH), batch.ego[:, 2])
         speed.copy_(torch.where(m.bool(), v, speed))
     return scratch
 

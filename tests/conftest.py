@@ -10,9 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "unverified: GPU test of device code that has compiled but never run on a device "
-                                       "(written after a round's GPU budget was spent).  Skipped unless MPCB200_RUN_UNVERIFIED=1; "
-                                       "tests/test_unverified_runner.py makes their first on-device run in a child process")
 
 
 def _has_gpu():
@@ -24,11 +21,6 @@ def _has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
-    if os.environ.get("MPCB200_RUN_UNVERIFIED") != "1":
-        gate = pytest.mark.skip(reason="device code not yet run on a GPU: set MPCB200_RUN_UNVERIFIED=1 (tests/test_unverified_runner.py does)")
-        for item in items:
-            if "unverified" in item.keywords:
-                item.add_marker(gate)
     if _has_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")

@@ -9,7 +9,7 @@ CSRC = os.path.join(ROOT, "rl_mpc_lanemerging_b200", "csrc")
 LIB = os.path.join(HERE, "libmpc_emu.so")
 DEPS = [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_harness.cpp")] + \
        [os.path.join(CSRC, f) for f in ("mpc_common.cuh", "mpc_solve_common.cuh", "mpc_derive.h", "mpc_predict.cu", "mpc_reach.cu",
-                                        "mpc_fast.cu")] + [os.path.join(ROOT, "include", "mpcb200.h")]
+                                        "mpc_fast.cu", "mpc_fast32.cuh")] + [os.path.join(ROOT, "include", "mpcb200.h")]
 
 
 def build(force: bool = False) -> str:

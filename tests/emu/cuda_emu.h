@@ -38,6 +38,8 @@
 
 // ---- vector types / runtime stubs -------------------------------------------------------------------------
 struct int2 { int x, y; };
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct alignas(16) int4 { int x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
 struct alignas(16) float4 { float x, y, z, w; };

@@ -72,6 +72,12 @@ class EmuEngine:
         check(self.L.mpc_last_counters(self.h, out))
         return {"kernels_launched": int(out[0]), "fallback_problems": int(out[1])}
 
+    def fast32_info(self):
+        out = (C.c_int64 * 6)()
+        check(self.L.mpc_fast32_info(self.h, out))
+        return {"in_use": bool(out[0]), "frac_bits": int(out[1]), "bound_fx": int(out[2]), "ring_cells": int(out[3]), "handed_on": int(out[4]),
+                "first_shape_handed_on": int(out[5])}
+
     def plan(self, S, mode=0):
         B = S["ego"].shape[0]
         o = self._out(B)

@@ -90,6 +90,65 @@ extern "C" int emu_plan(const mpc_params *params, int B, int nmax, const double 
     return MPC_OK;
 }
 
+// The fast mode's chain of mpc_plan (run_solve in mpc_api.cu): fast32_kernel on all B states, then fast_pull_kernel (64-bit words) on the
+// problems it handed on.  threads32 / ring32: launch shape of the 32-bit-key kernel (ring32 = 0: full row); threads / ring: of the other.
+// handed[b]: bit 0 = handed on by fast32_kernel, bit 1 = with the "bounded attempt failed" flag, bit 2 = handed back by fast_pull_kernel.
+// info3 = {f32_frac, f32_bound, f32_ok}.
+extern "C" int emu_plan32(const mpc_params *params, int B, int nmax, const double *ego, const double *cars_x, const double *cars_v,
+                          const int32_t *n_cars, int threads32, int ring32, int threads, int ring, int32_t *idx, double *s_seq,
+                          double *cost, int32_t *reached, uint8_t *crash, double *min_dist, uint8_t *handed, int64_t *info3) {
+    DevParams P;
+    emu::S().nodes = 0;
+    int rc = derive_params(params, &P);
+    if (rc) return rc;
+    if (info3) { info3[0] = P.f32_frac; info3[1] = P.f32_bound; info3[2] = P.f32_ok; }
+    if (!P.fast_ok || !P.f32_ok) return mpc_set_error(MPC_E_INVALID, "32-bit-key kernel not available for these params");
+    const int T = P.num_t;
+    std::vector<LayerDesc> desc((size_t)B * T);
+    std::vector<double> s0(B), ds(B);
+    std::vector<int32_t> num_s(B);
+    emu::launch((B + 3) / 4, 128, 0, [&] { predict_layers_kernel<false>(P, B, ego, cars_x, cars_v, n_cars, nmax, desc.data(), s0.data(), ds.data(), num_s.data(), nullptr, nullptr); });
+    const int W = (P.num_s_max + 7) & ~7;
+    const size_t clamp_bytes = (4 * (((size_t)P.num_s_max + 31) / 32) + 4) * 4 + 16;
+    std::vector<uint16_t> bp((size_t)T * W);
+    std::vector<int> counters(16, 0);
+    std::vector<int32_t> fb_list(3 * (size_t)B + 3, -1);
+    SolveIO io; memset(&io, 0, sizeof(io));
+    io.ego = ego;
+    io.idx = idx; io.s_seq = s_seq; io.cost = cost; io.reached = reached; io.crash = crash; io.min_dist = min_dist;
+    io.bp = bp.data(); io.bp_stride = W;
+    const LayerDesc *d = desc.data();
+    {   // first attempt: 32-bit keys
+        const bool wrap = ring32 > 0 && ring32 < W;
+        const int Wc = wrap ? (ring32 & ~7) : W;
+        if (Wc < 1024 || 2 * Wc < W) return mpc_set_error(MPC_E_INVALID, "ring32 too small");
+        const size_t smem = (size_t)Wc * 12 + clamp_bytes;
+        io.work_counter = &counters[0]; io.fallback_list = fb_list.data() + 2 * (size_t)B; io.fallback_count = &counters[5];
+#define EMU_RUN32(WRAPV, MAXTV) emu::launch(1, threads32, smem, [&] { fast32_kernel<WRAPV, MAXTV>(P, B, io, d, Wc); })
+        if (threads32 <= 192) { if (wrap) EMU_RUN32(true, 192); else EMU_RUN32(false, 192); }
+        else if (threads32 <= 512) { if (wrap) EMU_RUN32(true, 512); else EMU_RUN32(false, 512); }
+        else { if (wrap) EMU_RUN32(true, 1024); else EMU_RUN32(false, 1024); }
+    }
+    if (handed) {
+        memset(handed, 0, B);
+        for (int i = 0; i < counters[5]; i++) { const int32_t e = fb_list[2 * (size_t)B + i]; handed[e & 0x3fffffff] = (uint8_t)(1 | ((e >> 30) & 1) << 1); }
+    }
+    if (counters[5] > 0) {   // the problems it handed on: 64-bit words
+        const bool wrap = ring > 0 && ring < W;
+        const int Wc = wrap ? (ring & ~7) : W;
+        const size_t smem = (size_t)Wc * 16 + clamp_bytes;
+        io.work_counter = &counters[6]; io.subset = fb_list.data() + 2 * (size_t)B; io.B_dev = &counters[5];
+        io.fallback_list = fb_list.data(); io.fallback_count = &counters[2];
+        const unsigned long long bound = P.bound_fx;
+#define EMU_RUN64(WRAPV, MAXTV) emu::launch(1, threads, smem, [&] { fast_pull_kernel<FastDescProv, true, WRAPV, MAXTV, false>(P, B, io, d, nullptr, nullptr, 0, Wc, bound); })
+        if (threads <= 192) { if (wrap) EMU_RUN64(true, 192); else EMU_RUN64(false, 192); }
+        else if (threads <= 512) { if (wrap) EMU_RUN64(true, 512); else EMU_RUN64(false, 512); }
+        else { if (wrap) EMU_RUN64(true, 1024); else EMU_RUN64(false, 1024); }
+        if (handed) for (int i = 0; i < counters[2]; i++) if (fb_list[i] >= 0 && fb_list[i] < B) handed[fb_list[i]] |= 4;
+    }
+    return MPC_OK;
+}
+
 // HighwayState.predict_step_without_ego through the K4 kernel
 extern "C" int emu_predict_step_without_ego(const mpc_params *params, int B, int nmax, const double *ego, const double *cars_x,
                                             const double *cars_v, const double *cars_a, const int32_t *n_cars, double dt, double mcd,

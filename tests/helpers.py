@@ -24,3 +24,16 @@ def mpc_params_from_oracle(op):
 
 def rel(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def fast_mode_matches_model(O, info, op, st, idx, cost):
+    """Is (idx, cost) of a fast-mode plan bit-identical to the CPU model of the kernel that produced it?  `info` =
+    MpcEngine.fast32_info().  The 32-bit-key kernel makes the first attempt (2^-frac_bits labels under its bound); what it
+    hands on -- bounded attempt failed, or the frontier outgrew its ring -- is solved by the 64-bit kernel (2^-18 labels):
+    the model ladder is the normal case, the plain 2^-18 model the answer for a problem that was handed on for the ring."""
+    ob, di, sv = O.build_grid(op, st)
+    a = (op, ob, di, sv, op.t_disc, st.ego_v, st.ego_a)
+    cands = [O.solve_fast_ladder(*a, info["frac_bits"] if info["in_use"] else 0, info["bound_fx"])]
+    if info["in_use"]:
+        cands.append(O.solve_fast_model(*a))
+    return any(np.array_equal(m["idx"], idx) and m["cost"] == cost for m in cands), cands[0]

@@ -1,11 +1,12 @@
 """mpc_env_step (Settings.FUSED_ENV_STEP) on the device against the tensor version of MergeEnv.step.
 
-`unverified` (tests/conftest.py): bit-identical under the CPU emulation (tests/test_closed_loop_emulated_cpu.py), first
-on-device run pending.  On a GPU the fresh-episode traffic of the tensor version goes through torch.cumsum (a parallel scan),
+Bit-identical under the CPU emulation too (tests/test_closed_loop_emulated_cpu.py).  Its first device run (round 2) failed on the
+reward: `tensor / python_float` on a CUDA device multiplies by the rounded reciprocal, the kernel -- like the reference's float
+arithmetic (merge_gym.py:83-96) -- divides; the tensor version now divides as well (prediction.tdiv).  On a GPU the fresh-episode traffic of the tensor version goes through torch.cumsum (a parallel scan),
 the kernel sums left to right: rows that were reset agree to rounding, everything else bit for bit."""
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unverified]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("auto_reset", [False, True])

@@ -60,7 +60,10 @@ def test_edge_states(oracle, eng17, mode):
         ok = ref["cost"] > 0
         assert np.all(helpers.rel(out["cost"].cpu().numpy()[ok], ref["cost"][ok]) < 1e-6)
         assert (idx == ref["idx"]).all(1).sum() >= len(EDGE_STATES) - 1
-    assert np.array_equal(out["crash"].cpu().numpy().astype(bool), ref["crash"]) or mode == "fast"
+    # the crash verdict (st.py:790-802) is a function of the chosen sequence: wherever the sequence is the oracle's, so is the verdict
+    same = (idx == ref["idx"]).all(1)
+    assert same.all() or mode == "fast"
+    assert np.array_equal(out["crash"].cpu().numpy().astype(bool)[same], ref["crash"][same])
     assert eng.selftest_search(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"]) == 0
 
 
@@ -182,9 +185,8 @@ def test_other_settings_keep_parity(oracle, over):
     assert np.array_equal(fa["reached_t"], ref["reached_t"])
     ok = ref["cost"] > 0
     assert np.all(helpers.rel(fa["cost"][ok], ref["cost"][ok]) <= 1e-4)
+    info = eng.fast32_info()
     for b in range(0, B, 5):
-        st = helpers.oracle_state(oracle, S, b)
-        obst, dist, sv = oracle.build_grid(op, st)
-        m = oracle.solve_fast_model(op, obst, dist, sv, op.t_disc, st.ego_v, st.ego_a)
-        assert np.array_equal(m["idx"], fa["idx"][b]) and m["cost"] == fa["cost"][b], (b, m["cost"], fa["cost"][b])
+        ok, m = helpers.fast_mode_matches_model(oracle, info, op, helpers.oracle_state(oracle, S, b), fa["idx"][b], fa["cost"][b])
+        assert ok, (b, m["cost"], fa["cost"][b])
     eng.close()

@@ -1,10 +1,10 @@
 """mpc_plan_masked / mpc_finer_fit_masked and Settings.SYNC_FREE_TAKEOVER on the device.
 
-`unverified` (tests/conftest.py): verified under the CPU emulation (tests/test_library_emulation_cpu.py,
-tests/test_closed_loop_emulated_cpu.py), first on-device run pending."""
+Also run under the CPU emulation (tests/test_library_emulation_cpu.py, tests/test_closed_loop_emulated_cpu.py); passed on a B200 at the
+end of round 1."""
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unverified]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("mode", ["fast", "exact"])
