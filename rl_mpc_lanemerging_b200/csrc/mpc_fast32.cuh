@@ -22,8 +22,10 @@
 // The result equals the CPU model orc_solve_fast_model_q(f32_frac, 0, f32_bound) bit for bit (oracle/mpc_oracle.c).
 #pragma once
 
-#define F32_EMPTY 0xffffffffu
 #define F32_STATE 0xff000000u       // words >= this are state words / empty, words below are keys
+#define F32_EMPTY 0xff000000u       // "no node": the state word with v = 0, a = -128.  No word of the arrays is ever >= 0xffffff00
+                                    // (a state word has v <= 250), which is what lets a closed offer be issued with the key 0xffffffff
+#define F32_EMPTY64 0xff000000ff000000ULL
 #define F32_OVF 32                  // same-bucket candidates per layer (more: the problem is handed on)
 #define F32_L2 512                  // cells of layers 1 and 2 (off-grid history) the prologue can hold
 
@@ -32,8 +34,7 @@ struct F32Tables { unsigned v[256], aj[8 + 32 * 16 + 8]; };     // aj padded: th
 #ifdef MPC_HOST_EMU
 __device__ __forceinline__ unsigned lds_u32(unsigned a) { emu::preempt_point(); emu::S().cell_reads++; return *emu::from_shared<unsigned>(a); }
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { emu::preempt_point(); *emu::from_shared<unsigned>(a) = v; }
-__device__ __forceinline__ unsigned atoms_min_u32_if(unsigned a, unsigned val, bool doit) {
-    if (!doit) return F32_EMPTY;
+__device__ __forceinline__ unsigned atoms_min_u32(unsigned a, unsigned val) {
     emu::preempt_point();
     emu::S().cas_issued++;
     unsigned *p = emu::from_shared<unsigned>(a), old = *p; if (val < old) *p = val; return old;
@@ -41,12 +42,9 @@ __device__ __forceinline__ unsigned atoms_min_u32_if(unsigned a, unsigned val, b
 #else
 __device__ __forceinline__ unsigned lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-// predicated min: returns the previous word, or F32_EMPTY when `doit` is false (no branch around the atomic)
-__device__ __forceinline__ unsigned atoms_min_u32_if(unsigned a, unsigned val, bool doit) {
-    unsigned old;
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.b32 %0, 0xffffffff;\n\t@p atom.shared.min.u32 %0, [%1], %2;\n\t}"
-                 : "=&r"(old) : "r"(a), "r"(val), "r"((unsigned)doit) : "memory");
-    return old;
+// (ptxas turns a predicated atom.shared with a result into a branch around it: closed offers are issued with a neutral key instead)
+__device__ __forceinline__ unsigned atoms_min_u32(unsigned a, unsigned val) {
+    unsigned old; asm volatile("atom.shared.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(val) : "memory"); return old;
 }
 #endif
 
@@ -107,7 +105,7 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
         }
         // ---- prologue: layers 0 -> 1 -> 2 have off-grid history (st_cy.pyx:329-330): exact fp64 edges, quantised; the few
         // layer-2 cells are min-combined as 64-bit words in a scratch row (array 0, not yet in use) and then turned into keys ----
-        for (int k = tid; k < F32_L2; k += nth) { sts_u64(ab + 8u * k, FX_EMPTY); s_l2full[k] = F32_EMPTY; }
+        for (int k = tid; k < F32_L2; k += nth) { sts_u64(ab + 8u * k, FX_EMPTY); s_l2full[k] = 0xffffffffu; }
         int imin0, imax0;
         exact_window(P, g.s0, g.ds, g.s0, est_prev, est_second, imin0, imax0);
         if (imax0 > g.num_s) imax0 = g.num_s;
@@ -143,7 +141,7 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
             for (int e = tid; e < (hi1 - lo1 + 1) * lme; e += nth) {      // one thread per (layer-1 node, successor)
                 const int k1 = lo1 + e / lme, j = e % lme;
                 const unsigned l1 = s_l2full[k1];
-                if (l1 == F32_EMPTY) continue;
+                if (l1 == 0xffffffffu) continue;
                 const double s = g.sval(k1);
                 int imin, imax;
                 exact_window(P, g.s0, g.ds, s, g.s0, est_prev, imin, imax);
@@ -162,14 +160,14 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
             __syncthreads();
             dlo = S.nlo[2]; dhi = S.nhi[2];
             if (dhi < 0) fail = true;
-            else for (int kk = dlo + tid; kk <= dhi; kk += nth) { // winners of layer 2 -> keys in array 2, full labels aside
+            for (int kk = tid; kk < F32_L2; kk += nth) {          // winners of layer 2 -> keys in array 2, full labels aside; scratch row back to "empty"
                 const unsigned long long w2 = lds_u64(ab + 8u * kk);
                 if (w2 != FX_EMPTY) {
                     const unsigned tot = (unsigned)(w2 >> 16);
                     s_l2full[kk] = tot;
                     sts_u32(ab + 4u * (2 * Wc + ring(kk)), (tot & ~255u) | (unsigned)((w2 >> 8) & 255u));
-                    sts_u64(ab + 8u * kk, FX_EMPTY);
                 }
+                sts_u64(ab + 8u * kk, F32_EMPTY64);
             }
         }
         if (T > 4) prov.store(4);
@@ -255,23 +253,45 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
                                     const unsigned tva = tbv + 4u * vn, taja = tbaj + 4u * ((an + 16) * 16 + (jn + 8));
                                     const unsigned tie = 255u - (unsigned)vn;
                                     const int r0 = ring(wlo);
-                                    const bool flat = !WRAP || r0 + n <= Wc;      // the window does not cross the end of the ring
-                                    const unsigned ra = nxt + 4u * r0;
                                     // offer e: label + V[v'] + A[a'] + J[j'] with v' = vn + e, a' = an + e, j' = jn + e
-#define F32_OFFER(E)                                                                                                          \
+#define F32_KEY(E) (((label + lds_u32_nc(tva + 4u * (E)) + lds_u32_nc(taja + 68u * (E))) & ~255u) | (tie - (E)))
+#define F32_LIST(CELL, OLD, KEY)            /* same bucket: list the loser (rare) */                                           \
                                     {                                                                                         \
-                                        const unsigned key = ((label + lds_u32_nc(tva + 4u * (E)) + lds_u32_nc(taja + 68u * (E))) & ~255u) | (tie - (E)); \
-                                        const unsigned adr = flat ? ra + 4u * (E) : nxt + 4u * (unsigned)(r0 + (E) >= Wc ? r0 + (E) - Wc : r0 + (E)); \
-                                        const unsigned old = atoms_min_u32_if(adr, key, (open >> (E)) & 1u);                   \
-                                        if ((old ^ key) < 256u) {                 /* same bucket: list the loser (rare) */      \
-                                            const int oi = atomicAdd(&s_ovfn[n3], 1);                                         \
-                                            if (oi < F32_OVF) s_ovf[n3][oi] = make_uint2((unsigned)(wlo + (E)), old > key ? old : key); \
-                                            else S.need_fallback = 1;                                                         \
-                                        }                                                                                     \
+                                        const int oi = atomicAdd(&s_ovfn[n3], 1);                                             \
+                                        if (oi < F32_OVF) s_ovf[n3][oi] = make_uint2((unsigned)(CELL), (OLD) > (KEY) ? (OLD) : (KEY)); \
+                                        else S.need_fallback = 1;                                                             \
                                     }
-                                    F32_OFFER(0) F32_OFFER(1) F32_OFFER(2) F32_OFFER(3) F32_OFFER(4)
-                                    for (int e = 5; e < n; e++) F32_OFFER(e)       // (windows longer than 5 cells: other Settings)
-#undef F32_OFFER
+                                    if (!WRAP || r0 + 5 <= Wc) {
+                                        // Straight line: five keys, five unconditional mins, one test.  A closed offer (blocked cell, or
+                                        // past a window shorter than five cells) is issued with the key 0xffffffff: it changes nothing,
+                                        // and no word in the arrays shares its upper 24 bits, so it cannot look like a same-bucket pair.
+                                        const unsigned ra = nxt + 4u * (unsigned)r0;
+                                        unsigned k0 = F32_KEY(0), k1 = F32_KEY(1), k2 = F32_KEY(2), k3 = F32_KEY(3), k4 = F32_KEY(4);
+                                        k0 = (open & 1u) ? k0 : 0xffffffffu; k1 = (open & 2u) ? k1 : 0xffffffffu; k2 = (open & 4u) ? k2 : 0xffffffffu;
+                                        k3 = (open & 8u) ? k3 : 0xffffffffu; k4 = (open & 16u) ? k4 : 0xffffffffu;
+                                        const unsigned o0 = atoms_min_u32(ra, k0), o1 = atoms_min_u32(ra + 4u, k1), o2 = atoms_min_u32(ra + 8u, k2),
+                                                       o3 = atoms_min_u32(ra + 12u, k3), o4 = atoms_min_u32(ra + 16u, k4);
+                                        if (min(min(min(o0 ^ k0, o1 ^ k1), min(o2 ^ k2, o3 ^ k3)), o4 ^ k4) < 256u) {
+                                            if ((o0 ^ k0) < 256u) F32_LIST(wlo, o0, k0)
+                                            if ((o1 ^ k1) < 256u) F32_LIST(wlo + 1, o1, k1)
+                                            if ((o2 ^ k2) < 256u) F32_LIST(wlo + 2, o2, k2)
+                                            if ((o3 ^ k3) < 256u) F32_LIST(wlo + 3, o3, k3)
+                                            if ((o4 ^ k4) < 256u) F32_LIST(wlo + 4, o4, k4)
+                                        }
+                                        for (int e = 5; e < n; e++)                 // (windows longer than 5 cells: other Settings)
+                                            if ((open >> e) & 1u) {
+                                                const unsigned key = F32_KEY(e), old = atoms_min_u32(nxt + 4u * (unsigned)ring(wlo + e), key);
+                                                if ((old ^ key) < 256u) F32_LIST(wlo + e, old, key)
+                                            }
+                                    } else {                                        // the window crosses the end of the ring
+                                        for (int e = 0; e < n; e++)
+                                            if ((open >> e) & 1u) {
+                                                const unsigned key = F32_KEY(e), old = atoms_min_u32(nxt + 4u * (unsigned)(r0 + e >= Wc ? r0 + e - Wc : r0 + e), key);
+                                                if ((old ^ key) < 256u) F32_LIST(wlo + e, old, key)
+                                            }
+                                    }
+#undef F32_KEY
+#undef F32_LIST
                                 }
                             }
                         } else sts_u32(cur + 4u * rk, F32_EMPTY);   // dropped by the bound: the key must not be seen again

@@ -271,6 +271,40 @@ __global__ void __launch_bounds__(32 * QP_WARPS) finer_fit_kernel(DevParams P, i
         }
     }
     __syncwarp();
+    // Guard.  The QP is infeasible when the fixed history already breaks a limit that the first rows cannot repair -- an ego that
+    // has just braked to a standstill with a0 < ~-1 (speed, acceleration and jerk rows of step 0 contradict each other), or one
+    // near MAX_SPEED with a0 > 0; both are reachable in closed loop.  The slacks then collapse and the iterate turns into NaN
+    // (cvxopt in the reference stops after maxiters = 10 with a finite, slightly infeasible iterate; st.py:16-17).  An iterate
+    // that is not finite or breaks a limit by more than the tolerance is replaced by the interpolated plan tracked step by step
+    // through the limits in the order jerk, acceleration, speed (control.py:160-171 applied to every step): always finite,
+    // always inside the limits the environment enforces.  iters_out = max_iter + 1 marks such an episode.
+    {
+        double viol = 0.0;
+        for (int rr = lane; rr < R; rr += 32) {
+            const double rv = qp_row(m, rr, S.x);
+            const double e = fmax(rv - S.ub[rr], S.lb[rr] - rv);
+            viol = (e == e) ? fmax(viol, e) : 1.0e300;            // (NaN -> violation)
+        }
+        viol = wmax(viol);
+        if (!(viol <= 10.0 * tol + 1.0e-9)) {
+            if (lane == 0) {
+                double prev = sc[0], v = v0, a = a0;
+                for (int i = 0; i < m; i++) {
+                    const double vt = (S.bv[i] - prev) / dt;
+                    double jk = ((vt - v) / dt - a) / dt;
+                    jk = jk < P.p.j_min ? P.p.j_min : (jk > P.p.j_max ? P.p.j_max : jk);
+                    double an = a + jk * dt;
+                    an = an < P.p.a_min ? P.p.a_min : (an > P.p.a_max ? P.p.a_max : an);
+                    double vn = v + an * dt;
+                    if (vn < 0.0) { vn = 0.0; an = (vn - v) / dt; }
+                    else if (vn > P.p.max_speed) { vn = P.p.max_speed; an = (vn - v) / dt; }
+                    prev += vn * dt; S.x[i] = prev; v = vn; a = an;
+                }
+            }
+            it = max_iter + 1;
+            __syncwarp();
+        }
+    }
     if (lane == 0) out[0] = sc[0];
     for (int i = lane; i < m; i += 32) out[i + 1] = S.x[i];
     if (lane == 0) {

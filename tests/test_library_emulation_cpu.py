@@ -182,6 +182,31 @@ def test_remaining_entry_points_against_the_oracle():
     eng.close()
 
 
+def test_finer_fit_survives_infeasible_histories():
+    """an ego that has just braked to a standstill with a0 < ~-1, or sits near MAX_SPEED with a0 > 0, makes
+    the first rows of the QP (st.py:626-668) contradict each other; the interior-point iterate used to turn into NaN and the NaN
+    speed command poisoned the episode.  The kernel now replaces a non-finite / infeasible iterate by the plan tracked through
+    the limits step by step: the speed command is finite, inside [0, MAX_SPEED] and reachable under the jerk / acceleration clamp."""
+    op, p = _params(17)
+    eng = EA.EmuEngine(p, max_batch=8)
+    S = synthetic.make_states(6, "moderate", seed=4)
+    bad = [(0.5, -6.0), (0.0, -6.0), (29.9, 4.5), (0.3, -1.5), (30.0, 2.0), (12.0, 0.3)]
+    plan = eng.plan(S)                                         # ordinary plans ...
+    assert (plan["reached_t"] == 17).all()
+    for b, (v0, a0) in enumerate(bad):                         # ... fitted from histories that contradict the limits
+        S["ego"][b, 2], S["ego"][b, 3] = v0, a0
+    fine, n_fine, speed, iters = eng.finer_fit(plan["s_seq"], plan["reached_t"], S["ego"])
+    assert np.isfinite(speed).all() and all(np.isfinite(fine[b, :n_fine[b]]).all() for b in range(6))
+    tick = op.tick_length
+    assert (iters[:3] == 41).all() and iters[5] <= 40          # the three states of the report fall back, the ordinary one converges
+    for b, (v0, a0) in enumerate(bad):
+        assert -1e-9 <= speed[b] <= op.max_speed + 1e-9
+        if iters[b] == 41:                                     # the fallback equals control.get_ego_speed_from_jerk of the tracked step
+            acc = (speed[b] - v0) / tick
+            assert op.a_min - 1e-9 <= acc <= op.a_max + 1e-9 or speed[b] in (0.0, op.max_speed)
+    eng.close()
+
+
 @pytest.mark.parametrize("name,H,n", [("plan_h17.npz", 17, 40), ("plan_h50.npz", 50, 6)])
 def test_emulated_library_against_the_reference_golden_vectors(name, H, n):
     """The committed outputs of the UNMODIFIED reference (tests/golden/make_golden.py): exact mode reproduces positions, crash
