@@ -24,6 +24,7 @@ int exact_occupancy(int threads, size_t smem);
 int fast_occupancy(int threads, size_t smem, int wrap);
 cudaError_t launch_fast32_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
 int fast32_occupancy(int threads, size_t smem, int wrap);
+size_t fast32_head_bytes(int num_s_max);
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
                                   const int32_t *n, LayerDesc *desc, double *s0, double *ds, int32_t *ns, cudaStream_t st, const int32_t *subset = nullptr, const int *count = nullptr);
 cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const LayerDesc *desc, const double *s0, const double *ds,
@@ -175,10 +176,12 @@ static int configure(mpc_handle *h) {
     h->grid32 = 0; h->grid32b = 0;
     { const char *e = getenv("MPC_FAST32");
       if (P.fast_ok && P.f32_ok && h->use_bound && !(e && e[0] == '0')) {
-        const size_t static32 = 14336 + 1024;        // static shared of fast32_kernel (13.2 KB) + the per-block reserve
+        // dynamic shared memory of fast32_kernel: head (its tables, staging, bit arrays: ~18 KB at H=50) + 12 B per ring cell; the only
+        // static shared memory left is the back-track row of finish_problem (0.6 KB), plus the 1 KB per-block reserve
+        const size_t head32 = fast32_head_bytes(P.num_s_max), static32 = 1024 + 1024;
         auto ring_of = [&](int nb) -> size_t {
             const size_t per = (h->smem_optin + 1024) / nb;
-            return per > static32 + clamp_bytes ? (per - static32 - clamp_bytes) / 12 : 0;
+            return per > static32 + head32 ? (per - static32 - head32) / 12 : 0;
         };
         auto shape = [&](int nb, int threads_override, int *Wc, int *wrap, size_t *smem, int *threads, int *grid) {
             const size_t cap = ring_of(nb);
@@ -186,7 +189,7 @@ static int configure(mpc_handle *h) {
             *wrap = (size_t)h->W > cap;
             *Wc = *wrap ? (int)(cap & ~(size_t)7) : h->W;
             if (*Wc < 1024 || 2 * *Wc < h->W) return;        // prologue scratch row; ring() folds an index once
-            *smem = (size_t)*Wc * 12 + clamp_bytes;
+            *smem = (size_t)*Wc * 12 + head32;
             const int bps = (int)(h->smem_optin / (*smem + static32 - 1024));
             *threads = threads_override ? threads_override : (bps >= 5 ? 192 : (bps >= 4 ? 256 : (bps >= 3 ? 384 : (bps >= 2 ? 512 : 1024))));
             const int occ = fast32_occupancy(*threads, *smem, *wrap);

@@ -732,6 +732,8 @@ cudaError_t launch_fast32_desc(const DevParams &P, const SolveLaunch &L, const S
     return launch_fast32_desc_impl(P, L, io, desc, st);
 }
 
+size_t fast32_head_bytes(int num_s_max) { return fast32_smem_head(num_s_max); }
+
 int fast32_occupancy(int threads, size_t smem, int wrap) {
     int n = 0;
     cudaError_t e;

@@ -30,6 +30,17 @@
 #define F32_L2 512                  // cells of layers 1 and 2 (off-grid history) the prologue can hold
 
 struct F32Tables { unsigned v[256], aj[8 + 32 * 16 + 8]; };     // aj padded: the state rebuild of layer 2 may look 8 entries outside
+// Everything static in ONE struct: the hot loop addresses it as (one pinned base register) + (compile-time offset).  Left to itself
+// nvcc rebuilds the shared-window address of every static array from S2UR / UMOV / ULEA at each use (~25 instructions per node).
+struct __align__(16) F32Shared {
+    FastShared FS;                  // first: staged with 16-byte vector stores
+    F32Tables TB;
+    unsigned l2full[F32_L2];        // full labels of layer 1, then of layer 2 (their edges are not tabulated)
+    uint2 ovf[3][F32_OVF];          // layer t % 3: (cell, key) of candidates that lost to a key of their own bucket
+    int ovfn[3];
+    int chunk[3];
+    unsigned long long best;
+};
 
 #ifdef MPC_HOST_EMU
 __device__ __forceinline__ unsigned lds_u32(unsigned a) { emu::preempt_point(); emu::S().cell_reads++; return *emu::from_shared<unsigned>(a); }
@@ -56,19 +67,25 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
 #else
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
-    __shared__ FastShared FS;
-    __shared__ F32Tables TB;
-    __shared__ unsigned s_l2full[F32_L2];      // full labels of layer 1, then of layer 2 (their edges are not tabulated)
-    __shared__ uint2 s_ovf[3][F32_OVF];        // layer t % 3: (cell, key) of candidates that lost to a key of their own bucket
-    __shared__ int s_ovfn[3];
-    __shared__ unsigned long long s_best;
-    __shared__ int s_chunk[3];
+    // dynamic shared memory: [F32Shared | clamp bits lo, hi | blocked bits 0, 1 | three arrays of Wc words]
+    F32Shared &SH = *reinterpret_cast<F32Shared *>(smem_raw);
+    FastShared &FS = SH.FS;
+    F32Tables &TB = SH.TB;
+    unsigned (&s_l2full)[F32_L2] = SH.l2full;
+    uint2 (&s_ovf)[3][F32_OVF] = SH.ovf;
+    int (&s_ovfn)[3] = SH.ovfn;
+    int (&s_chunk)[3] = SH.chunk;
+    unsigned long long &s_best = SH.best;
     BlockShared &S = FS.S;
-    const unsigned ab = smem_u32(smem_raw);    // three arrays of Wc 32-bit words: layer t lives in array t % 3
+    unsigned sbase = smem_u32(smem_raw);
+#ifndef MPC_HOST_EMU
+    asm volatile("" : "+r"(sbase));            // pinned: see F32Shared
+#endif
     ClampBits CB;
     const int NW = (P.num_s_max + 31) >> 5;
-    CB.lo = reinterpret_cast<unsigned *>(smem_raw + (size_t)12 * Wc); CB.hi = CB.lo + NW;
+    CB.lo = reinterpret_cast<unsigned *>(smem_raw + sizeof(F32Shared)); CB.hi = CB.lo + NW;
     unsigned *const blkbits[2] = {CB.hi + NW, CB.hi + 2 * NW + 2};      // blocked cells of layer L in blkbits[L & 1]
+    const unsigned ab = sbase + (unsigned)sizeof(F32Shared) + 4u * (unsigned)(4 * NW + 4);    // three arrays of Wc 32-bit words: layer t lives in array t % 3
     uint16_t *bp = io.bp + (size_t)blockIdx.x * P.num_t * io.bp_stride;
     const int T = P.num_t, tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
     auto ring = [Wc](int k) -> int { return WRAP ? (k >= Wc ? k - Wc : k) : k; };
@@ -78,7 +95,7 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
     if (io.B_dev) B = *io.B_dev;
     const unsigned bnd = P.f32_bound;
     const float kw = P.kw32;
-    const unsigned tbv = smem_u32(TB.v), tbaj = smem_u32(TB.aj + 8), cba = smem_u32(CB.lo);
+    const unsigned tbv = sbase + (unsigned)offsetof(F32Shared, TB.v), tbaj = sbase + (unsigned)(offsetof(F32Shared, TB.aj) + 32), cba = sbase + (unsigned)sizeof(F32Shared);
     for (;;) {
         if (tid == 0) S.b = atomicAdd(io.work_counter, 1);
         __syncthreads();
@@ -188,9 +205,11 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
                 if (t + 3 < T) prov.store(t + 3);
                 if (t + 4 < T) prov.load(t + 4);
                 const bool last = (t == T - 1), first = (t == 2);
+                const unsigned l2a = sbase + (unsigned)offsetof(F32Shared, l2full);
                 if (t + 2 < T) build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
-                const unsigned edge0 = smem_u32(FS.layer[t & 3].edge), bucket0 = smem_u32(FS.layer[t & 3].bucket_edge);
-                const unsigned bwa = smem_u32(blkbits[(t + 1) & 1]);
+                const unsigned edge0 = sbase + (unsigned)(offsetof(F32Shared, FS.layer) + offsetof(LayerSearch, edge)) + (unsigned)(t & 3) * (unsigned)sizeof(LayerSearch);
+                const unsigned bucket0 = edge0 + (unsigned)(offsetof(LayerSearch, bucket_edge) - offsetof(LayerSearch, edge));
+                const unsigned bwa = cba + 4u * (unsigned)(2 * NW + ((t + 1) & 1) * (NW + 2));
                 uint16_t *bp_row = bp + (size_t)t * io.bp_stride;
 #ifndef MPC_HOST_EMU
                 asm volatile("" : "+l"(bp_row));
@@ -227,9 +246,12 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
                             }
                         }
                         unsigned full = (w & ~255u) | low;
-                        if (first) full = s_l2full[k];
+                        if (first) full = lds_u32_nc(l2a + 4u * (unsigned)k);
                         // distance penalty: nearest distance-field edge on either side; edge[-1] / edge[n_edge] are -/+1e300
-                        const double sv = g.sval(k);
+                        double sv = g.sval(k);
+#ifndef MPC_HOST_EMU
+                        asm volatile("" : "+d"(sv));              // (else it is computed twice: five fp64 instructions)
+#endif
                         unsigned ea = edge0 + 8u * lds_u8_nc(bucket0 + (k >> MPC_BUCKET_SHIFT));
                         double hi = lds_f64_nc(ea);
                         while (hi < sv) { ea += 8u; hi = lds_f64_nc(ea); }
@@ -324,6 +346,9 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
         finish_problem(P, io, prov, &S, b, g, bt, (int)(best_word & 0xffff), (double)(best_word >> 16) / P.f32_one, bp, true);
     }
 }
+
+// bytes of dynamic shared memory in front of the three key / state arrays (the host adds 12 B per ring cell)
+static size_t fast32_smem_head(int num_s_max) { return sizeof(F32Shared) + (size_t)4 * (4 * ((num_s_max + 31) >> 5) + 4); }
 
 static cudaError_t launch_fast32_desc_impl(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st) {
     cudaError_t e;
