@@ -239,6 +239,7 @@ typedef struct mpc_env_params {
     double ego_start_x, ego_start_y, start_speed, start_speed_var, min_start_speed, max_start_speed;
     double time_reward_step;        /* TIME_REWARD * TICK_LENGTH */
     double jerk_weight, crash_reward, success_reward;
+    double invalid_action_step;     /* INVALID_ACTION_PENALTY * TICK_LENGTH, added to the reward of a tick whose action was clipped (merge_gym.py:86-92) */
     int32_t max_ticks, auto_reset;
 } mpc_env_params;
 int mpc_env_step(mpc_handle *h, const mpc_env_params *ep, int B, double *d_ego, double *d_cars_x, double *d_cars_v,

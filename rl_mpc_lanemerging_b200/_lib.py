@@ -26,7 +26,7 @@ class MpcParams(C.Structure):
 
 ENV_PARAM_FIELDS = ("tick", "a_min", "a_max", "max_speed", "min_crash_distance", "sensor_radius", "spawn_x", "other_speed", "interval",
                     "arrival_x", "ego_start_x", "ego_start_y", "start_speed", "start_speed_var", "min_start_speed", "max_start_speed",
-                    "time_reward_step", "jerk_weight", "crash_reward", "success_reward")
+                    "time_reward_step", "jerk_weight", "crash_reward", "success_reward", "invalid_action_step")
 
 
 class MpcEnvParams(C.Structure):

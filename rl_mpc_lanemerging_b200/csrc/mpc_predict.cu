@@ -475,13 +475,22 @@ __global__ void __launch_bounds__(128) env_step_kernel(DevParams P, mpc_env_para
     // every per-episode scalar is read here, before the first collective: lane 0 overwrites them at the end of the kernel
     const double pa = prev_acc[b], delay_in = delay[b];
     const int ticks_in = ticks[b];
-    double acc = __dadd_rn(pa, __dmul_rn(jerk[b], E.tick));
-    acc = acc < E.a_min ? E.a_min : (acc > E.a_max ? E.a_max : acc);
-    double spd = __dadd_rn(e.v, __dmul_rn(acc, E.tick));
-    const bool clipped = spd > E.max_speed || spd < 0.0;
-    spd = spd < 0.0 ? 0.0 : (spd > E.max_speed ? E.max_speed : spd);
-    if (clipped) acc = __ddiv_rn(__dsub_rn(spd, e.v), E.tick);
-    const double pj = __ddiv_rn(__dsub_rn(acc, pa), E.tick);
+    // _handle_jerk (merge_gym.py:83-96): the projected acceleration is clipped, ELSE the projected speed (computed with the
+    // unclipped acceleration) is clipped and the acceleration follows from it; either way the action counts as invalid
+    double acc_p = __dadd_rn(pa, __dmul_rn(jerk[b], E.tick));
+    double spd_p = __dadd_rn(e.v, __dmul_rn(acc_p, E.tick));
+    const double acc_c = acc_p < E.a_min ? E.a_min : (acc_p > E.a_max ? E.a_max : acc_p);
+    bool invalid = false;
+    if (acc_p > E.a_max || acc_p < E.a_min) { invalid = true; acc_p = acc_c; }
+    else if (spd_p > E.max_speed || spd_p < 0.0) {
+        invalid = true;
+        spd_p = spd_p < 0.0 ? 0.0 : E.max_speed;
+        acc_p = __ddiv_rn(__dsub_rn(spd_p, e.v), E.tick);
+    }
+    const double pj = __ddiv_rn(__dsub_rn(acc_p, pa), E.tick);
+    // the command itself: control.set_ego_jerk -> get_ego_speed_from_jerk (control.py:160-176), both clamps in sequence
+    double spd = __dadd_rn(e.v, __dmul_rn(acc_c, E.tick));
+    spd = spd > E.max_speed ? E.max_speed : (spd < 0.0 ? 0.0 : spd);
     // world step: the reference predictor as dynamics (cars beyond n keep their values, like the in-place K4 call)
     double nx, nv, na;
     const bool crashed = warp_predict_with_ego(P, lane, n, e, x, v, spd, E.tick, E.min_crash_distance, eo, nx, nv, na);
@@ -504,10 +513,13 @@ __global__ void __launch_bounds__(128) env_step_kernel(DevParams P, mpc_env_para
     const bool arrived = eo.x > E.arrival_x && !crashed;
     const bool timeout = tk >= E.max_ticks && !crashed && !arrived;
     const bool done = crashed || arrived || timeout;
-    // dqn.py:557-563
-    double r = __dsub_rn(E.time_reward_step, __dmul_rn(__dmul_rn(E.jerk_weight, __dmul_rn(pj, pj)), E.tick));
+    // merge_gym.py:102-140 + dqn.py:557-563: a tick that ends in a crash / an arrival pays the terminal reward, every other tick
+    // the time + jerk reward of the MEASURED jerk (new acceleration against the previous one); a clipped action adds its penalty
+    const double jm = __ddiv_rn(__dsub_rn(eo.a, pa), E.tick);
+    double r = __dsub_rn(E.time_reward_step, __dmul_rn(__dmul_rn(E.jerk_weight, __dmul_rn(jm, jm)), E.tick));
     if (arrived) r = E.success_reward;
     if (crashed) r = E.crash_reward;
+    if (invalid) r = __dadd_rn(r, E.invalid_action_step);
     if (E.auto_reset && done) {
         // fresh initial conditions: spawner-spaced traffic (control.py:215-226), ego at the ramp start (control.py:41-44, 198-204)
         double g = slot_ok ? __dmul_rn(E.other_speed, __dadd_rn(E.interval, gap_u[o])) : 0.0;

@@ -76,6 +76,20 @@ class DDPGAgent(dqn.RLAgent):
         agent.policy.to(agent.device).eval()
         return agent
 
+    @classmethod
+    def load_npz(cls, path, device=None) -> "DDPGAgent":
+        """The same actor from a plain .npz of its tensors (keys model_{0,2,4}_{weight,bias}, tanh_scale, tanh_mean) -- the form in
+        which the published pretrained_models/ddpg_moderate1_extended/policy.pt is committed as a test fixture
+        (tests/golden/policy_moderate1.npz, written by tests/golden/make_golden_r2.py)."""
+        import numpy as np
+        z = np.load(path)
+        agent = cls(device)
+        sd = {f"model.{i}.{w}": torch.from_numpy(np.asarray(z[f"model_{i}_{w}"], np.float32)) for i in (0, 2, 4) for w in ("weight", "bias")}
+        agent.policy.load_state_dict(sd)
+        agent.policy.tanh_scale, agent.policy.tanh_mean = float(z["tanh_scale"]), float(z["tanh_mean"])
+        agent.policy.to(agent.device).eval()
+        return agent
+
     def reset_time(self, mask: Optional[torch.Tensor] = None):
         if self.timestep is not None:
             if mask is None:

@@ -105,6 +105,7 @@ class MergeEnv:
         ep.min_start_speed, ep.max_start_speed = float(S.MIN_START_SPEED), float(S.MAX_START_SPEED)
         ep.time_reward_step = S.TIME_REWARD * S.TICK_LENGTH
         ep.jerk_weight, ep.crash_reward, ep.success_reward = float(S.ALT_J_WEIGHT), float(S.CRASH_REWARD), float(S.SUCCESS_REWARD)
+        ep.invalid_action_step = float(S.INVALID_ACTION_PENALTY) * float(S.TICK_LENGTH)
         ep.max_ticks, ep.auto_reset = int(self.max_ticks), int(bool(self.auto_reset))
         u = self._rand(B) if S.VARY_TRAFFIC_START_TIMES else None
         fresh = None
@@ -131,13 +132,19 @@ class MergeEnv:
             return self._step_fused(action)
         S, tick, st8 = Settings, float(Settings.TICK_LENGTH), self.state
         jerk = action.to(self.device, torch.float64).reshape(self.B)
-        # merge_gym.py:83-96: clip the projected acceleration / speed, remember the realised jerk
-        acc = (self.prev_acc + jerk * tick).clamp(S.MAX_NEGATIVE_ACCELERATION, S.MAX_POSITIVE_ACCELERATION)
-        spd = st8.ego[:, 2] + acc * tick
-        clipped = (spd > S.MAX_SPEED) | (spd < 0)
-        spd = spd.clamp(0, S.MAX_SPEED)
-        acc = torch.where(clipped, tdiv(spd - st8.ego[:, 2], tick), acc)
-        projected_jerk = tdiv(acc - self.prev_acc, tick)
+        # _handle_jerk (merge_gym.py:83-96): the projected acceleration is clipped, ELSE the projected speed (computed with the
+        # unclipped acceleration) is clipped and the acceleration follows from it; either way the action counts as invalid
+        v_now, prev_acc = st8.ego[:, 2].clone(), self.prev_acc
+        acc_p = prev_acc + jerk * tick
+        spd_p = v_now + acc_p * tick
+        acc_c = acc_p.clamp(S.MAX_NEGATIVE_ACCELERATION, S.MAX_POSITIVE_ACCELERATION)
+        acc_bad = (acc_p > S.MAX_POSITIVE_ACCELERATION) | (acc_p < S.MAX_NEGATIVE_ACCELERATION)
+        spd_bad = ~acc_bad & ((spd_p > S.MAX_SPEED) | (spd_p < 0))
+        acc_proj = torch.where(acc_bad, acc_c, torch.where(spd_bad, tdiv(spd_p.clamp(0, S.MAX_SPEED) - v_now, tick), acc_p))
+        projected_jerk = tdiv(acc_proj - prev_acc, tick)
+        invalid = (acc_bad | spd_bad).to(torch.float64) * (float(S.INVALID_ACTION_PENALTY) * tick)
+        # the command itself: control.set_ego_jerk -> get_ego_speed_from_jerk (control.py:160-176), both clamps in sequence
+        spd = (v_now + acc_c * tick).clamp(0, S.MAX_SPEED)
         # world step: the reference predictor as dynamics (K4 kernel, in place)
         for t in st8.args():
             assert t.is_contiguous()
@@ -164,7 +171,9 @@ class MergeEnv:
         arrived = (st8.ego[:, 0] > ARRIVAL_X) & ~crashed
         timeout = (self.ticks >= self.max_ticks) & ~crashed & ~arrived
         done = crashed | arrived | timeout
-        reward = dqn.slotted_reward_with_jerk(None, projected_jerk, crashed, arrived)
+        # merge_gym.py:102-140: terminal reward on a crash / an arrival, else the time + jerk reward of the MEASURED jerk (new
+        # acceleration against the previous one); a clipped action adds its penalty (INVALID_ACTION_PENALTY, 0 in every published config)
+        reward = dqn.slotted_reward_with_jerk(None, tdiv(st8.ego[:, 3] - prev_acc, tick), crashed, arrived) + invalid
         info = {"crashed": crashed, "merged": arrived, "timeout": timeout, "projected_jerk": projected_jerk}
         if self.auto_reset:
             self._reset_where(done)

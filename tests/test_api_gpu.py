@@ -152,6 +152,55 @@ def test_merge_env_steps(api):
     assert api["merge_gym"].JerkEnv is not None
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_env_step_follows_the_reference_tick(api, fused):
+    """MergeEnv.step / mpc_env_step against the restatement of the reference's tick (oracle/env_oracle.py: merge_gym.py:83-140,
+    control.py:160-178, dqn.py:557-563): projected jerk with the reference's clipping order, the speed command, reward (terminal
+    rewards, measured jerk on ordinary ticks, invalid-action penalty), crash / arrival / time-out flags -- bit for bit, on jerks
+    wild enough to clip on most ticks and episodes short enough to time out."""
+    from oracle import env_oracle as EO
+    torch, S = api["torch"], api["Settings"]
+    old = (S.MAX_EPISODE_LENGTH, S.INVALID_ACTION_PENALTY, getattr(S, "FUSED_ENV_STEP", False))
+    S.MAX_EPISODE_LENGTH, S.INVALID_ACTION_PENALTY, S.FUSED_ENV_STEP = 5.0, -0.3, fused
+    try:
+        B = 96
+        env = api["merge_gym"].MergeEnv(B, seed=21, auto_reset=False)
+        env.reset()
+        env.state.ego[::3, 2] = 28.5                             # some episodes start near MAX_SPEED ...
+        env.state.ego[1::3, 2] = 0.4                             # ... and some nearly standing: speed clips on both sides
+        env.state.ego[::5, 0] = 60.0                             # and some close to the end of the route (arrival)
+        g = torch.Generator(device="cpu").manual_seed(5)
+        alive = np.ones(B, bool)
+        seen = dict(acc_clip=0, spd_clip=0, crashed=0, merged=0, timeout=0)
+        for tick in range(30):
+            jerk = ((torch.rand(B, generator=g, dtype=torch.float64) - 0.5) * 60.0).to(env.device)
+            v0, a0, t0 = env.state.ego[:, 2].cpu().numpy().copy(), env.prev_acc.cpu().numpy().copy(), env.ticks.cpu().numpy().copy()
+            obs, reward, done, info = env.step(jerk)
+            a1, v1 = env.state.ego[:, 3].cpu().numpy(), env.state.ego[:, 2].cpu().numpy()
+            rw, dn, pj = reward.cpu().numpy(), done.cpu().numpy(), info["projected_jerk"].cpu().numpy()
+            cr, mg, to = info["crashed"].cpu().numpy(), info["merged"].cpu().numpy(), info["timeout"].cpu().numpy()
+            jk = jerk.cpu().numpy()
+            for b in np.nonzero(alive)[0]:
+                o = EO.env_step(S, float(v0[b]), float(a0[b]), float(jk[b]), int(t0[b]), bool(cr[b]), bool(mg[b]), float(a1[b]))
+                # (the reward to one ulp: the reference squares the jerk with Python's float ** -> libm pow(x, 2.0), which is not
+                # correctly rounded -- it differs from x * x in the last bit on ~0.06 % of the inputs; kernel and tensors multiply)
+                assert pj[b] == o["projected_jerk"] and abs(rw[b] - o["reward"]) <= 4e-16 * abs(o["reward"]), (tick, b, pj[b], o["projected_jerk"], rw[b], o["reward"])
+                assert bool(dn[b]) == o["done"] and bool(to[b]) == o["timeout"], (tick, b)
+                if not cr[b]:
+                    assert v1[b] == o["speed_command"], (tick, b, v1[b], o["speed_command"])      # the world applies the commanded speed
+                if o["zero_observation"]:
+                    assert not obs[b].any()
+                acc_p = a0[b] + jk[b] * S.TICK_LENGTH
+                seen["acc_clip"] += acc_p > S.MAX_POSITIVE_ACCELERATION or acc_p < S.MAX_NEGATIVE_ACCELERATION
+                seen["spd_clip"] += (S.MAX_NEGATIVE_ACCELERATION <= acc_p <= S.MAX_POSITIVE_ACCELERATION) and not (0 <= v0[b] + acc_p * S.TICK_LENGTH <= S.MAX_SPEED)
+                for k in ("crashed", "merged", "timeout"):
+                    seen[k] += bool(o[k])
+            alive &= ~dn
+        assert seen["acc_clip"] > 50 and seen["spd_clip"] > 5 and seen["merged"] > 0 and seen["timeout"] > 0, seen
+    finally:
+        S.MAX_EPISODE_LENGTH, S.INVALID_ACTION_PENALTY, S.FUSED_ENV_STEP = old
+
+
 def test_fused_rollout_step_equals_its_pieces(api):
     """mpc_rollout_step (one launch per rollout step) == jerk->speed + predict_step_with_ego + the masked bookkeeping of
     dqn.py:129-141 composed from the individually parity-tested K4 entry points, bit for bit, over 5 steps."""
@@ -191,3 +240,67 @@ def test_fused_rollout_step_equals_its_pieces(api):
         assert torch.equal(sel, r_sel) and torch.equal(rlen, r_len)
         assert torch.allclose(rs, r_rs, rtol=0, atol=1e-12)         # arclength: kernel fp64 get_ego_s vs the torch expression
     assert 0 < int(r_alive.sum()) and int(r_crash.sum()) > 0        # both branches exercised
+
+
+# ---- the published actor and the combined controller against the UNMODIFIED reference (tests/golden/make_golden_r2.py) ----------
+COMBINED_MODERATE_1 = dict(BASE_TRAFFIC_INTERVAL=1.2, OTHER_CAR_SPEED=11.0, ALT_J_WEIGHT=0.1, CRASH_MIN_S=20, ROLLOUT_LENGTH=5,
+                           ST_TEST_ROLLOUTS=5, LIMIT_DQN_SPEED=False, TEST_ROLLOUT_STATE=True, CHECK_ROLLOUT_CRASH=True,
+                           COMBINATION_MIN_DISTANCE=5.1, STOP_X=65, REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED=False)
+
+
+def test_published_actor_matches_the_reference_forward(api):
+    """DDPGAgent.get_control with the published weights (pretrained_models/ddpg_moderate1_extended/policy.pt, committed as
+    tests/golden/policy_moderate1.npz): K4 observation kernel + time feature + PyTorch MLP against the reference-side forward on
+    the reference's own observation vectors, at three values of the time feature."""
+    torch = api["torch"]
+    from rl_mpc_lanemerging_b200.prediction import BatchedState
+    P = np.load(os.path.join(GOLD, "policy_moderate1.npz"))
+    G = dict(np.load(os.path.join(GOLD, "rollout.npz")))
+    agent = api["ddpg"].DDPGAgent.load_npz(os.path.join(GOLD, "policy_moderate1.npz"), device=api["device"])
+    assert agent.policy.tanh_scale == 5.0 and agent.policy.tanh_mean == 0.0 and float(P["time_feature_scale"]) == api["ddpg"].TIME_FEATURE_SCALE
+    batch = BatchedState.from_numpy(G, api["device"])
+    for i, t in enumerate(P["times"]):
+        agent.get_control(batch)                                   # allocates the time feature
+        agent.timestep.fill_(float(t))
+        jerk = agent.get_control(batch).cpu().numpy()
+        assert np.abs(jerk - P["actions"][i]).max() < 2e-4, (t, np.abs(jerk - P["actions"][i]).max())
+        assert float(agent.timestep[0]) == float(t) + 1          # TimeFeature advances on every call (ddpg.py:83-87)
+
+
+@pytest.mark.parametrize("tag", ["plain", "b"])
+def test_combined_control_matches_the_reference(api, tag):
+    """RLAgent.do_combined_control (batched, masks) against reference dqn.py:117-200 run unmodified on 96 states with the
+    published actor: configs/combined_moderate_1.json (veto chain) and combined_moderate_1b.json (TEST_ST_STRICTLY_BETTER, the "b"
+    branch of dqn.py:156-197).  Take-over decisions agree (a borderline rollout may flip with the fp32 forward), RL speed
+    commands agree to 1e-5, planner / QP speed commands to 1e-3 (the golden QP is solved to its optimum, the reference's cvxopt
+    stops after 10 iterations; both unpinned against each other)."""
+    torch, S = api["torch"], api["Settings"]
+    from rl_mpc_lanemerging_b200.prediction import BatchedState
+    G = dict(np.load(os.path.join(GOLD, "combined.npz")))
+    old = {k: getattr(S, k) for k in list(COMBINED_MODERATE_1) + ["TEST_ST_STRICTLY_BETTER"]}
+    for k, v in COMBINED_MODERATE_1.items():
+        setattr(S, k, v)
+    S.TEST_ST_STRICTLY_BETTER = tag == "b"
+    api["st"].refresh_engine()
+    try:
+        agent = api["ddpg"].DDPGAgent.load_npz(os.path.join(GOLD, "policy_moderate1.npz"), device=api["device"])
+        batch = BatchedState.from_numpy(G, api["device"])
+        agent.get_control(batch)
+        agent.timestep.copy_(torch.as_tensor(G["t0"], dtype=torch.float32))
+        first = agent.get_control(batch).cpu().numpy()
+        assert np.abs(first - G[tag + "_first_action"]).max() < 2e-4
+        agent.timestep.copy_(torch.as_tensor(G["t0"], dtype=torch.float32))
+        speed, takeover = agent.do_combined_control(batch)
+        speed, takeover = speed.cpu().numpy(), takeover.cpu().numpy()
+        ref_t, ref_s = G[tag + "_takeover"], G[tag + "_speed"]
+        same = takeover == ref_t
+        assert same.sum() >= len(ref_t) - 2, (int(same.sum()), np.nonzero(~same)[0])
+        assert ref_t.sum() >= 20 and (~ref_t).sum() >= 20                 # both outcomes are exercised
+        rl = same & ~ref_t
+        assert np.abs(speed[rl] - ref_s[rl]).max() < 1e-5
+        pl = same & ref_t
+        assert np.abs(speed[pl] - ref_s[pl]).max() < 1e-3, np.abs(speed[pl] - ref_s[pl]).max()
+    finally:
+        for k, v in old.items():
+            setattr(S, k, v)
+        api["st"].refresh_engine()

@@ -207,7 +207,7 @@ def test_finer_fit_survives_infeasible_histories():
     eng.close()
 
 
-@pytest.mark.parametrize("name,H,n", [("plan_h17.npz", 17, 40), ("plan_h50.npz", 50, 6)])
+@pytest.mark.parametrize("name,H,n", [("plan_h17.npz", 17, 40), ("plan_h50.npz", 50, 6), ("plan_h25.npz", 25, 12), ("plan_h50b.npz", 50, 6)])
 def test_emulated_library_against_the_reference_golden_vectors(name, H, n):
     """The committed outputs of the UNMODIFIED reference (tests/golden/make_golden.py): exact mode reproduces positions, crash
     verdict and start_s bit for bit, fast mode the same plans with the cost within 1e-6; the hinted path returns the same."""

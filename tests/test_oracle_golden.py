@@ -35,13 +35,14 @@ def _load(name):
     return dict(np.load(os.path.join(GOLD, name)))
 
 
-@pytest.mark.parametrize("name,H", [("plan_h17.npz", 17), ("plan_h50.npz", 50)])
+@pytest.mark.parametrize("name,H", [("plan_h17.npz", 17), ("plan_h50.npz", 50), ("plan_h25.npz", 25), ("plan_h50b.npz", 50),
+                                    ("plan_h100.npz", 100)])
 def test_plan_matches_reference(oracle, name, H):
     G = _load(name)
     p = oracle.horizon_params(H)
     B = G["ego"].shape[0]
     stride = int(G["sample_stride"])
-    for layered in (False, True):
+    for layered in ((False, True) if H <= 50 and B <= 40 else (True,)):     # (the Dijkstra port takes ~1 s per state at H=50, 4 s at H=100)
         r = helpers.oracle_plan_batch(oracle, p, G, H + 1, layered=layered)
         assert np.array_equal(r["s_seq"], G["s_seq"])                      # bit-identical positions, incl. zero tails
         assert np.array_equal(r["crash"], G["crash"])
