@@ -199,6 +199,71 @@ def run_reference(args):
     print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
+
+def work_counts(H: int, traffic: str):
+    """Nodes finalised / offers made per gap-evaluation (CPU model of the kernel on 200 states of the same generator) and executed
+    warp instructions per launch of the dominant kernel (ncu), from the committed profiles/r02_work_counts.json
+    (tools/work_counts.py writes it; the bench never runs the model itself)."""
+    try:
+        W = json.load(open(os.path.join(ROOT, "profiles", "r02_work_counts.json")))
+        rec = W["model"].get(f"{H}:{traffic}")
+        ncu = W.get("ncu", {}).get(str(H))
+        return rec, ncu
+    except Exception:
+        return None, None
+
+
+def time_plan(eng, D, out, steps, flush, torch, mode="fast"):
+    """(mean step ms by CUDA events, mean kernel ms [predictor, first DP launch, later DP launches]) over `steps` plans, L2 flushed between."""
+    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
+    for _ in range(3):
+        eng.plan(*a, mode=mode, out=out); flush.zero_()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for e0, e1 in ev:
+        e0.record(); eng.plan(*a, mode=mode, out=out); e1.record(); flush.zero_()
+    torch.cuda.synchronize()
+    eng.set_timing(True)
+    km = []
+    for _ in range(2):
+        eng.plan(*a, mode=mode, out=out)
+        km.append(eng.last_kernel_ms()); flush.zero_()
+    eng.set_timing(False)
+    return sum(e0.elapsed_time(e1) for e0, e1 in ev) / steps, [float(np.mean([k[i] for k in km])) for i in range(3)]
+
+
+def run_sweep(args, local, world, rank, first, flush, torch, sharding):
+    """BASELINE.json configs[4]: traffic density x horizon, same batch per GPU, device-resident inputs, CUDA events, max over ranks."""
+    from rl_mpc_lanemerging_b200 import synthetic
+    from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
+    dev, B = f"cuda:{local}", args.batch
+    peak = peak_hbm()[0]
+    rows, meta = [], []
+    for H in (17, 25, 50, 100):
+        eng = MpcEngine(make_params(H), device=local, max_batch=B)
+        out = None
+        for traffic in ("low", "medium", "default", "moderate", "fast"):
+            D = states_to_device(synthetic.make_states(B, traffic, seed=args.seed, first_episode=first), dev)
+            if out is None:
+                out = eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=args.mode)
+            ms, km = time_plan(eng, D, out, args.sweep_steps, flush, torch, args.mode)
+            info, c = eng.fast32_info(), eng.counters()
+            rows.append([ms] + km)
+            meta.append((H, traffic, eng.num_t, eng.num_s_max - 1, info["handed_on"], info["first_shape_handed_on"], c["fallback_problems"],
+                         float((out["reached_t"] == eng.num_t - 1).float().mean())))
+        eng.close()
+    red = sharding.reduce_max([x for r in rows for x in r], dev)
+    res = {}
+    for i, (H, traffic, T, num_s, handed, handedA, back, full) in enumerate(meta):
+        ms, pred, dp, fb = (float(x) for x in red[4 * i:4 * i + 4])
+        res[f"H{H}:{traffic}"] = {"gap_evals_per_s": world * B / (ms * 1e-3), "ms": ms, "predict_ms": pred, "dp_ms": dp, "dp_later_ms": fb,
+                                  "roofline_frac": b_alg(T, num_s) * B / ((dp + fb) * 1e-3) / 1e9 / peak,
+                                  "handed_to_64bit_kernel": handed, "outgrew_first_ring": handedA - handed if handedA >= handed else 0,
+                                  "exact_kernel_problems": back, "full_horizon_fraction": full}
+    res["note"] = (f"{B} episodes per GPU, {args.sweep_steps} timed steps per point; roofline_frac = dense-grid-equivalent bytes / all DP launches "
+                   "of the step / measured HBM peak; rank 0's counters")
+    return res
+
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -236,35 +301,41 @@ def run_ours(args):
         sampler.start()                   # NVML comes up during the warm-up; only samples inside the timed region are kept
     for _ in range(W):
         step(); flush.zero_()
-    eng.set_timing(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     if rank == 0:
         sampler.begin()
     t_wall = time.perf_counter()
-    dp_ms, pred_ms, fb_ms = [], [], []
-    for i in range(K):
+    for i in range(K):                                                       # the host only enqueues: no synchronisation inside the timed region
         ev[i][0].record(); step(); ev[i][1].record()
-        a, b_, c = eng.last_kernel_ms()
-        pred_ms.append(a); dp_ms.append(b_); fb_ms.append(c)
-        flush.zero_()                                                        # L2 flush between timed iterations (not timed)
+        flush.zero_()                                                        # L2 flush between timed iterations (outside the events)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     clocks = sampler.stop() if rank == 0 else None
     step_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
+    # per-kernel times (events recorded inside the library; reading them synchronises, hence a separate, untimed pass)
+    eng.set_timing(True)
+    dp_ms, pred_ms, fb_ms = [], [], []
+    for i in range(min(K, 5)):
+        step()
+        a, b_, c = eng.last_kernel_ms()
+        pred_ms.append(a); dp_ms.append(b_); fb_ms.append(c)
+        flush.zero_()
     counters = eng.counters()
+    f32_info = eng.fast32_info()
     eng.set_timing(False)
 
     # ---- end-to-end through the host-buffer API: H2D of the step's states + D2H of its results, every step ----
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Sp = {k: torch.from_numpy(np.ascontiguousarray(S[k])).pin_memory() for k in ("ego", "cars_x", "cars_v", "cars_a", "n_cars")}   # the step's inputs: pinned host memory
     for _ in range(2):
-        eng.plan_host(S["ego"], S["cars_x"], S["cars_v"], S["cars_a"], S["n_cars"], mode=args.mode)
+        eng.plan_host(Sp["ego"], Sp["cars_x"], Sp["cars_v"], Sp["cars_a"], Sp["n_cars"], mode=args.mode)
     barrier()
     e2e_ms = 0.0
     for _ in range(K):
         t0 = time.perf_counter()
         e0.record()
-        r = eng.plan_host(S["ego"], S["cars_x"], S["cars_v"], S["cars_a"], S["n_cars"], mode=args.mode)
+        r = eng.plan_host(Sp["ego"], Sp["cars_x"], Sp["cars_v"], Sp["cars_a"], Sp["n_cars"], mode=args.mode)
         e1.record(); e1.synchronize()
         e2e_ms += max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
         flush.zero_()
@@ -295,6 +366,41 @@ def run_ours(args):
                     "reference's solver consumes); used only by the drop-in API, the fused planner never materialises it"}
     except Exception as e:              # noqa: BLE001
         grid_res = {"error": repr(e)}
+    # ---- K2, the st_cy drop-in itself: the DP kernel fed by DENSE grids resident in HBM (mpc_solve_dense, st_cy.pyx:315) ----
+    dense_res = None
+    if rank == 0 and args.mode == "fast":
+        try:
+            Bg = min(B, 256)
+            sub = [D[k][:Bg].contiguous() for k in ("ego", "cars_x", "cars_v", "cars_a", "n_cars")]
+            v0, a0 = sub[0][:, 2].contiguous(), sub[0][:, 3].contiguous()
+            ref = eng.plan(*sub, mode="fast")
+            ref = {k: v.clone() for k, v in ref.items()}
+            dense_res = {}
+            for name, dt, cell in (("fp32_distances", torch.float32, 5), ("fp64_distances", torch.float64, 9)):
+                g_ = eng.build_grid(*sub, dist_dtype=dt)
+                eng.set_timing(True)
+                dms = []
+                for i in range(4):
+                    r_ = eng.solve_dense(g_["obstacles"], g_["distances"], g_["start_s"], g_["delta_s"], g_["num_s"], v0, a0, mode="fast")
+                    if i:
+                        dms.append(eng.last_kernel_ms()[1])
+                    flush.zero_()
+                eng.set_timing(False)
+                dbytes = (T * (eng.num_s_max - 1) * cell + T * 4) * Bg
+                dense_res[name] = {"ms": min(dms), "gap_evals_per_s": Bg / (min(dms) * 1e-3), "algorithmic_gbs": dbytes / (min(dms) * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": dbytes / (min(dms) * 1e-3) / 1e9 / peak_hbm()[0],
+                                   "same_sequences_as_fused": bool(torch.equal(r_["idx"], ref["idx"]))}
+                del g_, r_
+            dense_res["episodes"] = Bg
+        except Exception as e:          # noqa: BLE001
+            dense_res = {"error": repr(e)}
+    sweep_res = None
+    if not args.no_sweep and args.mode == "fast":
+        try:
+            eng.close()
+            sweep_res = run_sweep(args, local, world, rank, first, flush, torch, sharding)
+        except Exception as e:          # noqa: BLE001
+            sweep_res = {"error": repr(e)}
     env_res = None
     if args.env_ticks > 0:              # every rank runs its own environments; the job rate is the sum over ranks
         try:
@@ -303,8 +409,9 @@ def run_ours(args):
             r = sharding.reduce_sum([rate, take], dev)
             env_res = {"value": float(r[0]), "unit": "env-steps/s", "envs_per_gpu": args.env_envs, "ticks": args.env_ticks,
                        "controller": "RL proposes + MPC vetoes (combined_moderate_1 semantics), H=17 grid, fast mode",
-                       "planner_takeover_fraction": float(r[1]) / world,
-                       "world_model": "reference predictor as dynamics (SUMO-free, parity vs SUMO unpinned)"}
+                       "planner_takeover_fraction": float(r[1]) / world, "published_takeover_fraction": 0.037,
+                       "policy": "published actor pretrained_models/ddpg_moderate1_extended (tests/golden/policy_moderate1.npz)",
+                       "world_model": "reference predictor as dynamics (SUMO-free); published fraction: saved_data.csv:46 (SUMO)"}
         except Exception as e:          # noqa: BLE001  -- the secondary figure must never break the headline line
             env_res = {"error": repr(e)}
     train_res = None
@@ -323,46 +430,62 @@ def run_ours(args):
         num_s = eng.num_s_max - 1
         ms_per_step = step_ms / K
         value = world * B / (ms_per_step * 1e-3)
-        dp = float(np.mean(dp_ms))
+        dp, fb, pred = float(np.mean(dp_ms)), float(np.mean(fb_ms)), float(np.mean(pred_ms))
         peak, peak_src = peak_hbm()
-        bytes_per_launch = b_alg(T, num_s) * B
+        f32 = f32_info
+        solved = B - (f32["handed_on"] if f32["in_use"] else 0)          # problems the dominant kernel finished itself
+        bytes_per_launch = b_alg(T, num_s) * solved
         achieved = bytes_per_launch / (dp * 1e-3) / 1e9
+        kernel = ("fast32_kernel" if f32["in_use"] else "fast_pull_kernel") if args.mode == "fast" else "exact_push_kernel"
+        wc, ncu = work_counts(H, args.traffic)
+        compute = None
+        if wc is not None and args.mode == "fast":
+            clk = (clocks or {}).get("sm_mhz") or 1965.0
+            compute = {"nodes_per_gap_eval": wc["nodes"], "offers_per_gap_eval": wc["pushes"],
+                       "nodes_per_s": value * wc["nodes"], "offers_per_s": value * wc["pushes"],
+                       "source": f"CPU model of the kernel on {wc['states']} states of this workload (profiles/r02_work_counts.json)"}
+            if ncu:
+                wi = ncu["warp_instructions"] * B / ncu["episodes"]
+                compute.update({"warp_instructions_per_gap_eval": wi / B, "issue_slot_frac": wi / (dp * 1e-3 * 148 * 4 * clk * 1e6),
+                                "issue_slots": f"148 SMs x 4 schedulers x {clk:.0f} MHz; warp instructions of {ncu['kernel']} from ncu ({ncu['profile']})"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "i64" if args.mode == "fast" else "f64", "data": "synthetic",
+                "dtype": "u32" if (args.mode == "fast" and f32["in_use"]) else ("i64" if args.mode == "fast" else "f64"), "data": "synthetic",
                 "config": {"workload": f"batched MPC gap-evaluation: {B} parallel episodes per GPU, {args.traffic} traffic, "
                                        f"horizon={H} ({T}x{num_s} cells)", "horizon": H, "traffic": args.traffic,
                            "episodes_per_gpu": B, "mode": args.mode, "parallelism": f"replicas x{world} (episodes sharded, no collective)",
-                           "arithmetic": "integer-cell kinematics, 2^-18 fixed-point 48-bit labels, fp64 obstacle/threshold tests" if args.mode == "fast"
-                           else "fp64, reference operation order",
+                           "arithmetic": (f"integer-cell kinematics; first attempt: 32-bit fixed-point labels (2^-{f32['frac_bits']}) min-combined with the native "
+                                          "32-bit shared-memory atomic; hand-overs: 48-bit labels (2^-18); fp64 obstacle / threshold tests")
+                           if args.mode == "fast" else "fp64, reference operation order",
                            "l2": "256 MiB buffer written between timed iterations (outside the timed events)",
                            "inputs": "resident in HBM (fp64 SoA state)"},
                 "wall_ms_per_step_incl_flush": wall_ms / K,
-                "kernel_ms": {"predict_layers": float(np.mean(pred_ms)), "dp": dp, "dp_fallback": float(np.mean(fb_ms))},
-                "full_horizon_fraction": full, "fallback_problems": counters["fallback_problems"],
+                "kernel_ms": {"predict_layers": pred, "dp": dp, "dp_later_launches": fb},
+                "full_horizon_fraction": full, "handed_to_64bit_kernel": f32["handed_on"], "exact_kernel_problems": counters["fallback_problems"],
                 "gpu_launches": counters["kernels_launched"] * K,
                 "e2e": {"value": world * B / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "MpcEngine.plan_host -> mpc_plan_host (pinned host buffers, copies inside the timed region)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": measured_traffic(H, B), "kernel": "fast_pull_kernel" if args.mode == "fast" else "exact_push_kernel",
-                             "peak_source": peak_src,
+                             "traffic": measured_traffic(H, B), "kernel": kernel, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": bytes_per_launch,
-                             "note": "achieved = dense-grid-equivalent bytes (num_t*num_s*5 + num_t*4 per gap-eval, SURVEY 8d) / DP-kernel time; "
-                                     "the fused kernel never materialises the grid: `traffic` is its physical DRAM bytes per launch (ncu), "
-                                     "the kernel is bound by instruction issue and shared-memory latency (profiles/)"},
+                             "stage_frac": b_alg(T, num_s) * B / ((dp + fb) * 1e-3) / 1e9 / peak,
+                             "note": "achieved = dense-grid-equivalent bytes (num_t*num_s*5 + num_t*4 per gap-eval, SURVEY 8d) of the problems the kernel "
+                                     "finished / its launch time; stage_frac = all problems / all DP launches; the fused kernel never materialises the "
+                                     "grid (`traffic` = its DRAM bytes, ncu): it is bound by instruction issue, see `compute`"},
                 "clocks": clocks}
+        if compute is not None:
+            line["compute"] = compute
+        if dense_res is not None:
+            line["dense_solve"] = dense_res
+        if sweep_res is not None:
+            line["sweep"] = sweep_res
         if grid_res is not None:
             line["grid_build"] = grid_res
         if env_res is not None:
             line["env_steps"] = env_res
         if train_res is not None:
             line["train"] = train_res
-        if world == 1 and args.mode == "fast" and os.environ.get("MPCB200_BENCH_HINT_LEG", "1") != "0":
-            aux = hint_leg_subprocess(args)
-            if "dense_solve" in aux:
-                line["dense_solve"] = aux.pop("dense_solve")
-            line["hinted_solve"] = aux
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             probe = cpu_port_rate(H, args.traffic, args.seed, cores * 2, cores)
@@ -376,234 +499,12 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_hint_leg(args):
-    """Child process of the default run (see `hinted_solve` below): the cost-hint entry points on the bench workload.
-    Checks that mpc_plan_probed / mpc_plan_hinted return exactly what mpc_plan returns, then times them the same way
-    the headline is timed (CUDA events around each step, L2 flushed in between).  Prints one JSON object."""
-    import torch
-    from rl_mpc_lanemerging_b200 import synthetic
-    from rl_mpc_lanemerging_b200.engine import MpcEngine, states_to_device
-    torch.cuda.set_device(0)
-    H, B, K = args.horizon, args.batch, max(args.steps, 3)
-    eng = MpcEngine(make_params(H), device=0, max_batch=B)
-    D = states_to_device(synthetic.make_states(B, args.traffic, seed=args.seed), "cuda:0")
-    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
-    ref = {k: v.clone() for k, v in eng.plan(*a).items()}
-    out = eng.plan(*a)
-    probe, pout, probe_err = None, None, None
-    try:
-        probe = eng.make_probe(20, 3)
-        pout = probe.plan(*a)
-        torch.cuda.synchronize()
-    except Exception as e:                # noqa: BLE001
-        probe_err = repr(e)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
-
-    def timed(fn):
-        for _ in range(3):
-            fn(); flush.zero_()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        torch.cuda.synchronize()
-        for e0, e1 in ev:
-            e0.record(); fn(); e1.record(); flush.zero_()
-        torch.cuda.synchronize()
-        return sum(e0.elapsed_time(e1) for e0, e1 in ev) / K
-
-    def same(got):
-        return bool(all(torch.equal(got[k], ref[k]) for k in ref))
-
-    res = {"workload": f"{B} episodes, {args.traffic} traffic, horizon={H}",
-           "probe_grid": [probe.num_t, probe.num_s_max - 1] if probe is not None and probe_err is None else {"error": probe_err}}
-
-    def section(name, fn):                # every figure on its own: a failure is recorded and the rest still runs
-        try:
-            res[name] = fn()
-        except Exception as e:            # noqa: BLE001
-            res[name] = {"error": repr(e)}
-
-    def probed(e_, m):
-        ok = same(e_.plan_probed(probe, *a, margin=m))
-        ms = timed(lambda: e_.plan_probed(probe, *a, margin=m, out=out))
-        return {"identical_outputs": ok, "ms": ms, "gap_evals_per_s": B / (ms * 1e-3), "fallback_problems": e_.counters()["fallback_problems"]}
-
-    def other_engine(var, val, m):        # MPC_FAST_* are read when a handle is created
-        os.environ[var] = val
-        try:
-            e2 = MpcEngine(make_params(H), device=0, max_batch=B)
-        finally:
-            del os.environ[var]
-        try:
-            return probed(e2, m)
-        finally:
-            e2.close()
-
-    section("plain_ms", lambda: timed(lambda: eng.plan(*a, out=out)))
-    section("probe_only_ms", lambda: timed(lambda: probe.plan(*a, out=pout)))
-    section("probed_1.1", lambda: probed(eng, 1.1))
-    section("probed_1.3", lambda: probed(eng, 1.3))
-    # what a perfect estimate would give (diagnostic only: the hint is the answer's own cost)
-    section("oracle_hint_1.02", lambda: {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=ref["cost"], hint_scale=1.02)),
-                                         "ms": timed(lambda: eng.plan_hinted(*a, hint_cost=ref["cost"], hint_scale=1.02, out=out))})
-    # without the reachability heuristic: separates the two effects
-    section("probed_1.1_no_heuristic", lambda: other_engine("MPC_FAST_HEUR", "0", 1.1))
-    # the pruned frontier is narrow enough for three resident blocks per SM (DESIGN.md §8): same call, other launch shape
-    section("probed_1.1_three_blocks_per_sm", lambda: other_engine("MPC_FAST_BLOCKS", "96", 1.1))
-    def other_probe(sm, tm):              # CPU model: 12x2 (26 x 751 cells) misses less often than 20x3 but costs more itself
-        p2 = eng.make_probe(sm, tm)
-        try:
-            ok = same(eng.plan_probed(p2, *a, margin=1.1))
-            ms = timed(lambda: eng.plan_probed(p2, *a, margin=1.1, out=out))
-            return {"identical_outputs": ok, "ms": ms, "probe_grid": [p2.num_t, p2.num_s_max - 1]}
-        finally:
-            p2.close()
-
-    section("probed_1.1_probe_12x2", lambda: other_probe(12, 2))
-    # the probe plan on a second stream, next to the real predictor (MPC_PROBE_OVERLAP)
-    section("probed_1.1_probe_overlapped", lambda: other_engine("MPC_PROBE_OVERLAP", "1", 1.1))
-    section("low_hint_0.5", lambda: {"identical_outputs": same(eng.plan_hinted(*a, hint_cost=ref["cost"] * 0.5))})
-    # ---- K2, the st_cy drop-in itself: the DP kernel fed by DENSE grids in HBM (mpc_solve_dense), i.e. the solver boundary of the
-    #      reference (st_cy.pyx:315) with the grid read from memory instead of being evaluated from the layer descriptors ----
-    T, Bg = eng.num_t, min(B, 256)
-    sub = [D[k][:Bg].contiguous() for k in ("ego", "cars_x", "cars_v", "cars_a", "n_cars")]
-    v0, a0 = sub[0][:, 2].contiguous(), sub[0][:, 3].contiguous()
-    dense = {}
-    for name, dt, cell in (("fp32_distances", torch.float32, 5), ("fp64_distances", torch.float64, 9)):
-        try:
-            g_ = eng.build_grid(*sub, dist_dtype=dt)
-            eng.set_timing(True)
-            dms = []
-            for i in range(4):
-                r_ = eng.solve_dense(g_["obstacles"], g_["distances"], g_["start_s"], g_["delta_s"], g_["num_s"], v0, a0, mode="fast")
-                if i:
-                    dms.append(eng.last_kernel_ms()[1])
-                flush.zero_()
-            eng.set_timing(False)
-            if not min(dms) > 0:
-                raise RuntimeError(f"no kernel time measured ({dms})")
-            dbytes = (T * (eng.num_s_max - 1) * cell + T * 4) * Bg
-            dense[name] = {"ms": min(dms), "gap_evals_per_s": Bg / (min(dms) * 1e-3), "algorithmic_gbs": dbytes / (min(dms) * 1e-3) / 1e9,
-                           "frac_of_hbm_peak": dbytes / (min(dms) * 1e-3) / 1e9 / peak_hbm()[0],
-                           "same_plan_as_fused": bool(torch.equal(r_["idx"], ref["idx"][:Bg]) and torch.equal(r_["cost"], ref["cost"][:Bg]))}
-            del g_, r_
-        except Exception as e:          # noqa: BLE001
-            dense[name] = {"error": repr(e)}
-    dense["note"] = (f"{Bg} episodes; grids (u8 mask + distance, built by mpc_build_grid) resident in HBM, L2 flushed between calls; "
-                     "algorithmic bytes = whole grid once (SURVEY 8d) -- the kernel only touches the cells the DP reaches; fp32 "
-                     "distances may move a near-tie (same_plan_as_fused compares with the descriptor-fed fp64 plan)")
-    res["dense_solve"] = dense
-    # ---- closed loop with the two switches that are off by default until they have run on a device ----
-    def closed_loop(extra):
-        rate, take = env_steps_per_sec(0, 1, args.env_envs, args.env_ticks, args.seed, extra)
-        return {"env_steps_per_s": rate, "planner_takeover_fraction": take}
-
-    eng.close()
-    if probe is not None:
-        probe.close()
-    # the reference's own grid (H=17, 18 x 3001): plain vs probed on the same batch
-    def h17():
-        e17 = MpcEngine(make_params(17), device=0, max_batch=B)
-        p17 = e17.make_probe(20, 3)
-        try:
-            o17 = e17.plan(*a)
-            r17 = {k: v.clone() for k, v in o17.items()}
-            ok = bool(all(torch.equal(e17.plan_probed(p17, *a, margin=1.1)[k], r17[k]) for k in r17))
-            return {"plain_ms": timed(lambda: e17.plan(*a, out=o17)), "probed_1.1_ms": timed(lambda: e17.plan_probed(p17, *a, margin=1.1, out=o17)),
-                    "oracle_hint_1.02_ms": timed(lambda: e17.plan_hinted(*a, hint_cost=r17["cost"], hint_scale=1.02, out=o17)),
-                    "identical_outputs": ok, "probe_grid": [p17.num_t, p17.num_s_max - 1]}
-        finally:
-            p17.close(); e17.close()
-
-    section("horizon_17", h17)
-    section("closed_loop_default", lambda: closed_loop({}))
-    section("closed_loop_cost_hints", lambda: closed_loop({"PLAN_COST_HINTS": True}))
-    section("closed_loop_fused_env_step", lambda: closed_loop({"FUSED_ENV_STEP": True}))
-    section("closed_loop_fused_env_step_and_cost_hints", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True}))
-    section("closed_loop_sync_free_takeover", lambda: closed_loop({"SYNC_FREE_TAKEOVER": True}))
-    section("closed_loop_all_three", lambda: closed_loop({"FUSED_ENV_STEP": True, "PLAN_COST_HINTS": True, "SYNC_FREE_TAKEOVER": True}))
-    # ---- last (a failed capture can leave the context unusable): the whole tick -- no host sync left with the three switches on --
-    #      captured ONCE in a CUDA graph and replayed, i.e. one launch per tick instead of ~100 ----
-    def closed_loop_graph():
-        from rl_mpc_lanemerging_b200 import ddpg, merge_gym, st
-        from rl_mpc_lanemerging_b200.config import Settings
-        Settings.reset()
-        Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL = 20, 11.0, 1.2
-        Settings.TEST_ST_STRICTLY_BETTER, Settings.CUDA_DEVICE, Settings.ALT_J_WEIGHT = False, 0, 0.1
-        Settings.FUSED_ENV_STEP = Settings.PLAN_COST_HINTS = Settings.SYNC_FREE_TAKEOVER = True
-        st.refresh_engine()
-        try:
-            env = merge_gym.MergeEnv(args.env_envs, seed=args.seed)
-            agent = ddpg.DDPGAgent(device="cuda:0", seed=args.seed)
-            env.reset()
-            agent.takeover_history = _Sink()
-
-            def tick():
-                speed, _take = agent.do_combined_control(env.state)
-                jerk = ((speed - env.state.ego[:, 2]) / Settings.TICK_LENGTH - env.state.ego[:, 3]) / Settings.TICK_LENGTH
-                _o, _r, done, _i = env.step(jerk)
-                agent.reset_time(done)
-
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(30):
-                    tick()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            if hasattr(g, "register_generator_state"):
-                g.register_generator_state(env.gen)
-            with torch.cuda.graph(g):
-                tick()
-            t_before = env.ticks.clone()
-            n = max(args.env_ticks, 10)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); e0.record()
-            for _ in range(n):
-                g.replay()
-            e1.record(); torch.cuda.synchronize()
-            moved = bool((env.ticks != t_before).any()) and bool(torch.isfinite(env.state.ego).all())
-            return {"env_steps_per_s": args.env_envs * n / (e0.elapsed_time(e1) * 1e-3), "state_advanced_and_finite": moved,
-                    "note": "one graph launch per tick; the random numbers of the environment are drawn inside the graph"}
-        finally:
-            Settings.reset()
-            st.refresh_engine()
-
-    section("closed_loop_all_three_cuda_graph", closed_loop_graph)
-    print(json.dumps(res), file=RESULT_OUT, flush=True)
-
-
-class _Sink(list):
-    """takeover_history stand-in that keeps nothing (a captured tick must not accumulate references on the host)."""
-
-    def append(self, _x):
-        pass
-
-
-def hint_leg_subprocess(args):
-    """Runs run_hint_leg in a child process with a time limit: the cost-hint kernels were written after this round's GPU
-    budget was spent, so their first on-device run must not be able to take the headline line down with it."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--hint-leg", "--horizon", str(args.horizon), "--batch", str(args.batch),
-           "--steps", str(min(args.steps, 10)), "--traffic", args.traffic, "--seed", str(args.seed),
-           "--env-envs", str(args.env_envs), "--env-ticks", str(max(args.env_ticks, 10))]
-    try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=420, cwd=ROOT)
-        lines = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
-        if r.returncode != 0 or not lines:
-            return {"error": f"exit {r.returncode}: " + r.stderr.decode(errors="replace")[-400:]}
-        res = json.loads(lines[-1])
-    except Exception as e:              # noqa: BLE001
-        return {"error": repr(e)}
-    res["note"] = ("EXPERIMENTAL, not part of `value`: mpc_plan_probed = coarse probe plan (probe_grid) whose scaled cost bounds the first "
-                   "attempt of the real solve; identical_outputs compares every output tensor with mpc_plan's on the same states")
-    return res
-
-
 def env_steps_per_sec(local, world, n_envs, ticks, seed, extra=None):
     """Secondary figure of BASELINE.json's metric: closed-loop env-steps/s of the combined controller
     (configs/combined_moderate_1.json semantics: 5 policy forwards + 5 predictor steps + 1 gap-evaluation per tick,
     + a second gap-evaluation for the episodes the planner takes over; reference dqn.py:117-200) on the published
-    solver grid (H=17).  World model = merge_gym.MergeEnv (SUMO-free, unpinned); policy = random-init DDPG actor of
-    the reference's architecture.  Returns (env-steps/s over all ranks' envs of this rank, takeover fraction)."""
+    solver grid (H=17).  World model = merge_gym.MergeEnv (SUMO-free); policy = the PUBLISHED actor
+    pretrained_models/ddpg_moderate1_extended/policy.pt (committed as tests/golden/policy_moderate1.npz).  Returns (env-steps/s over all ranks' envs of this rank, takeover fraction)."""
     import torch
     from rl_mpc_lanemerging_b200 import ddpg, merge_gym, st
     from rl_mpc_lanemerging_b200.config import Settings
@@ -614,7 +515,7 @@ def env_steps_per_sec(local, world, n_envs, ticks, seed, extra=None):
         setattr(Settings, k, v)
     st.refresh_engine()
     env = merge_gym.MergeEnv(n_envs, seed=seed)
-    agent = ddpg.DDPGAgent(device=f"cuda:{local}", seed=seed)
+    agent = ddpg.DDPGAgent.load_npz(os.path.join(ROOT, "tests", "golden", "policy_moderate1.npz"), device=f"cuda:{local}")
     env.reset()
     take = torch.zeros((), dtype=torch.float32, device=f"cuda:{local}")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -693,11 +594,10 @@ def main():
     ap.add_argument("--env-ticks", type=int, default=40, help="ticks of the closed-loop env-steps/s measurement (0 = skip)")
     ap.add_argument("--env-envs", type=int, default=8192, help="environments per GPU for it (BASELINE configs[2])")
     ap.add_argument("--train-ticks", type=int, default=10, help="ticks of the DDPG training throughput figure (0 = skip)")
-    ap.add_argument("--hint-leg", action="store_true", help="(internal) child process of the default run: cost-hint entry points")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the traffic x horizon sweep (BASELINE.json configs[4])")
+    ap.add_argument("--sweep-steps", type=int, default=5)
     args = ap.parse_args()
-    if args.hint_leg:
-        run_hint_leg(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -91,6 +91,17 @@ class Settings(metaclass=_SettingsMeta):
         return logdir
 
     @classmethod
+    def seed_value(cls) -> int:
+        """The run's seed as an integer: Settings.SEED, or fresh entropy when it is "Random" (reference main.py:93-97 seeds numpy /
+        torch / random from it; here the simulated world and the learner are seeded explicitly).  The *_1 / *_2 / *_3 configs of the
+        reference differ in nothing but SEED = 100 / 101 / 102."""
+        seed = getattr(cls, "SEED", "Random")
+        if isinstance(seed, str):
+            import os
+            return int.from_bytes(os.urandom(4), "little")
+        return int(seed)
+
+    @classmethod
     def reset(cls):
         for key in [k for k in vars(cls) if k.isupper()]:
             delattr(cls, key)

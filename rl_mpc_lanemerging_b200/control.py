@@ -141,12 +141,12 @@ class EpisodeTracker:
         self.seg_speeds += self.seg["speeds"][idx].sum(0)                 # the histograms cover finished episodes (stats.py:43-52)
         tick = float(Settings.TICK_LENGTH)
         rows = {n: t[idx].cpu().numpy() for n, t in self.v.items()}
-        cr, mg = crashed[idx].cpu().numpy(), merged[idx].cpu().numpy()
+        cr, mg, slots = crashed[idx].cpu().numpy(), merged[idx].cpu().numpy(), idx.cpu().numpy()
         out = []
         for i in range(idx.numel()):
             n = max(rows["steps"][i], 1.0)
             out.append(dict(
-                crashed=bool(cr[i]), merged=bool(mg[i]), mean_speed=rows["sum_speed"][i] / n, max_speed=rows["max_speed"][i],
+                slot=int(slots[i]), crashed=bool(cr[i]), merged=bool(mg[i]), mean_speed=rows["sum_speed"][i] / n, max_speed=rows["max_speed"][i],
                 mean_abs_jerk=rows["sum_abs_jerk"][i] / n, time_taken=rows["steps"][i] * tick,
                 clock_time_per_episode=wall_per_env_tick * n, clock_time_per_step=wall_per_env_tick,
                 n_closest=int(rows["n_closest"][i]), closest_distance=rows["min_closest"][i],
@@ -159,7 +159,7 @@ class EpisodeTracker:
 
 def evaluate_control(control_function, num_episodes=1000, state_function=None, custom_stats_function=None,
                      end_episode_callback=None, max_episode_length=100, start_velocity=None, wait_before_start=50,
-                     save_state_on_crash=False, verbose=False, crash_callback=None, num_envs=None, seed=0, env=None):
+                     save_state_on_crash=False, verbose=False, crash_callback=None, num_envs=None, seed=None, env=None):
     """Run `num_episodes` lane-merging episodes under `control_function` and aggregate the reference's statistics
     (reference control.py:343-363).  Episodes run `num_envs` at a time in merge_gym.MergeEnv.
 
@@ -167,18 +167,24 @@ def evaluate_control(control_function, num_episodes=1000, state_function=None, c
     end_episode_callback(done_mask) is called after every tick that finished episodes.  state_function,
     wait_before_start, start_velocity, crash_callback exist for signature parity (the batched world has no SUMO warm-up).
     clock_time_per_step is the wall time of a batched tick divided by the number of environments.  `env` may be any object
-    with MergeEnv's interface (state, device, B, reset(), step(jerk))."""
+    with MergeEnv's interface (state, device, B, reset(), step(jerk)).
+
+    Which episodes are counted does not depend on how long they last: environment slot b contributes its j-th episode iff
+    j * B + b < num_episodes, i.e. every slot a fixed quota (the reference runs its episodes one after another and counts all of
+    them; counting "the first num_episodes that finish" would over-represent short episodes -- early crashes, quick merges --
+    and drop the slow tail of jams and time-outs).  seed=None takes Settings.seed_value()."""
     import time
     from . import merge_gym, stats
     B = int(num_envs or min(max(num_episodes, 1), 4096))
     Settings.MAX_EPISODE_LENGTH = max_episode_length
     if env is None:
-        env = merge_gym.MergeEnv(B, seed=seed)
+        env = merge_gym.MergeEnv(B, seed=Settings.seed_value() if seed is None else seed)
     B = env.B
     agg = stats.StatsAggregator(save_state_on_crash)
     if custom_stats_function is not None:
         agg.add_custom_stat_callback(custom_stats_function)
     tracker = EpisodeTracker(B, env.device)
+    slot_episodes = [0] * B                                    # episodes slot b has finished so far
     env.reset()
     tick = float(Settings.TICK_LENGTH)
     t_prev, wall = time.perf_counter(), 0.0
@@ -191,7 +197,9 @@ def evaluate_control(control_function, num_episodes=1000, state_function=None, c
         if bool(done.any()):                                   # (host sync: evaluation bookkeeping, not the hot path)
             now = time.perf_counter(); wall = 0.9 * wall + 0.1 * (now - t_prev) if wall else now - t_prev
             for ep in tracker.finished(done, info["crashed"], info["merged"], wall / B):
-                if agg.episodes < num_episodes:
+                b = ep.pop("slot")
+                j, slot_episodes[b] = slot_episodes[b], slot_episodes[b] + 1
+                if j * B + b < num_episodes:
                     agg.add_episode_stats(ep)
                     if verbose and ep["crashed"]:
                         print("crashed")

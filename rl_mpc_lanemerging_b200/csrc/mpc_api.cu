@@ -88,6 +88,7 @@ struct mpc_handle {
     size_t smem_fast_big;        // full-row variant used to re-solve ring overflows (0 = does not fit)
     int Wc32, wrap32, threads32, grid32; size_t smem32;             // 32-bit-key kernel (mpc_fast32.cuh): ring capacity / launch shape; grid32 == 0: not used
     int Wc32b, wrap32b, threads32b, grid32b; size_t smem32b;        // its second shape (wider ring) for the problems that outgrew the first; grid32b == 0: none
+    int nb32, nb32b, adapt32, threads32_override, calls32, last_B32; // blocks per SM of the two shapes; calls left in which shape A may still be widened
     int use_bound;               // first fast pass runs under DevParams::bound_fx (MPC_FAST_BOUND=0|1 overrides)
     int grid_max;
     // scratch
@@ -127,7 +128,7 @@ static int env_int(const char *name, int lo, int hi, int dflt) {
     return (x >= lo && x <= hi && x % 32 == 0) ? x : dflt;
 }
 
-static int configure(mpc_handle *h) {
+static int configure(mpc_handle *h, int want_nb32 = 0) {
     const DevParams &P = h->P;
     h->W = (P.num_s_max + 7) & ~7;
     const size_t static_smem = 11264;                // static shared of the kernels (upper bound: 10.2 KB in the fast kernel) + 1 KB/block reserve
@@ -200,9 +201,13 @@ static int configure(mpc_handle *h) {
             if (ring_of(nb) * 2 >= (size_t)h->W) autoA = nb;
             if (ring_of(nb) * 100 >= (size_t)h->W * 88) autoB = nb;
         }
-        const int nbA = env_int("MPC_F32_BLOCKS", 32, 192, 32 * autoA) / 32;
-        shape(nbA, env_int("MPC_F32_THREADS", 64, 1024, 0), &h->Wc32, &h->wrap32, &h->smem32, &h->threads32, &h->grid32);
-        if (h->grid32 > 0 && h->wrap32 && autoB < nbA) {
+        const int forced = env_int("MPC_F32_BLOCKS", 32, 192, 0) / 32;
+        if (want_nb32 > 0) autoA = want_nb32;                // (re-configuration after an adaptive step, see run_solve)
+        h->nb32 = forced ? forced : autoA; h->nb32b = autoB;
+        h->threads32_override = env_int("MPC_F32_THREADS", 64, 1024, 0);
+        if (want_nb32 == 0) h->adapt32 = forced ? 0 : 4;
+        shape(h->nb32, h->threads32_override, &h->Wc32, &h->wrap32, &h->smem32, &h->threads32, &h->grid32);
+        if (h->grid32 > 0 && h->wrap32 && autoB < h->nb32) {
             shape(autoB, 0, &h->Wc32b, &h->wrap32b, &h->smem32b, &h->threads32b, &h->grid32b);
             if (h->Wc32b <= h->Wc32) h->grid32b = 0;
         }
@@ -385,6 +390,20 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
                      int stride, cudaStream_t st) {
     if (mode != MPC_MODE_FAST && mode != MPC_MODE_EXACT) return mpc_set_error(MPC_E_INVALID, "unknown mode");
     if (mode == MPC_MODE_FAST && (!h->P.fast_ok || h->grid_fast == 0)) mode = MPC_MODE_EXACT;   // still on the GPU
+    // Shape A adapts during the first calls on a handle: frontier widths depend on the traffic (H=50: <= 0.46 of the row in
+    // moderate traffic, 0.9 for 10 % of the problems in low traffic), and a problem that outgrows ring A is solved twice.  When
+    // more than 2 % of the previous call's problems did, A gets one block per SM less (a wider ring).  Results never depend on it.
+    if (mode == MPC_MODE_FAST && !dense && h->grid32 > 0 && io.hint_cost == nullptr && h->adapt32 > 0 && h->calls32 > 0) {
+        int c[16];
+        MPC_CUDA_OK(cudaMemcpyAsync(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+        MPC_CUDA_OK(cudaStreamSynchronize(st));
+        h->adapt32--;
+        if (c[9] * 50 > h->last_B32 && h->nb32 > h->nb32b) {
+            const int keep = h->adapt32;
+            configure(h, h->nb32 - 1);
+            h->adapt32 = keep;
+        }
+    }
     MPC_CUDA_OK(cudaMemsetAsync(h->counters, 0, 16 * sizeof(int), st));
     io.bp = h->bp; io.bp_stride = h->W;
     io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
@@ -411,6 +430,8 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             // First attempt by the 32-bit-key kernel (bounded, zones closed).  What it cannot finish -- plans that cross a penalty
             // zone or do not reach the horizon (list entries with bit 30: straight to the unbounded pass), frontiers wider than
             // its ring -- goes to the 64-bit kernel through a device-side list, like that kernel's own hand-backs below.
+            h->calls32++; h->last_B32 = B;
+            io.overflow_count = h->counters + 9;
             SolveLaunch F3 = F;
             F3.threads = h->threads32; F3.smem = h->smem32; F3.W = h->Wc32; F3.wrap = h->wrap32;
             F3.grid = h->grid32 < B ? h->grid32 : B;
@@ -427,6 +448,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
                 io.work_counter = h->counters + 8;
                 io.subset = handed; io.B_dev = handed_n;
                 io.fallback_list = h->fallback_list + 3 * (size_t)h->max_batch; io.fallback_count = h->counters + 7;
+                io.overflow_count = nullptr;
                 e = launch_fast32_desc(h->P, F3, io, h->desc, st);
                 if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast32 wide-ring launch");
                 h->kernels_launched++;

@@ -181,6 +181,7 @@ struct SolveIO {
     const int32_t *subset;       // optional list of problem ids (fallback re-solve); NULL = 0..B-1
     const int *B_dev;            // optional: number of problems read on the device (overrides B)
     int32_t *fallback_list; int *fallback_count;   // fast kernel: problems that need the exact kernel
+    int *overflow_count;         // 32-bit-key kernel (optional): how many of its hand-overs were frontiers wider than its ring
     // optional per-problem cost hint of the fast kernel (mpc_plan_hinted): first bound = hint_scale * hint_cost[b], used when
     // hint_reached == NULL or hint_reached[b] == hint_full_t
     const double *hint_cost; const int32_t *hint_reached; int hint_full_t; double hint_scale;

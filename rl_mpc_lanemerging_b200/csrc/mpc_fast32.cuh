@@ -339,7 +339,10 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
             // the 64-bit kernel goes straight to its unbounded pass; without it (ring / table overflow) it starts over.
             const bool overflow = S.need_fallback != 0;
             for (int k = tid; k < 3 * Wc; k += nth) sts_u32(ab + 4u * k, F32_EMPTY);
-            if (tid == 0) { const int q = atomicAdd(io.fallback_count, 1); io.fallback_list[q] = b | (overflow ? 0 : (1 << 30)); }
+            if (tid == 0) {
+                const int q = atomicAdd(io.fallback_count, 1); io.fallback_list[q] = b | (overflow ? 0 : (1 << 30));
+                if (overflow && io.overflow_count) atomicAdd(io.overflow_count, 1);
+            }
             __syncthreads();
             continue;
         }

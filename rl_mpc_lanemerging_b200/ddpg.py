@@ -120,10 +120,11 @@ class DDPGAgent(dqn.RLAgent):
 
     # ---- training entry points with the reference's names (ddpg.py:46-81) ----
     @classmethod
-    def _trainer(cls, seed=0, num_envs=None):
+    def _trainer(cls, seed=None, num_envs=None):
         from . import merge_gym, trainer
         import torch.distributed as dist
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        seed = Settings.seed_value() if seed is None else int(seed)       # (every rank must see the same Settings.SEED: "Random" is for 1 rank)
         dev = int(os.environ.get("LOCAL_RANK", getattr(Settings, "CUDA_DEVICE", 0)))
         Settings.CUDA_DEVICE = dev
         st.refresh_engine()

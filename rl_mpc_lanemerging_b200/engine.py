@@ -238,15 +238,21 @@ class MpcEngine:
         return t
 
     def plan_host(self, ego, cars_x, cars_v, cars_a, n_cars, mode="fast", probe: Optional["MpcEngine"] = None, margin: float = 1.1):
-        """Same through HOST buffers (numpy in, numpy out): the end-to-end call a CPU rollout loop makes.
-        Inputs are staged through pinned memory; results come back in (re-used) pinned arrays.
+        """Same through HOST buffers (numpy or CPU tensors in, numpy out): the end-to-end call a CPU rollout loop makes.
+        Inputs are staged through pinned memory unless they already are pinned CPU tensors; results come back in (re-used) pinned arrays.
         probe: a make_probe() engine -> mpc_plan_host_probed (fast mode; same outputs)."""
         B, T = int(ego.shape[0]), self.num_t
         f64, i32 = torch.float64, torch.int32
-        pe = self._pin("ego", (B, 4), f64); pe.numpy()[...] = ego
-        px = self._pin("cx", (B, self.nmax), f64); px.numpy()[...] = cars_x
-        pv = self._pin("cv", (B, self.nmax), f64); pv.numpy()[...] = cars_v
-        pn = self._pin("n", (B,), i32); pn.numpy()[...] = n_cars
+
+        def stage(name, a, shape, dt):
+            # a pinned CPU tensor of the right type is handed to the copy engine as it is; anything else goes through a pinned buffer
+            if torch.is_tensor(a) and a.device.type == "cpu" and a.is_pinned() and a.dtype == dt and a.is_contiguous() and tuple(a.shape) == shape:
+                return a
+            p = self._pin(name, shape, dt)
+            p.numpy()[...] = a.numpy() if torch.is_tensor(a) else a
+            return p
+        pe, px = stage("ego", ego, (B, 4), f64), stage("cx", cars_x, (B, self.nmax), f64)
+        pv, pn = stage("cv", cars_v, (B, self.nmax), f64), stage("n", n_cars, (B,), i32)
         o = dict(idx=self._pin("idx", (B, T), i32), s_seq=self._pin("seq", (B, T), f64), cost=self._pin("cost", (B,), f64),
                  reached_t=self._pin("reached", (B,), i32), crash=self._pin("crash", (B,), torch.uint8),
                  min_dist=self._pin("mind", (B,), f64), start_s=self._pin("s0", (B,), f64))

@@ -41,6 +41,7 @@ def main(argv=None):
     Settings.setup_logging()
     if Settings.SEED != "Random":
         np.random.seed(Settings.SEED); torch.manual_seed(Settings.SEED); random.seed(Settings.SEED)
+    # (the batched world and the learner take their seed from Settings.seed_value(): control.evaluate_control, ddpg.DDPGAgent._trainer)
     st.refresh_engine()
     return do_task()
 

@@ -103,6 +103,7 @@ extern "C" int emu_plan32(const mpc_params *params, int B, int nmax, const doubl
     if (rc) return rc;
     if (info3) { info3[0] = P.f32_frac; info3[1] = P.f32_bound; info3[2] = P.f32_ok; }
     if (!P.fast_ok || !P.f32_ok) return mpc_set_error(MPC_E_INVALID, "32-bit-key kernel not available for these params");
+    if (B <= 0) return MPC_OK;                   // (info3 only)
     const int T = P.num_t;
     std::vector<LayerDesc> desc((size_t)B * T);
     std::vector<double> s0(B), ds(B);

@@ -172,3 +172,28 @@ def test_evaluate_control_aggregates_like_the_reference_loop():
     assert all(abs(d - 1.5) < 1e-12 for d in st["mean_disruption"]) and all(abs(d - 1.5) < 1e-12 for d in st["max_disruption"])
     assert st["percent st solver"] == [0.0, 0.0, 1.0]
     assert agg.counts.sum() == 6 + 7 + 8                                                          # per-segment histogram of ticks
+
+
+def test_evaluate_control_counts_a_fixed_quota_per_slot():
+    """the episodes that are counted must not depend on how long they last.  Scripted world: slot b's episodes last
+    6 + b ticks.  With 3 slots and num_episodes = 7 the counted episodes are (slot 0: 3, slot 1: 2, slot 2: 2) -- every slot its
+    quota -- although slot 0 has finished four episodes by the time slot 2 has finished its second."""
+    from rl_mpc_lanemerging_b200 import control
+    from rl_mpc_lanemerging_b200.config import Settings
+    Settings.reset()
+    env = _ScriptedEnv(3)
+    agg = control.evaluate_control(lambda state: state.ego[:, 2] + 0.0, num_episodes=7, env=env)
+    st = agg.get_stats()
+    assert agg.episodes == 7
+    assert sorted(round(t / 0.2) for t in st["time_taken"]) == [6, 6, 6, 7, 7, 8, 8]
+
+
+def test_seed_value_follows_settings():
+    from rl_mpc_lanemerging_b200.config import Settings
+    Settings.reset()
+    Settings.SEED = 101
+    assert Settings.seed_value() == 101
+    Settings.SEED = "Random"
+    assert Settings.seed_value() != Settings.seed_value() or True         # entropy; (two equal draws are possible, not an error)
+    assert isinstance(Settings.seed_value(), int)
+    Settings.reset()
