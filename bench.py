@@ -240,18 +240,18 @@ def run_sweep(args, local, world, rank, first, flush, torch, sharding):
     peak = peak_hbm()[0]
     rows, meta = [], []
     for H in (17, 25, 50, 100):
-        eng = MpcEngine(make_params(H), device=local, max_batch=B)
-        out = None
         for traffic in ("low", "medium", "default", "moderate", "fast"):
+            # one handle per point: a handle fits the ring of its first launch shape to the traffic it sees in its first calls
+            eng = MpcEngine(make_params(H), device=local, max_batch=B)
             D = states_to_device(synthetic.make_states(B, traffic, seed=args.seed, first_episode=first), dev)
-            if out is None:
-                out = eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=args.mode)
+            out = eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=args.mode)
             ms, km = time_plan(eng, D, out, args.sweep_steps, flush, torch, args.mode)
             info, c = eng.fast32_info(), eng.counters()
             rows.append([ms] + km)
             meta.append((H, traffic, eng.num_t, eng.num_s_max - 1, info["handed_on"], info["first_shape_handed_on"], c["fallback_problems"],
                          float((out["reached_t"] == eng.num_t - 1).float().mean())))
-        eng.close()
+            eng.close()
+            del out, D
     red = sharding.reduce_max([x for r in rows for x in r], dev)
     res = {}
     for i, (H, traffic, T, num_s, handed, handedA, back, full) in enumerate(meta):

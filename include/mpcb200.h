@@ -198,6 +198,13 @@ int mpc_predict_step_with_ego(mpc_handle *h, int B, const double *d_ego, const d
                               double min_crash_distance, double *d_ego_out, double *d_cars_x_out,
                               double *d_cars_v_out, double *d_cars_a_out, uint8_t *d_crashed,
                               void *stream);
+/* One tick of the SUMO-free world with the car-following model of the reference's traffic (merge_impossible.rou.xml:3: Krauss,
+ * accel / decel / tau / minGap; max_speed = OTHER_CAR_SPEED, sumo.py:60), IN PLACE: every car follows its leader (the next car
+ * ahead, or the ego once it is on the junction / highway), the ego moves at d_selected_speed as in predict_step_with_ego, whose
+ * crash test is applied.  Alternative to mpc_predict_step_with_ego as the dynamics of merge_gym.MergeEnv (Settings.WORLD_MODEL). */
+int mpc_krauss_step(mpc_handle *h, int B, double *d_ego, double *d_cars_x, double *d_cars_v, double *d_cars_a,
+                    const int32_t *d_n_cars, const double *d_selected_speed, double dt, double min_crash_distance,
+                    double accel, double decel, double tau, double min_gap, double max_speed, uint8_t *d_crashed, void *stream);
 /* HighwayState.predict_step_without_ego (prediction.py:22-44): the traffic-only step the S-T grid builder applies per
  * layer (st.py:42-43) -- the ego is replaced by a pseudo-ego (stays put before the merge point, ignored when it leads all
  * cars, otherwise placed CAR_LENGTH + 5 m behind the car ahead of it at that car's speed) and the state advances with

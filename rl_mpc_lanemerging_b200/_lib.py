@@ -53,6 +53,7 @@ SYMBOLS = {
     "mpc_grid_stride": (_i, [_vp]),
     "mpc_last_counters": (_i, [_vp, C.POINTER(C.c_int64)]),
     "mpc_fast32_info": (_i, [_vp, C.POINTER(C.c_int64)]),
+    "mpc_krauss_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _d, _vp, _vp]),
     "mpc_set_timing": (_i, [_vp, _i]),
     "mpc_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "mpc_selftest_search": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp]),

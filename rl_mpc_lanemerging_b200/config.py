@@ -50,6 +50,9 @@ _HOT_PATH_DEFAULTS = {
     # combined controller: hand the vetoed episodes to the planner through mpc_plan_masked / mpc_finer_fit_masked (episode list
     # built and counted on the device) instead of nonzero() + gather on the host side: no host sync in the tick.  Same speeds.
     "SYNC_FREE_TAKEOVER": False,
+    # dynamics of merge_gym.MergeEnv: "predictor" = the reference's own traffic predictor (prediction.py:46-105) applied as the world,
+    # "krauss" = SUMO's Krauss car-following model with the vType of merge_impossible.rou.xml:3 (mpc_krauss_step)
+    "WORLD_MODEL": "predictor",
 }
 
 

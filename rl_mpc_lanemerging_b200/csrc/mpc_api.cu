@@ -729,6 +729,23 @@ extern "C" int mpc_predict_step_with_ego(mpc_handle *h, int B, const double *d_e
     return MPC_OK;
 }
 
+cudaError_t launch_krauss_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca, const int32_t *n,
+                               const double *sel, double dt, double mcd, double accel, double decel, double tau, double min_gap,
+                               double max_speed, uint8_t *crashed, cudaStream_t st);
+extern "C" int mpc_krauss_step(mpc_handle *h, int B, double *d_ego, double *d_cars_x, double *d_cars_v, double *d_cars_a,
+                               const int32_t *d_n_cars, const double *d_selected_speed, double dt, double min_crash_distance,
+                               double accel, double decel, double tau, double min_gap, double max_speed, uint8_t *d_crashed, void *stream) {
+    int rc = check_batch(h, B); if (rc) return rc;
+    if (B == 0) return MPC_OK;
+    if (!d_ego || !d_cars_x || !d_cars_v || !d_cars_a || !d_n_cars || !d_selected_speed || !d_crashed)
+        return mpc_set_error(MPC_E_INVALID, "mpc_krauss_step: null pointer");
+    if (!(dt > 0) || !(decel > 0) || !(accel > 0) || !(tau >= 0)) return mpc_set_error(MPC_E_INVALID, "mpc_krauss_step: bad model parameter");
+    MPC_CUDA_OK(launch_krauss_step(h->P, B, h->nmax, d_ego, d_cars_x, d_cars_v, d_cars_a, d_n_cars, d_selected_speed, dt, min_crash_distance,
+                                   accel, decel, tau, min_gap, max_speed, d_crashed, (cudaStream_t)stream));
+    h->kernels_launched = 1;
+    return MPC_OK;
+}
+
 extern "C" int mpc_predict_step_without_ego(mpc_handle *h, int B, const double *d_ego, const double *d_cars_x, const double *d_cars_v,
                                             const double *d_cars_a, const int32_t *d_n_cars, double dt, double min_crash_distance,
                                             double *d_ego_out, double *d_cars_x_out, double *d_cars_v_out, double *d_cars_a_out,

@@ -60,6 +60,65 @@ __device__ __forceinline__ bool warp_predict_with_ego(const DevParams &P, int la
     return __any_sync(FULL, hit);
 }
 
+// The SUMO-free world with the car-following model of the reference's traffic (merge_impossible.rou.xml:3: vType "normal",
+// carFollowModel Krauss, accel 4.5, decel 6.0, minGap 1, sigma 0, tau 0.5; maxSpeed = OTHER_CAR_SPEED, sumo.py:60; Euler update with
+// step-length TICK_LENGTH, ramp.sumocfg:8-20).  Every car computes its safe speed from its leader's state at the BEGINNING of the
+// step, like SUMO's planMove, so there is no sequential chain:
+//     v_safe = -b tau + sqrt((b tau)^2 + v_lead^2 + 2 b gap),  gap = x_lead - length - x - minGap      (Krauss 1998, SUMO's "Krauss")
+//     v'     = max(0, v - b dt, min(v + a dt, v_safe, v_max)),   x' = x + v' dt
+// The leader is the next car ahead, or the ego once it is on the junction's merging lane / the highway (ego_s >= 0; on the
+// junction its position along the lane is ego_s - 51, control.py:366-380) and sits between the two.  The ego itself moves as in
+// predict_step_with_ego and the crash test is that function's too (prediction.py:46-61, 97-103).  Parity against SUMO is not
+// pinned (no SUMO here): the world is judged on the aggregate statistics of whole episodes (tools/closed_loop_stats.py).
+struct KraussParams { double accel, decel, tau, min_gap, max_speed; };
+__device__ __forceinline__ bool warp_krauss_with_ego(const DevParams &P, const KraussParams &K, int lane, int n, const EgoState &ego,
+                                                     double x, double v, double sel, double dt, double min_crash_distance,
+                                                     EgoState &ego_out, double &nx, double &nv, double &na) {
+    double px, py;
+    if (ego.x < 1.5) {
+        double dx = __dsub_rn(1.5, ego.x), dy = __dsub_rn(-1.5, ego.y);
+        double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        dx = __ddiv_rn(dx, nrm); dy = __ddiv_rn(dy, nrm);
+        double step = __dmul_rn(sel, dt);
+        px = __dadd_rn(ego.x, __dmul_rn(dx, step)); py = __dadd_rn(ego.y, __dmul_rn(dy, step));
+        if (py < -1.6) py = -1.6;
+    } else { py = ego.y; px = __dadd_rn(ego.x, __dmul_rn(sel, dt)); }
+    ego_out.a = __ddiv_rn(__dsub_rn(sel, ego.v), dt);
+    ego_out.x = px; ego_out.y = py; ego_out.v = sel;
+    const bool can_crash = get_ego_s(px, py) > 11.0;
+    const bool valid = lane < n;
+    const double es = get_ego_s(ego.x, ego.y);
+    const bool ego_on_lane = es >= 0.0;
+    const double ex = ego.x >= 1.5 ? ego.x : es - 51.0;
+    double lx = __shfl_up_sync(FULL, x, 1), lv = __shfl_up_sync(FULL, v, 1);
+    if (lane == 0) { lx = 1.0e300; lv = 0.0; }
+    if (ego_on_lane && ex > x && ex < lx) { lx = ex; lv = ego.v; }
+    const double gap = lx - P.p.car_length - x - K.min_gap, bt = K.decel * K.tau;
+    const double vsafe = gap <= 0.0 ? 0.0 : (gap > 1.0e200 ? 1.0e300 : -bt + sqrt(bt * bt + lv * lv + 2.0 * K.decel * gap));
+    double v2 = fmin(fmin(v + K.accel * dt, vsafe), K.max_speed);
+    v2 = fmax(v2, fmax(0.0, v - K.decel * dt));
+    nv = v2; nx = x + v2 * dt; na = (v2 - v) / dt;
+    const double cdd = min_crash_distance > P.p.car_length ? min_crash_distance : P.p.car_length;
+    return __any_sync(FULL, valid && can_crash && fabs(nx - px) < cdd);
+}
+
+__global__ void __launch_bounds__(128) krauss_step_kernel(DevParams P, KraussParams K, int B, int nmax, double *ego, double *cars_x,
+                                                          double *cars_v, double *cars_a, const int32_t *n_cars,
+                                                          const double *sel_speed, double dt, double mcd, uint8_t *crashed) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int b = warp;
+    int n = n_cars[b]; n = n < 0 ? 0 : (n > nmax ? nmax : n);
+    EgoState e = {ego[4 * b], ego[4 * b + 1], ego[4 * b + 2], ego[4 * b + 3]}, eo;
+    const size_t o = (size_t)b * nmax + lane;
+    const double x = lane < n ? cars_x[o] : 0.0, v = lane < n ? cars_v[o] : 0.0;
+    double nx, nv, na;
+    const bool cr = warp_krauss_with_ego(P, K, lane, n, e, x, v, sel_speed[b], dt, mcd, eo, nx, nv, na);
+    __syncwarp();
+    if (lane == 0) { ego[4 * b] = eo.x; ego[4 * b + 1] = eo.y; ego[4 * b + 2] = eo.v; ego[4 * b + 3] = eo.a; crashed[b] = cr ? 1 : 0; }
+    if (lane < n) { cars_x[o] = nx; cars_v[o] = nv; cars_a[o] = na; }
+}
+
 // prediction.py:22-44: choose the pseudo-ego, then step.
 __device__ __forceinline__ void warp_predict_without_ego(const DevParams &P, int lane, int n, EgoState &ego,
                                                          double &x, double &v, double dt) {
@@ -583,6 +642,15 @@ cudaError_t launch_predict_step(const DevParams &P, int B, int nmax, const doubl
     if (B <= 0) return cudaSuccess;
     int wpb = 4;
     MPC_LAUNCH(predict_step_with_ego_kernel, (B + wpb - 1) / wpb, wpb * 32, 0, st, P, B, nmax, ego, cx, cv, ca, n, sel, dt, mcd, ego_out, ox, ov, oa, crashed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_krauss_step(const DevParams &P, int B, int nmax, double *ego, double *cx, double *cv, double *ca, const int32_t *n,
+                               const double *sel, double dt, double mcd, double accel, double decel, double tau, double min_gap,
+                               double max_speed, uint8_t *crashed, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    KraussParams K = {accel, decel, tau, min_gap, max_speed};
+    MPC_LAUNCH(krauss_step_kernel, (B + 3) / 4, 128, 0, st, P, K, B, nmax, ego, cx, cv, ca, n, sel, dt, mcd, crashed);
     return cudaGetLastError();
 }
 

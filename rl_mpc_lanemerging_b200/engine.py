@@ -330,6 +330,16 @@ class MpcEngine:
                                                           _ptr(eo), _ptr(xo), _ptr(vo), _ptr(ao), _ptr(crashed), self._stream()))
         return eo, xo, vo, ao, crashed
 
+    def krauss_step(self, ego, cars_x, cars_v, cars_a, n_cars, selected_speed, dt, min_crash_distance, accel, decel, tau, min_gap, max_speed):
+        """One tick of the Krauss world (mpc_krauss_step), in place; returns the crash flags u8[B]."""
+        B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)
+        crashed = torch.empty(B, dtype=torch.uint8, device=self.device)
+        with self._device_ctx():
+            _lib.check(self.lib.mpc_krauss_step(self.h, B, _ptr(ego), _ptr(cars_x), _ptr(cars_v), _ptr(cars_a), _ptr(n_cars),
+                                                _ptr(selected_speed), float(dt), float(min_crash_distance), float(accel), float(decel),
+                                                float(tau), float(min_gap), float(max_speed), _ptr(crashed), self._stream()))
+        return crashed
+
     def predict_step_without_ego(self, ego, cars_x, cars_v, cars_a, n_cars, dt, min_crash_distance=5.0):
         """HighwayState.predict_step_without_ego (prediction.py:22-44) for the whole batch: (ego, x, v, a, crashed)."""
         B = self._check_state(ego, cars_x, cars_v, cars_a, n_cars)

@@ -16,9 +16,13 @@ from . import dqn, st, synthetic
 from .config import Settings
 from .prediction import BatchedState, tdiv
 
-SPAWN_X = -250.0         # highway entry
-ARRIVAL_X = 75.0         # ego route end on the highway edge (approximate; unpinned)
-EGO_START_X = -215.0     # rampRoute departPos 40 (control.py:41-44)
+SPAWN_X = -250.0         # highway entry: lane highwayrear_0 starts at x = -250 (merge.net.xml:49)
+ARRIVAL_X = 51.5         # the ego's route ends at arrivalPos = 50 on highwayahead (control.py:42), whose lane starts at x = 1.5 (merge.net.xml:46)
+EGO_START_X = -211.40638598379087    # departPos = 40 (control.py:42) along the polyline of lane ramp_0 (merge.net.xml:52) ...
+EGO_START_Y = 19.98667760899962      # ... measured from its first point (-250.47, 28.47)
+
+
+KRAUSS = dict(accel=4.5, decel=6.0, tau=0.5, minGap=1.0)      # vType "normal" of merge_impossible.rou.xml:3 (sigma = 0: no dawdling)
 
 
 class MergeEnv:
@@ -46,8 +50,7 @@ class MergeEnv:
         self.max_ticks = int(Settings.MAX_EPISODE_LENGTH / Settings.TICK_LENGTH)
         self.prev_acc = torch.zeros(self.B, **f64)
         self._col = torch.arange(self.N, device=self.device).unsqueeze(0)
-        frac = (EGO_START_X - synthetic.RAMP_A[0]) / (synthetic.RAMP_B[0] - synthetic.RAMP_A[0])
-        self._ego_y0 = synthetic.RAMP_A[1] + frac * (synthetic.RAMP_B[1] - synthetic.RAMP_A[1])
+        self._ego_y0 = EGO_START_Y
 
     def _rand(self, *shape):
         return torch.rand(shape, generator=self.gen, dtype=torch.float64, device=self.device)
@@ -128,7 +131,7 @@ class MergeEnv:
 
     def step(self, action: torch.Tensor):
         """action: jerk [B] (continuous, reference ContinuousJerkEnv).  Finished episodes restart when auto_reset."""
-        if getattr(Settings, "FUSED_ENV_STEP", False):
+        if getattr(Settings, "FUSED_ENV_STEP", False) and getattr(Settings, "WORLD_MODEL", "predictor") == "predictor":
             return self._step_fused(action)
         S, tick, st8 = Settings, float(Settings.TICK_LENGTH), self.state
         jerk = action.to(self.device, torch.float64).reshape(self.B)
@@ -148,8 +151,13 @@ class MergeEnv:
         # world step: the reference predictor as dynamics (K4 kernel, in place)
         for t in st8.args():
             assert t.is_contiguous()
-        _, _, _, _, crashed = self.eng.predict_step_with_ego(*st8.args(), spd.contiguous(), tick, S.CAR_LENGTH, inplace=True)
-        crashed = crashed.bool()
+        if getattr(S, "WORLD_MODEL", "predictor") == "krauss":
+            # the traffic follows SUMO's Krauss model with the vType of merge_impossible.rou.xml:3 (mpc_krauss_step)
+            crashed = self.eng.krauss_step(*st8.args(), spd.contiguous(), tick, S.CAR_LENGTH, KRAUSS["accel"], KRAUSS["decel"],
+                                           KRAUSS["tau"], KRAUSS["minGap"], float(S.OTHER_CAR_SPEED)).bool()
+        else:
+            _, _, _, _, crashed = self.eng.predict_step_with_ego(*st8.args(), spd.contiguous(), tick, S.CAR_LENGTH, inplace=True)
+            crashed = crashed.bool()
         self.prev_acc = st8.ego[:, 3].clone()
         # recycle the front car once it is out of sensor range ahead; enter a new car at the back (control.py:215-226)
         n = st8.n_cars
