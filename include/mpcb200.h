@@ -247,7 +247,9 @@ typedef struct mpc_env_params {
     double time_reward_step;        /* TIME_REWARD * TICK_LENGTH */
     double jerk_weight, crash_reward, success_reward;
     double invalid_action_step;     /* INVALID_ACTION_PENALTY * TICK_LENGTH, added to the reward of a tick whose action was clipped (merge_gym.py:86-92) */
+    double krauss_accel, krauss_decel, krauss_tau, krauss_min_gap;   /* world == 1: the traffic's Krauss model (mpc_krauss_step) */
     int32_t max_ticks, auto_reset;
+    int32_t world, pad_;            /* 0 = the reference's predictor as dynamics (mpc_predict_step_with_ego), 1 = Krauss traffic */
 } mpc_env_params;
 int mpc_env_step(mpc_handle *h, const mpc_env_params *ep, int B, double *d_ego, double *d_cars_x, double *d_cars_v,
                  double *d_cars_a, int32_t *d_n_cars, double *d_prev_acc, double *d_delay, int32_t *d_ticks,

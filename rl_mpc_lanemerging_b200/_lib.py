@@ -26,11 +26,13 @@ class MpcParams(C.Structure):
 
 ENV_PARAM_FIELDS = ("tick", "a_min", "a_max", "max_speed", "min_crash_distance", "sensor_radius", "spawn_x", "other_speed", "interval",
                     "arrival_x", "ego_start_x", "ego_start_y", "start_speed", "start_speed_var", "min_start_speed", "max_start_speed",
-                    "time_reward_step", "jerk_weight", "crash_reward", "success_reward", "invalid_action_step")
+                    "time_reward_step", "jerk_weight", "crash_reward", "success_reward", "invalid_action_step",
+                    "krauss_accel", "krauss_decel", "krauss_tau", "krauss_min_gap")
 
 
 class MpcEnvParams(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ENV_PARAM_FIELDS] + [("max_ticks", C.c_int32), ("auto_reset", C.c_int32)]
+    _fields_ = [(n, C.c_double) for n in ENV_PARAM_FIELDS] + [("max_ticks", C.c_int32), ("auto_reset", C.c_int32), ("world", C.c_int32),
+                                                              ("pad_", C.c_int32)]
 
 
 class MpcError(RuntimeError):

@@ -37,8 +37,11 @@ _HOT_PATH_DEFAULTS = {
     "TEST_ROLLOUT_STATE": True, "CHECK_ROLLOUT_CRASH": True, "COMBINATION_MIN_DISTANCE": 5.1, "STOP_X": 65,
     "REMEMBER_LAST_CHOICE_FOR_SWITCHING_COMBINED": False, "LEARNING_RATE": 2e-4,
     # this implementation only
-    # training (reference ddpg.py:46-117; per-rank environment count and update cadence are this implementation's)
-    "TRAIN_NUM_ENVS": 8192, "TRAIN_UPDATES_PER_TICK": 1, "TRAIN_MINIBATCH": 4096, "EVAL_NUM_ENVS": 4096,
+    # training (reference ddpg.py:46-117).  The reference's preset makes one gradient step on a minibatch of 100 per environment frame
+    # (update_frequency 1): 100 replayed samples per frame.  A tick here yields TRAIN_NUM_ENVS frames per rank, so it is followed by
+    # TRAIN_NUM_ENVS * TRAIN_SAMPLES_PER_FRAME / TRAIN_MINIBATCH gradient steps (TRAIN_UPDATES_PER_TICK = None), which keeps that
+    # update-to-data ratio with larger minibatches; an integer overrides it (throughput runs).
+    "TRAIN_NUM_ENVS": 256, "TRAIN_UPDATES_PER_TICK": None, "TRAIN_MINIBATCH": 1024, "TRAIN_SAMPLES_PER_FRAME": 100, "EVAL_NUM_ENVS": 4096,
     "ST_MODE": "exact",       # arithmetic of the single-state drop-in calls: "exact" (fp64, st_cy-identical) or "fast"
     "CUDA_DEVICE": 0,
     # closed loop: bound each episode's plan by PLAN_HINT_SCALE x the cost of its previous plan (mpc_plan_hinted; the plans are
@@ -52,7 +55,7 @@ _HOT_PATH_DEFAULTS = {
     "SYNC_FREE_TAKEOVER": False,
     # dynamics of merge_gym.MergeEnv: "predictor" = the reference's own traffic predictor (prediction.py:46-105) applied as the world,
     # "krauss" = SUMO's Krauss car-following model with the vType of merge_impossible.rou.xml:3 (mpc_krauss_step)
-    "WORLD_MODEL": "predictor",
+    "WORLD_MODEL": "krauss",
 }
 
 

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
                                                             const int32_t *__restrict__ subset, const int *__restrict__ count) {
     __shared__ double s_edge[4][2 * MPC_NMAX];
     __shared__ int2 s_band[4][MPC_NMAX], s_blk[4][MPC_NMAX];
+    __shared__ int s_hist[4][2][MPC_MAX_BUCKETS];
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (warp >= B) return;
     int b = warp;
@@ -235,14 +236,35 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
         int r_f = 0, r_b = 0, r_band = 0, r_blk = 0;
         bool hasband = act && imin < imax, hasblk = act && zlo < zhi;
         unsigned bm = __ballot_sync(FULL, hasband), zm = __ballot_sync(FULL, hasblk);
-        for (int j = 0; j < 32; j++) {
-            if (!((am >> j) & 1u)) continue;                                        // warp-uniform
-            double fj = __shfl_sync(FULL, ef, j), bj = __shfl_sync(FULL, eb, j);
-            int ij = __shfl_sync(FULL, imin, j), zj = __shfl_sync(FULL, zlo, j);
-            r_f += (fj < ef || (fj == ef && 2 * j < 2 * lane)) + (bj < ef || (bj == ef && 2 * j + 1 < 2 * lane));
-            r_b += (fj < eb || (fj == eb && 2 * j < 2 * lane + 1)) + (bj < eb || (bj == eb && 2 * j + 1 < 2 * lane + 1));
-            if ((bm >> j) & 1u) r_band += (ij < imin || (ij == imin && j < lane));
-            if ((zm >> j) & 1u) r_blk += (zj < zlo || (zj == zlo && j < lane));
+        // Fast path.  The cars come front -> back, so with ordinary spacing (gap > 2 (CAR_LENGTH + uncertainty)) the ascending
+        // order is simply "rearmost car's front edge, its back edge, the next car's front edge, ...": rank = 2 x (active cars
+        // behind me) (+1), and bands / blocked intervals are ordered like the cars.  The guess is checked below on the sorted
+        // arrays themselves; when it does not hold (perturbed states, large uncertainty) the ranks are counted.
+        const unsigned above = lane == 31 ? 0u : ~((2u << lane) - 1u);                // lanes behind me
+        r_f = 2 * __popc(am & above); r_b = r_f + 1;
+        r_band = __popc(bm & above); r_blk = __popc(zm & above);
+        {
+            // sorted <=> every edge is <= the next car-in-front's front edge ... checked pairwise between neighbouring active cars
+            const int nxt = (am & ((1u << lane) - 1u)) ? 31 - __clz(am & ((1u << lane) - 1u)) : -1;     // next active car in front of me
+            const double nef = __shfl_sync(FULL, ef, nxt < 0 ? 0 : nxt);
+            const int nimin = __shfl_sync(FULL, imin, nxt < 0 ? 0 : nxt), nzlo = __shfl_sync(FULL, zlo, nxt < 0 ? 0 : nxt);
+            const int nband = __shfl_sync(FULL, (int)hasband, nxt < 0 ? 0 : nxt), nblk = __shfl_sync(FULL, (int)hasblk, nxt < 0 ? 0 : nxt);
+            bool bad = act && (ef > eb);
+            if (act && nxt >= 0) bad = bad || eb > nef || (hasband && nband && imin > nimin) || (hasblk && nblk && zlo > nzlo);
+            // (a car without a band / interval between two that have one: compare with the next one that has; rare -> count)
+            if (act && nxt >= 0 && ((hasband && !nband) || (hasblk && !nblk))) bad = true;
+            if (__any_sync(FULL, bad)) {
+                r_f = 0; r_b = 0; r_band = 0; r_blk = 0;
+                for (int j = 0; j < 32; j++) {
+                    if (!((am >> j) & 1u)) continue;                                        // warp-uniform
+                    double fj = __shfl_sync(FULL, ef, j), bj = __shfl_sync(FULL, eb, j);
+                    int ij = __shfl_sync(FULL, imin, j), zj = __shfl_sync(FULL, zlo, j);
+                    r_f += (fj < ef || (fj == ef && 2 * j < 2 * lane)) + (bj < ef || (bj == ef && 2 * j + 1 < 2 * lane));
+                    r_b += (fj < eb || (fj == eb && 2 * j < 2 * lane + 1)) + (bj < eb || (bj == eb && 2 * j + 1 < 2 * lane + 1));
+                    if ((bm >> j) & 1u) r_band += (ij < imin || (ij == imin && j < lane));
+                    if ((zm >> j) & 1u) r_blk += (zj < zlo || (zj == zlo && j < lane));
+                }
+            }
         }
         double *se = s_edge[wib]; int2 *sb = s_band[wib], *sz = s_blk[wib];
         if (act) { se[r_f] = ef; se[r_b] = eb; }
@@ -257,16 +279,35 @@ __global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B,
         if (lane < n_blk) L->blk[lane] = sz[lane];
         if (lane == 0) { L->n_act = n_act; L->n_edge = n_edge; L->n_band = n_band; L->n_blk = n_blk; L->edge[n_edge] = 1e300; }
         __syncwarp();
-        // bucket tables: bucket j starts at cell 64*j
+        // bucket tables: bucket j starts at cell 64*j; bucket_edge[j] = #edges < s_(64 j), bucket_band[j] = #bands ending <= 64 j.
+        // Every edge / band adds one to the first bucket it counts for (estimated by division, fixed up with the exact
+        // comparison), an inclusive prefix sum over the buckets does the rest: ~130 warp instructions per layer where one
+        // binary search per bucket took ~350.
         int nbuck = (g.num_s + (1 << MPC_BUCKET_SHIFT) - 1) >> MPC_BUCKET_SHIFT;
-        for (int j = lane; j < nbuck; j += 32) {
-            double sj = g.sval(j << MPC_BUCKET_SHIFT);
-            int lo_ = 0, hi_ = n_edge;                                              // first index with edge >= sj
-            while (lo_ < hi_) { int mid = (lo_ + hi_) >> 1; if (se[mid] < sj) lo_ = mid + 1; else hi_ = mid; }
-            L->bucket_edge[j] = (unsigned char)lo_;
-            int cnt = 0, cell = j << MPC_BUCKET_SHIFT;
-            for (int q = 0; q < n_band; q++) cnt += (sb[q].y <= cell);
-            L->bucket_band[j] = (unsigned char)cnt;
+        int *he = s_hist[wib][0], *hb = s_hist[wib][1];
+        for (int j = lane; j < nbuck; j += 32) { he[j] = 0; hb[j] = 0; }
+        __syncwarp();
+        for (int i = lane; i < n_edge; i += 32) {
+            const double ev = se[i];
+            int j = (int)floor(__ddiv_rn(__dsub_rn(ev, g.s0), __dmul_rn(g.ds, 64.0))) + 1;
+            j = j < 0 ? 0 : (j > nbuck ? nbuck : j);
+            while (j > 0 && ev < g.sval((j - 1) << MPC_BUCKET_SHIFT)) j--;            // first j with ev < s_(64 j)
+            while (j < nbuck && !(ev < g.sval(j << MPC_BUCKET_SHIFT))) j++;
+            if (j < nbuck) atomicAdd(&he[j], 1);
+        }
+        if (lane < n_band) { const int j = (sb[lane].y + (1 << MPC_BUCKET_SHIFT) - 1) >> MPC_BUCKET_SHIFT; if (j < nbuck) atomicAdd(&hb[j], 1); }
+        __syncwarp();
+        {
+            const int per = (nbuck + 31) >> 5, j0 = lane * per;                       // consecutive buckets per lane
+            int se_ = 0, sb_ = 0;
+            for (int q = 0; q < per; q++) if (j0 + q < nbuck) { se_ += he[j0 + q]; sb_ += hb[j0 + q]; }
+            int pe = se_, pb = sb_;
+            for (int o = 1; o < 32; o <<= 1) { int a_ = __shfl_up_sync(FULL, pe, o), b_ = __shfl_up_sync(FULL, pb, o); if (lane >= o) { pe += a_; pb += b_; } }
+            pe -= se_; pb -= sb_;                                                     // exclusive
+            for (int q = 0; q < per; q++) if (j0 + q < nbuck) {
+                pe += he[j0 + q]; pb += hb[j0 + q];
+                L->bucket_edge[j0 + q] = (unsigned char)pe; L->bucket_band[j0 + q] = (unsigned char)pb;
+            }
         }
         __syncwarp();
     }
@@ -552,7 +593,9 @@ __global__ void __launch_bounds__(128) env_step_kernel(DevParams P, mpc_env_para
     spd = spd > E.max_speed ? E.max_speed : (spd < 0.0 ? 0.0 : spd);
     // world step: the reference predictor as dynamics (cars beyond n keep their values, like the in-place K4 call)
     double nx, nv, na;
-    const bool crashed = warp_predict_with_ego(P, lane, n, e, x, v, spd, E.tick, E.min_crash_distance, eo, nx, nv, na);
+    const KraussParams KP = {E.krauss_accel, E.krauss_decel, E.krauss_tau, E.krauss_min_gap, E.other_speed};
+    const bool crashed = E.world == 1 ? warp_krauss_with_ego(P, KP, lane, n, e, x, v, spd, E.tick, E.min_crash_distance, eo, nx, nv, na)
+                                      : warp_predict_with_ego(P, lane, n, e, x, v, spd, E.tick, E.min_crash_distance, eo, nx, nv, na);
     if (lane < n) { x = nx; v = nv; a = na; }
     double new_prev_acc = eo.a;
     // recycle the front car once it is out of sensor range ahead (all slots shift), enter a new car at the back

@@ -128,9 +128,13 @@ class DDPGAgent(dqn.RLAgent):
         dev = int(os.environ.get("LOCAL_RANK", getattr(Settings, "CUDA_DEVICE", 0)))
         Settings.CUDA_DEVICE = dev
         st.refresh_engine()
-        env = merge_gym.MergeEnv(int(num_envs or Settings.TRAIN_NUM_ENVS), seed=seed + 104729 * rank)
-        return trainer.DDPGTrainer(env, device=f"cuda:{dev}", lr=Settings.LEARNING_RATE, seed=seed,
-                                   minibatch_size=int(Settings.TRAIN_MINIBATCH), updates_per_tick=int(Settings.TRAIN_UPDATES_PER_TICK))
+        n_envs, mb = int(num_envs or Settings.TRAIN_NUM_ENVS), int(Settings.TRAIN_MINIBATCH)
+        upt = Settings.TRAIN_UPDATES_PER_TICK
+        if upt is None:                                        # the reference's update-to-data ratio (config.py)
+            upt = max(1, round(n_envs * float(Settings.TRAIN_SAMPLES_PER_FRAME) / mb))
+        env = merge_gym.MergeEnv(n_envs, seed=seed + 104729 * rank)
+        return trainer.DDPGTrainer(env, device=f"cuda:{dev}", lr=Settings.LEARNING_RATE, seed=seed, minibatch_size=mb, updates_per_tick=int(upt),
+                                   replay_start_size=max(5000, 4 * mb))
 
     @classmethod
     def train(cls, num_frames: int, num_envs=None):
@@ -148,16 +152,25 @@ class DDPGAgent(dqn.RLAgent):
 
 
 def train_ddpg_all_with_lr_drop(num_frames, third=False, num_envs=None):
-    """Reference ddpg.py:96-117: train, divide the learning rate by 10, train again from the first run's weights
-    (optionally a third time), then evaluate NUM_EPISODES episodes with the result."""
+    """Reference ddpg.py:96-117: train, divide the learning rate by 10, train again from the first run's weights into
+    <LOG_DIR>_extended; with `third`: evaluate that, divide the learning rate once more and train into <LOG_DIR>_extended2; then
+    evaluate NUM_EPISODES episodes with the final weights."""
     if not hasattr(Settings, "FULL_LOG_DIR"):
         Settings.setup_logging()
     DDPGAgent.train(num_frames, num_envs)
-    stages = 2 if third else 1
-    for i in range(stages):
+    Settings.LEARNING_RATE /= 10
+    old_log_dir = Settings.FULL_LOG_DIR
+    Settings.LOG_DIR = Settings.LOG_DIR + "_extended"
+    Settings.setup_logging()
+    DDPGAgent.resume_training(old_log_dir, num_frames, num_envs)
+    if third:                                                   # ddpg.py:104-113
+        Settings.TASK = "EVALUATE_DDPG"
+        Settings.MODEL_NAME = Settings.FULL_LOG_DIR
+        DDPGAgent.load(Settings.FULL_LOG_DIR).evaluate(Settings.NUM_EPISODES)
+        Settings.TASK = "TRAIN_DDPG"
         Settings.LEARNING_RATE /= 10
         old_log_dir = Settings.FULL_LOG_DIR
-        Settings.LOG_DIR = Settings.LOG_DIR + ("_extended" if i == 0 else "2")
+        Settings.LOG_DIR = Settings.LOG_DIR + "2"
         Settings.setup_logging()
         DDPGAgent.resume_training(old_log_dir, num_frames, num_envs)
     Settings.TASK = "EVALUATE_DDPG"

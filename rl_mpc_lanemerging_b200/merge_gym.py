@@ -109,6 +109,8 @@ class MergeEnv:
         ep.time_reward_step = S.TIME_REWARD * S.TICK_LENGTH
         ep.jerk_weight, ep.crash_reward, ep.success_reward = float(S.ALT_J_WEIGHT), float(S.CRASH_REWARD), float(S.SUCCESS_REWARD)
         ep.invalid_action_step = float(S.INVALID_ACTION_PENALTY) * float(S.TICK_LENGTH)
+        ep.world = 1 if getattr(S, "WORLD_MODEL", "krauss") == "krauss" else 0
+        ep.krauss_accel, ep.krauss_decel, ep.krauss_tau, ep.krauss_min_gap = KRAUSS["accel"], KRAUSS["decel"], KRAUSS["tau"], KRAUSS["minGap"]
         ep.max_ticks, ep.auto_reset = int(self.max_ticks), int(bool(self.auto_reset))
         u = self._rand(B) if S.VARY_TRAFFIC_START_TIMES else None
         fresh = None
@@ -131,7 +133,7 @@ class MergeEnv:
 
     def step(self, action: torch.Tensor):
         """action: jerk [B] (continuous, reference ContinuousJerkEnv).  Finished episodes restart when auto_reset."""
-        if getattr(Settings, "FUSED_ENV_STEP", False) and getattr(Settings, "WORLD_MODEL", "predictor") == "predictor":
+        if getattr(Settings, "FUSED_ENV_STEP", False):
             return self._step_fused(action)
         S, tick, st8 = Settings, float(Settings.TICK_LENGTH), self.state
         jerk = action.to(self.device, torch.float64).reshape(self.B)
@@ -151,7 +153,7 @@ class MergeEnv:
         # world step: the reference predictor as dynamics (K4 kernel, in place)
         for t in st8.args():
             assert t.is_contiguous()
-        if getattr(S, "WORLD_MODEL", "predictor") == "krauss":
+        if getattr(S, "WORLD_MODEL", "krauss") == "krauss":
             # the traffic follows SUMO's Krauss model with the vType of merge_impossible.rou.xml:3 (mpc_krauss_step)
             crashed = self.eng.krauss_step(*st8.args(), spd.contiguous(), tick, S.CAR_LENGTH, KRAUSS["accel"], KRAUSS["decel"],
                                            KRAUSS["tau"], KRAUSS["minGap"], float(S.OTHER_CAR_SPEED)).bool()

@@ -9,8 +9,11 @@ flat fp32 buffer (policy 129 401 + critic 129 801 parameters = 1.04 MB) that is 
 step, so the replicas stay bit-identical (same initial weights by broadcast, same averaged gradients, local Adam and
 Polyak updates).  No collective touches the environment / planner path.
 
-Network shapes, checkpoint layout (`<run dir>/policy.pt`, `q.pt`, state_dict keys `model.{0,2,4}.{weight,bias}`), the
-learning rate (Settings.LEARNING_RATE) and the two-stage schedule are the reference's.  The remaining DDPG
+Network shapes, the files of a run (`<run dir>/policy.pt`, `q.pt`), their state_dict keys (`model.{0,2,4}.{weight,bias}`), the
+learning rate (Settings.LEARNING_RATE) and the two-stage schedule are the reference's.  Checkpoints travel ONE WAY: this package
+reads the reference's whole-module pickles (ddpg._load_legacy_state_dict) and its own files, but writes plain state_dicts -- the
+reference's loaders (`torch.load(...).to(device).state_dict()`, GreedyAgent.load) expect pickled `all.*` module objects, which
+cannot be produced without that library.  The remaining DDPG
 hyper-parameters live inside the third-party library, not in the reference tree: the values below are that library's
 published 0.5.3 defaults as far as known -- UNPINNED.
 """
@@ -164,7 +167,7 @@ class DDPGTrainer:
                     self.update()
         return self
 
-    # ---- checkpoints: reference layout runs/<LOG_DIR>/{policy,q}.pt (ddpg.py:56-57, 62-81) ----
+    # ---- checkpoints: runs/<LOG_DIR>/{policy,q}.pt like the reference (ddpg.py:56-57, 62-81), as plain state_dicts (one way, see above) ----
     def save(self, path: str):
         if self.rank == 0:
             os.makedirs(path, exist_ok=True)

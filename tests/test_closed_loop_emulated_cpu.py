@@ -78,8 +78,9 @@ def test_plan_cost_hints_do_not_change_the_closed_loop(settings):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("auto_reset,randomize", [(True, True), (True, False), (False, True)])
-def test_fused_env_step_equals_the_tensor_version(settings, auto_reset, randomize):
+@pytest.mark.parametrize("auto_reset,randomize,world", [(True, True, "predictor"), (True, False, "krauss"), (False, True, "krauss"),
+                                                        (True, True, "krauss")])
+def test_fused_env_step_equals_the_tensor_version(settings, auto_reset, randomize, world):
     """Settings.FUSED_ENV_STEP: MergeEnv.step as one kernel (mpc_env_step).  Two environments with the same seed, one stepped
     by the kernel, one by the ~150 tensor operations, fed the same jerks: states, rewards, flags and observations must stay
     bit-identical over resets, recycled and entering cars, clipped actions, crashes and timeouts."""
@@ -87,6 +88,7 @@ def test_fused_env_step_equals_the_tensor_version(settings, auto_reset, randomiz
     from rl_mpc_lanemerging_b200 import merge_gym
     settings.MAX_EPISODE_LENGTH = 2.4                            # 12 ticks: timeouts (and their resets) inside the run
     settings.RANDOMIZE_START_SPEED = randomize
+    settings.WORLD_MODEL = world                                 # both dynamics: the reference's predictor, SUMO's Krauss model
     envs = {}
     for fused in (False, True):
         e = merge_gym.MergeEnv(12, seed=9, auto_reset=auto_reset)

@@ -9,14 +9,16 @@ import pytest
 pytestmark = [pytest.mark.gpu]
 
 
+@pytest.mark.parametrize("world", ["predictor", "krauss"])
 @pytest.mark.parametrize("auto_reset", [False, True])
-def test_fused_env_step_matches_tensor_version(auto_reset):
+def test_fused_env_step_matches_tensor_version(auto_reset, world):
     import torch
     from rl_mpc_lanemerging_b200 import merge_gym, st
     from rl_mpc_lanemerging_b200.config import Settings
     Settings.reset()
     Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL = 20, 11.0, 1.2
     Settings.MAX_EPISODE_LENGTH = 3.0
+    Settings.WORLD_MODEL = world
     st.refresh_engine()
     try:
         B = 256
