@@ -334,34 +334,55 @@ __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int 
     __syncthreads();
     SGrid g; g.s0 = s0v[b]; g.ds = dsv[b]; g.num_s = nsv[b];
     const size_t row = (size_t)bt * stride_s;
-    for (int k4 = threadIdx.x * 4; k4 < stride_s; k4 += blockDim.x * 4) {
-        unsigned char ob4[4]; DT d4[4];
-        // the four cells are consecutive: look the bucket up once, then only advance the edge / band cursors
-        const int jb = min(k4, g.num_s - 1) >> MPC_BUCKET_SHIFT;
+    const int M = L.n_edge, m = L.n_band;
+    // 8 consecutive cells per thread: the bucket is looked up once, the two distance-field edges that bracket the cell and the
+    // current band stay in registers and are advanced only when a cell passes them (edges are >= 10 m = 200 cells apart), the cell
+    // index becomes a double with one add (2^52 trick) instead of a conversion; one 64-bit mask store, two 128-bit distance stores.
+    for (int k8 = threadIdx.x * 8; k8 < stride_s; k8 += blockDim.x * 8) {
+        const int jb = min(k8, g.num_s - 1) >> MPC_BUCKET_SHIFT;
         int e = L.bucket_edge[jb], i = L.bucket_band[jb];
-        const int M = L.n_edge, m = L.n_band;
+        {   // position the cursors on the first cell (at most a few steps: the bucket starts <= 63 cells earlier)
+            const double sv0 = g.sval(min(k8, g.num_s - 1));
+            while (e < M && L.edge[e] < sv0) e++;
+            while (i < m && L.mband[i].y <= k8) i++;
+        }
+        double lo = e > 0 ? L.edge[e - 1] : -1.0e300, hi = e < M ? L.edge[e] : 1.0e300;
+        int2 band = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX);
+        unsigned ob_lo = 0, ob_hi = 0;
+        DT d8[8];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int k = k4 + c;
-            bool ob = true; double d = 0.0;
+        for (int c = 0; c < 8; c++) {
+            const int k = k8 + c;
+            double d = 0.0; bool ob = true;
             if (k < g.num_s) {
-                const double sv = g.sval(k);
-                while (e < M && L.edge[e] < sv) e++;
-                d = 1E10;
-                if (e > 0) { double x = __dsub_rn(sv, L.edge[e - 1]); d = x < d ? x : d; }
-                if (e < M) { double x = fabs(__dsub_rn(sv, L.edge[e])); d = x < d ? x : d; }
-                while (i < m && L.mband[i].y <= k) i++;
-                ob = i < m && L.mband[i].x <= k;
+                const double kd = __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);      // (double)k, exactly
+                const double sv = __dadd_rn(g.s0, __dmul_rn(kd, g.ds));
+                while (hi < sv) { e++; lo = hi; hi = e < M ? L.edge[e] : 1.0e300; }
+                const double dl = __dsub_rn(sv, lo), dr = fabs(__dsub_rn(sv, hi));          // (lo < sv <= hi; -1e300 / 1e300 give > 1e10)
+                d = 1E10; d = dl < d ? dl : d; d = dr < d ? dr : d;
+                while (band.y <= k) { i++; band = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX); }
+                ob = band.x <= k;
                 if (ob) d = 0.0;
             }
-            ob4[c] = ob ? 1 : 0; d4[c] = (DT)d;
+            if (c < 4) ob_lo |= (ob ? 1u : 0u) << (8 * c); else ob_hi |= (ob ? 1u : 0u) << (8 * (c - 4));
+            d8[c] = (DT)d;
         }
-        if (vec_ok && k4 + 3 < stride_s) {
-            *reinterpret_cast<uchar4 *>(obstacles + row + k4) = make_uchar4(ob4[0], ob4[1], ob4[2], ob4[3]);
-            if (sizeof(DT) == 4) *reinterpret_cast<float4 *>(distances + row + k4) = make_float4((float)d4[0], (float)d4[1], (float)d4[2], (float)d4[3]);
-            else { double2 *q = reinterpret_cast<double2 *>(distances + row + k4); q[0] = make_double2((double)d4[0], (double)d4[1]); q[1] = make_double2((double)d4[2], (double)d4[3]); }
+        if (vec_ok && k8 + 7 < stride_s) {
+            *reinterpret_cast<uint2 *>(obstacles + row + k8) = make_uint2(ob_lo, ob_hi);
+            if (sizeof(DT) == 4) {
+                float4 *q = reinterpret_cast<float4 *>(distances + row + k8);
+                q[0] = make_float4((float)d8[0], (float)d8[1], (float)d8[2], (float)d8[3]);
+                q[1] = make_float4((float)d8[4], (float)d8[5], (float)d8[6], (float)d8[7]);
+            } else {
+                double2 *q = reinterpret_cast<double2 *>(distances + row + k8);
+                q[0] = make_double2((double)d8[0], (double)d8[1]); q[1] = make_double2((double)d8[2], (double)d8[3]);
+                q[2] = make_double2((double)d8[4], (double)d8[5]); q[3] = make_double2((double)d8[6], (double)d8[7]);
+            }
         } else {
-            for (int c = 0; c < 4 && k4 + c < stride_s; c++) { obstacles[row + k4 + c] = ob4[c]; distances[row + k4 + c] = d4[c]; }
+            for (int c = 0; c < 8 && k8 + c < stride_s; c++) {
+                obstacles[row + k8 + c] = (unsigned char)(((c < 4 ? ob_lo : ob_hi) >> (8 * (c & 3))) & 1u);
+                distances[row + k8 + c] = d8[c];
+            }
         }
     }
 }
@@ -673,7 +694,7 @@ cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const Laye
                              const double *ds, const int32_t *ns, uint8_t *obstacles, void *distances, int dist_f32,
                              cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    const int vec_ok = (stride_s % 4 == 0) && ((uintptr_t)obstacles % 4 == 0) && ((uintptr_t)distances % 16 == 0);
+    const int vec_ok = (stride_s % 8 == 0) && ((uintptr_t)obstacles % 8 == 0) && ((uintptr_t)distances % 16 == 0);
     if (dist_f32) MPC_LAUNCH(rasterise_kernel<float>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances, vec_ok);
     else MPC_LAUNCH(rasterise_kernel<double>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances, vec_ok);
     return cudaGetLastError();

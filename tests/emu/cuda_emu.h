@@ -257,6 +257,7 @@ static inline unsigned __float2uint_rn(float a) { return a <= 0.0f ? 0u : (unsig
 static inline long long __double2ll_rn(double a) { return std::isnan(a) ? (long long)0x8000000000000000ull : llrint(a); }
 static inline long long __double_as_longlong(double a) { return (long long)emu_bits(a); }
 static inline double __longlong_as_double(long long a) { return emu_unbits<double>((unsigned long long)a); }
+static inline double __hiloint2double(int hi, int lo) { return emu_unbits<double>(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
