@@ -350,22 +350,45 @@ __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int 
         int2 band = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX);
         unsigned ob_lo = 0, ob_hi = 0;
         DT d8[8];
+        // Straight-line path: at most ONE edge and ONE band boundary inside the 8 cells (edges and bands of a layer are metres
+        // apart; 8 cells are 0.4 m) -- the bracketing pair is then a select between two register pairs, no loop, no branch.
+        const double hi2 = e + 1 < M ? L.edge[e + 1] : 1.0e300;
+        const int2 band2 = i + 1 < m ? L.mband[i + 1] : make_int2(INT_MAX, INT_MAX);
+        const int klast = min(k8 + 7, g.num_s - 1);
+        if (M > 0 && !(hi2 < g.sval(klast)) && band2.y > klast) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int k = k8 + c;
-            double d = 0.0; bool ob = true;
-            if (k < g.num_s) {
+            for (int c = 0; c < 8; c++) {
+                const int k = k8 + c;
                 const double kd = __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);      // (double)k, exactly
                 const double sv = __dadd_rn(g.s0, __dmul_rn(kd, g.ds));
-                while (hi < sv) { e++; lo = hi; hi = e < M ? L.edge[e] : 1.0e300; }
-                const double dl = __dsub_rn(sv, lo), dr = fabs(__dsub_rn(sv, hi));          // (lo < sv <= hi; -1e300 / 1e300 give > 1e10)
-                d = 1E10; d = dl < d ? dl : d; d = dr < d ? dr : d;
-                while (band.y <= k) { i++; band = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX); }
-                ob = band.x <= k;
+                const bool past = hi < sv;
+                const double lo_c = past ? hi : lo, hi_c = past ? hi2 : hi;
+                const double dl = __dsub_rn(sv, lo_c), dr = __dsub_rn(hi_c, sv);        // (== fabs(sv - hi_c): hi_c >= sv)
+                double d = dl < dr ? dl : dr;
+                const int2 bc = band.y <= k ? band2 : band;
+                bool ob = bc.x <= k;                                                     // (k < bc.y holds: bc is the first band ending behind k)
+                if (k >= g.num_s) { ob = true; }
                 if (ob) d = 0.0;
+                if (c < 4) ob_lo |= (ob ? 1u : 0u) << (8 * c); else ob_hi |= (ob ? 1u : 0u) << (8 * (c - 4));
+                d8[c] = (DT)d;
             }
-            if (c < 4) ob_lo |= (ob ? 1u : 0u) << (8 * c); else ob_hi |= (ob ? 1u : 0u) << (8 * (c - 4));
-            d8[c] = (DT)d;
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < 8; c++) {
+                const int k = k8 + c;
+                double d = 0.0; bool ob = true;
+                if (k < g.num_s) {
+                    const double sv = g.sval(k);
+                    while (hi < sv) { e++; lo = hi; hi = e < M ? L.edge[e] : 1.0e300; }
+                    const double dl = __dsub_rn(sv, lo), dr = fabs(__dsub_rn(sv, hi));
+                    d = 1E10; d = dl < d ? dl : d; d = dr < d ? dr : d;
+                    while (band.y <= k) { i++; band = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX); }
+                    ob = band.x <= k;
+                    if (ob) d = 0.0;
+                }
+                if (c < 4) ob_lo |= (ob ? 1u : 0u) << (8 * c); else ob_hi |= (ob ? 1u : 0u) << (8 * (c - 4));
+                d8[c] = (DT)d;
+            }
         }
         if (vec_ok && k8 + 7 < stride_s) {
             *reinterpret_cast<uint2 *>(obstacles + row + k8) = make_uint2(ob_lo, ob_hi);

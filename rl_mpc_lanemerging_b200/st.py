@@ -30,8 +30,8 @@ def get_engine(min_batch: int = 1) -> MpcEngine:
     dev = int(getattr(Settings, "CUDA_DEVICE", 0))
     key = (params_key(p), dev)
     if _engine is None or key != _engine_key or _engine.max_batch < min_batch:
-        if _engine is not None:
-            _engine.close()
+        # (the previous engine is NOT closed here: environments / agents created earlier may still hold it; it is destroyed with
+        # its last reference.  refresh_engine() closes explicitly.)
         cap = max(min_batch, 64)
         _engine = MpcEngine(p, device=dev, max_batch=cap)
         _engine_key = key
