@@ -45,10 +45,10 @@ _HOT_PATH_DEFAULTS = {
     "ST_MODE": "exact",       # arithmetic of the single-state drop-in calls: "exact" (fp64, st_cy-identical) or "fast"
     "CUDA_DEVICE": 0,
     # closed loop: bound each episode's plan by PLAN_HINT_SCALE x the cost of its previous plan (mpc_plan_hinted; the plans are
-    # identical either way, DESIGN.md §3 "Cost hints").  Off until the hinted kernels have run on a device.
+    # identical either way, DESIGN.md §3 "Cost hints"; hinted solves run on the 64-bit kernel).  Off by default.
     "PLAN_COST_HINTS": False, "PLAN_HINT_SCALE": 1.15,
     # MergeEnv.step as ONE kernel (mpc_env_step) instead of ~150 tensor operations; same random numbers, same trajectories
-    # (bit-identical under the CPU emulation of tests/emu).  Off until it has run on a device.
+    # (bit-identical to the tensor version on the device and under the CPU emulation, both world models).  Off by default.
     "FUSED_ENV_STEP": False,
     # combined controller: hand the vetoed episodes to the planner through mpc_plan_masked / mpc_finer_fit_masked (episode list
     # built and counted on the device) instead of nonzero() + gather on the host side: no host sync in the tick.  Same speeds.

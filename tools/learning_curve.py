@@ -55,7 +55,7 @@ for stage in (1, 2):
         tr.train(frames // chunks)
         curve.append(dict(frames=tr.frames, stage=stage, lr=tr.lr, grad_steps=tr.grad_steps, wall_s=time.time() - t0, **evaluate(tr)))
         print(curve[-1], file=sys.stderr, flush=True)
-res = dict(config="train_moderate_1.json semantics; SUMO-free world (predictor dynamics); greedy evaluation on %d fresh episodes" % n_eval,
+res = dict(config="train_moderate_1.json semantics; SUMO-free world (Settings.WORLD_MODEL default); greedy evaluation on %d fresh episodes" % n_eval,
            num_envs=tr.env.B, minibatch=tr.h["minibatch_size"], updates_per_tick=tr.h.get("updates_per_tick"), frames_per_stage=frames,
            improved=bool(curve[-1]["mean_return"] > curve[0]["mean_return"]), curve=curve)
 print(json.dumps(res, indent=1))

@@ -11,6 +11,9 @@ p = _lib.default_params(); p.future_t, p.future_s = synthetic.horizon_settings(H
 eng = MpcEngine(p, 0, max_batch=B)
 D = states_to_device(synthetic.make_states(B, "moderate", seed=0), "cuda:0")
 for _ in range(3):
-    out = eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=mode)
+    if mode == "grid":
+        out = eng.build_grid(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], dist_dtype=torch.float32)
+    else:
+        out = eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=mode)
 torch.cuda.synchronize()
 print("done", eng.counters())

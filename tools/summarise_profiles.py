@@ -41,20 +41,28 @@ for H in (50, 17):
                 n, us = agg[k]
                 o.write(f"{k[:70]:70s} {n:8d} {us:12.1f} {100 * us / tot:6.1f}% {us / n:10.1f}\n")
         print("wrote", o.name)
-    rep = f"gpurun_out/{src}_fast_h{H}.ncu-rep"
-    if os.path.exists(rep):
+    for kern, tag, regex in (("fast32", "fast32", "fast32"), ("fast", "fast_pull", "fast_pull"), ("fallback", "fallback_fast_pull", "fast_pull"),
+                             ("predict", "predict_layers", "predict_layers"), ("rasterise", "rasterise", "rasterise")):
+        rep = f"gpurun_out/{src}_{kern}_h{H}.ncu-rep"
+        if not os.path.exists(rep):
+            continue
         out = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "--so", f"gpurun_out/{src}_lib.so", "--top", "30"],
                              capture_output=True, text=True).stdout
-        with open(f"profiles/{dst}_fast_pull_h{H}.txt", "w") as o:
-            o.write(f"# ncu --set full --clock-control none --import-source on -k regex:fast_pull -s 2 -c 1   python tools/prof_run.py {H} 4096 fast\n")
-            o.write("# key raw metrics, then per-source-line attribution (tools/ncu_lines.py: SASS counters joined with nvdisasm line info)\n")
+        sass = subprocess.run([sys.executable, "tools/ncu_sass.py", rep, "--min", "2.0"], capture_output=True, text=True).stdout
+        with open(f"profiles/{dst}_{tag}_h{H}.txt", "w") as o:
+            o.write(f"# ncu --set full --clock-control none --import-source on -k regex:{regex} -c 1   python tools/prof_run.py {H} 4096 fast\n")
+            o.write("# key raw metrics, per-source-line attribution (tools/ncu_lines.py), then executed instructions by opcode (tools/ncu_sass.py)\n")
             o.write(out)
+            o.write(sass)
         print("wrote", o.name)
 # DRAM traffic of the dominant kernel per launch, for bench.py's roofline.traffic
 import json, re
 traffic = {}
 for H in (50, 17):
-    rep = f"gpurun_out/{src}_fast_h{H}.ncu-rep"
+    rep = f"gpurun_out/{src}_fast32_h{H}.ncu-rep"
+    kname = "fast32_kernel"
+    if not os.path.exists(rep):
+        rep, kname = f"gpurun_out/{src}_fast_h{H}.ncu-rep", "fast_pull_kernel"
     if not os.path.exists(rep):
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -64,8 +72,8 @@ for H in (50, 17):
         i = hdr.index(name)
         mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
         return float(vals[i]) * mult
-    traffic[str(H)] = {"episodes": 4096, "kernel": "fast_pull_kernel", "dram_bytes_read": get("dram__bytes_read.sum"),
-                       "dram_bytes_write": get("dram__bytes_write.sum"), "source": f"profiles/{dst}_fast_pull_h{H}.txt"}
+    traffic[str(H)] = {"episodes": 4096, "kernel": kname, "dram_bytes_read": get("dram__bytes_read.sum"),
+                       "dram_bytes_write": get("dram__bytes_write.sum"), "source": f"profiles/{dst}_{'fast32' if kname == 'fast32_kernel' else 'fast_pull'}_h{H}.txt"}
 if traffic:
     json.dump(traffic, open(f"profiles/{dst}_traffic.json", "w"), indent=1)
     print("wrote", f"profiles/{dst}_traffic.json")
