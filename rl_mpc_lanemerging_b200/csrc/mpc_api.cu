@@ -125,7 +125,9 @@ static int env_int(const char *name, int lo, int hi, int dflt) {
     const char *v = getenv(name);
     if (!v) return dflt;
     int x = atoi(v);
-    return (x >= lo && x <= hi && x % 32 == 0) ? x : dflt;
+    if (x >= lo && x <= hi && (x % 32 == 0 || hi <= 1)) return x;
+    fprintf(stderr, "libmpcb200: ignoring %s=%s (expected a multiple of 32 in [%d, %d])\n", name, v, lo, hi);   // dev overrides only
+    return dflt;
 }
 
 static int configure(mpc_handle *h, int want_nb32 = 0) {

@@ -14,14 +14,17 @@ from . import _lib
 from .engine import MpcEngine, params_key
 
 _engines = {}
+_MAX_ENGINES = 4            # one per (Settings snapshot, device); the least recently used one is closed beyond that
 
 
 def _engine_for(p, device=0) -> MpcEngine:
     key = (params_key(p), device)
-    e = _engines.get(key)
+    e = _engines.pop(key, None)
     if e is None:
         e = MpcEngine(p, device=device, max_batch=16)
-        _engines[key] = e
+        while len(_engines) >= _MAX_ENGINES:
+            _engines.pop(next(iter(_engines))).close()
+    _engines[key] = e                                         # (re-inserted: most recently used last)
     return e
 
 

@@ -259,6 +259,13 @@ def test_error_conventions_and_set_params():
     lone["n_cars"][0] = 0                                       # an empty road
     assert eng.plan(lone)["reached_t"][0] == 17
     eng.close()
+    # a grid wider than the per-layer lookup tables (288 buckets of 64 cells) is refused, not silently mis-planned
+    p3 = _lib.MpcParams()
+    for n in _lib.PARAM_FIELDS:
+        setattr(p3, n, getattr(p, n))
+    p3.future_s = 1000.0                                        # 20002 cells
+    h = C.c_void_p()
+    assert L.mpc_create(C.byref(p3), 0, 4, 32, C.byref(h)) == _lib.E_CAPACITY and b"lookup tables" in L.mpc_last_error()
 
 
 @pytest.mark.parametrize("mode", [_lib.MODE_FAST, _lib.MODE_EXACT])
