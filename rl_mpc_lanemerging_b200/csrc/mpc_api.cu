@@ -132,7 +132,7 @@ static int env_int(const char *name, int lo, int hi, int dflt) {
 
 static int configure(mpc_handle *h, int want_nb32 = 0) {
     const DevParams &P = h->P;
-    h->W = (P.num_s_max + 7) & ~7;
+    h->W = (P.num_s_max + 15) & ~15;             // rows of the dense grids / back-pointer scratch: multiples of 16 cells (vector and bulk stores)
     const size_t static_smem = 11264;                // static shared of the kernels (upper bound: 10.2 KB in the fast kernel) + 1 KB/block reserve
     // ---- exact kernel: 24 B per cell, full row ----
     size_t need = (size_t)h->W * 24;

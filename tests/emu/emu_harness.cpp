@@ -58,7 +58,7 @@ extern "C" int emu_plan(const mpc_params *params, int B, int nmax, const double 
         emu::launch((B + RC_WARPS - 1) / RC_WARPS, 32 * RC_WARPS, 0, [&] { reach_caps_kernel(P, B, desc.data(), num_s.data(), capb.data(), stride); });
     }
     // K3
-    const int W = (P.num_s_max + 7) & ~7;
+    const int W = (P.num_s_max + 15) & ~15;
     const bool wrap = ring > 0 && ring < W;
     const int Wc = wrap ? (ring & ~7) : W;
     const size_t clamp_bytes = (4 * (((size_t)P.num_s_max + 31) / 32) + 4) * 4 + 16;
@@ -109,7 +109,7 @@ extern "C" int emu_plan32(const mpc_params *params, int B, int nmax, const doubl
     std::vector<double> s0(B), ds(B);
     std::vector<int32_t> num_s(B);
     emu::launch((B + 3) / 4, 128, 0, [&] { predict_layers_kernel<false>(P, B, ego, cars_x, cars_v, n_cars, nmax, desc.data(), s0.data(), ds.data(), num_s.data(), nullptr, nullptr); });
-    const int W = (P.num_s_max + 7) & ~7;
+    const int W = (P.num_s_max + 15) & ~15;
     const size_t clamp_bytes = (4 * (((size_t)P.num_s_max + 31) / 32) + 4) * 4 + 16;
     std::vector<uint16_t> bp((size_t)T * W);
     std::vector<int> counters(16, 0);
