@@ -410,29 +410,22 @@ __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int 
     }
 }
 
-// ---- K1b, row version (round 2): the whole row of one (episode, layer) is assembled in shared memory and leaves the SM with two
-// bulk copies (cp.async.bulk.global.shared::cta -> UBLKCP in SASS), issued by one thread.  What makes it fast is not the copy but
-// the assembly: the <= 64 distance-field edges cut the row into segments with ONE bracketing pair (lo, hi) each; the first cell
-// of every segment is found once per edge (estimate by division, fix up with the reference's own comparison), and a warp that
-// works on 32 consecutive cells inside one segment has lo / hi in uniform registers -- 11 instructions per cell (cell -> double
-// by the 2^52 trick, s = s0 + k ds, two differences, a min, one conversion, one shared store) where the 8-cells-per-thread
-// version with its per-thread cursors and selects needs ~26.  Chunks that straddle a segment boundary (one in seven) take a
-// per-lane path.  Obstacle bands are written afterwards (mask = 1, distance = 0), like the reference does (st.py:60-65).
-// Bit-identical to rasterise_kernel and to the oracle (tests).
+// ---- K1b, segment version (round 2).  The <= 64 distance-field edges cut the row into segments with ONE bracketing pair (lo, hi)
+// each; the first cell of every segment is found once per edge (estimate by division, fix up with the reference's own
+// comparison).  A warp works on 32 consecutive cells (lane = cell): when the chunk lies inside one segment -- six chunks in
+// seven -- lo / hi and the current obstacle band are the same for all lanes and the cell costs 16 warp instructions per 32 cells
+// (cell -> double by the 2^52 trick, s = s0 + k ds, two differences, a min, one conversion, band test, two coalesced stores)
+// where the 8-cells-per-thread version with its per-thread cursors and selects needs 26 per 32; chunks that straddle a boundary
+// take a per-lane path.  Bit-identical to rasterise_kernel and to the oracle (tests).
+// (A variant that assembled the row in shared memory and wrote it with cp.async.bulk -- UBLKCP -- was measured 40 % slower than
+// the old kernel: assembly and store serialise inside a block.)
 template <typename DT>
 __global__ void __launch_bounds__(256) rasterise_rows_kernel(DevParams P, int B, int stride_s, const LayerDesc *__restrict__ desc,
                                                              const double *__restrict__ s0v, const double *__restrict__ dsv,
                                                              const int32_t *__restrict__ nsv, uint8_t *__restrict__ obstacles,
                                                              DT *__restrict__ distances) {
-#ifdef MPC_HOST_EMU
-    unsigned char *const rsm = emu::S().dyn_smem;
-#else
-    extern __shared__ __align__(128) unsigned char rsm[];
-#endif
-    DT *drow = reinterpret_cast<DT *>(rsm);
-    uint8_t *orow = rsm + sizeof(DT) * (size_t)stride_s;
-    LayerSearch &L = *reinterpret_cast<LayerSearch *>(orow + stride_s);
-    int *kx = reinterpret_cast<int *>(orow + stride_s + sizeof(LayerSearch));        // kx[j] = first cell k with edge[j] < s_k
+    __shared__ __align__(16) LayerSearch L;
+    __shared__ int kx[2 * MPC_NMAX + 4];                                             // kx[j] = first cell k with edge[j] < s_k
     const int bt = blockIdx.x, b = bt / P.num_t, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const char *src = reinterpret_cast<const char *>(desc + bt);
@@ -452,57 +445,36 @@ __global__ void __launch_bounds__(256) rasterise_rows_kernel(DevParams P, int B,
         while (k < ns && !(ev < g.sval(k))) k++;
         kx[j] = k;
     }
-    if (tid == 0) { kx[M] = INT_MAX; }
-    for (int w = tid; w < stride_s / 4; w += blockDim.x) {                           // mask: 0 inside the row, 1 behind its end
-        const int k = 4 * w;
-        reinterpret_cast<unsigned *>(orow)[w] = (k >= ns ? 1u : 0u) | (k + 1 >= ns ? 0x100u : 0u) | (k + 2 >= ns ? 0x10000u : 0u) | (k + 3 >= ns ? 0x1000000u : 0u);
-    }
+    if (tid == 0) kx[M] = INT_MAX;
     __syncthreads();
-    if (M == 0) {
-        for (int k = tid; k < stride_s; k += blockDim.x) drow[k] = (DT)(k < ns ? 1E10 : 0.0);
-    } else {
-        const double *E = &L.edge_lo;                                                // E[i + 1] = edge[i]
-        int j = 0;
-        for (int kb = warp * 32; kb < stride_s; kb += 256) {
-            const int k = kb + lane;
-            while (kx[j] <= kb) j++;                                                 // (uniform) edges left of the chunk's first cell
-            const double kd = __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);      // (double)k, exactly
-            const double sv = __dadd_rn(g.s0, __dmul_rn(kd, g.ds));
-            double d;
-            if (kb + 31 < kx[j]) {                                                   // (uniform) the whole chunk lies in segment j
-                const double lo = E[j], hi = E[j + 1];                               // E[0] = edge[-1] = -1e300, edge[M] = +1e300
-                const double dl = __dsub_rn(sv, lo), dr = __dsub_rn(hi, sv);
-                d = dl < dr ? dl : dr;
-            } else {
-                int jj = j;
-                while (kx[jj] <= k) jj++;
-                const double dl = __dsub_rn(sv, E[jj]), dr = __dsub_rn(E[jj + 1], sv);
-                d = dl < dr ? dl : dr;
-            }
-            if (k < stride_s) drow[k] = (DT)(k < ns ? d : 0.0);
-        }
-    }
-    __syncthreads();
-    for (int q = warp; q < m; q += 8) {                                              // obstacle bands (disjoint, inside the row)
-        const int2 bd = L.mband[q];
-        for (int k = bd.x + lane; k < bd.y && k < ns; k += 32) { orow[k] = 1; drow[k] = (DT)0.0; }
-    }
+    const double *E = &L.edge_lo;                                                    // E[i + 1] = edge[i]; E[0] = -1e300, edge[M] = +1e300
     const size_t row = (size_t)bt * stride_s;
-#ifdef MPC_HOST_EMU
-    __syncthreads();
-    for (int k = tid; k < stride_s; k += blockDim.x) { distances[row + k] = drow[k]; obstacles[row + k] = orow[k]; }
-#else
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                     // generic-proxy writes -> visible to the bulk copy engine
-    __syncthreads();
-    if (tid == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     :: "l"(distances + row), "r"((unsigned)__cvta_generic_to_shared(drow)), "r"((unsigned)(sizeof(DT) * stride_s)) : "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     :: "l"(obstacles + row), "r"((unsigned)__cvta_generic_to_shared(orow)), "r"((unsigned)stride_s) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");                 // the row may leave shared memory before the block exits
+    int j = 0, i = 0;                                                                // (uniform) segment / band cursors of this warp
+    for (int kb = warp * 32; kb < stride_s; kb += 256) {
+        const int k = kb + lane;
+        while (kx[j] <= kb) j++;                                                     // edges left of the chunk's first cell
+        while (i < m && L.mband[i].y <= kb) i++;                                     // first band that ends behind it
+        const double kd = __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);      // (double)k, exactly
+        const double sv = __dadd_rn(g.s0, __dmul_rn(kd, g.ds));
+        double d;
+        if (kb + 31 < kx[j]) {                                                       // (uniform) the whole chunk lies in segment j
+            const double dl = __dsub_rn(sv, E[j]), dr = __dsub_rn(E[j + 1], sv);
+            d = dl < dr ? dl : dr;
+        } else {
+            int jj = j;
+            while (kx[jj] <= k) jj++;
+            const double dl = __dsub_rn(sv, E[jj]), dr = __dsub_rn(E[jj + 1], sv);
+            d = dl < dr ? dl : dr;
+        }
+        if (M == 0) d = 1E10;
+        bool ob;
+        const int2 bd = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX);
+        if (kb + 31 < bd.y) ob = bd.x <= k;                                          // (uniform) no band ends inside the chunk
+        else { int ii = i; while (ii < m && L.mband[ii].y <= k) ii++; ob = ii < m && L.mband[ii].x <= k; }
+        if (k >= ns) ob = true;
+        if (ob) d = 0.0;
+        if (k < stride_s) { distances[row + k] = (DT)d; obstacles[row + k] = ob ? 1 : 0; }
     }
-#endif
 }
 
 // ---- self-test: the sorted search structure must reproduce the reference-order evaluation bit for bit ----
@@ -812,19 +784,14 @@ cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const Laye
                              const double *ds, const int32_t *ns, uint8_t *obstacles, void *distances, int dist_f32,
                              cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    // row version: needs rows that are multiples of 16 bytes in both arrays (bulk copies) and room for one row in shared memory
-    const size_t rsm = (size_t)stride_s * ((dist_f32 ? 4 : 8) + 1) + sizeof(LayerSearch) + (2 * MPC_NMAX + 4) * sizeof(int);
-    static int rows_off = -1;
-    if (rows_off < 0) { const char *e = getenv("MPC_RASTER_ROWS"); rows_off = (e && e[0] == '0') ? 1 : 0; }
-    if (!rows_off && stride_s % 16 == 0 && (uintptr_t)obstacles % 16 == 0 && (uintptr_t)distances % 16 == 0 && rsm <= 200 * 1024) {
-        cudaError_t e;
-        if (dist_f32) {
-            if ((e = cudaFuncSetAttribute(rasterise_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm)) != cudaSuccess) return e;
-            MPC_LAUNCH(rasterise_rows_kernel<float>, B * P.num_t, 256, rsm, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances);
-        } else {
-            if ((e = cudaFuncSetAttribute(rasterise_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm)) != cudaSuccess) return e;
-            MPC_LAUNCH(rasterise_rows_kernel<double>, B * P.num_t, 256, rsm, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances);
-        }
+    // Measured on a B200 (256 episodes, H=50): segment version 0.304 ms for fp32 and fp64 distances alike (it is latency bound: one
+    // dependent fp64 chain per lane and chunk), the 8-cells-per-thread kernel below 0.167 ms (fp32, 0.54 of the HBM peak) / 0.380 ms
+    // (fp64).  Default: segments for fp64 output, the kernel below for fp32; MPC_RASTER_ROWS=0|1 forces one of them (dev A/B).
+    static int rows_on = -1;
+    if (rows_on < 0) { const char *e = getenv("MPC_RASTER_ROWS"); rows_on = !e ? 2 : (e[0] == '0' ? 0 : 1); }
+    if (rows_on == 1 || (rows_on == 2 && !dist_f32)) {
+        if (dist_f32) MPC_LAUNCH(rasterise_rows_kernel<float>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances);
+        else MPC_LAUNCH(rasterise_rows_kernel<double>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances);
         return cudaGetLastError();
     }
     const int vec_ok = (stride_s % 8 == 0) && ((uintptr_t)obstacles % 8 == 0) && ((uintptr_t)distances % 16 == 0);
