@@ -412,13 +412,14 @@ __global__ void __launch_bounds__(256) rasterise_kernel(DevParams P, int B, int 
 
 // ---- K1b, segment version (round 2).  The <= 64 distance-field edges cut the row into segments with ONE bracketing pair (lo, hi)
 // each; the first cell of every segment is found once per edge (estimate by division, fix up with the reference's own
-// comparison).  A warp works on 32 consecutive cells (lane = cell): when the chunk lies inside one segment -- six chunks in
-// seven -- lo / hi and the current obstacle band are the same for all lanes and the cell costs 16 warp instructions per 32 cells
-// (cell -> double by the 2^52 trick, s = s0 + k ds, two differences, a min, one conversion, band test, two coalesced stores)
-// where the 8-cells-per-thread version with its per-thread cursors and selects needs 26 per 32; chunks that straddle a boundary
-// take a per-lane path.  Bit-identical to rasterise_kernel and to the oracle (tests).
+// comparison).  A warp owns a contiguous run of 32-cell chunks (lane = cell) and walks it with warp-uniform cursors: up to the next
+// EVENT (a segment boundary, a band boundary, the end of the episode's grid) every chunk has the same (lo, hi) and the same
+// blocked / free state for all lanes, and a free cell costs: s = s0 + k ds, two differences, a min, one conversion, two coalesced
+// stores; a blocked chunk is two stores.  Only the chunk an event falls into takes the per-lane path (cursor loops), after which
+// the uniform state is derived again.  Bit-identical to rasterise_kernel and to the oracle (tests).
 // (A variant that assembled the row in shared memory and wrote it with cp.async.bulk -- UBLKCP -- was measured 40 % slower than
-// the old kernel: assembly and store serialise inside a block.)
+// the old kernel: assembly and store serialise inside a block.  The first segment version interleaved the chunks of a row over
+// the warps and re-derived the cursors for every chunk: 93 instructions per cell against 44, ncu capture of round 2.)
 template <typename DT>
 __global__ void __launch_bounds__(256) rasterise_rows_kernel(DevParams P, int B, int stride_s, const LayerDesc *__restrict__ desc,
                                                              const double *__restrict__ s0v, const double *__restrict__ dsv,
@@ -426,16 +427,18 @@ __global__ void __launch_bounds__(256) rasterise_rows_kernel(DevParams P, int B,
                                                              DT *__restrict__ distances) {
     __shared__ __align__(16) LayerSearch L;
     __shared__ int kx[2 * MPC_NMAX + 4];                                             // kx[j] = first cell k with edge[j] < s_k
-    const int bt = blockIdx.x, b = bt / P.num_t, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bt = blockIdx.x, b = bt / P.num_t, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    SGrid g; g.s0 = s0v[b]; g.ds = dsv[b]; g.num_s = nsv[b];                         // (in flight together with the descriptor)
     {
         const char *src = reinterpret_cast<const char *>(desc + bt);
-        constexpr int kTail = (int)(sizeof(LayerSearch) - offsetof(LayerSearch, edge)) / 16;
-        if (tid < kTail) reinterpret_cast<int4 *>(reinterpret_cast<char *>(&L) + offsetof(LayerSearch, edge))[tid] =
-            reinterpret_cast<const int4 *>(src + offsetof(LayerDesc, edge))[tid];
-        else if (tid == kTail) { *reinterpret_cast<int4 *>(&L) = make_int4(desc[bt].n_edge, desc[bt].n_band, 0, 0); L.edge_lo = -1.0e300; }
+        constexpr int kTail = (int)(offsetof(LayerSearch, bucket_edge) - offsetof(LayerSearch, edge)) / 16;    // edges + bands
+        static_assert((offsetof(LayerSearch, bucket_edge) - offsetof(LayerSearch, edge)) % 16 == 0, "copied as int4");
+        for (int t = tid; t < kTail; t += blockDim.x)
+            reinterpret_cast<int4 *>(reinterpret_cast<char *>(&L) + offsetof(LayerSearch, edge))[t] =
+                reinterpret_cast<const int4 *>(src + offsetof(LayerDesc, edge))[t];
+        if (tid == blockDim.x - 1) { *reinterpret_cast<int4 *>(&L) = make_int4(desc[bt].n_edge, desc[bt].n_band, 0, 0); L.edge_lo = -1.0e300; }
     }
     __syncthreads();
-    SGrid g; g.s0 = s0v[b]; g.ds = dsv[b]; g.num_s = nsv[b];
     const int M = L.n_edge, m = L.n_band, ns = g.num_s;
     for (int j = tid; j < M; j += blockDim.x) {
         const double ev = L.edge[j];
@@ -448,32 +451,66 @@ __global__ void __launch_bounds__(256) rasterise_rows_kernel(DevParams P, int B,
     if (tid == 0) kx[M] = INT_MAX;
     __syncthreads();
     const double *E = &L.edge_lo;                                                    // E[i + 1] = edge[i]; E[0] = -1e300, edge[M] = +1e300
-    const size_t row = (size_t)bt * stride_s;
-    int j = 0, i = 0;                                                                // (uniform) segment / band cursors of this warp
-    for (int kb = warp * 32; kb < stride_s; kb += 256) {
-        const int k = kb + lane;
-        while (kx[j] <= kb) j++;                                                     // edges left of the chunk's first cell
-        while (i < m && L.mband[i].y <= kb) i++;                                     // first band that ends behind it
-        const double kd = __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);      // (double)k, exactly
-        const double sv = __dadd_rn(g.s0, __dmul_rn(kd, g.ds));
-        double d;
-        if (kb + 31 < kx[j]) {                                                       // (uniform) the whole chunk lies in segment j
-            const double dl = __dsub_rn(sv, E[j]), dr = __dsub_rn(E[j + 1], sv);
-            d = dl < dr ? dl : dr;
+    const int chunks = (stride_s + 31) >> 5, per_warp = (chunks + nwarps - 1) / nwarps;
+    const int full = stride_s & ~31;                                                 // chunks from here on are partial: per-lane path
+    int kb = warp * per_warp * 32;
+    const int kend = min(kb + per_warp * 32, stride_s);
+    if (kb >= kend) return;
+    DT *dp = distances + (size_t)bt * stride_s + kb + lane;                          // this lane's cell of the current chunk
+    uint8_t *op = obstacles + (size_t)bt * stride_s + kb + lane;
+    double kd = __dsub_rn(__hiloint2double(0x43300000, kb + lane), 4503599627370496.0);         // (double)k, exactly (k < 2^31)
+    const double s0 = g.s0, ds = g.ds;
+    const int lim0 = min(full, kend);                                                // whole chunks of this warp end here
+    // (uniform) segment / band cursors of the warp at its first cell: counted by the lanes (kx and the band ends ascend)
+    int j = __popc(__ballot_sync(0xffffffffu, lane < M && kx[lane] <= kb)) + __popc(__ballot_sync(0xffffffffu, lane + 32 < M && kx[lane + 32] <= kb));
+    int i = __popc(__ballot_sync(0xffffffffu, lane < m && L.mband[lane].y <= kb));
+    while (kb < kend) {
+        // uniform state at cell kb: bracketing pair, blocked or free, and the next EVENT (segment / band boundary, end of the grid)
+        while (kx[j] <= kb) j++;
+        while (i < m && L.mband[i].y <= kb) i++;
+        const int2 bd = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX);
+        const bool blocked = bd.x <= kb || kb >= ns;
+        const int ev = min(kx[j], kb >= ns ? INT_MAX : (bd.x <= kb ? bd.y : min(bd.x, ns)));   // > kb
+        int r = (min(ev, lim0) - kb) >> 5;                                           // whole chunks before it: no per-lane decisions
+        kb += r << 5;
+        if (!blocked && M > 0) {
+            const double lo = E[j], hi = E[j + 1];
+            for (; r >= 2; r -= 2, dp += 64, op += 64, kd = __dadd_rn(kd, 64.0)) {
+                const double sa = __dadd_rn(s0, __dmul_rn(kd, ds)), sb = __dadd_rn(s0, __dmul_rn(__dadd_rn(kd, 32.0), ds));
+                const double la = __dsub_rn(sa, lo), ra = __dsub_rn(hi, sa), lb = __dsub_rn(sb, lo), rb = __dsub_rn(hi, sb);
+                dp[0] = (DT)(la < ra ? la : ra); dp[32] = (DT)(lb < rb ? lb : rb);
+                op[0] = 0; op[32] = 0;
+            }
+            if (r) {
+                const double sa = __dadd_rn(s0, __dmul_rn(kd, ds));
+                const double la = __dsub_rn(sa, lo), ra = __dsub_rn(hi, sa);
+                dp[0] = (DT)(la < ra ? la : ra); op[0] = 0;
+                dp += 32; op += 32; kd = __dadd_rn(kd, 32.0);
+            }
         } else {
+            const DT dv = blocked ? (DT)0.0 : (DT)1E10;
+            const uint8_t ov = blocked ? 1 : 0;
+            kd = __dadd_rn(kd, (double)(r << 5));
+            for (; r > 0; r--, dp += 32, op += 32) { dp[0] = dv; op[0] = ov; }
+        }
+        if (kb >= kend) break;
+        if (kb == ev) continue;                                                      // the event sits on a chunk boundary
+        {                                                                            // the chunk with the event (or the row's partial
+            const int k = kb + lane;                                                 // last chunk): per-lane cursors
+            const double sv = __dadd_rn(s0, __dmul_rn(kd, ds));
             int jj = j;
             while (kx[jj] <= k) jj++;
             const double dl = __dsub_rn(sv, E[jj]), dr = __dsub_rn(E[jj + 1], sv);
-            d = dl < dr ? dl : dr;
+            double d = dl < dr ? dl : dr;
+            if (M == 0) d = 1E10;
+            int ii = i;
+            while (ii < m && L.mband[ii].y <= k) ii++;
+            bool ob = ii < m && L.mband[ii].x <= k;
+            if (k >= ns) ob = true;
+            if (ob) d = 0.0;
+            if (k < stride_s) { dp[0] = (DT)d; op[0] = ob ? 1 : 0; }
+            kb += 32; dp += 32; op += 32; kd = __dadd_rn(kd, 32.0);
         }
-        if (M == 0) d = 1E10;
-        bool ob;
-        const int2 bd = i < m ? L.mband[i] : make_int2(INT_MAX, INT_MAX);
-        if (kb + 31 < bd.y) ob = bd.x <= k;                                          // (uniform) no band ends inside the chunk
-        else { int ii = i; while (ii < m && L.mband[ii].y <= k) ii++; ob = ii < m && L.mband[ii].x <= k; }
-        if (k >= ns) ob = true;
-        if (ob) d = 0.0;
-        if (k < stride_s) { distances[row + k] = (DT)d; obstacles[row + k] = ob ? 1 : 0; }
     }
 }
 
@@ -784,14 +821,16 @@ cudaError_t launch_rasterise(const DevParams &P, int B, int stride_s, const Laye
                              const double *ds, const int32_t *ns, uint8_t *obstacles, void *distances, int dist_f32,
                              cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    // Measured on a B200 (256 episodes, H=50): segment version 0.304 ms for fp32 and fp64 distances alike (it is latency bound: one
-    // dependent fp64 chain per lane and chunk), the 8-cells-per-thread kernel below 0.167 ms (fp32, 0.54 of the HBM peak) / 0.380 ms
-    // (fp64).  Default: segments for fp64 output, the kernel below for fp32; MPC_RASTER_ROWS=0|1 forces one of them (dev A/B).
-    static int rows_on = -1;
-    if (rows_on < 0) { const char *e = getenv("MPC_RASTER_ROWS"); rows_on = !e ? 2 : (e[0] == '0' ? 0 : 1); }
-    if (rows_on == 1 || (rows_on == 2 && !dist_f32)) {
-        if (dist_f32) MPC_LAUNCH(rasterise_rows_kernel<float>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances);
-        else MPC_LAUNCH(rasterise_rows_kernel<double>, B * P.num_t, 256, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances);
+    // Measured on a B200 (256 episodes, H=50, 51 x 9008 cells; HBM copy peak 6551 GB/s): the segment kernel writes the fp32 grid in
+    // 0.116 ms (5.08 TB/s, 0.78 of the peak; 128 threads per row) and the fp64 grid in 0.185 ms (5.71 TB/s, 0.87; 256 threads);
+    // the 8-cells-per-thread kernel below needs 0.167 / 0.380 ms.  MPC_RASTER_ROWS=0 selects the latter (kept for the A/B tests and
+    // for rows whose descriptor the segment kernel cannot take -- none today), MPC_RASTER_THREADS overrides the block size (dev).
+    const char *e_rows = getenv("MPC_RASTER_ROWS"), *e_thr = getenv("MPC_RASTER_THREADS");
+    if (!(e_rows && e_rows[0] == '0')) {
+        const int v = e_thr ? atoi(e_thr) : 0;
+        const int rows_threads = (v >= 32 && v <= 256 && v % 32 == 0) ? v : (dist_f32 ? 128 : 256);
+        if (dist_f32) MPC_LAUNCH(rasterise_rows_kernel<float>, B * P.num_t, rows_threads, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (float *)distances);
+        else MPC_LAUNCH(rasterise_rows_kernel<double>, B * P.num_t, rows_threads, 0, st, P, B, stride_s, desc, s0, ds, ns, obstacles, (double *)distances);
         return cudaGetLastError();
     }
     const int vec_ok = (stride_s % 8 == 0) && ((uintptr_t)obstacles % 8 == 0) && ((uintptr_t)distances % 16 == 0);

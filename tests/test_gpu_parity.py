@@ -111,6 +111,17 @@ def test_build_grid_matches_oracle(oracle, engines, torch_mod, traffic, kind):
         assert g["start_s"][b].item() == sv[0] and g["delta_s"][b].item() == sv[1] - sv[0]
         assert np.array_equal(ob[b, :, :ns[b]], o2)
         assert np.array_equal(di[b, :, :ns[b]], d2)              # bit-identical fp64 distance field
+    # fp32 distances = the fp64 field rounded once; the 8-cells-per-thread kernel (MPC_RASTER_ROWS=0) writes the same bytes
+    g32 = eng.build_grid(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], dist_dtype=torch_mod.float32)
+    assert np.array_equal(g32["distances"].cpu().numpy(), di.astype(np.float32)) and np.array_equal(g32["obstacles"].cpu().numpy(), ob)
+    import os
+    os.environ["MPC_RASTER_ROWS"] = "0"
+    try:
+        for dt, want in ((torch_mod.float64, di), (torch_mod.float32, di.astype(np.float32))):
+            g0 = eng.build_grid(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], dist_dtype=dt)
+            assert np.array_equal(g0["distances"].cpu().numpy(), want) and np.array_equal(g0["obstacles"].cpu().numpy(), ob)
+    finally:
+        del os.environ["MPC_RASTER_ROWS"]
 
 
 @pytest.mark.parametrize("H", [17, 50])

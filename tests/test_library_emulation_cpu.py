@@ -306,3 +306,33 @@ def test_masked_plan_and_fit_touch_only_the_masked_episodes(mode):
         sub = {k: np.ascontiguousarray(v[[3, 500, 1023, 1024, 1099]]) for k, v in Sb.items()}
         assert np.array_equal(out["cost"][[3, 500, 1023, 1024, 1099]], big.plan(sub)["cost"])
         big.close()
+
+
+@pytest.mark.parametrize("H", [17, 50])
+def test_the_two_row_rasterisers_write_the_same_grids(H, monkeypatch):
+    """mpc_build_grid: the segment kernel (default) against the 8-cells-per-thread kernel (MPC_RASTER_ROWS=0) and the oracle, fp32
+    and fp64 distances, block sizes 32..256, episodes without cars / with one car / with a grid shorter than the row stride."""
+    op, p = _params(H)
+    eng = EA.EmuEngine(p, max_batch=16)
+    for traffic in ("moderate", "fast"):
+        S = synthetic.make_states(10, traffic, seed=11, kind="mixed")
+        S["n_cars"][0] = 0
+        S["n_cars"][1] = 1
+        for f32 in (False, True):
+            monkeypatch.setenv("MPC_RASTER_ROWS", "0")
+            ref = eng.build_grid(S, f32=f32)
+            monkeypatch.delenv("MPC_RASTER_ROWS")
+            for threads in ("", "32", "96", "256"):
+                if threads:
+                    monkeypatch.setenv("MPC_RASTER_THREADS", threads)
+                got = eng.build_grid(S, f32=f32)
+                monkeypatch.delenv("MPC_RASTER_THREADS", raising=False)
+                assert np.array_equal(got["obstacles"], ref["obstacles"]) and np.array_equal(got["distances"], ref["distances"]), (traffic, f32, threads)
+        if traffic == "moderate":
+            g64 = eng.build_grid(S)
+            for b in range(4):
+                ob, di, sv = O.build_grid(op, helpers.oracle_state(O, S, b))
+                n = sv.size
+                assert np.array_equal(g64["obstacles"][b, :, :n], ob) and np.array_equal(g64["distances"][b, :, :n], di)
+                assert g64["obstacles"][b, :, n:].all() and not g64["distances"][b, :, n:].any()        # beyond the grid: blocked, 0
+    eng.close()

@@ -18,3 +18,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:fast
     python tools/prof_run.py 50 4096 fast > gpurun_out/${TAG}_ncufb_h50.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rasterise -s 1 -c 1 -o gpurun_out/${TAG}_rasterise_h50 \
     python tools/prof_run.py 50 256 grid > gpurun_out/${TAG}_ncuras_h50.log 2>&1
+MPC_RASTER_ROWS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rasterise_rows -s 1 -c 1 -o gpurun_out/${TAG}_rasterise_rows_h50 \
+    python tools/prof_run.py 50 256 grid > gpurun_out/${TAG}_ncurasrows_h50.log 2>&1

@@ -42,7 +42,7 @@ for H in (50, 17):
                 o.write(f"{k[:70]:70s} {n:8d} {us:12.1f} {100 * us / tot:6.1f}% {us / n:10.1f}\n")
         print("wrote", o.name)
     for kern, tag, regex in (("fast32", "fast32", "fast32"), ("fast", "fast_pull", "fast_pull"), ("fallback", "fallback_fast_pull", "fast_pull"),
-                             ("predict", "predict_layers", "predict_layers"), ("rasterise", "rasterise", "rasterise")):
+                             ("predict", "predict_layers", "predict_layers"), ("rasterise", "rasterise", "rasterise"), ("rasterise_rows", "rasterise_rows", "rasterise_rows")):
         rep = f"gpurun_out/{src}_{kern}_h{H}.ncu-rep"
         if not os.path.exists(rep):
             continue
