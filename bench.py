@@ -379,7 +379,7 @@ def run_ours(args):
     dense_res = None
     if rank == 0 and args.mode == "fast":
         try:
-            Bg = min(B, 256)
+            Bg = min(B, 1024)
             sub = [D[k][:Bg].contiguous() for k in ("ego", "cars_x", "cars_v", "cars_a", "n_cars")]
             v0, a0 = sub[0][:, 2].contiguous(), sub[0][:, 3].contiguous()
             ref = eng.plan(*sub, mode="fast")
@@ -401,6 +401,13 @@ def run_ours(args):
                                    "same_sequences_as_fused": bool(torch.equal(r_["idx"], ref["idx"]))}
                 del g_, r_
             dense_res["episodes"] = Bg
+            tr = measured_traffic("dense32_50", Bg) if H == 50 else None
+            if tr:                              # ncu --set full of the same kernel (profiles/r02_dense_fast_pull_f32_h50.txt)
+                alg = (T * (eng.num_s_max - 1) * 5 + T * 4) * Bg
+                dense_res["fp32_distances"].update({"dram_bytes_per_launch": tr, "algorithmic_bytes_per_launch": alg, "dram_over_algorithmic": tr / alg,
+                                                    "note": "the DP reads only the cells its frontier reaches (mask byte for every offered cell, distance for "
+                                                            "every winner): dram_over_algorithmic is that reachable share of the dense grid; the kernel is "
+                                                            "issue bound like the fused one, not HBM bound"})
         except Exception as e:          # noqa: BLE001
             dense_res = {"error": repr(e)}
     sweep_res = None
@@ -420,7 +427,14 @@ def run_ours(args):
                        "controller": "RL proposes + MPC vetoes (combined_moderate_1 semantics), H=17 grid, fast mode",
                        "planner_takeover_fraction": float(r[1]) / world, "published_takeover_fraction": 0.037,
                        "policy": "published actor pretrained_models/ddpg_moderate1_extended (tests/golden/policy_moderate1.npz)",
-                       "world_model": "reference predictor as dynamics (SUMO-free); published fraction: saved_data.csv:46 (SUMO)"}
+                       "world_model": "merge_gym.MergeEnv, Krauss car-following traffic (SUMO-free); published fraction: saved_data.csv:46 (SUMO)"}
+            try:                        # the same tick as ONE CUDA-graph launch (bit-identical trajectories: tests/test_graphed_tick_gpu.py)
+                grate = env_steps_graphed(local, args.env_envs, args.env_ticks, args.seed + rank)
+                gr = sharding.reduce_sum([grate], dev)
+                env_res["cuda_graph_tick"] = {"value": float(gr[0]), "unit": "env-steps/s", "launches_per_tick": 1,
+                                              "switches": "FUSED_ENV_STEP + SYNC_FREE_TAKEOVER (no host sync in the tick)"}
+            except Exception as e:      # noqa: BLE001
+                env_res["cuda_graph_tick"] = {"error": repr(e)}
         except Exception as e:          # noqa: BLE001  -- the secondary figure must never break the headline line
             env_res = {"error": repr(e)}
     train_res = None
@@ -551,6 +565,33 @@ def env_steps_per_sec(local, world, n_envs, ticks, seed, extra=None):
     st.refresh_engine()
     Settings.reset()
     return n_envs * ticks / (ms * 1e-3), float(take) / ticks
+
+
+def env_steps_graphed(local, n_envs, ticks, seed):
+    """env_steps_per_sec's tick captured once in a CUDA graph and replayed (rl_mpc_lanemerging_b200/graphed_tick.py)."""
+    import torch
+    from rl_mpc_lanemerging_b200 import ddpg, merge_gym, st
+    from rl_mpc_lanemerging_b200.config import Settings
+    from rl_mpc_lanemerging_b200.graphed_tick import GraphedTick
+    Settings.reset()
+    Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL = 20, 11.0, 1.2      # combined_moderate_1.json
+    Settings.TEST_ST_STRICTLY_BETTER, Settings.CUDA_DEVICE, Settings.ALT_J_WEIGHT = False, local, 0.1
+    Settings.FUSED_ENV_STEP = Settings.SYNC_FREE_TAKEOVER = True
+    st.refresh_engine()
+    try:
+        env = merge_gym.MergeEnv(n_envs, seed=seed)
+        agent = ddpg.DDPGAgent.load_npz(os.path.join(ROOT, "tests", "golden", "policy_moderate1.npz"), device=f"cuda:{local}")
+        env.reset()
+        gt = GraphedTick(env, agent).capture(warmup_ticks=32)
+        gt.replay(4)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        gt.replay(ticks)
+        e1.record(); torch.cuda.synchronize()
+        return n_envs * ticks / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        Settings.reset()
+        st.refresh_engine()
 
 
 def train_steps_per_sec(local, world, n_envs, ticks, seed):

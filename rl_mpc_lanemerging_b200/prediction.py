@@ -111,7 +111,18 @@ class HighwayState:
 def tdiv(t, scalar):
     """IEEE division of a tensor by a Python scalar.  `tensor / scalar` on a CUDA device multiplies by the rounded reciprocal
     (x / 0.2 becomes x * 5.0), which differs from the reference's numpy / float division in the last bit; dividing by a 0-dim
-    tensor is a true division on every device."""
-    import torch
-    return t / torch.as_tensor(float(scalar), dtype=t.dtype, device=t.device)
+    tensor is a true division on every device.  (The divisors are cached per device: creating one copies from the host, which a
+    CUDA-graph capture does not allow.)"""
+    key = (float(scalar), t.dtype, t.device)
+    d = _TDIV_CACHE.get(key)
+    if d is None:
+        import torch
+        if t.is_cuda and torch.cuda.is_current_stream_capturing():
+            d = torch.full((), float(scalar), dtype=t.dtype, device=t.device)          # (a fill kernel: capturable; not cached)
+            return t / d
+        d = _TDIV_CACHE[key] = torch.as_tensor(float(scalar), dtype=t.dtype, device=t.device)
+    return t / d
+
+
+_TDIV_CACHE: dict = {}
 

@@ -16,7 +16,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:pred
     python tools/prof_run.py 50 4096 fast > gpurun_out/${TAG}_ncupred_h50.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fast_pull -s 4 -c 1 -o gpurun_out/${TAG}_fallback_h50 \
     python tools/prof_run.py 50 4096 fast > gpurun_out/${TAG}_ncufb_h50.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rasterise -s 1 -c 1 -o gpurun_out/${TAG}_rasterise_h50 \
+MPC_RASTER_ROWS=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rasterise -s 1 -c 1 -o gpurun_out/${TAG}_rasterise_h50 \
     python tools/prof_run.py 50 256 grid > gpurun_out/${TAG}_ncuras_h50.log 2>&1
-MPC_RASTER_ROWS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rasterise_rows -s 1 -c 1 -o gpurun_out/${TAG}_rasterise_rows_h50 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rasterise_rows -s 1 -c 1 -o gpurun_out/${TAG}_rasterise_rows_h50 \
     python tools/prof_run.py 50 256 grid > gpurun_out/${TAG}_ncurasrows_h50.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fast_pull -s 2 -c 1 -o gpurun_out/${TAG}_dense32_h50 \
+    python tools/prof_run.py 50 1024 dense32 > gpurun_out/${TAG}_ncudense32_h50.log 2>&1

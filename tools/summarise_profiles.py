@@ -42,7 +42,7 @@ for H in (50, 17):
                 o.write(f"{k[:70]:70s} {n:8d} {us:12.1f} {100 * us / tot:6.1f}% {us / n:10.1f}\n")
         print("wrote", o.name)
     for kern, tag, regex in (("fast32", "fast32", "fast32"), ("fast", "fast_pull", "fast_pull"), ("fallback", "fallback_fast_pull", "fast_pull"),
-                             ("predict", "predict_layers", "predict_layers"), ("rasterise", "rasterise", "rasterise"), ("rasterise_rows", "rasterise_rows", "rasterise_rows")):
+                             ("predict", "predict_layers", "predict_layers"), ("rasterise", "rasterise", "rasterise"), ("rasterise_rows", "rasterise_rows", "rasterise_rows"), ("dense32", "dense_fast_pull_f32", "fast_pull")):
         rep = f"gpurun_out/{src}_{kern}_h{H}.ncu-rep"
         if not os.path.exists(rep):
             continue
@@ -74,6 +74,16 @@ for H in (50, 17):
         return float(vals[i]) * mult
     traffic[str(H)] = {"episodes": 4096, "kernel": kname, "dram_bytes_read": get("dram__bytes_read.sum"),
                        "dram_bytes_write": get("dram__bytes_write.sum"), "source": f"profiles/{dst}_{'fast32' if kname == 'fast32_kernel' else 'fast_pull'}_h{H}.txt"}
+rep = f"gpurun_out/{src}_dense32_h50.ncu-rep"
+if os.path.exists(rep):                     # K2 on dense fp32 grids (tools/prof_run.py 50 1024 dense32)
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    def getd(name):
+        i = hdr.index(name)
+        return float(vals[i]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+    traffic["dense32_50"] = {"episodes": 1024, "kernel": "fast_pull_kernel<FastDenseProv<float>>", "dram_bytes_read": getd("dram__bytes_read.sum"),
+                             "dram_bytes_write": getd("dram__bytes_write.sum"), "source": f"profiles/{dst}_dense_fast_pull_f32_h50.txt"}
 if traffic:
     json.dump(traffic, open(f"profiles/{dst}_traffic.json", "w"), indent=1)
     print("wrote", f"profiles/{dst}_traffic.json")
