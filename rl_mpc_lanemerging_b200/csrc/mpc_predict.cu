@@ -164,7 +164,7 @@ __device__ __forceinline__ int merge_sorted_intervals(int lane, int nb, int2 *sb
 // desc[B][num_t]; hdr_s0/ds/num_s per problem.
 // SUBSET: only the episodes listed in subset[0 .. *count) are predicted (masked plans; the default instance is unchanged)
 template <bool SUBSET>
-__global__ void __launch_bounds__(128) predict_layers_kernel(DevParams P, int B, const double *__restrict__ ego,
+__global__ void __launch_bounds__(128, 7) predict_layers_kernel(DevParams P, int B, const double *__restrict__ ego,
                                                             const double *__restrict__ cars_x,
                                                             const double *__restrict__ cars_v,
                                                             const int32_t *__restrict__ n_cars, int nmax,

@@ -43,5 +43,9 @@ if __name__ == "__main__":
     ref = run(H, B, {"MPC_FAST32": "0"}, traffic=traffic)
     run(H, B, {}, ref=ref, traffic=traffic)
     for cfg in sys.argv[3:]:
+        if cfg.startswith("fb"):                      # fbN:T -> launch shape of the 64-bit kernel (the hand-over launches)
+            nb, th = cfg[2:].split(":")
+            run(H, B, {"MPC_FAST_BLOCKS": str(32 * int(nb)), "MPC_FAST_THREADS": th}, ref=ref, traffic=traffic)
+            continue
         nb, th = cfg.split(":")
         run(H, B, {"MPC_F32_BLOCKS": str(32 * int(nb)), "MPC_F32_THREADS": th}, ref=ref, traffic=traffic)
