@@ -23,6 +23,8 @@ int qp_max_fine();
 int exact_occupancy(int threads, size_t smem);
 int fast_occupancy(int threads, size_t smem, int wrap);
 cudaError_t launch_fast32_desc(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st);
+cudaError_t launch_fast32_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
+                                int dist_f32, int stride, cudaStream_t st);
 int fast32_occupancy(int threads, size_t smem, int wrap);
 size_t fast32_head_bytes(int num_s_max);
 cudaError_t launch_predict_layers(const DevParams &P, int B, int nmax, const double *ego, const double *cx, const double *cv,
@@ -428,7 +430,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
         F.glab = nullptr; F.ghist = nullptr;
         F.bound = h->use_bound ? h->P.bound_fx : ~0ULL;
         F.grid = h->grid_fast < B ? h->grid_fast : B;
-        if (!dense && h->grid32 > 0 && io.hint_cost == nullptr) {
+        if (h->grid32 > 0 && io.hint_cost == nullptr && (!dense || h->P.zone_ok)) {
             // First attempt by the 32-bit-key kernel (bounded, zones closed).  What it cannot finish -- plans that cross a penalty
             // zone or do not reach the horizon (list entries with bit 30: straight to the unbounded pass), frontiers wider than
             // its ring -- goes to the 64-bit kernel through a device-side list, like that kernel's own hand-backs below.
@@ -439,7 +441,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             F3.grid = h->grid32 < B ? h->grid32 : B;
             io.work_counter = h->counters + 0;
             io.fallback_list = h->fallback_list + 2 * (size_t)h->max_batch; io.fallback_count = h->counters + 5;
-            e = launch_fast32_desc(h->P, F3, io, h->desc, st);
+            e = dense ? launch_fast32_dense(h->P, F3, io, ob, dist, dist_f32, stride, st) : launch_fast32_desc(h->P, F3, io, h->desc, st);
             if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast32 solve launch");
             h->kernels_launched++;
             if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
@@ -451,7 +453,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
                 io.subset = handed; io.B_dev = handed_n;
                 io.fallback_list = h->fallback_list + 3 * (size_t)h->max_batch; io.fallback_count = h->counters + 7;
                 io.overflow_count = nullptr;
-                e = launch_fast32_desc(h->P, F3, io, h->desc, st);
+                e = dense ? launch_fast32_dense(h->P, F3, io, ob, dist, dist_f32, stride, st) : launch_fast32_desc(h->P, F3, io, h->desc, st);
                 if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast32 wide-ring launch");
                 h->kernels_launched++;
                 handed = h->fallback_list + 3 * (size_t)h->max_batch; handed_n = h->counters + 7;
@@ -459,7 +461,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             io.work_counter = h->counters + 6;
             io.subset = handed; io.B_dev = handed_n;
             io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
-            e = launch_fast_desc(h->P, F, io, h->desc, st);
+            e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
             if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the 32-bit-key kernel)");
             h->kernels_launched++;
         } else {

@@ -65,6 +65,7 @@ struct FastDescProv {
         else if (threadIdx.x == kTail) { *reinterpret_cast<int4 *>(dst) = pre; dst->edge_lo = -1e300; }
     }
     static constexpr bool kClipAtPush = true;               // successors are tested against the next layer's bands before the push
+    static constexpr bool kDense = false;
     __device__ __forceinline__ double eval_staged(int t, int k, double s, bool &ob) const { return cell_distance_sorted(sm[t & 3], s, k, ob); }
     // distance only (the caller knows the cell is not in a band)
     __device__ __forceinline__ double distance_staged(int t, int k, double s) const {
@@ -120,6 +121,13 @@ struct FastDenseProv {
         return (double)d_base[o];
     }
     static constexpr bool kClipAtPush = false;              // dense grids: the obstacle test stays at the destination
+    static constexpr bool kDense = true;
+    // (fast32_kernel) in a band, or inside a penalty zone: the cells the bounded pass never enters
+    __device__ __forceinline__ bool is_blocked_zone(int t, int k, double min_allowed) const {
+        const size_t o = (size_t)t * stride + k;
+        return ob_base[o] != 0 || (double)d_base[o] < min_allowed;
+    }
+    __device__ __forceinline__ double distance_at(int t, int k) const { return (double)d_base[(size_t)t * stride + k]; }
     __device__ __forceinline__ double distance_staged(int t, int k, double s) const { bool ob; return eval_staged(t, k, s, ob); }
     __device__ __forceinline__ void bands_near(int, int, int2 &b0, int2 &b1) const { b0 = make_int2(INT_MAX, INT_MAX); b1 = b0; }
     __device__ __forceinline__ bool is_obstacle(int t, int k, int) const { return ob_base[(size_t)t * stride + k] != 0; }
@@ -732,6 +740,12 @@ cudaError_t launch_fast32_desc(const DevParams &P, const SolveLaunch &L, const S
     return launch_fast32_desc_impl(P, L, io, desc, st);
 }
 
+cudaError_t launch_fast32_dense(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
+                                int dist_f32, int stride, cudaStream_t st) {
+    if (L.B <= 0) return cudaSuccess;
+    return launch_fast32_dense_impl(P, L, io, ob, dist, dist_f32, stride, st);
+}
+
 size_t fast32_head_bytes(int num_s_max) { return fast32_smem_head(num_s_max); }
 
 int fast32_occupancy(int threads, size_t smem, int wrap) {
@@ -739,7 +753,7 @@ int fast32_occupancy(int threads, size_t smem, int wrap) {
     cudaError_t e;
 #define MPC_OCC(WRAPV, MAXTV)                                                                              \
     do {                                                                                                   \
-        auto k = fast32_kernel<WRAPV, MAXTV>;                                                              \
+        auto k = fast32_kernel<FastDescProv, WRAPV, MAXTV>;                                                \
         if (set_smem(k, smem) != cudaSuccess) { cudaGetLastError(); return 0; }                            \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem);                           \
     } while (0)

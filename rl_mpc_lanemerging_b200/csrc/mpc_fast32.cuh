@@ -59,9 +59,26 @@ __device__ __forceinline__ unsigned atoms_min_u32(unsigned a, unsigned val) {
 }
 #endif
 
-template <bool WRAP, int MAXT>
+// blocked cells of layer t from DENSE grids (K2): in an obstacle band, or closer than MIN_ALLOWED_DISTANCE to a distance-field edge
+// (the penalty zone the bound excludes) -- the set LayerDesc::blk describes for the descriptor-fed kernel.  One warp per 32-cell
+// word: coalesced reads of the mask bytes and the distances, one ballot.
+template <class Prov>
+__device__ __forceinline__ void build_blocked_bits_dense(const Prov &prov, int t, unsigned *bits, int klo, int khi, int num_s, double min_allowed,
+                                                         int tid, int nth) {
+    const int w1 = khi >> 5, lane = tid & 31;
+    for (int w = (klo >> 5) + (tid >> 5); w <= w1; w += nth >> 5) {
+        const int k = (w << 5) + lane;
+        bool blocked = true;
+        if (k < num_s) blocked = prov.is_blocked_zone(t, k, min_allowed);
+        const unsigned m = __ballot_sync(0xffffffffu, blocked);
+        if (lane == 0) bits[w] = m;
+    }
+}
+
+template <class Prov, bool WRAP, int MAXT>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1))
-fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
+fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc) {
+    constexpr bool DENSE = Prov::kDense;
 #ifdef MPC_HOST_EMU
     unsigned char *const smem_raw = emu::S().dyn_smem;
 #else
@@ -107,10 +124,18 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
             __syncthreads();
             continue;
         }
-        const SGrid g = make_sgrid(P, io.ego[4 * b], io.ego[4 * b + 1]);
-        const double v0 = io.ego[4 * b + 2], a0 = io.ego[4 * b + 3];
-        FastDescProv prov;
-        prov.base = desc + (size_t)b * T; prov.sm = FS.layer;
+        SGrid g;
+        double v0, a0;
+        Prov prov;
+        if constexpr (!DENSE) {
+            g = make_sgrid(P, io.ego[4 * b], io.ego[4 * b + 1]); v0 = io.ego[4 * b + 2]; a0 = io.ego[4 * b + 3];
+            prov.base = desc + (size_t)b * T; prov.sm = FS.layer;
+        } else {
+            g.s0 = io.s0[b]; g.ds = io.ds[b]; g.num_s = io.num_s[b]; v0 = io.v0[b]; a0 = io.a0[b];
+            prov.ob_base = dense_ob + (size_t)b * T * dense_stride;
+            prov.d_base = reinterpret_cast<decltype(prov.d_base)>(dense_d) + (size_t)b * T * dense_stride;
+            prov.stride = dense_stride;
+        }
         build_clamp_bits(P, g, CB);
         const double est_prev = __dsub_rn(g.s0, __dmul_rn(v0, P.p.t_disc));
         const double est_second = __dsub_rn(est_prev, __dmul_rn(P.p.t_disc, __dsub_rn(v0, __dmul_rn(a0, P.p.t_disc))));
@@ -164,7 +189,9 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
                 exact_window(P, g.s0, g.ds, s, g.s0, est_prev, imin, imax);
                 const int kk = imin + j;
                 if (kk >= imax || kk >= g.num_s) continue;
-                if (prov.is_blocked(2, kk)) continue;             // band or penalty zone (st_cy.pyx:383-384 / the bound)
+                bool blocked2;                                    // band or penalty zone (st_cy.pyx:383-384 / the bound)
+                if constexpr (DENSE) blocked2 = prov.is_blocked_zone(2, kk, P.p.min_allowed_distance); else blocked2 = prov.is_blocked(2, kk);
+                if (blocked2) continue;
                 const int vn = kk - k1, an = vn - k1;
                 if (vn > 255 || an < -16 || an > 15 || kk >= F32_L2) { S.need_fallback = 1; continue; }
                 const unsigned long long tot = (unsigned long long)l1 + (unsigned long long)__double2ll_rn(__dmul_rn(exact_kin(P, g.sval(kk), s, g.s0, est_prev), P.f32_one));
@@ -191,7 +218,10 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
         int bt = 0; unsigned long long best_word = 0ULL;
         if (!fail) {
             if (T > 5) prov.load(5);
-            if (T > 3) build_blocked_bits(FS.layer[3], blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), tid, nth);
+            if (T > 3) {
+                if constexpr (DENSE) build_blocked_bits_dense(prov, 3, blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), g.num_s, P.p.min_allowed_distance, tid, nth);
+                else build_blocked_bits(FS.layer[3], blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), tid, nth);
+            }
             // ---- layers 2 .. T-1: one barrier per layer; warps take 32-cell chunks of the layer's span ----
             for (int t = 2; t < T; t++) {
                 const int s3 = t % 3, n3 = (t + 1) % 3, p3 = (t + 2) % 3;
@@ -206,7 +236,10 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
                 if (t + 4 < T) prov.load(t + 4);
                 const bool last = (t == T - 1), first = (t == 2);
                 const unsigned l2a = sbase + (unsigned)offsetof(F32Shared, l2full);
-                if (t + 2 < T) build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
+                if (t + 2 < T) {
+                    if constexpr (DENSE) build_blocked_bits_dense(prov, t + 2, blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), g.num_s, P.p.min_allowed_distance, tid, nth);
+                    else build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
+                }
                 const unsigned edge0 = sbase + (unsigned)(offsetof(F32Shared, FS.layer) + offsetof(LayerSearch, edge)) + (unsigned)(t & 3) * (unsigned)sizeof(LayerSearch);
                 const unsigned bucket0 = edge0 + (unsigned)(offsetof(LayerSearch, bucket_edge) - offsetof(LayerSearch, edge));
                 const unsigned bwa = cba + 4u * (unsigned)(2 * NW + ((t + 1) & 1) * (NW + 2));
@@ -247,6 +280,11 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
                         }
                         unsigned full = (w & ~255u) | low;
                         if (first) full = lds_u32_nc(l2a + 4u * (unsigned)k);
+                        unsigned label;
+                        if constexpr (DENSE) {
+                            // distance penalty: the cell's value in the dense grid (a finalised cell is outside the bands and zones)
+                            label = full + fx_inv_penalty(kw, prov.distance_at(t, k));
+                        } else {
                         // distance penalty: nearest distance-field edge on either side; edge[-1] / edge[n_edge] are -/+1e300
                         double sv = g.sval(k);
 #ifndef MPC_HOST_EMU
@@ -256,7 +294,8 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
                         double hi = lds_f64_nc(ea);
                         while (hi < sv) { ea += 8u; hi = lds_f64_nc(ea); }
                         const double dl = __dsub_rn(sv, lds_f64_nc(ea - 8u)), dr = __dsub_rn(hi, sv);
-                        const unsigned label = full + fx_inv_penalty(kw, dr < dl ? dr : dl);
+                        label = full + fx_inv_penalty(kw, dr < dl ? dr : dl);
+                        }
                         if (label <= bnd) {
                             MPC_EMU_COUNT_NODE();
                             sts_u32(cur + 4u * rk, F32_STATE | ((label & 255u) << 16) | ((unsigned)v << 8) | (unsigned)(a + 128));
@@ -353,13 +392,15 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, int Wc) {
 // bytes of dynamic shared memory in front of the three key / state arrays (the host adds 12 B per ring cell)
 static size_t fast32_smem_head(int num_s_max) { return sizeof(F32Shared) + (size_t)4 * (4 * ((num_s_max + 31) >> 5) + 4); }
 
-static cudaError_t launch_fast32_desc_impl(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st) {
+template <class Prov>
+static cudaError_t launch_fast32_impl(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, const uint8_t *ob,
+                                      const void *dist, int stride, cudaStream_t st) {
     cudaError_t e;
 #define MPC_LAUNCH_F32(WRAPV, MAXTV)                                                                       \
     do {                                                                                                   \
-        auto k = fast32_kernel<WRAPV, MAXTV>;                                                              \
+        auto k = fast32_kernel<Prov, WRAPV, MAXTV>;                                                        \
         if ((e = set_smem(k, L.smem)) != cudaSuccess) return e;                                            \
-        MPC_LAUNCH(k, L.grid, L.threads, L.smem, st, P, L.B, io, desc, L.W);                               \
+        MPC_LAUNCH(k, L.grid, L.threads, L.smem, st, P, L.B, io, desc, ob, dist, stride, L.W);             \
     } while (0)
     if (L.threads <= 192) { if (L.wrap) MPC_LAUNCH_F32(true, 192); else MPC_LAUNCH_F32(false, 192); }
     else if (L.threads <= 256) { if (L.wrap) MPC_LAUNCH_F32(true, 256); else MPC_LAUNCH_F32(false, 256); }
@@ -368,4 +409,15 @@ static cudaError_t launch_fast32_desc_impl(const DevParams &P, const SolveLaunch
     else { if (L.wrap) MPC_LAUNCH_F32(true, 1024); else MPC_LAUNCH_F32(false, 1024); }
 #undef MPC_LAUNCH_F32
     return cudaGetLastError();
+}
+
+static cudaError_t launch_fast32_desc_impl(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const LayerDesc *desc, cudaStream_t st) {
+    return launch_fast32_impl<FastDescProv>(P, L, io, desc, nullptr, nullptr, 0, st);
+}
+
+// K2: the same kernel on dense grids resident in HBM (mpc_solve_dense); fp32 or fp64 distances
+static cudaError_t launch_fast32_dense_impl(const DevParams &P, const SolveLaunch &L, const SolveIO &io, const uint8_t *ob, const void *dist,
+                                            int dist_f32, int stride, cudaStream_t st) {
+    return dist_f32 ? launch_fast32_impl<FastDenseProv<float>>(P, L, io, nullptr, ob, dist, stride, st)
+                    : launch_fast32_impl<FastDenseProv<double>>(P, L, io, nullptr, ob, dist, stride, st);
 }

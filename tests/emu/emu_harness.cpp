@@ -125,7 +125,7 @@ extern "C" int emu_plan32(const mpc_params *params, int B, int nmax, const doubl
         if (Wc < 1024 || 2 * Wc < W) return mpc_set_error(MPC_E_INVALID, "ring32 too small");
         const size_t smem = (size_t)Wc * 12 + fast32_smem_head(P.num_s_max);
         io.work_counter = &counters[0]; io.fallback_list = fb_list.data() + 2 * (size_t)B; io.fallback_count = &counters[5];
-#define EMU_RUN32(WRAPV, MAXTV) emu::launch(1, threads32, smem, [&] { fast32_kernel<WRAPV, MAXTV>(P, B, io, d, Wc); })
+#define EMU_RUN32(WRAPV, MAXTV) emu::launch(1, threads32, smem, [&] { fast32_kernel<FastDescProv, WRAPV, MAXTV>(P, B, io, d, nullptr, nullptr, 0, Wc); })
         if (threads32 <= 192) { if (wrap) EMU_RUN32(true, 192); else EMU_RUN32(false, 192); }
         else if (threads32 <= 512) { if (wrap) EMU_RUN32(true, 512); else EMU_RUN32(false, 512); }
         else { if (wrap) EMU_RUN32(true, 1024); else EMU_RUN32(false, 1024); }

@@ -223,3 +223,27 @@ def test_rollout_step_pieces(oracle, engines, torch_mod):
         assert bool(cr[b]) == crashed
         assert np.allclose(sv[b, :20], oracle.state_vector(op, st).astype(np.float32), rtol=0, atol=1e-7)
         assert sp[b] == oracle.speed_from_jerk(op, st.ego_v, st.ego_a, jerk[b])
+
+
+@pytest.mark.parametrize("H,traffic,n", [(17, "moderate", 192), (17, "low", 96), (50, "moderate", 96), (50, "fast", 64)])
+def test_dense_solve_equals_the_fused_plan(engines, torch_mod, H, traffic, n):
+    """K2 through the 32-bit-key kernel on dense grids (mpc_build_grid output): on fp64 grids bit-identical to the fused plan --
+    hand-overs to the 64-bit kernel included --, on fp32 distances same horizon reached and cost within 1e-4."""
+    torch = torch_mod
+    _, eng = engines[H]
+    D = _dev(_states(traffic, "mixed", n, seed=23), torch)
+    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
+    ref = {k: v.clone() for k, v in eng.plan(*a, mode="fast").items()}
+    fused = eng.fast32_info()
+    v0, a0 = D["ego"][:, 2].contiguous(), D["ego"][:, 3].contiguous()
+    g = eng.build_grid(*a)
+    d64 = eng.solve_dense(g["obstacles"], g["distances"], g["start_s"], g["delta_s"], g["num_s"], v0, a0, mode="fast")
+    dense = eng.fast32_info()
+    assert dense["in_use"] and dense["handed_on"] == fused["handed_on"] > 0
+    for k in ("idx", "s_seq", "cost", "reached_t"):
+        assert torch.equal(d64[k], ref[k]), k
+    g = eng.build_grid(*a, dist_dtype=torch.float32)
+    d32 = eng.solve_dense(g["obstacles"], g["distances"], g["start_s"], g["delta_s"], g["num_s"], v0, a0, mode="fast")
+    assert torch.equal(d32["reached_t"], ref["reached_t"])
+    ok = ref["cost"] > 0
+    assert bool(((d32["cost"][ok] - ref["cost"][ok]).abs() <= 1e-4 * ref["cost"][ok]).all())

@@ -336,3 +336,26 @@ def test_the_two_row_rasterisers_write_the_same_grids(H, monkeypatch):
                 assert np.array_equal(g64["obstacles"][b, :, :n], ob) and np.array_equal(g64["distances"][b, :, :n], di)
                 assert g64["obstacles"][b, :, n:].all() and not g64["distances"][b, :, n:].any()        # beyond the grid: blocked, 0
     eng.close()
+
+
+@pytest.mark.parametrize("H,n,traffic", [(17, 20, "moderate"), (17, 12, "low"), (50, 5, "fast")])
+def test_dense_solve_runs_the_32bit_key_kernel(H, n, traffic):
+    """K2 goes through the same launch chain as the fused planner: fast32_kernel on the dense grids (blocked bits from the mask and
+    the zone test d < MIN_ALLOWED_DISTANCE, penalty from the grid's distance), its hand-overs to the 64-bit kernel.  On fp64 grids
+    the result is the fused plan bit for bit -- including the problems that were handed over."""
+    op, p = _params(H)
+    eng = EA.EmuEngine(p, max_batch=32)
+    S = synthetic.make_states(n, traffic, seed=9, kind="mixed")
+    ref = eng.plan(S)
+    fused = eng.fast32_info()
+    v0, a0 = S["ego"][:, 2].copy(), S["ego"][:, 3].copy()
+    d64 = eng.solve_dense(eng.build_grid(S), v0, a0)
+    dense = eng.fast32_info()
+    assert dense["in_use"] and dense["handed_on"] == fused["handed_on"] and dense["first_shape_handed_on"] == fused["first_shape_handed_on"]
+    assert fused["handed_on"] > 0                                        # the set holds plans that cross a penalty zone
+    _same(d64, ref, ("idx", "cost", "reached_t"))
+    d32 = eng.solve_dense(eng.build_grid(S, f32=True), v0, a0)
+    assert np.array_equal(d32["reached_t"], ref["reached_t"])
+    ok = ref["cost"] > 0
+    assert np.all(helpers.rel(d32["cost"][ok], ref["cost"][ok]) < 1e-4)
+    eng.close()
