@@ -403,12 +403,12 @@ def run_ours(args):
                 del g_, r_
             dense_res["episodes"] = Bg
             tr = measured_traffic("dense32_50", Bg) if H == 50 else None
-            if tr:                              # ncu --set full of the same kernel (profiles/r02_dense_fast_pull_f32_h50.txt)
+            if tr:                              # ncu --set full of the same kernel (profiles/r02_dense_fast32_f32_h50.txt)
                 alg = (T * (eng.num_s_max - 1) * 5 + T * 4) * Bg
                 dense_res["fp32_distances"].update({"dram_bytes_per_launch": tr, "algorithmic_bytes_per_launch": alg, "dram_over_algorithmic": tr / alg,
-                                                    "note": "the DP reads only the cells its frontier reaches (mask byte for every offered cell, distance for "
-                                                            "every winner): dram_over_algorithmic is that reachable share of the dense grid; the kernel is "
-                                                            "issue bound like the fused one, not HBM bound"})
+                                                    "note": "the DP reads only the span its frontier can reach (mask byte + distance of every cell of that span for the "
+                                                            "blocked bits, the distance again for every winner): dram_over_algorithmic is that reachable share "
+                                                            "of the dense grid; the kernel is issue bound like the fused one, not HBM bound"})
         except Exception as e:          # noqa: BLE001
             dense_res = {"error": repr(e)}
     sweep_res = None

@@ -65,13 +65,20 @@ __device__ __forceinline__ unsigned atoms_min_u32(unsigned a, unsigned val) {
 template <class Prov>
 __device__ __forceinline__ void build_blocked_bits_dense(const Prov &prov, int t, unsigned *bits, int klo, int khi, int num_s, double min_allowed,
                                                          int tid, int nth) {
-    const int w1 = khi >> 5, lane = tid & 31;
-    for (int w = (klo >> 5) + (tid >> 5); w <= w1; w += nth >> 5) {
-        const int k = (w << 5) + lane;
-        bool blocked = true;
-        if (k < num_s) blocked = prov.is_blocked_zone(t, k, min_allowed);
-        const unsigned m = __ballot_sync(0xffffffffu, blocked);
-        if (lane == 0) bits[w] = m;
+    const int w1 = khi >> 5, lane = tid & 31, nw = nth >> 5;
+    for (int w = (klo >> 5) + (tid >> 5); w <= w1; w += 4 * nw) {          // four words per warp and trip: four independent loads in flight
+        bool blocked[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = ((w + u * nw) << 5) + lane;
+            blocked[u] = true;
+            if (w + u * nw <= w1 && k < num_s) blocked[u] = prov.is_blocked_zone(t, k, min_allowed);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned m = __ballot_sync(0xffffffffu, blocked[u]);
+            if (lane == 0 && w + u * nw <= w1) bits[w + u * nw] = m;
+        }
     }
 }
 
@@ -259,6 +266,8 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8
                     const int k = base + lane, rk = ring(k);
                     unsigned w = F32_EMPTY;
                     if (k <= dhi) w = lds_u32(cur + 4u * rk);
+                    double dcell = 0.0;                           // (dense grids) the cell's distance: in flight while the key is decoded
+                    if constexpr (DENSE) { if (k <= dhi) dcell = prov.distance_at(t, k); }
                     if (w < F32_STATE) {
                         // the winning offer: v' from the key, the rest from the predecessor's state word
                         int v = 255 - (int)(w & 255u);
@@ -283,7 +292,7 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8
                         unsigned label;
                         if constexpr (DENSE) {
                             // distance penalty: the cell's value in the dense grid (a finalised cell is outside the bands and zones)
-                            label = full + fx_inv_penalty(kw, prov.distance_at(t, k));
+                            label = full + fx_inv_penalty(kw, dcell);
                         } else {
                         // distance penalty: nearest distance-field edge on either side; edge[-1] / edge[n_edge] are -/+1e300
                         double sv = g.sval(k);

@@ -126,3 +126,15 @@ def test_reference_configs_load_unchanged(tmp_path, monkeypatch):
     d = Settings.setup_logging()
     assert os.path.exists(os.path.join(d, "settings.json")) and Settings.FULL_LOG_DIR == d
     Settings.reset()
+
+
+def test_numa_binding_helper_never_raises(tmp_path, monkeypatch):
+    """sharding.bind_to_local_cores: cpulist parsing, and a quiet None where the PCI topology cannot be read (this container has no
+    GPU; a box without sysfs PCI entries behaves the same) -- affinity is an optimisation, never an error."""
+    import os
+    from rl_mpc_lanemerging_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_to_local_cores(0, 1, sysfs=str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before

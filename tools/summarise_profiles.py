@@ -42,7 +42,7 @@ for H in (50, 17):
                 o.write(f"{k[:70]:70s} {n:8d} {us:12.1f} {100 * us / tot:6.1f}% {us / n:10.1f}\n")
         print("wrote", o.name)
     for kern, tag, regex in (("fast32", "fast32", "fast32"), ("fast", "fast_pull", "fast_pull"), ("fallback", "fallback_fast_pull", "fast_pull"),
-                             ("predict", "predict_layers", "predict_layers"), ("rasterise", "rasterise", "rasterise"), ("rasterise_rows", "rasterise_rows", "rasterise_rows"), ("dense32", "dense_fast_pull_f32", "fast_pull")):
+                             ("predict", "predict_layers", "predict_layers"), ("rasterise", "rasterise", "rasterise"), ("rasterise_rows", "rasterise_rows", "rasterise_rows"), ("dense32", "dense_fast32_f32", "fast32")):
         rep = f"gpurun_out/{src}_{kern}_h{H}.ncu-rep"
         if not os.path.exists(rep):
             continue
@@ -82,8 +82,8 @@ if os.path.exists(rep):                     # K2 on dense fp32 grids (tools/prof
     def getd(name):
         i = hdr.index(name)
         return float(vals[i]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
-    traffic["dense32_50"] = {"episodes": 1024, "kernel": "fast_pull_kernel<FastDenseProv<float>>", "dram_bytes_read": getd("dram__bytes_read.sum"),
-                             "dram_bytes_write": getd("dram__bytes_write.sum"), "source": f"profiles/{dst}_dense_fast_pull_f32_h50.txt"}
+    traffic["dense32_50"] = {"episodes": 1024, "kernel": "fast32_kernel<FastDenseProv<float>>", "dram_bytes_read": getd("dram__bytes_read.sum"),
+                             "dram_bytes_write": getd("dram__bytes_write.sum"), "source": f"profiles/{dst}_dense_fast32_f32_h50.txt"}
 if traffic:
     json.dump(traffic, open(f"profiles/{dst}_traffic.json", "w"), indent=1)
     print("wrote", f"profiles/{dst}_traffic.json")

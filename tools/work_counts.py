@@ -63,7 +63,7 @@ def main():
     a = ap.parse_args()
     res = json.load(open(OUT)) if os.path.exists(OUT) else {"model": {}, "ncu": {}}
     with ProcessPoolExecutor(8) as ex:
-        for H in (17, 25, 50, 100):
+        for H in ((17, 25, 50, 100) if a.states > 0 else ()):             # --states 0: keep the model counts, refresh the ncu part only
             frac, bound = frac_and_bound(H)
             n = a.states if H <= 50 else max(a.states // 4, 16)
             for traffic in ("low", "medium", "default", "moderate", "fast"):
