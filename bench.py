@@ -277,10 +277,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
-    bound_cores = None
+    bound_cores, bound_how = None, "single rank"
     if world > 1:
         # one process per GPU: keep the launch thread and the pinned buffers on the GPU's own NUMA node
-        bound_cores = sharding.bind_to_local_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        bound_cores, bound_how = sharding.bind_to_local_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         dist.init_process_group("nccl", device_id=torch.device(dev))
     H, B, K, W = args.horizon, args.batch, args.steps, max(args.warmup, 3)
     eng = MpcEngine(make_params(H), device=local, max_batch=B)
@@ -300,21 +300,19 @@ def run_ours(args):
         eng.plan(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], mode=args.mode, out=out)
 
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()                   # NVML comes up during the warm-up; only samples inside the timed region are kept
+    sampler.start()                       # (every rank: its GPU's clocks explain its step time) NVML comes up during the warm-up; only samples inside the timed region are kept
     for _ in range(W):
         step(); flush.zero_()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
-    if rank == 0:
-        sampler.begin()
+    sampler.begin()
     t_wall = time.perf_counter()
     for i in range(K):                                                       # the host only enqueues: no synchronisation inside the timed region
         ev[i][0].record(); step(); ev[i][1].record()
         flush.zero_()                                                        # L2 flush between timed iterations (outside the events)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     step_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
     # per-kernel times (events recorded inside the library; reading them synchronises, hence a separate, untimed pass)
     eng.set_timing(True)
@@ -348,6 +346,9 @@ def run_ours(args):
     d2h = B * (T * 4 + T * 8 + 8 + 4 + 1 + 8 + 8)
     full = float((r["reached_t"] == T - 1).mean())
 
+    # per-rank view (multi-GPU runs): the slowest rank defines the step; its clocks and kernel times say why
+    per_rank = sharding.gather([step_ms / K, e2e_ms / K, float(np.mean(pred_ms)), float(np.mean(dp_ms)), float(np.mean(fb_ms)),
+                                float((clocks or {}).get("sm_mhz") or 0.0)], dev) if world > 1 else None
     step_ms, e2e_ms = sharding.reduce_max([step_ms, e2e_ms], dev)        # the slowest rank defines the step
     # ---- the one HBM-bound kernel of the path: the dense S-T rasteriser behind mpc_build_grid (st.py:25-70 output) ----
     grid_res = None
@@ -483,8 +484,8 @@ def run_ours(args):
                            if args.mode == "fast" else "fp64, reference operation order",
                            "l2": "256 MiB buffer written between timed iterations (outside the timed events)",
                            "inputs": "resident in HBM (fp64 SoA state)",
-                           "cpu_affinity": (f"rank 0 bound to {len(bound_cores)} cores of its GPU's NUMA node" if bound_cores
-                                            else "not bound")},
+                           "cpu_affinity": (f"rank 0 bound to {len(bound_cores)} cores ({bound_how})" if bound_cores
+                                            else f"not bound ({bound_how})")},
                 "wall_ms_per_step_incl_flush": wall_ms / K,
                 "kernel_ms": {"predict_layers": pred, "dp": dp, "dp_later_launches": fb},
                 "full_horizon_fraction": full, "handed_to_64bit_kernel": f32["handed_on"], "exact_kernel_problems": counters["fallback_problems"],
@@ -500,6 +501,9 @@ def run_ours(args):
                                      "finished / its launch time; stage_frac = all problems / all DP launches; the fused kernel never materialises the "
                                      "grid (`traffic` = its DRAM bytes, ncu): it is bound by instruction issue, see `compute`"},
                 "clocks": clocks}
+        if per_rank is not None:
+            line["per_rank"] = {"columns": ["ms_per_step", "e2e_ms_per_step", "predict_ms", "dp_ms", "dp_later_ms", "sm_mhz_median"],
+                                "rows": [[round(x, 4) for x in r] for r in per_rank]}
         if compute is not None:
             line["compute"] = compute
         if dense_res is not None:

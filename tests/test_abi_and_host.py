@@ -136,5 +136,6 @@ def test_numa_binding_helper_never_raises(tmp_path, monkeypatch):
     assert sharding._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
     assert sharding._parse_cpulist("") == []
     before = os.sched_getaffinity(0)
-    assert sharding.bind_to_local_cores(0, 1, sysfs=str(tmp_path)) is None
+    cores, why = sharding.bind_to_local_cores(0, 1, sysfs=str(tmp_path))
+    assert cores is None and isinstance(why, str)
     assert os.sched_getaffinity(0) == before
