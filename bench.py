@@ -523,6 +523,31 @@ def run_ours(args):
             rate = cpu_port_rate(H, args.traffic, args.seed, n, cores)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {n} episodes of the same workload, C restatement (layered DP, fp64), {cores} threads"}
+        # the last ~2 KB of the line: the secondary figures in compact form (a record that keeps only the tail of stdout still has them)
+        def _r(x, n=3):
+            return None if x is None else round(float(x), n)
+        summ = {"gap_evals_per_s": _r(value, 0), "e2e_gap_evals_per_s": _r(line["e2e"]["value"], 0), "roofline_frac": _r(line["roofline"]["frac"]),
+                "issue_slot_frac": _r((line.get("compute") or {}).get("issue_slot_frac")),
+                "kernel_ms": [_r(pred), _r(dp), _r(fb)]}
+        if isinstance(grid_res, dict) and "frac_of_hbm_peak" in grid_res:
+            summ["rasteriser_frac_of_hbm_peak"] = {"fp32": _r(grid_res["frac_of_hbm_peak"]), "fp64": _r(grid_res["fp64_distances"]["frac_of_hbm_peak"])}
+        if isinstance(dense_res, dict) and "fp32_distances" in dense_res:
+            summ["k2_dense_solve"] = {"episodes": dense_res.get("episodes"), "gap_evals_per_s_fp32": _r(dense_res["fp32_distances"]["gap_evals_per_s"], 0),
+                                      "gap_evals_per_s_fp64": _r(dense_res["fp64_distances"]["gap_evals_per_s"], 0),
+                                      "dram_over_algorithmic": _r(dense_res["fp32_distances"].get("dram_over_algorithmic")),
+                                      "same_sequences_as_fused": dense_res["fp32_distances"]["same_sequences_as_fused"] and dense_res["fp64_distances"]["same_sequences_as_fused"]}
+        if isinstance(sweep_res, dict) and "error" not in sweep_res:
+            summ["sweep_M_gap_evals_per_s"] = {k: _r(v["gap_evals_per_s"] / 1e6) for k, v in sweep_res.items() if isinstance(v, dict) and "gap_evals_per_s" in v}
+        if isinstance(env_res, dict) and "value" in env_res:
+            summ["env_steps_per_s"] = {"eager": _r(env_res["value"], 0), "cuda_graph_tick": _r((env_res.get("cuda_graph_tick") or {}).get("value"), 0),
+                                       "takeover_fraction": _r(env_res.get("planner_takeover_fraction"))}
+        if isinstance(train_res, dict) and "value" in train_res:
+            summ["train_env_frames_per_s"] = _r(train_res["value"], 0)
+        if per_rank is not None:
+            summ["per_rank_ms_per_step"] = [_r(r[0]) for r in per_rank]
+        if "cpu_baseline" in line:
+            summ["cpu_port_gap_evals_per_s"] = _r(line["cpu_baseline"]["value"], 0)
+        line["summary"] = summ
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     eng.close()
     if world > 1:

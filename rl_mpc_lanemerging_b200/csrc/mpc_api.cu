@@ -96,6 +96,7 @@ struct mpc_handle {
     // scratch
     LayerDesc *desc; double *s0, *ds; int32_t *num_s;
     uint16_t *bp; int *counters; int32_t *fallback_list;
+    uint16_t *bp_side;           // back-pointer scratch of the launch that runs on `side` (MPC_SIDE_BLOCKS blocks)
     unsigned long long *glab; unsigned *ghist;
     // staging for the host-buffer entry point
     double *st_ego, *st_cx, *st_cv, *st_ca; int32_t *st_n;
@@ -105,6 +106,7 @@ struct mpc_handle {
     int use_heur;                                // MPC_FAST_HEUR=0 disables the heuristic pruning of hinted solves (dev A/B)
     int probe_overlap;                           // MPC_PROBE_OVERLAP=1: mpc_plan_probed runs the probe plan on a second stream, next to the real predictor
     cudaStream_t aux; cudaEvent_t ev_fork, ev_join;
+    cudaStream_t side; cudaEvent_t ev_side_fork, ev_side_join;      // run_solve: fast32 shape B next to the 64-bit kernel's hand-over launch
     double hint_retry;                           // middle rung of the hinted ladder (MPC_HINT_RETRY, default 1.36 = 1.5 / 1.1; <= 1 disables)
     int64_t kernels_launched;
     // optional per-kernel timing (bench.py roofline): events around [predict | DP | fallback DP]
@@ -117,11 +119,13 @@ static void free_scratch(mpc_handle *h) {
     if (h->capb) { cudaFree(h->capb); h->capb = nullptr; }
     if (h->mask_list) { cudaFree(h->mask_list); h->mask_list = nullptr; }
     if (h->mask_count) { cudaFree(h->mask_count); h->mask_count = nullptr; }
-    void *ptrs[] = {h->desc, h->s0, h->ds, h->num_s, h->bp, h->counters, h->fallback_list, h->glab, h->ghist, h->st_ego,
+    void *ptrs[] = {h->desc, h->s0, h->ds, h->num_s, h->bp, h->bp_side, h->counters, h->fallback_list, h->glab, h->ghist, h->st_ego,
                     h->st_cx, h->st_cv, h->st_ca, h->st_n, h->st_idx, h->st_seq, h->st_cost, h->st_mind, h->st_s0,
                     h->st_reached, h->st_crash};
     for (void *p : ptrs) if (p) cudaFree(p);
 }
+
+#define MPC_SIDE_BLOCKS 48          // grid of the launch on the side stream (fast32 wide-ring shape next to the 64-bit hand-over launch)
 
 static int env_int(const char *name, int lo, int hi, int dflt) {
     const char *v = getenv(name);
@@ -231,7 +235,11 @@ static int alloc_scratch(mpc_handle *h) {
     MPC_CUDA_OK(cudaMalloc(&h->desc, B * T * sizeof(LayerDesc)));
     MPC_CUDA_OK(cudaMalloc(&h->s0, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->ds, B * 8)); MPC_CUDA_OK(cudaMalloc(&h->num_s, B * 4));
     MPC_CUDA_OK(cudaMalloc(&h->bp, (size_t)h->grid_max * T * h->W * sizeof(uint16_t)));
+    MPC_CUDA_OK(cudaMalloc(&h->bp_side, (size_t)MPC_SIDE_BLOCKS * T * h->W * sizeof(uint16_t)));
     MPC_CUDA_OK(cudaMalloc(&h->counters, 16 * sizeof(int)));
+    MPC_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    MPC_CUDA_OK(cudaEventCreateWithFlags(&h->ev_side_fork, cudaEventDisableTiming));
+    MPC_CUDA_OK(cudaEventCreateWithFlags(&h->ev_side_join, cudaEventDisableTiming));
     MPC_CUDA_OK(cudaMalloc(&h->fallback_list, 4 * B * 4));
     if (h->smem == 0) {
         MPC_CUDA_OK(cudaMalloc(&h->glab, (size_t)h->grid_exact * 2 * h->W * 8));
@@ -284,6 +292,7 @@ extern "C" int mpc_destroy(mpc_handle *h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->aux) { cudaStreamDestroy(h->aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+    if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_side_fork); cudaEventDestroy(h->ev_side_join); }
     free_scratch(h);
     free(h);
     return MPC_OK;
@@ -314,7 +323,8 @@ extern "C" int mpc_fast32_info(const mpc_handle *h, int64_t *out6) {
     MPC_CUDA_OK(cudaSetDevice(h->device));
     MPC_CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
     out6[0] = h->grid32 > 0; out6[1] = h->P.f32_frac; out6[2] = h->P.f32_bound; out6[3] = h->Wc32;
-    out6[4] = h->grid32 > 0 ? c[h->grid32b > 0 ? 7 : 5] : 0; out6[5] = h->grid32 > 0 ? c[5] : 0;
+    // handed to the 64-bit kernel: with two shapes the flagged entries of the first (c[11]) + what the wide ring handed on (c[7])
+    out6[4] = h->grid32 > 0 ? (h->grid32b > 0 ? c[11] + c[7] : c[5]) : 0; out6[5] = h->grid32 > 0 ? c[5] : 0;
     return MPC_OK;
 }
 
@@ -435,7 +445,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             // zone or do not reach the horizon (list entries with bit 30: straight to the unbounded pass), frontiers wider than
             // its ring -- goes to the 64-bit kernel through a device-side list, like that kernel's own hand-backs below.
             h->calls32++; h->last_B32 = B;
-            io.overflow_count = h->counters + 9;
+            io.overflow_count = h->counters + 9; io.flagged_count = h->counters + 11;
             SolveLaunch F3 = F;
             F3.threads = h->threads32; F3.smem = h->smem32; F3.W = h->Wc32; F3.wrap = h->wrap32;
             F3.grid = h->grid32 < B ? h->grid32 : B;
@@ -446,24 +456,45 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             h->kernels_launched++;
             if (h->timing) MPC_CUDA_OK(cudaEventRecord(h->ev[2], st));
             const int32_t *handed = h->fallback_list + 2 * (size_t)h->max_batch; const int *handed_n = h->counters + 5;
-            if (h->grid32b > 0) {                    // frontiers wider than ring A: once more with the wide ring (flagged entries pass through)
+            // Two kinds of entries in that list, two independent launches that run side by side: the flagged ones (bit 30: bounded
+            // attempt failed) go to the 64-bit kernel's unbounded pass on the caller's stream; the frontiers that outgrew ring A
+            // go once more through the 32-bit-key kernel with the wide ring, on a second stream (a single such problem occupies
+            // one block for ~0.3 ms at H=50 -- serialised in front of the 64-bit launch it cost that much per step on the ranks
+            // whose episodes held one).  What the wide ring cannot finish either follows in a second 64-bit launch after the join.
+            const bool two_shapes = h->grid32b > 0;
+            if (two_shapes) {
+                MPC_CUDA_OK(cudaEventRecord(h->ev_side_fork, st));
+                MPC_CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_side_fork, 0));
+                SolveIO iob = io;
                 F3.threads = h->threads32b; F3.smem = h->smem32b; F3.W = h->Wc32b; F3.wrap = h->wrap32b;
                 F3.grid = h->grid32b < B ? h->grid32b : B;
-                io.work_counter = h->counters + 8;
-                io.subset = handed; io.B_dev = handed_n;
-                io.fallback_list = h->fallback_list + 3 * (size_t)h->max_batch; io.fallback_count = h->counters + 7;
-                io.overflow_count = nullptr;
-                e = dense ? launch_fast32_dense(h->P, F3, io, ob, dist, dist_f32, stride, st) : launch_fast32_desc(h->P, F3, io, h->desc, st);
+                if (F3.grid > MPC_SIDE_BLOCKS) F3.grid = MPC_SIDE_BLOCKS;        // few problems by construction (shape A adapts above 2 %)
+                iob.bp = h->bp_side;                                              // the two launches run at the same time: own scratch rows
+                iob.work_counter = h->counters + 8;
+                iob.subset = handed; iob.B_dev = handed_n; iob.skip_flagged = 1;
+                iob.fallback_list = h->fallback_list + 3 * (size_t)h->max_batch; iob.fallback_count = h->counters + 7;
+                iob.overflow_count = nullptr; iob.flagged_count = nullptr;
+                e = dense ? launch_fast32_dense(h->P, F3, iob, ob, dist, dist_f32, stride, h->side) : launch_fast32_desc(h->P, F3, iob, h->desc, h->side);
                 if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast32 wide-ring launch");
                 h->kernels_launched++;
-                handed = h->fallback_list + 3 * (size_t)h->max_batch; handed_n = h->counters + 7;
+                MPC_CUDA_OK(cudaEventRecord(h->ev_side_join, h->side));
             }
+            io.overflow_count = nullptr; io.flagged_count = nullptr;
             io.work_counter = h->counters + 6;
-            io.subset = handed; io.B_dev = handed_n;
+            io.subset = handed; io.B_dev = handed_n; io.only_flagged = two_shapes ? 1 : 0;
             io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
             e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
             if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the 32-bit-key kernel)");
             h->kernels_launched++;
+            io.only_flagged = 0;
+            if (two_shapes) {
+                MPC_CUDA_OK(cudaStreamWaitEvent(st, h->ev_side_join, 0));
+                io.work_counter = h->counters + 10;
+                io.subset = h->fallback_list + 3 * (size_t)h->max_batch; io.B_dev = h->counters + 7;
+                e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
+                if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the wide ring)");
+                h->kernels_launched++;
+            }
         } else {
         io.work_counter = h->counters + 0;
         e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);

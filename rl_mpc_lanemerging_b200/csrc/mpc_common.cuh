@@ -182,6 +182,9 @@ struct SolveIO {
     const int *B_dev;            // optional: number of problems read on the device (overrides B)
     int32_t *fallback_list; int *fallback_count;   // fast kernel: problems that need the exact kernel
     int *overflow_count;         // 32-bit-key kernel (optional): how many of its hand-overs were frontiers wider than its ring
+    int *flagged_count;          // 32-bit-key kernel (optional): how many of its hand-overs carry bit 30 (bounded attempt failed)
+    int skip_flagged;            // 32-bit-key kernel, second shape: list entries with bit 30 belong to the 64-bit kernel's concurrent launch
+    int only_flagged;            // 64-bit kernel: take only the list entries with bit 30 (the others are with the second shape)
     // optional per-problem cost hint of the fast kernel (mpc_plan_hinted): first bound = hint_scale * hint_cost[b], used when
     // hint_reached == NULL or hint_reached[b] == hint_full_t
     const double *hint_cost; const int32_t *hint_reached; int hint_full_t; double hint_scale;

@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
         if (wi >= B) break;
         int b = io.subset ? io.subset[wi] : wi;
         // bit 30 of a list entry (set by fast32_kernel): the bounded attempt has already failed for this problem
+        if (io.only_flagged && !((b >> 30) & 1)) { __syncthreads(); continue; }      // (with fast32_kernel's second shape, running concurrently)
         const unsigned long long bound_b = ((b >> 30) & 1) ? FX_EMPTY : bound;
         b &= 0x3fffffff;
         SGrid g;

@@ -126,9 +126,9 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8
         const int wi = S.b;
         if (wi >= B) break;
         const int b = io.subset ? io.subset[wi] : wi;
-        if (b & (1 << 30)) {                  // (second shape) the bounded attempt has already failed: pass the entry on
-            if (tid == 0) { const int q = atomicAdd(io.fallback_count, 1); io.fallback_list[q] = b; }
-            __syncthreads();
+        if (b & (1 << 30)) {                  // (second shape) the bounded attempt has already failed: not for this kernel --
+            if (tid == 0 && !io.skip_flagged) { const int q = atomicAdd(io.fallback_count, 1); io.fallback_list[q] = b; }   // passed on, unless the
+            __syncthreads();                                                                                              // 64-bit kernel reads the same list
             continue;
         }
         SGrid g;
@@ -267,7 +267,7 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8
                     unsigned w = F32_EMPTY;
                     if (k <= dhi) w = lds_u32(cur + 4u * rk);
                     double dcell = 0.0;                           // (dense grids) the cell's distance: in flight while the key is decoded
-                    if constexpr (DENSE) { if (k <= dhi) dcell = prov.distance_at(t, k); }
+                    if constexpr (DENSE) { if (k <= dhi) dcell = prov.distance_at(t, k); }     // (one chunk ahead was measured slower)
                     if (w < F32_STATE) {
                         // the winning offer: v' from the key, the rest from the predecessor's state word
                         int v = 255 - (int)(w & 255u);
@@ -390,6 +390,7 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8
             if (tid == 0) {
                 const int q = atomicAdd(io.fallback_count, 1); io.fallback_list[q] = b | (overflow ? 0 : (1 << 30));
                 if (overflow && io.overflow_count) atomicAdd(io.overflow_count, 1);
+                if (!overflow && io.flagged_count) atomicAdd(io.flagged_count, 1);
             }
             __syncthreads();
             continue;

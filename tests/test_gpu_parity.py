@@ -247,3 +247,33 @@ def test_dense_solve_equals_the_fused_plan(engines, torch_mod, H, traffic, n):
     assert torch.equal(d32["reached_t"], ref["reached_t"])
     ok = ref["cost"] > 0
     assert bool(((d32["cost"][ok] - ref["cost"][ok]).abs() <= 1e-4 * ref["cost"][ok]).all())
+
+
+def test_wide_ring_launch_next_to_the_handover_launch(oracle, engines, torch_mod, monkeypatch):
+    """The problems whose frontier outgrew the first ring (second launch shape of the 32-bit-key kernel, side stream) and the
+    flagged problems (64-bit kernel, caller's stream) are solved at the same time, each launch with its own scratch: low traffic at
+    H=50 with a forced small ring has dozens of both; plans equal to the 64-bit kernel's alone, on every repetition."""
+    from rl_mpc_lanemerging_b200.engine import MpcEngine
+    op, _ = engines[50]
+    S = _states("low", "onramp", 512, seed=31)
+    D = _dev(S, torch_mod)
+    a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
+    monkeypatch.setenv("MPC_FAST32", "0")
+    alone = MpcEngine(helpers.mpc_params_from_oracle(op), device=0, max_batch=512, nmax=32)
+    ref = {k: v.clone() for k, v in alone.plan(*a, mode="fast").items()}
+    alone.close()
+    monkeypatch.delenv("MPC_FAST32")
+    monkeypatch.setenv("MPC_F32_BLOCKS", "96")
+    eng = MpcEngine(helpers.mpc_params_from_oracle(op), device=0, max_batch=512, nmax=32)
+    try:
+        for rep in range(4):
+            out = eng.plan(*a, mode="fast")
+            info = eng.fast32_info()
+            for k in ("idx", "s_seq", "reached_t", "crash", "min_dist"):
+                assert torch_mod.equal(out[k], ref[k]), (k, rep)
+            assert bool(((out["cost"] - ref["cost"]).abs() <= 1e-6 * ref["cost"].clamp(min=1.0)).all())      # 2^-17 against 2^-18 labels
+            if rep == 0:
+                wide = info["first_shape_handed_on"] - info["handed_on"]           # solved by the wide ring
+                assert wide >= 10 and info["handed_on"] >= 10, info
+    finally:
+        eng.close()

@@ -14,7 +14,7 @@ def run(H, B, env, reps=4, traffic="moderate", ref=None):
     p = _lib.default_params()
     p.future_t, p.future_s = synthetic.horizon_settings(H)
     eng = MpcEngine(p, 0, max_batch=B)
-    D = states_to_device(synthetic.make_states(B, traffic, seed=0), "cuda:0")
+    D = states_to_device(synthetic.make_states(B, traffic, seed=0, first_episode=int(os.environ.get("SWEEP_FIRST", "0"))), "cuda:0")
     a = (D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"])
     out = eng.plan(*a, mode="fast")
     torch.cuda.synchronize()
@@ -32,7 +32,7 @@ def run(H, B, env, reps=4, traffic="moderate", ref=None):
         same = (res["idx"] == ref["idx"]).all(1)
         rel = np.abs(res["cost"] - ref["cost"]) / np.maximum(ref["cost"], 1e-9)
         msg = f" | vs 64-bit kernel: idx identical {same.mean():.4f}, cost rel max {rel.max():.2e}, reached equal {np.array_equal(res['reached_t'], ref['reached_t'])}, crash equal {np.array_equal(res['crash'], ref['crash'])}"
-    print(f"H={H} B={B} {traffic} {env}: {best:.3f} ms -> {B / best * 1e3:.0f} gap-evals/s  (pred, dp, fb) = {tuple(round(x, 3) for x in km)}  f32={info} 64-bit hand-backs={c['fallback_problems']}{msg}", flush=True)
+    print(f"H={H} B={B} {traffic} {env}: {best:.3f} ms -> {B / best * 1e3:.0f} gap-evals/s  (pred, dp, fb) = {tuple(round(x, 3) for x in km)}  f32={info} 64-bit hand-backs={c['fallback_problems']} counters={eng.raw_counters() if hasattr(eng, 'raw_counters') else ''}{msg}", flush=True)
     eng.close()
     return res
 

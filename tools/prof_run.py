@@ -9,7 +9,7 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 mode = sys.argv[3] if len(sys.argv) > 3 else "fast"
 p = _lib.default_params(); p.future_t, p.future_s = synthetic.horizon_settings(H)
 eng = MpcEngine(p, 0, max_batch=B)
-D = states_to_device(synthetic.make_states(B, "moderate", seed=0), "cuda:0")
+D = states_to_device(synthetic.make_states(B, os.environ.get("PROF_TRAFFIC", "moderate"), seed=0, first_episode=int(os.environ.get("PROF_FIRST", "0"))), "cuda:0")
 if mode in ("dense32", "dense64"):            # K2: the DP kernel on dense grids resident in HBM (mpc_solve_dense)
     g = eng.build_grid(D["ego"], D["cars_x"], D["cars_v"], D["cars_a"], D["n_cars"], dist_dtype=torch.float32 if mode == "dense32" else torch.float64)
     v0, a0 = D["ego"][:, 2].contiguous(), D["ego"][:, 3].contiguous()
