@@ -106,7 +106,7 @@ struct mpc_handle {
     int use_heur;                                // MPC_FAST_HEUR=0 disables the heuristic pruning of hinted solves (dev A/B)
     int probe_overlap;                           // MPC_PROBE_OVERLAP=1: mpc_plan_probed runs the probe plan on a second stream, next to the real predictor
     cudaStream_t aux; cudaEvent_t ev_fork, ev_join;
-    cudaStream_t side; cudaEvent_t ev_side_fork, ev_side_join;      // run_solve: fast32 shape B next to the 64-bit kernel's hand-over launch
+    int use_side; cudaStream_t side; cudaEvent_t ev_side_fork, ev_side_join;      // run_solve: fast32 shape B next to the 64-bit kernel's hand-over launch
     double hint_retry;                           // middle rung of the hinted ladder (MPC_HINT_RETRY, default 1.36 = 1.5 / 1.1; <= 1 disables)
     int64_t kernels_launched;
     // optional per-kernel timing (bench.py roofline): events around [predict | DP | fallback DP]
@@ -220,6 +220,7 @@ static int configure(mpc_handle *h, int want_nb32 = 0) {
             if (h->Wc32b <= h->Wc32) h->grid32b = 0;
         }
       } }
+    { const char *e = getenv("MPC_SIDE_STREAM"); h->use_side = !(e && e[0] == '0'); }
     { const char *e = getenv("MPC_FAST_HEUR"); h->use_heur = !(e && e[0] == '0'); }
     { const char *e = getenv("MPC_PROBE_OVERLAP"); h->probe_overlap = (e && e[0] == '1'); }
     { const char *e = getenv("MPC_HINT_RETRY"); h->hint_retry = e ? atof(e) : 1.36; if (!(h->hint_retry >= 0.0 && h->hint_retry < 100.0)) h->hint_retry = 1.36; }
@@ -462,9 +463,12 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             // one block for ~0.3 ms at H=50 -- serialised in front of the 64-bit launch it cost that much per step on the ranks
             // whose episodes held one).  What the wide ring cannot finish either follows in a second 64-bit launch after the join.
             const bool two_shapes = h->grid32b > 0;
+            cudaStream_t sside = h->use_side ? h->side : st;        // MPC_SIDE_STREAM=0: one after the other on the caller's stream
             if (two_shapes) {
-                MPC_CUDA_OK(cudaEventRecord(h->ev_side_fork, st));
-                MPC_CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_side_fork, 0));
+                if (h->use_side) {
+                    MPC_CUDA_OK(cudaEventRecord(h->ev_side_fork, st));
+                    MPC_CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_side_fork, 0));
+                }
                 SolveIO iob = io;
                 F3.threads = h->threads32b; F3.smem = h->smem32b; F3.W = h->Wc32b; F3.wrap = h->wrap32b;
                 F3.grid = h->grid32b < B ? h->grid32b : B;
@@ -474,10 +478,10 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
                 iob.subset = handed; iob.B_dev = handed_n; iob.skip_flagged = 1;
                 iob.fallback_list = h->fallback_list + 3 * (size_t)h->max_batch; iob.fallback_count = h->counters + 7;
                 iob.overflow_count = nullptr; iob.flagged_count = nullptr;
-                e = dense ? launch_fast32_dense(h->P, F3, iob, ob, dist, dist_f32, stride, h->side) : launch_fast32_desc(h->P, F3, iob, h->desc, h->side);
+                e = dense ? launch_fast32_dense(h->P, F3, iob, ob, dist, dist_f32, stride, sside) : launch_fast32_desc(h->P, F3, iob, h->desc, sside);
                 if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast32 wide-ring launch");
                 h->kernels_launched++;
-                MPC_CUDA_OK(cudaEventRecord(h->ev_side_join, h->side));
+                if (h->use_side) MPC_CUDA_OK(cudaEventRecord(h->ev_side_join, h->side));
             }
             io.overflow_count = nullptr; io.flagged_count = nullptr;
             io.work_counter = h->counters + 6;
@@ -488,7 +492,7 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             h->kernels_launched++;
             io.only_flagged = 0;
             if (two_shapes) {
-                MPC_CUDA_OK(cudaStreamWaitEvent(st, h->ev_side_join, 0));
+                if (h->use_side) MPC_CUDA_OK(cudaStreamWaitEvent(st, h->ev_side_join, 0));
                 io.work_counter = h->counters + 10;
                 io.subset = h->fallback_list + 3 * (size_t)h->max_batch; io.B_dev = h->counters + 7;
                 e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
