@@ -272,7 +272,12 @@ extern "C" int mpc_create(const mpc_params *p, int device, int max_batch, int nm
     h->smem_optin = prop.sharedMemPerBlockOptin;
     configure(h);
     rc = alloc_scratch(h);
-    if (rc) { free_scratch(h); free(h); return rc; }
+    if (rc) {
+        if (h->side) cudaStreamDestroy(h->side);
+        if (h->ev_side_fork) cudaEventDestroy(h->ev_side_fork);
+        if (h->ev_side_join) cudaEventDestroy(h->ev_side_join);
+        free_scratch(h); free(h); return rc;
+    }
     *out = h;
     return MPC_OK;
 }
