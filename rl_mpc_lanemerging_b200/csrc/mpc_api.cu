@@ -87,6 +87,8 @@ struct mpc_handle {
     size_t smem;                 // dynamic shared memory of the exact kernel (0 -> it uses global label scratch)
     int threads, grid_exact;
     int Wc, wrap_fast, threads_fast, grid_fast; size_t smem_fast;   // fast kernel: ring capacity / launch shape
+    int Wc_alt, wrap_alt, threads_alt, grid_alt; size_t smem_alt;   // second shape for long hand-over lists (one block per SM more); grid_alt = 0: none
+    int alt_mode;                                                   // MPC_HANDOVER_ALT: 0 never, 1 by the list's length (default), 2 always (tests)
     size_t smem_fast_big;        // full-row variant used to re-solve ring overflows (0 = does not fit)
     int Wc32, wrap32, threads32, grid32; size_t smem32;             // 32-bit-key kernel (mpc_fast32.cuh): ring capacity / launch shape; grid32 == 0: not used
     int Wc32b, wrap32b, threads32b, grid32b; size_t smem32b;        // its second shape (wider ring) for the problems that outgrew the first; grid32b == 0: none
@@ -175,6 +177,27 @@ static int configure(mpc_handle *h, int want_nb32 = 0) {
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
+    // Second shape for the hand-over list of the 32-bit-key kernel: one block per SM more (H=50: 3 x 384 instead of 2 x 512).  Every
+    // problem of that list takes 0.2-0.3 ms whatever its size (latency: two barriers per layer), so what matters is that none of the
+    // slow ones starts in a second round: with more entries than ~9/8 of the resident blocks the wider grid wins although each
+    // block is a little slower (measured at H=50: 327 entries 0.38 vs 0.43 ms, 339 / 382 entries 0.52 / 0.53 vs 0.43 / 0.44 ms).
+    h->grid_alt = 0;
+    h->alt_mode = env_int("MPC_HANDOVER_ALT", 0, 2, 1);
+    if (P.fast_ok && h->alt_mode && fast_blocks >= 2 && fast_blocks <= 4) {
+        const int nb = fast_blocks + 1;
+        const size_t per = (h->smem_optin + 1024) / nb;
+        if (per > 1024 + static_smem + clamp_bytes) {
+            const size_t cap_alt = (per - 1024 - static_smem - clamp_bytes) / 16;
+            if (cap_alt * 5 >= (size_t)h->W * 2) {                                   // ring >= 0.4 of the row (what outgrows it goes to the full-row launch)
+                h->wrap_alt = (size_t)h->W > cap_alt;
+                h->Wc_alt = h->wrap_alt ? (int)(cap_alt & ~(size_t)7) : h->W;
+                h->smem_alt = (size_t)h->Wc_alt * 16 + clamp_bytes;
+                h->threads_alt = nb >= 5 ? 192 : (nb >= 4 ? 256 : 384);
+                const int occ_alt = fast_occupancy(h->threads_alt, h->smem_alt, h->wrap_alt);
+                if (occ_alt >= nb) h->grid_alt = h->sm_count * occ_alt;
+            }
+        }
+    }
     h->use_bound = env_int("MPC_FAST_BOUND", 0, 1, 1) && P.bound_fx != 0;
     // ---- 32-bit-key kernel: 12 B per cell (three rotating arrays of 32-bit words) behind a ring window ----
     // Two launch shapes.  A: as many blocks per SM (<= 5) as leave a ring of half the row -- frontier spans at H=50: <= 0.46 of the
@@ -227,6 +250,7 @@ static int configure(mpc_handle *h, int want_nb32 = 0) {
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     if (h->grid32 > h->grid_max) h->grid_max = h->grid32;
     if (h->grid32b > h->grid_max) h->grid_max = h->grid32b;
+    if (h->grid_alt > h->grid_max) h->grid_max = h->grid_alt;
     return MPC_OK;
 }
 
@@ -492,9 +516,24 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             io.work_counter = h->counters + 6;
             io.subset = handed; io.B_dev = handed_n; io.only_flagged = two_shapes ? 1 : 0;
             io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
+            // two shapes enqueued, the list's length (on the device) picks one: see configure()
+            const bool alt = h->grid_alt > 0 && (h->alt_mode == 2 || F.grid == h->grid_fast);
+            const int n_split = h->alt_mode == 2 ? 0 : h->grid_fast + h->grid_fast / 8;
+            if (alt) { io.n_lo = 0; io.n_hi = h->alt_mode == 2 ? -1 : n_split; }
             e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
             if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the 32-bit-key kernel)");
             h->kernels_launched++;
+            if (alt) {
+                SolveLaunch FA = F;
+                FA.threads = h->threads_alt; FA.smem = h->smem_alt; FA.W = h->Wc_alt; FA.wrap = h->wrap_alt;
+                FA.grid = h->grid_alt < B ? h->grid_alt : B;
+                io.n_lo = n_split + 1; io.n_hi = INT_MAX;
+                io.work_counter = h->counters + 12;
+                e = dense ? launch_fast_dense(h->P, FA, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, FA, io, h->desc, st);
+                if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs, wide grid)");
+                h->kernels_launched++;
+                io.n_lo = 0; io.n_hi = 0;
+            }
             io.only_flagged = 0;
             if (two_shapes) {
                 if (h->use_side) MPC_CUDA_OK(cudaStreamWaitEvent(st, h->ev_side_join, 0));

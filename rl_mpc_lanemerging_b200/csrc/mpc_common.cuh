@@ -183,6 +183,8 @@ struct SolveIO {
     int32_t *fallback_list; int *fallback_count;   // fast kernel: problems that need the exact kernel
     int *overflow_count;         // 32-bit-key kernel (optional): how many of its hand-overs were frontiers wider than its ring
     int *flagged_count;          // 32-bit-key kernel (optional): how many of its hand-overs carry bit 30 (bounded attempt failed)
+    int n_lo, n_hi;              // 64-bit kernel: when n_hi != 0 the launch only works if its list holds n_lo <= n <= n_hi entries (two
+                                 // launch shapes are enqueued for the hand-over list; its length, known on the device only, picks one)
     int skip_flagged;            // 32-bit-key kernel, second shape: list entries with bit 30 belong to the 64-bit kernel's concurrent launch
     int only_flagged;            // 64-bit kernel: take only the list entries with bit 30 (the others are with the second shape)
     // optional per-problem cost hint of the fast kernel (mpc_plan_hinted): first bound = hint_scale * hint_cost[b], used when

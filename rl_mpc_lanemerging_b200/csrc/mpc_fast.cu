@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAX
     for (int i = tid; i < 512; i += nth) TB.aj[i] = P.atab[i >> 4] + P.jtab[i & 15];
     for (int k = tid; k < 2 * Wc; k += nth) sts_u64(sb0 + 8u * k, FX_EMPTY);       // both buffers; every pass leaves them empty again
     if (io.B_dev) B = *io.B_dev;
+    if (io.n_hi != 0 && (B < io.n_lo || B > io.n_hi)) return;         // (uniform) the other launch shape has this list
     for (;;) {
         if (tid == 0) S.b = atomicAdd(io.work_counter, 1);
         __syncthreads();

@@ -139,7 +139,8 @@ def test_sorted_search_structure_is_exact(engines, torch_mod, H, traffic, kind):
                                    (50, {"MPC_FAST_BLOCKS": "96", "MPC_FAST_THREADS": "384"}),
                                    (17, {"MPC_FAST32": "0"}), (50, {"MPC_FAST32": "0"}),
                                    (17, {"MPC_F32_BLOCKS": "64", "MPC_F32_THREADS": "512"}), (50, {"MPC_F32_BLOCKS": "64", "MPC_F32_THREADS": "1024"}),
-                                   (50, {"MPC_F32_BLOCKS": "96", "MPC_F32_THREADS": "256", "MPC_FAST_BLOCKS": "96"})])
+                                   (50, {"MPC_F32_BLOCKS": "96", "MPC_F32_THREADS": "256", "MPC_FAST_BLOCKS": "96"}),
+                                   (50, {"MPC_HANDOVER_ALT": "2"}), (17, {"MPC_HANDOVER_ALT": "2"}), (50, {"MPC_SIDE_STREAM": "0"})])
 def test_fast_result_does_not_depend_on_bound_or_launch_shape(oracle, engines, torch_mod, monkeypatch, H, env):
     """The 32-bit-key kernel followed by the 64-bit kernel (default), the 64-bit kernel alone (MPC_FAST32=0: lean bounded first
     pass, retry without the bound inside the kernel), its plain unbounded pass (MPC_FAST_BOUND=0, which also switches the
