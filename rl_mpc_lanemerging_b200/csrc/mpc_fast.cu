@@ -128,6 +128,19 @@ struct FastDenseProv {
         return ob_base[o] != 0 || (double)d_base[o] < min_allowed;
     }
     __device__ __forceinline__ double distance_at(int t, int k) const { return (double)d_base[(size_t)t * stride + k]; }
+    // Bulk L2 prefetch (cp.async.bulk.prefetch.L2, one instruction per array) of the mask bytes and the distances of cells
+    // [klo, khi] of layer t: issued by ONE thread a layer before build_blocked_bits_dense reads them, so that those reads -- the
+    // first touch of every byte of the grid the DP uses -- find the lines in L2 instead of waiting for HBM.
+    __device__ __forceinline__ void prefetch_span(int t, int klo, int khi) const {
+#ifndef MPC_HOST_EMU
+        if (khi < klo) return;
+        const size_t o = (size_t)t * stride;
+        const uintptr_t a0 = (uintptr_t)(ob_base + o + klo) & ~(uintptr_t)15, a1 = ((uintptr_t)(ob_base + o + khi + 1) + 15) & ~(uintptr_t)15;
+        const uintptr_t b0 = (uintptr_t)(d_base + o + klo) & ~(uintptr_t)15, b1 = ((uintptr_t)(d_base + o + khi + 1) + 15) & ~(uintptr_t)15;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(b0), "r"((unsigned)(b1 - b0)) : "memory");
+#endif
+    }
     __device__ __forceinline__ double distance_staged(int t, int k, double s) const { bool ob; return eval_staged(t, k, s, ob); }
     __device__ __forceinline__ void bands_near(int, int, int2 &b0, int2 &b1) const { b0 = make_int2(INT_MAX, INT_MAX); b1 = b0; }
     __device__ __forceinline__ bool is_obstacle(int t, int k, int) const { return ob_base[(size_t)t * stride + k] != 0; }

@@ -226,7 +226,10 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8
         if (!fail) {
             if (T > 5) prov.load(5);
             if (T > 3) {
-                if constexpr (DENSE) build_blocked_bits_dense(prov, 3, blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), g.num_s, P.p.min_allowed_distance, tid, nth);
+                if constexpr (DENSE) {
+                    if (tid == 0 && T > 4) prov.prefetch_span(4, dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1));      // read by the build at t = 2
+                    build_blocked_bits_dense(prov, 3, blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), g.num_s, P.p.min_allowed_distance, tid, nth);
+                }
                 else build_blocked_bits(FS.layer[3], blkbits[1], dlo, min(dhi + P.vmax_c, g.num_s - 1), tid, nth);
             }
             // ---- layers 2 .. T-1: one barrier per layer; warps take 32-cell chunks of the layer's span ----
@@ -244,7 +247,11 @@ fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8
                 const bool last = (t == T - 1), first = (t == 2);
                 const unsigned l2a = sbase + (unsigned)offsetof(F32Shared, l2full);
                 if (t + 2 < T) {
-                    if constexpr (DENSE) build_blocked_bits_dense(prov, t + 2, blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), g.num_s, P.p.min_allowed_distance, tid, nth);
+                    if constexpr (DENSE) {
+                        // next iteration's build (layer t + 3 over the span of layer t + 1 + 2 v_max): ask L2 for it now
+                        if (tid == 0 && t + 3 < T) prov.prefetch_span(t + 3, dlo, min(dhi + 3 * P.vmax_c, g.num_s - 1));
+                        build_blocked_bits_dense(prov, t + 2, blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), g.num_s, P.p.min_allowed_distance, tid, nth);
+                    }
                     else build_blocked_bits(FS.layer[(t + 2) & 3], blkbits[t & 1], dlo, min(dhi + 2 * P.vmax_c, g.num_s - 1), tid, nth);
                 }
                 const unsigned edge0 = sbase + (unsigned)(offsetof(F32Shared, FS.layer) + offsetof(LayerSearch, edge)) + (unsigned)(t & 3) * (unsigned)sizeof(LayerSearch);
