@@ -448,7 +448,13 @@ def run_ours(args):
             train_res = {"value": float(r[0]), "unit": "env-frames/s", "grad_steps_per_s": float(g[0]), "envs_per_gpu": args.env_envs,
                          "ticks": args.train_ticks, "minibatch_per_gpu": 4096, "allreduce_bytes_per_step": nbytes if world > 1 else 0,
                          "collective": "NCCL all-reduce of ONE flat fp32 gradient (actor + critic)" if world > 1 else "none (1 rank)",
-                         "config": "train_medium_1.json semantics (DDPG, traffic 7 m/s / 1.8 s); library hyper-parameters unpinned"}
+                         "config": "train_medium_1.json semantics (DDPG, traffic 7 m/s / 1.8 s); library hyper-parameters unpinned; THROUGHPUT "
+                                   "setting (one gradient step of 4096 samples per tick of envs_per_gpu frames)"}
+            if rank == 0 and world == 1:            # the library defaults = the reference's update-to-data ratio (what the learning curve used)
+                try:
+                    train_res["reference_update_ratio"] = train_reference_ratio(local, args.seed)
+                except Exception as e:  # noqa: BLE001
+                    train_res["reference_update_ratio"] = {"error": repr(e)}
         except Exception as e:          # noqa: BLE001
             train_res = {"error": repr(e)}
     if rank == 0:
@@ -622,6 +628,37 @@ def env_steps_graphed(local, n_envs, ticks, seed):
     finally:
         Settings.reset()
         st.refresh_engine()
+
+
+def train_reference_ratio(local, seed, ticks=12):
+    """The trainer at the library defaults (config.py: TRAIN_NUM_ENVS 256, TRAIN_MINIBATCH 1024, TRAIN_SAMPLES_PER_FRAME 100): the
+    reference's update-to-data ratio -- one gradient step on 100 replayed samples per environment frame (ddpg.py:46-81 with the
+    preset's update_frequency 1) -- kept with larger minibatches: 25 gradient steps of 1024 samples per tick of 256 frames.  This is
+    the configuration tools/learning_curve.py trains with; returns env-frames/s and grad steps/s of this rank."""
+    import torch
+    from rl_mpc_lanemerging_b200 import merge_gym, st, trainer
+    from rl_mpc_lanemerging_b200.config import Settings
+    Settings.reset()
+    Settings.CRASH_MIN_S, Settings.OTHER_CAR_SPEED, Settings.BASE_TRAFFIC_INTERVAL, Settings.CUDA_DEVICE = 20, 7.0, 1.8, local   # train_medium_1.json
+    st.refresh_engine()
+    try:
+        n_envs, mb = int(Settings.TRAIN_NUM_ENVS), int(Settings.TRAIN_MINIBATCH)
+        upt = max(1, round(n_envs * float(Settings.TRAIN_SAMPLES_PER_FRAME) / mb))
+        env = merge_gym.MergeEnv(n_envs, seed=seed)
+        tr = trainer.DDPGTrainer(env, device=f"cuda:{local}", lr=2e-4, seed=0, minibatch_size=mb, updates_per_tick=upt,
+                                 replay_start_size=n_envs * 4, replay_buffer_size=65536)
+        tr.train(n_envs * 8)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0 = tr.grad_steps
+        torch.cuda.synchronize(); e0.record()
+        tr.train(n_envs * ticks)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return {"env_frames_per_s": n_envs * ticks / (ms * 1e-3), "grad_steps_per_s": (tr.grad_steps - g0) / (ms * 1e-3), "envs": n_envs,
+                "minibatch": mb, "updates_per_tick": upt, "samples_per_frame": float(Settings.TRAIN_SAMPLES_PER_FRAME)}
+    finally:
+        st.refresh_engine()
+        Settings.reset()
 
 
 def train_steps_per_sec(local, world, n_envs, ticks, seed):

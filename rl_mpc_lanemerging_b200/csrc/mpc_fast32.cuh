@@ -65,17 +65,18 @@ __device__ __forceinline__ unsigned atoms_min_u32(unsigned a, unsigned val) {
 template <class Prov>
 __device__ __forceinline__ void build_blocked_bits_dense(const Prov &prov, int t, unsigned *bits, int klo, int khi, int num_s, double min_allowed,
                                                          int tid, int nth) {
+    constexpr int DEPTH = 4;                                                // words per warp and trip: that many independent loads in flight
     const int w1 = khi >> 5, lane = tid & 31, nw = nth >> 5;
-    for (int w = (klo >> 5) + (tid >> 5); w <= w1; w += 4 * nw) {          // four words per warp and trip: four independent loads in flight
-        bool blocked[4];
+    for (int w = (klo >> 5) + (tid >> 5); w <= w1; w += DEPTH * nw) {
+        bool blocked[DEPTH];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < DEPTH; u++) {
             const int k = ((w + u * nw) << 5) + lane;
             blocked[u] = true;
             if (w + u * nw <= w1 && k < num_s) blocked[u] = prov.is_blocked_zone(t, k, min_allowed);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < DEPTH; u++) {
             const unsigned m = __ballot_sync(0xffffffffu, blocked[u]);
             if (lane == 0 && w + u * nw <= w1) bits[w + u * nw] = m;
         }
