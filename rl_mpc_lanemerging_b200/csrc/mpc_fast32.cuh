@@ -84,7 +84,7 @@ __device__ __forceinline__ void build_blocked_bits_dense(const Prov &prov, int t
 }
 
 template <class Prov, bool WRAP, int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 5 : MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1))
+__global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 6 : MAXT <= 256 ? 4 : MAXT <= 384 ? 3 : MAXT <= 512 ? 2 : 1))
 fast32_kernel(DevParams P, int B, SolveIO io, const LayerDesc *desc, const uint8_t *dense_ob, const void *dense_d, int dense_stride, int Wc) {
     constexpr bool DENSE = Prov::kDense;
 #ifdef MPC_HOST_EMU
