@@ -139,3 +139,26 @@ def test_numa_binding_helper_never_raises(tmp_path, monkeypatch):
     cores, why = sharding.bind_to_local_cores(0, 1, sysfs=str(tmp_path))
     assert cores is None and isinstance(why, str)
     assert os.sched_getaffinity(0) == before
+
+
+def test_graphed_tick_refuses_a_tick_with_host_syncs():
+    """GraphedTick only captures the tick that has no host synchronisation left (FUSED_ENV_STEP + SYNC_FREE_TAKEOVER) on an
+    auto-resetting environment; anything else is refused before any CUDA call."""
+    import types
+    from rl_mpc_lanemerging_b200.config import Settings
+    from rl_mpc_lanemerging_b200.graphed_tick import GraphedTick
+    env = types.SimpleNamespace(B=4, device="cpu", auto_reset=True)
+    Settings.reset()
+    try:
+        with pytest.raises(RuntimeError, match="FUSED_ENV_STEP"):
+            GraphedTick(env, agent=None)
+        Settings.FUSED_ENV_STEP = Settings.SYNC_FREE_TAKEOVER = True
+        env.auto_reset = False
+        with pytest.raises(RuntimeError, match="auto-resetting"):
+            GraphedTick(env, agent=None)
+        env.auto_reset = True
+        gt = GraphedTick(env, agent=None)
+        with pytest.raises(RuntimeError, match="capture"):
+            gt.replay()
+    finally:
+        Settings.reset()
