@@ -87,8 +87,9 @@ struct mpc_handle {
     size_t smem;                 // dynamic shared memory of the exact kernel (0 -> it uses global label scratch)
     int threads, grid_exact;
     int Wc, wrap_fast, threads_fast, grid_fast; size_t smem_fast;   // fast kernel: ring capacity / launch shape
-    int Wc_alt, wrap_alt, threads_alt, grid_alt; size_t smem_alt;   // second shape for long hand-over lists (one block per SM more); grid_alt = 0: none
-    int alt_mode;                                                   // MPC_HANDOVER_ALT: 0 never, 1 by the list's length (default), 2 always (tests)
+    struct Shape64 { int Wc, wrap, threads, grid; size_t smem; };   // a launch shape of the 64-bit kernel (grid = 0: not available)
+    Shape64 hand_few, hand_many;                                    // hand-over list: few large blocks (short lists) / many smaller ones (long lists)
+    int alt_mode;                                                   // MPC_HANDOVER_ALT: 0 main shape only, 1 by the list's length (default), 2 always hand_many (tests)
     size_t smem_fast_big;        // full-row variant used to re-solve ring overflows (0 = does not fit)
     int Wc32, wrap32, threads32, grid32; size_t smem32;             // 32-bit-key kernel (mpc_fast32.cuh): ring capacity / launch shape; grid32 == 0: not used
     int Wc32b, wrap32b, threads32b, grid32b; size_t smem32b;        // its second shape (wider ring) for the problems that outgrew the first; grid32b == 0: none
@@ -177,26 +178,31 @@ static int configure(mpc_handle *h, int want_nb32 = 0) {
     int occ = fast_occupancy(h->threads_fast, h->smem_fast, h->wrap_fast);
     h->grid_fast = P.fast_ok ? h->sm_count * (occ < 1 ? 1 : occ) : 0;
     h->smem_fast_big = ((size_t)h->W * 16 + clamp_bytes + static_smem <= h->smem_optin) ? (size_t)h->W * 16 + clamp_bytes : 0;
-    // Second shape for the hand-over list of the 32-bit-key kernel: one block per SM more (H=50: 3 x 384 instead of 2 x 512).  Every
-    // problem of that list takes 0.2-0.3 ms whatever its size (latency: two barriers per layer), so what matters is that none of the
-    // slow ones starts in a second round: with more entries than ~9/8 of the resident blocks the wider grid wins although each
-    // block is a little slower (measured at H=50: 327 entries 0.38 vs 0.43 ms, 339 / 382 entries 0.52 / 0.53 vs 0.43 / 0.44 ms).
-    h->grid_alt = 0;
-    h->alt_mode = env_int("MPC_HANDOVER_ALT", 0, 2, 1);
-    if (P.fast_ok && h->alt_mode && fast_blocks >= 2 && fast_blocks <= 4) {
-        const int nb = fast_blocks + 1;
+    // Launch shapes for the hand-over list of the 32-bit-key kernel.  Every problem of that list takes 0.1-0.3 ms whatever its size
+    // (latency: two barriers per layer), so a SHORT list wants few large blocks (lowest latency per problem: H=17, 311 entries:
+    // 2 x 512 threads 0.11 ms against 0.13 ms for the bulk shape 5 x 192) and a LONG list must not leave a slow problem for a second
+    // round: beyond ~9/8 of the resident blocks the wider grid wins although each block is a little slower (H=50: 327 entries 0.38
+    // vs 0.43 ms, 339 / 382 entries 0.52 / 0.53 vs 0.43 / 0.44 ms).  Both launches are enqueued; the list's length, known on the
+    // device only, lets one of them work (SolveIO::n_lo / n_hi).
+    auto shape64 = [&](int nb, mpc_handle::Shape64 *S) {
+        S->grid = 0;
         const size_t per = (h->smem_optin + 1024) / nb;
-        if (per > 1024 + static_smem + clamp_bytes) {
-            const size_t cap_alt = (per - 1024 - static_smem - clamp_bytes) / 16;
-            if (cap_alt * 5 >= (size_t)h->W * 2) {                                   // ring >= 0.4 of the row (what outgrows it goes to the full-row launch)
-                h->wrap_alt = (size_t)h->W > cap_alt;
-                h->Wc_alt = h->wrap_alt ? (int)(cap_alt & ~(size_t)7) : h->W;
-                h->smem_alt = (size_t)h->Wc_alt * 16 + clamp_bytes;
-                h->threads_alt = nb >= 5 ? 192 : (nb >= 4 ? 256 : 384);
-                const int occ_alt = fast_occupancy(h->threads_alt, h->smem_alt, h->wrap_alt);
-                if (occ_alt >= nb) h->grid_alt = h->sm_count * occ_alt;
-            }
-        }
+        if (!P.fast_ok || per <= 1024 + static_smem + clamp_bytes) return;
+        const size_t c = (per - 1024 - static_smem - clamp_bytes) / 16;
+        if (c * 5 < (size_t)h->W * 2) return;                                        // ring >= 0.4 of the row (what outgrows it goes to the full-row launch)
+        S->wrap = (size_t)h->W > c;
+        S->Wc = S->wrap ? (int)(c & ~(size_t)7) : h->W;
+        S->smem = (size_t)S->Wc * 16 + clamp_bytes;
+        S->threads = nb >= 5 ? 192 : (nb >= 4 ? 256 : (nb >= 3 ? 384 : (nb >= 2 ? 512 : 1024)));
+        const int o = fast_occupancy(S->threads, S->smem, S->wrap);
+        if (o >= nb) S->grid = h->sm_count * nb;
+    };
+    h->alt_mode = env_int("MPC_HANDOVER_ALT", 0, 2, 1);
+    h->hand_few.grid = 0; h->hand_many.grid = 0;
+    if (h->alt_mode) {
+        shape64(fast_blocks < 2 ? fast_blocks : 2, &h->hand_few);
+        shape64(fast_blocks > 3 ? fast_blocks : 3, &h->hand_many);
+        if (h->hand_few.grid == 0 || h->hand_many.grid == 0 || h->hand_few.grid >= h->hand_many.grid) { h->hand_few.grid = 0; h->hand_many.grid = 0; }
     }
     h->use_bound = env_int("MPC_FAST_BOUND", 0, 1, 1) && P.bound_fx != 0;
     // ---- 32-bit-key kernel: 12 B per cell (three rotating arrays of 32-bit words) behind a ring window ----
@@ -250,7 +256,8 @@ static int configure(mpc_handle *h, int want_nb32 = 0) {
     h->grid_max = h->grid_fast > h->grid_exact ? h->grid_fast : h->grid_exact;
     if (h->grid32 > h->grid_max) h->grid_max = h->grid32;
     if (h->grid32b > h->grid_max) h->grid_max = h->grid32b;
-    if (h->grid_alt > h->grid_max) h->grid_max = h->grid_alt;
+    if (h->hand_many.grid > h->grid_max) h->grid_max = h->hand_many.grid;
+    if (h->hand_few.grid > h->grid_max) h->grid_max = h->hand_few.grid;
     return MPC_OK;
 }
 
@@ -517,22 +524,24 @@ static int run_solve(mpc_handle *h, int B, int mode, bool dense, SolveIO io, con
             io.subset = handed; io.B_dev = handed_n; io.only_flagged = two_shapes ? 1 : 0;
             io.fallback_list = h->fallback_list; io.fallback_count = h->counters + 2;
             // two shapes enqueued, the list's length (on the device) picks one: see configure()
-            const bool alt = h->grid_alt > 0 && (h->alt_mode == 2 || F.grid == h->grid_fast);
-            const int n_split = h->alt_mode == 2 ? 0 : h->grid_fast + h->grid_fast / 8;
-            if (alt) { io.n_lo = 0; io.n_hi = h->alt_mode == 2 ? -1 : n_split; }
-            e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
-            if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the 32-bit-key kernel)");
-            h->kernels_launched++;
-            if (alt) {
-                SolveLaunch FA = F;
-                FA.threads = h->threads_alt; FA.smem = h->smem_alt; FA.W = h->Wc_alt; FA.wrap = h->wrap_alt;
-                FA.grid = h->grid_alt < B ? h->grid_alt : B;
-                io.n_lo = n_split + 1; io.n_hi = INT_MAX;
-                io.work_counter = h->counters + 12;
-                e = dense ? launch_fast_dense(h->P, FA, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, FA, io, h->desc, st);
-                if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs, wide grid)");
-                h->kernels_launched++;
+            if (h->hand_many.grid > 0) {
+                const int n_split = h->alt_mode == 2 ? -1 : h->hand_few.grid + h->hand_few.grid / 8;
+                const mpc_handle::Shape64 *shapes[2] = {&h->hand_few, &h->hand_many};
+                for (int v = 0; v < 2; v++) {
+                    SolveLaunch FH = F;
+                    FH.threads = shapes[v]->threads; FH.smem = shapes[v]->smem; FH.W = shapes[v]->Wc; FH.wrap = shapes[v]->wrap;
+                    FH.grid = shapes[v]->grid < B ? shapes[v]->grid : B;
+                    if (v == 0) { io.n_lo = 0; io.n_hi = n_split < 0 ? -1 : n_split; io.work_counter = h->counters + 6; }
+                    else { io.n_lo = n_split + 1; io.n_hi = INT_MAX; io.work_counter = h->counters + 12; }
+                    e = dense ? launch_fast_dense(h->P, FH, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, FH, io, h->desc, st);
+                    if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the 32-bit-key kernel)");
+                    h->kernels_launched++;
+                }
                 io.n_lo = 0; io.n_hi = 0;
+            } else {
+                e = dense ? launch_fast_dense(h->P, F, io, ob, dist, dist_f32, stride, st) : launch_fast_desc(h->P, F, io, h->desc, st);
+                if (e != cudaSuccess) return mpc_set_cuda_error(e, "fast solve launch (hand-backs of the 32-bit-key kernel)");
+                h->kernels_launched++;
             }
             io.only_flagged = 0;
             if (two_shapes) {
