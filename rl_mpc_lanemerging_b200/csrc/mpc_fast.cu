@@ -128,6 +128,29 @@ struct FastDenseProv {
         return ob_base[o] != 0 || (double)d_base[o] < min_allowed;
     }
     __device__ __forceinline__ double distance_at(int t, int k) const { return (double)d_base[(size_t)t * stride + k]; }
+    // the same test for the four cells k4 .. k4+3 (k4 % 4 == 0) with one vector load per array; bit j = cell k4 + j.  Needs vec_ok().
+    __device__ __forceinline__ bool vec_ok() const {
+        return (stride & 3) == 0 && ((uintptr_t)ob_base & 3) == 0 && ((uintptr_t)d_base & 15) == 0;
+    }
+    __device__ __forceinline__ unsigned blocked4(int t, int k4, double min_allowed, int num_s) const {
+        if (k4 >= stride) return 0xfu;
+        const size_t o = (size_t)t * stride + k4;
+        const uchar4 m = *reinterpret_cast<const uchar4 *>(ob_base + o);
+        double d0, d1, d2, d3;
+        if constexpr (sizeof(DT) == 4) {
+            const float4 d = *reinterpret_cast<const float4 *>(d_base + o);
+            d0 = (double)d.x; d1 = (double)d.y; d2 = (double)d.z; d3 = (double)d.w;
+        } else {
+            const double2 a = *reinterpret_cast<const double2 *>(d_base + o), b = *reinterpret_cast<const double2 *>(d_base + o + 2);
+            d0 = a.x; d1 = a.y; d2 = b.x; d3 = b.y;
+        }
+        unsigned r = 0;
+        r |= (k4 + 0 >= num_s || m.x != 0 || d0 < min_allowed) ? 1u : 0u;
+        r |= (k4 + 1 >= num_s || m.y != 0 || d1 < min_allowed) ? 2u : 0u;
+        r |= (k4 + 2 >= num_s || m.z != 0 || d2 < min_allowed) ? 4u : 0u;
+        r |= (k4 + 3 >= num_s || m.w != 0 || d3 < min_allowed) ? 8u : 0u;
+        return r;
+    }
     // Bulk L2 prefetch (cp.async.bulk.prefetch.L2, one instruction per array) of the mask bytes and the distances of cells
     // [klo, khi] of layer t: issued by ONE thread a layer before build_blocked_bits_dense reads them, so that those reads -- the
     // first touch of every byte of the grid the DP uses -- find the lines in L2 instead of waiting for HBM.

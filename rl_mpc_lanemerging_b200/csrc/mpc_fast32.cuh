@@ -65,6 +65,28 @@ __device__ __forceinline__ unsigned atoms_min_u32(unsigned a, unsigned val) {
 template <class Prov>
 __device__ __forceinline__ void build_blocked_bits_dense(const Prov &prov, int t, unsigned *bits, int klo, int khi, int num_s, double min_allowed,
                                                          int tid, int nth) {
+    if (prov.vec_ok()) {
+        // (uniform) aligned grids -- every grid mpc_build_grid writes: a warp takes 128 cells per trip, four per lane with one vector
+        // load per array (two load instructions per thread instead of eight, a quarter of the trips), eight lanes OR their nibbles
+        // into one word.  Words below klo >> 5 that the first group covers get their true bits too.
+        const int w1 = khi >> 5, lane = tid & 31, nw = nth >> 5;
+        for (int g = (klo >> 7) + (tid >> 5); g <= (khi >> 7); g += 2 * nw) {      // two groups per trip: independent loads in flight
+            unsigned v[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int gg = g + u * nw;
+                v[u] = gg <= (khi >> 7) ? prov.blocked4(t, (gg << 7) + (lane << 2), min_allowed, num_s) << ((lane & 7) << 2) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                unsigned x = v[u];
+                x |= __shfl_xor_sync(0xffffffffu, x, 1); x |= __shfl_xor_sync(0xffffffffu, x, 2); x |= __shfl_xor_sync(0xffffffffu, x, 4);
+                const int w = ((g + u * nw) << 2) + (lane >> 3);
+                if ((lane & 7) == 0 && w <= w1) bits[w] = x;
+            }
+        }
+        return;
+    }
     constexpr int DEPTH = 4;                                                // words per warp and trip: that many independent loads in flight
     const int w1 = khi >> 5, lane = tid & 31, nw = nth >> 5;
     for (int w = (klo >> 5) + (tid >> 5); w <= w1; w += DEPTH * nw) {
