@@ -19,7 +19,8 @@ def _worker(rank, world, port, total, q):
     r = O.plan_batch(O.default_params(), S["ego"], S["cars_x"], S["cars_v"], S["cars_a"], S["n_cars"], 18, layered=True, nthreads=2)
     mx = sharding.reduce_max([1.0 + rank, 5.0 - rank], "cpu")
     sm = sharding.reduce_sum([float(hi - lo)], "cpu")
-    q.put((rank, lo, hi, r["idx"], r["cost"], mx, sm))
+    ga = sharding.gather([float(rank), 10.0 * rank], "cpu")       # the bench's per-rank diagnostics
+    q.put((rank, lo, hi, r["idx"], r["cost"], mx, sm, ga))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -44,3 +45,4 @@ def test_two_rank_sharding_matches_single_process(oracle):
     assert np.array_equal(np.concatenate([r[4] for r in res]), ref["cost"])
     for r in res:
         assert r[5] == [2.0, 5.0] and r[6] == [float(total)]
+        assert r[7] == [[0.0, 0.0], [1.0, 10.0]]
